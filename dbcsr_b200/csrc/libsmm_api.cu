@@ -1,0 +1,171 @@
+// dbcsr_b200/csrc/libsmm_api.cu -- the SMM half of the drop-in C ABI (include/dbcsr_acc_libsmm.h).
+//
+// libsmm_acc_process / libsmm_acc_transpose / c_calculate_norms with the reference's argument meaning and return codes
+// (src/acc/libsmm_acc/libsmm_acc.cpp:324-339,482-487; src/acc/cuda_hip/calculate_norms.cpp:98-117), dispatching to the
+// ahead-of-time compiled sm_100a kernels of this library.  No JIT, no CPU fall-back inside the library: an unsupported request
+// returns a negative code and leaves C untouched (DBCSR then runs the stack on its own CPU driver).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/dbcsr_acc_libsmm.h"
+#include "smm_generic.cuh"
+#include "smm_launch.h"
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_num_sms{0};
+
+int num_sms() {
+  int n = g_num_sms.load(std::memory_order_relaxed);
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      g_num_sms.store(n, std::memory_order_relaxed);
+    else
+      n = 148;
+  }
+  return n;
+}
+
+// End address of the device allocation that contains `p` (0 = unknown).  The DMMA kernel stages 16-byte-aligned windows and may
+// over-read up to 8 bytes behind a block; for the last block of an allocation that must not cross the allocation's end.
+// cuMemGetAddressRange is fetched through the runtime so that the library has no link-time dependency on libcuda.
+typedef int (*cuMemGetAddressRange_t)(unsigned long long* pbase, size_t* psize, unsigned long long dptr);
+uint64_t allocation_end(const void* p) {
+  static cuMemGetAddressRange_t fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<cuMemGetAddressRange_t>(f);
+  }();
+  if (fn == nullptr || p == nullptr) return 0;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<unsigned long long>(p)) != 0) return 0;
+  return base + size;
+}
+
+smm::launch_fn lookup(int m, int n, int k) {
+  switch (m) {
+    case 5: return smm::lookup_m5(n, k);
+    case 13: return smm::lookup_m13(n, k);
+    case 23: return smm::lookup_m23(n, k);
+    case 26: return smm::lookup_m26(n, k);
+    case 32: return smm::lookup_m32(n, k);
+    default: return nullptr;
+  }
+}
+
+int launch_generic(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k,
+                   int b_transposed, cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  const int max_grid = num_sms() * 8;
+  int grid = (stack_size + smm::GEN_WPC * 2 - 1) / (smm::GEN_WPC * 2);
+  if (grid > max_grid) grid = max_grid;
+  const int warps = grid * smm::GEN_WPC;
+  const int chunk = (stack_size + warps - 1) / warps;
+  smm::smm_generic_kernel<<<grid, smm::GEN_WPC * 32, 0, stream>>>(dev_stack, stack_size, a, b, c, m, n, k, b_transposed, chunk);
+  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+}
+
+}  // namespace
+
+extern "C" {
+
+int libsmm_acc_init(void) { return 0; }      // kernels are compiled ahead of time; nothing to set up per thread
+int libsmm_acc_finalize(void) { return 0; }
+c_dbcsr_acc_bool_t libsmm_acc_is_thread_safe(void) { return 1; }
+int libsmm_acc_gpu_warp_size(void) { return 32; }
+long long libsmm_acc_b200_launch_count(void) { return g_launches.load(); }
+const char* libsmm_acc_b200_version(void) { return "dbcsr_acc_b200 r1 (sm_100a, DMMA.8x8x4 + TMA bulk staging)"; }
+
+int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype) {
+  if (datatype != dbcsr_type_real_8) return 0;
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  return lookup(m, n, k) != nullptr ? 1 : 2;
+}
+
+int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, int stack_size, libsmm_acc_data_t datatype,
+                       const void* dev_a_data, const void* dev_b_data, void* dev_c_data, int m_max, int n_max, int k_max,
+                       int max_kernel_dim, c_dbcsr_acc_bool_t def_mnk, void* stack_stream, void* c_stream) {
+  (void)host_param_stack;
+  if (def_mnk != 1) return -1;                      // inhomogeneous stack: not handled (reference: libsmm_acc.cpp:327)
+  if (datatype != dbcsr_type_real_8) return -10;    // reference: libsmm_acc.cpp:338
+  if (stack_size < 0 || m_max <= 0 || n_max <= 0 || k_max <= 0) return -2;
+  if (stack_stream == nullptr) return -2;
+  const double* a = static_cast<const double*>(dev_a_data);
+  const double* b = static_cast<const double*>(dev_b_data);
+  double* c = static_cast<double*>(dev_c_data);
+
+  if (m_max > max_kernel_dim || n_max > max_kernel_dim || k_max > max_kernel_dim) {
+    // Large blocks.  The reference loops cublasDgemm over the HOST stack on c_stream and synchronises (libsmm_acc.cpp:256-278);
+    // here one generic launch drains the device stack asynchronously on c_stream (which already waits for the stack upload,
+    // src/mm/dbcsr_mm_accdrv.F:516).  B is transposed only if both n and k fit max_kernel_dim (libsmm_acc.cpp:267-270).
+    if (c_stream == nullptr) return -2;
+    const int b_transposed = (n_max <= max_kernel_dim && k_max <= max_kernel_dim) ? 1 : 0;
+    const int rc = launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, b_transposed,
+                                  *static_cast<cudaStream_t*>(c_stream));
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc == 0 ? 10 : rc;
+  }
+
+  cudaStream_t stream = *static_cast<cudaStream_t*>(stack_stream);
+  const smm::launch_fn fn = lookup(m_max, n_max, k_max);
+  if (fn != nullptr) {
+    const int rc = fn(dev_param_stack, stack_size, a, b, c, allocation_end(a), allocation_end(b), stream);
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
+  const int rc = launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, 1, stream);
+  if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return rc == 0 ? 10 : rc;  // 10 = "ran with an untuned kernel" (reference: libsmm_acc.cpp:319)
+}
+
+int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, void* dev_data, libsmm_acc_data_t datatype, int m,
+                         int n, int max_kernel_dim, void* stream) {
+  if (datatype != dbcsr_type_real_8) return 0;               // transpose not needed (reference: libsmm_acc.cpp:484)
+  if (m > max_kernel_dim || n > max_kernel_dim) return 0;    // reference: libsmm_acc.cpp:485
+  if (stack_size <= 0 || m <= 0 || n <= 0) return 0;
+  if (stream == nullptr) return -2;
+  const size_t blk_bytes = (size_t)m * n * sizeof(double);
+  int wpc = (int)((96 * 1024) / blk_bytes);
+  if (wpc > 8) wpc = 8;
+  if (wpc < 1) return -3;  // cannot happen for m,n <= 80 (51 KB)
+  const size_t smem = blk_bytes * wpc;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(smm::transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return -30;
+    attr_set.store(true, std::memory_order_release);
+  }
+  int grid = (stack_size + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::transpose_kernel<<<grid, wpc * 32, smem, *static_cast<cudaStream_t*>(stream)>>>(dev_trs_stack + offset, stack_size,
+                                                                                        static_cast<double*>(dev_data), m, n);
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int c_calculate_norms(const double* mat, int nblks, const int* offsets, const int* nelems, float* norms, void* stream_ptr) {
+  if (nblks <= 0) return 0;
+  if (stream_ptr == nullptr) return -2;
+  const int wpc = 8;
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::norms_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream_ptr)>>>(mat, nblks, offsets, nelems, norms);
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// dbcsr_b200/csrc/smm_generic.cuh -- shape-agnostic kernels: generic stack drain (any m,n,k; B transposed or not),
+// batched in-place block transpose, batched block norms.
+//
+// Reference counterparts: the untuned default of src/acc/libsmm_acc/libsmm_acc.cpp:222-231 and the per-entry cuBLAS loop
+// :256-278 (generic drain); src/acc/libsmm_acc/kernels/smm_acc_transpose.h:41-65 (transpose);
+// src/acc/cuda_hip/calculate_norms.cpp:48-117 (norms).  All new code; run-time shapes, no JIT.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "smm_dmma.cuh"
+
+namespace smm {
+
+// One warp per stack entry (grid-stride over chunks of the C-sorted stack); lanes own C elements round-robin.
+// A and B are read straight from global memory (L1/L2 serve the reuse inside a block product); consecutive entries with the
+// same c_first are accumulated in registers when m*n <= 32*GEN_ACC, otherwise every entry is flushed on its own.
+constexpr int GEN_ACC = 8;   // C elements per lane held in registers
+constexpr int GEN_WPC = 8;   // warps per CTA
+
+__global__ void __launch_bounds__(GEN_WPC * 32) smm_generic_kernel(const int* __restrict__ stack, int stack_size,
+                                                                    const double* __restrict__ a_data, const double* __restrict__ b_data,
+                                                                    double* __restrict__ c_data, int m, int n, int k, int b_transposed,
+                                                                    int chunk) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * GEN_WPC + warp;
+  const int e0 = gw * chunk;
+  const int e1 = min(e0 + chunk, stack_size);
+  if (e0 >= e1) return;
+  const int mn = m * n;
+
+  if (mn <= 32 * GEN_ACC) {
+    double acc[GEN_ACC];
+#pragma unroll
+    for (int q = 0; q < GEN_ACC; ++q) acc[q] = 0.0;
+    int cur_c = -1;
+    for (int e = e0; e <= e1; ++e) {
+      int3 p = make_int3(0, 0, -2);
+      if (e < e1) p = ld_entry(stack, e);
+      if (p.z != cur_c) {
+        if (cur_c >= 0) {
+          double* cb = c_data + (cur_c - 1);
+#pragma unroll
+          for (int q = 0; q < GEN_ACC; ++q) {
+            const int idx = lane + 32 * q;
+            if (idx < mn) atomicAdd(cb + idx, acc[q]);
+            acc[q] = 0.0;
+          }
+        }
+        cur_c = p.z;
+      }
+      if (e == e1) break;
+      const double* __restrict__ A = a_data + (p.x - 1);
+      const double* __restrict__ B = b_data + (p.y - 1);
+#pragma unroll
+      for (int q = 0; q < GEN_ACC; ++q) {
+        const int idx = lane + 32 * q;
+        if (idx < mn) {
+          const int col = idx / m, row = idx - col * m;
+          double s = 0.0;
+          if (b_transposed) {
+            for (int l = 0; l < k; ++l) s = fma(__ldg(A + l * m + row), __ldg(B + l * n + col), s);
+          }
+          else {
+            for (int l = 0; l < k; ++l) s = fma(__ldg(A + l * m + row), __ldg(B + col * k + l), s);
+          }
+          acc[q] += s;
+        }
+      }
+    }
+  }
+  else {
+    for (int e = e0; e < e1; ++e) {
+      const int3 p = ld_entry(stack, e);
+      const double* __restrict__ A = a_data + (p.x - 1);
+      const double* __restrict__ B = b_data + (p.y - 1);
+      double* cb = c_data + (p.z - 1);
+      for (int idx = lane; idx < mn; idx += 32) {
+        const int col = idx / m, row = idx - col * m;
+        double s = 0.0;
+        if (b_transposed) {
+          for (int l = 0; l < k; ++l) s = fma(__ldg(A + l * m + row), __ldg(B + l * n + col), s);
+        }
+        else {
+          for (int l = 0; l < k; ++l) s = fma(__ldg(A + l * m + row), __ldg(B + col * k + l), s);
+        }
+        atomicAdd(cb + idx, s);
+      }
+    }
+  }
+}
+
+// In-place transpose of m x n col-major blocks (result n x m col-major): out[i] = in[(i % n) * m + i / n].
+// One warp per block, grid-stride; the block is parked in the warp's slice of dynamic shared memory.
+__global__ void transpose_kernel(const int* __restrict__ trs_stack, int nblks, double* __restrict__ data, int m, int n) {
+  extern __shared__ double tr_smem[];
+  const int wpc = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mn = m * n;
+  double* buf = tr_smem + (size_t)warp * mn;
+  for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
+    double* blk = data + __ldg(trs_stack + b);
+    for (int i = lane; i < mn; i += 32) buf[i] = blk[i];
+    __syncwarp();
+    for (int i = lane; i < mn; i += 32) {
+      const int r_out = i % n, c_out = i / n;
+      blk[i] = buf[r_out * m + c_out];
+    }
+    __syncwarp();
+  }
+}
+
+// norms[b] = sum_i mat[offsets[b] + i]^2 as float; one warp per block, grid-stride.
+__global__ void norms_kernel(const double* __restrict__ mat, int nblks, const int* __restrict__ offsets, const int* __restrict__ nelems,
+                             float* __restrict__ norms) {
+  const int wpc = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
+    const double* __restrict__ p = mat + __ldg(offsets + b);
+    const int ne = __ldg(nelems + b);
+    double s = 0.0;
+    for (int i = lane; i < ne; i += 32) {
+      const double d = __ldg(p + i);
+      s = fma(d, d, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) norms[b] = (float)s;
+  }
+}
+
+}  // namespace smm

@@ -1,0 +1,73 @@
+/*
+ * include/dbcsr_acc_libsmm.h -- C ABI of the B200-native small-matrix-multiplication (SMM) backend.
+ *
+ * Drop-in boundary, part 2 of 2: the entry points DBCSR binds for the stack-drain hot path
+ * (reference interface: src/acc/acc_libsmm.h:31-49; Fortran callers src/mm/dbcsr_acc_operations.F:38-67,120-131,171-179,
+ * src/mm/dbcsr_mm_common.F:117-129, src/core/dbcsr_lib.F:86-116).
+ */
+#ifndef DBCSR_B200_ACC_LIBSMM_H
+#define DBCSR_B200_ACC_LIBSMM_H
+
+#include "dbcsr_acc.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* acc_libsmm.h:31-36.  dbcsr_type_bf16_ext is an EXTENSION of this library (DBCSR has no 16-bit type): A/B panels
+ * stored as bf16, C accumulated in fp32; same stack format, element offsets count elements of the respective type. */
+typedef enum libsmm_acc_data_t {
+  dbcsr_type_real_4 = 1,
+  dbcsr_type_real_8 = 3,
+  dbcsr_type_complex_4 = 5,
+  dbcsr_type_complex_8 = 7,
+  dbcsr_type_bf16_ext = 9
+} libsmm_acc_data_t;
+
+/* acc_libsmm.h:38-40.  init/finalize may be called more than once (src/core/dbcsr_lib.F:241).
+ * is_thread_safe must report 1 for an OpenMP build of DBCSR (src/core/dbcsr_lib.F:248-261): this library is thread safe. */
+int libsmm_acc_init(void);
+int libsmm_acc_finalize(void);
+c_dbcsr_acc_bool_t libsmm_acc_is_thread_safe(void);
+
+/* acc_libsmm.h:42-43 (src/acc/libsmm_acc/libsmm_acc.cpp:482-487).  For i in [offset, offset+stack_size): in-place transpose
+ * of the m x n column-major block at 0-BASED element offset dev_trs_stack[i] of dev_data (result n x m column-major).
+ * Returns 0 and does nothing for datatype != real_8 or m,n > max_kernel_dim (reference behaviour); non-zero aborts DBCSR. */
+int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, void* dev_data, libsmm_acc_data_t datatype, int m,
+  int n, int max_kernel_dim, void* stream);
+
+/* acc_libsmm.h:45-47 (src/acc/libsmm_acc/libsmm_acc.cpp:324-339).  Enqueue, without synchronising, for every entry i of the stack
+ *     C[c_i .. c_i+m*n) += A[a_i .. a_i+m*k) (m x k col-major)  *  B_i ,   B_i = n x k col-major (i.e. stored TRANSPOSED)
+ * when n,k <= max_kernel_dim, else k x n col-major.
+ *   host_param_stack : 7 ints/entry (m,n,k,a_first,b_first,c_first,c_blk), 1-based, original order, host memory
+ *   dev_param_stack  : 3 ints/entry (a_first,b_first,c_first), 1-based, (mostly) sorted by c_first, device memory,
+ *                      its H2D copy already enqueued on stack_stream
+ *   m_max,n_max,k_max: the (m,n,k) of every entry when def_mnk == 1
+ * Return: 0 ok (specialised kernel), 10 ok (generic untuned kernel), <0 nothing was enqueued and C is untouched
+ * (-1 inhomogeneous stack not handled, -10 datatype not handled): DBCSR then re-does the stack on the CPU
+ * (src/mm/dbcsr_acc_operations.F:134-135). */
+int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, int stack_size, libsmm_acc_data_t datatype,
+  const void* dev_a_data, const void* dev_b_data, void* dev_c_data, int m_max, int n_max, int k_max, int max_kernel_dim,
+  c_dbcsr_acc_bool_t def_mnk, void* stack_stream, void* c_stream);
+
+/* acc_libsmm.h:49 (src/acc/cuda_hip/calculate_norms.cpp:98-117): norms[b] = sum_i mat[offsets[b]+i]^2 (float, no sqrt),
+ * offsets 0-based, all pointers device memory. */
+int c_calculate_norms(const double* mat, int nblks, const int* offsets, const int* nelems, float* norms, void* stream_ptr);
+
+/* Declared by DBCSR (interface in src/core/dbcsr_lib.F:111-116) but never defined by the reference; exported for safety. */
+int libsmm_acc_gpu_warp_size(void);
+
+/* ---- extensions of this library (not part of the reference ABI) -------------------------------------------------- */
+
+/* Which kernel would libsmm_acc_process use for (m,n,k)?  0 = none, 1 = specialised DMMA kernel, 2 = generic kernel. */
+int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype);
+/* Number of kernel launches this library has enqueued since load (all threads). */
+long long libsmm_acc_b200_launch_count(void);
+/* Library identification string (static storage). */
+const char* libsmm_acc_b200_version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif /* DBCSR_B200_ACC_LIBSMM_H */

@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the library loads without a GPU/driver and exports every symbol that
+include/dbcsr_acc.h and include/dbcsr_acc_libsmm.h declare (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from dbcsr_b200 import lib as acclib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(r"\b((?:c_dbcsr_|libsmm_acc_|c_calculate_)\w+)\s*\(", txt))
+
+
+def test_library_exports_every_declared_symbol():
+    L = acclib.load()
+    declared = _declared_symbols("dbcsr_acc.h") | _declared_symbols("dbcsr_acc_libsmm.h")
+    assert declared == set(acclib.ACC_SYMBOLS) | set(acclib.SMM_SYMBOLS), declared ^ (set(acclib.ACC_SYMBOLS) | set(acclib.SMM_SYMBOLS))
+    for s in declared:
+        assert hasattr(L, s), "missing export: " + s
+
+
+def test_reference_abi_symbol_names_are_all_present():
+    """The 26 + 6 names of the reference's src/acc/acc.h:34-71 and src/acc/acc_libsmm.h:38-49 (hard-coded list)."""
+    ref = """c_dbcsr_acc_init c_dbcsr_acc_finalize c_dbcsr_acc_clear_errors c_dbcsr_acc_get_ndevices c_dbcsr_acc_set_active_device
+    c_dbcsr_acc_device_synchronize c_dbcsr_acc_stream_priority_range c_dbcsr_acc_stream_create c_dbcsr_acc_stream_destroy
+    c_dbcsr_acc_stream_sync c_dbcsr_acc_stream_wait_event c_dbcsr_acc_event_create c_dbcsr_acc_event_destroy c_dbcsr_acc_event_record
+    c_dbcsr_acc_event_query c_dbcsr_acc_event_synchronize c_dbcsr_acc_dev_mem_allocate c_dbcsr_acc_dev_mem_deallocate
+    c_dbcsr_acc_dev_mem_set_ptr c_dbcsr_acc_host_mem_allocate c_dbcsr_acc_host_mem_deallocate c_dbcsr_acc_memcpy_h2d
+    c_dbcsr_acc_memcpy_d2h c_dbcsr_acc_memcpy_d2d c_dbcsr_acc_memset_zero c_dbcsr_acc_dev_mem_info
+    libsmm_acc_init libsmm_acc_finalize libsmm_acc_is_thread_safe libsmm_acc_transpose libsmm_acc_process c_calculate_norms""".split()
+    assert len(ref) == 32
+    out = subprocess.check_output(["nm", "-D", "--defined-only", acclib.LIB_PATH]).decode()
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    assert not (set(ref) - exported), set(ref) - exported
+
+
+def test_no_libcuda_link_dependency():
+    """The library must load on a box without a driver (this container): only libc/libstdc++ are needed."""
+    out = subprocess.check_output(["ldd", acclib.LIB_PATH]).decode()
+    assert "libcuda.so" not in out and "not found" not in out
+
+
+def test_thread_safety_flag_and_version():
+    L = acclib.load()
+    assert L.libsmm_acc_is_thread_safe() == 1  # src/core/dbcsr_lib.F:248-261 aborts otherwise in OpenMP builds
+    assert L.libsmm_acc_gpu_warp_size() == 32
+    assert b"sm_100a" in L.libsmm_acc_b200_version()
+    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 3) == 1
+    assert L.libsmm_acc_b200_kernel_kind(7, 9, 11, 3) == 2
+    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 1) == 0
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped path must never route through oracle/ (CPU) code."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dbcsr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f == "lib.py" and False, os.path.join(dirpath, f)

@@ -1,0 +1,261 @@
+"""GPU parity tests of the stack-drain hot path, called through the C ABI (libsmm_acc_process & co) and checked against the
+oracle (oracle/dbcsr_oracle.c).  Modelled on the reference's own unit tests:
+  tests/libsmm_acc_unittest_multiply.cpp.template + src/acc/libsmm_acc/libsmm_acc_benchmark.cpp:45-52,103-170,287-291
+  (integer-valued inputs => exact checksum comparison), tests/libsmm_acc_unittest_transpose.cpp.
+FP64 tolerance for real-valued inputs: relative Frobenius error <= 1e-10 (BASELINE.json north_star); integer inputs: bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TUNED = [5, 13, 23, 26, 32]
+
+
+@pytest.fixture(scope="module")
+def acc():
+    from dbcsr_b200 import lib as acclib
+
+    a = acclib.Acc(0)
+    a.s = a.stream_create("test", 0)
+    yield a
+    a.stream_destroy(a.s)
+    a.finalize()
+
+
+def run_process(acc, stack3, a, b, c_size, m, n, k, host7=None, def_mnk=True, pad_elems=0):
+    """Upload, run libsmm_acc_process on a device stack, download C. `pad_elems` doubles are put in front of A/B so that
+    block offsets start at an odd element (8 mod 16 byte alignment)."""
+    stack3 = np.ascontiguousarray(stack3, dtype=np.int32).reshape(-1, 3)
+    if pad_elems:
+        stack3 = stack3.copy()
+        stack3[:, 0] += pad_elems
+        stack3[:, 1] += pad_elems
+        a = np.concatenate([np.full(pad_elems, np.nan), a])
+        b = np.concatenate([np.full(pad_elems, np.nan), b])
+    d_a, d_b = acc.to_device(a, acc.s), acc.to_device(b, acc.s)
+    d_s = acc.to_device(stack3, acc.s)
+    d_c = acc.dev_alloc(c_size * 8)
+    acc.memset_zero(d_c, acc.s)
+    if host7 is None:
+        host7 = np.zeros((stack3.shape[0], 7), dtype=np.int32)
+        host7[:, 0], host7[:, 1], host7[:, 2] = m, n, k
+        host7[:, 3:6] = stack3
+    rc = acc.process(host7, d_s.ptr, stack3.shape[0], d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, def_mnk, acc.s, acc.s)
+    c = acc.to_host(d_c, (c_size,), np.float64, acc.s)
+    for d in (d_a, d_b, d_s, d_c):
+        d.free()
+    return rc, c
+
+
+def ref_test_problem(m, n, k, n_a=100, n_b=100, n_c=10, n_stack=100, seed=1):
+    """The reference's `test` benchmark problem (libsmm_acc_benchmark.cpp:45-52): matInit(42/24) + rand() stack."""
+    L = orc.lib()
+    a, b = np.empty(n_a * m * k), np.empty(n_b * k * n)
+    L.orc_mat_init(a, n_a, m, k, 42)
+    L.orc_mat_init(b, n_b, k, n, 24)
+    stack = np.empty(3 * n_stack, dtype=np.int32)
+    orc.srand(seed)
+    L.orc_stack_init(stack, n_stack, n_c, n_a, n_b, m, n, k)
+    return a, b, stack.reshape(-1, 3), n_c * m * n
+
+
+@pytest.mark.parametrize("m", TUNED)
+def test_tuned_triplets_exact_checksum(acc, m):
+    """All 25 (n,k) per m: integer-valued inputs, exact equality of every C element and of checkSum (reference :287-291)."""
+    for n in TUNED:
+        for k in TUNED:
+            a, b, stack, csz = ref_test_problem(m, n, k)
+            rc, c = run_process(acc, stack, a, b, csz, m, n, k)
+            assert rc == 0, (m, n, k, rc)
+            c_ref = orc.stack_calc(stack, np.zeros(csz), a, b, m, n, k)
+            assert np.array_equal(c, c_ref), (m, n, k, np.abs(c - c_ref).max())
+            assert orc.lib().orc_checksum(c, csz // (m * n), m, n) == orc.lib().orc_checksum(c_ref, csz // (m * n), m, n)
+
+
+@pytest.mark.parametrize("mnk", [(23, 23, 23), (5, 5, 5), (13, 13, 13), (26, 26, 26), (32, 32, 32), (23, 5, 32), (13, 32, 5), (32, 13, 26)])
+def test_random_values_frobenius(acc, mnk):
+    """Uniform(0,1) data (dlarnv-like), 16005-entry C-sorted stack of the reference's timing problem scaled down:
+    relative Frobenius error <= 1e-10 (north_star tolerance; observed ~1e-16)."""
+    m, n, k = mnk
+    rng = np.random.default_rng(7)
+    n_a, n_b, n_c, S = 2000, 2000, 300, 4000
+    a, b = rng.random(n_a * m * k), rng.random(n_b * k * n)
+    stack = np.empty(3 * S, dtype=np.int32)
+    orc.srand(3)
+    orc.lib().orc_stack_init(stack, S, n_c, n_a, n_b, m, n, k)
+    stack = stack.reshape(-1, 3)
+    for pad in (0, 1):  # pad=1: every block of an even-sized shape sits at 8 mod 16 bytes, odd-sized ones alternate
+        rc, c = run_process(acc, stack, a, b, n_c * m * n, m, n, k, pad_elems=pad)
+        assert rc == 0
+        c_ref = orc.stack_calc(stack, np.zeros(n_c * m * n), a, b, m, n, k)
+        err = np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref)
+        assert err <= 1e-10, (mnk, pad, err)
+
+
+def test_last_block_of_allocation_and_alignment(acc):
+    """A and B sized exactly to their blocks: the last block ends at the end of the allocation (the TMA window would over-read
+    8 bytes there; the kernel must take the guarded path) and odd block sizes alternate between 0 and 8 mod 16 alignment."""
+    m = n = k = 23
+    rng = np.random.default_rng(11)
+    for nblk in (1, 2, 3, 8):
+        a, b = rng.random(nblk * m * k), rng.random(nblk * k * n)
+        S = 4 * nblk
+        stack = np.zeros((S, 3), dtype=np.int32)
+        stack[:, 0] = (np.arange(S) % nblk) * m * k + 1
+        stack[:, 1] = ((np.arange(S) // 2) % nblk) * k * n + 1
+        stack[:, 2] = (np.arange(S) // 4) * m * n + 1
+        # make sure the very last block of both panels is used
+        stack[-1, 0] = (nblk - 1) * m * k + 1
+        stack[-1, 1] = (nblk - 1) * k * n + 1
+        rc, c = run_process(acc, stack, a, b, nblk * m * n, m, n, k)
+        assert rc == 0
+        c_ref = orc.stack_calc(stack, np.zeros(nblk * m * n), a, b, m, n, k)
+        assert np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref) <= 1e-13
+
+
+def test_edge_stacks(acc):
+    """Empty stack, single entry, unsorted stack (atomics make order irrelevant), one C block hit by every entry,
+    and a full 30000-entry stack (MM_STACK_SIZE of GPU builds, src/core/dbcsr_config.F:76-82)."""
+    m = n = k = 23
+    rng = np.random.default_rng(5)
+    n_a = n_b = 500
+    a, b = rng.random(n_a * m * k), rng.random(n_b * k * n)
+    # empty
+    rc, c = run_process(acc, np.zeros((0, 3), dtype=np.int32), a, b, m * n, m, n, k)
+    assert rc == 0 and not c.any()
+    for S, n_c, shuffle in [(1, 1, False), (7, 7, False), (1000, 1, False), (5000, 50, True), (30000, 3000, False)]:
+        stack = np.zeros((S, 3), dtype=np.int32)
+        stack[:, 0] = rng.integers(0, n_a, S) * m * k + 1
+        stack[:, 1] = rng.integers(0, n_b, S) * k * n + 1
+        stack[:, 2] = np.sort(rng.integers(0, n_c, S)) * m * n + 1
+        if shuffle:
+            stack = stack[rng.permutation(S)]
+        rc, c = run_process(acc, stack, a, b, n_c * m * n, m, n, k)
+        assert rc == 0
+        c_ref = orc.stack_calc(stack, np.zeros(n_c * m * n), a, b, m, n, k)
+        assert np.linalg.norm(c - c_ref) / max(np.linalg.norm(c_ref), 1e-300) <= 1e-10, (S, n_c)
+
+
+def test_accumulates_into_existing_c(acc):
+    """C += A*B: a second process call on the same C buffer adds on top (device C buffer lives across stacks,
+    src/mm/dbcsr_mm_accdrv.F:209-216)."""
+    m, n, k = 13, 23, 5
+    a, b, stack, csz = ref_test_problem(m, n, k)
+    d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
+    d_c = acc.to_device(np.full(csz, 1.5), acc.s)
+    for _ in range(3):
+        assert acc.process(None, d_s.ptr, stack.shape[0], d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s) == 0
+    c = acc.to_host(d_c, (csz,), np.float64, acc.s)
+    c_ref = np.full(csz, 1.5)
+    for _ in range(3):
+        orc.stack_calc(stack, c_ref, a, b, m, n, k)
+    assert np.array_equal(c, c_ref)
+
+
+@pytest.mark.parametrize("mnk", [(7, 9, 11), (1, 1, 1), (4, 4, 4), (14, 29, 32), (45, 67, 78), (80, 80, 80), (3, 64, 2)])
+def test_generic_kernel_shapes(acc, mnk):
+    """Shapes without a specialised kernel run on the generic kernel and report 10 (= untuned, libsmm_acc.cpp:319)."""
+    m, n, k = mnk
+    a, b, stack, csz = ref_test_problem(m, n, k, n_a=20, n_b=20, n_c=5, n_stack=40)
+    rc, c = run_process(acc, stack, a, b, csz, m, n, k)
+    assert rc == 10
+    c_ref = orc.stack_calc(stack, np.zeros(csz), a, b, m, n, k)
+    assert np.array_equal(c, c_ref)
+
+
+def test_large_blocks_b_not_transposed(acc):
+    """Any dim > max_kernel_dim: B is NOT transposed by DBCSR (src/acc/libsmm_acc/libsmm_acc.cpp:267-270), path runs on c_stream."""
+    rng = np.random.default_rng(3)
+    for (m, n, k) in [(100, 5, 90), (5, 100, 7), (81, 81, 81)]:
+        n_a = n_b = 6
+        n_c = 3
+        S = 12
+        a, b = rng.random(n_a * m * k), rng.random(n_b * k * n)
+        host = np.zeros((S, 7), dtype=np.int32)
+        host[:, 0], host[:, 1], host[:, 2] = m, n, k
+        host[:, 3] = rng.integers(0, n_a, S) * m * k + 1
+        host[:, 4] = rng.integers(0, n_b, S) * k * n + 1
+        cb = np.sort(rng.integers(0, n_c, S))
+        host[:, 5], host[:, 6] = cb * m * n + 1, cb + 1
+        b_dev = b.copy()
+        if n <= 80 and k <= 80:
+            orc.transpose_blocks(np.arange(n_b, dtype=np.int32) * k * n, b_dev, k, n)
+        rc, c = run_process(acc, host[:, 3:6].copy(), a, b_dev, n_c * m * n, m, n, k, host7=host)
+        assert rc == 10
+        c_ref = orc.host_stack(host, a, b, np.zeros(n_c * m * n))
+        assert np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref) <= 1e-12
+
+
+def test_unsupported_requests_leave_c_untouched(acc):
+    """def_mnk=0 -> -1, dtype != real_8 -> -10 (reference return codes); C must not be modified so that DBCSR can redo the stack on the CPU."""
+    m = n = k = 23
+    a, b, stack, csz = ref_test_problem(m, n, k)
+    rc, c = run_process(acc, stack, a, b, csz, m, n, k, def_mnk=False)
+    assert rc == -1 and not c.any()
+    d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
+    d_c = acc.dev_alloc(csz * 8)
+    acc.memset_zero(d_c, acc.s)
+    for dt in (1, 5, 7):
+        assert acc.process(None, d_s.ptr, stack.shape[0], d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s, datatype=dt) == -10
+    assert not acc.to_host(d_c, (csz,), np.float64, acc.s).any()
+
+
+def test_transpose_all_tuned_pairs(acc):
+    """libsmm_acc_transpose vs the oracle for every (m,n) pair incl. offset argument (tests/libsmm_acc_unittest_transpose.cpp)."""
+    for m in TUNED + [1, 7, 80]:
+        for n in TUNED + [1, 80]:
+            nblk = 37
+            mat = np.empty(nblk * m * n)
+            orc.lib().orc_mat_init(mat, nblk, m, n, 42)
+            offs = (np.arange(nblk, dtype=np.int32) * m * n).astype(np.int32)
+            skip = 5
+            d_m, d_o = acc.to_device(mat, acc.s), acc.to_device(offs, acc.s)
+            acc.transpose(d_o.ptr, skip, nblk - skip, d_m.ptr, m, n, acc.s)
+            out = acc.to_host(d_m, mat.shape, np.float64, acc.s)
+            ref = mat.copy()
+            orc.transpose_blocks(offs[skip:], ref, m, n)
+            assert np.array_equal(out, ref), (m, n)
+            d_m.free()
+            d_o.free()
+
+
+def test_transpose_then_process_matches_host_path(acc):
+    """DBCSR flow: right panel uploaded untransposed, libsmm_acc_transpose in place, then process == CPU path on host stacks."""
+    m, n, k = 23, 13, 26
+    rng = np.random.default_rng(9)
+    n_a = n_b = 64
+    n_c, S = 16, 256
+    a, b = rng.random(n_a * m * k), rng.random(n_b * k * n)
+    host = np.zeros((S, 7), dtype=np.int32)
+    host[:, 0], host[:, 1], host[:, 2] = m, n, k
+    host[:, 3] = rng.integers(0, n_a, S) * m * k + 1
+    host[:, 4] = rng.integers(0, n_b, S) * k * n + 1
+    cb = rng.integers(0, n_c, S)
+    host[:, 5], host[:, 6] = cb * m * n + 1, cb + 1
+    dev3 = host[np.argsort(host[:, 5], kind="stable")][:, 3:6].copy()  # stack_sort, src/mm/dbcsr_mm_accdrv.F:364-384
+    d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(dev3, acc.s)
+    d_t = acc.to_device((np.arange(n_b, dtype=np.int32) * k * n), acc.s)
+    acc.transpose(d_t.ptr, 0, n_b, d_b.ptr, k, n, acc.s)
+    d_c = acc.dev_alloc(n_c * m * n * 8)
+    acc.memset_zero(d_c, acc.s)
+    assert acc.process(host, d_s.ptr, S, d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s) == 0
+    c = acc.to_host(d_c, (n_c * m * n,), np.float64, acc.s)
+    c_ref = orc.host_stack(host, a, b, np.zeros(n_c * m * n))
+    assert np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref) <= 1e-10
+
+
+def test_norms(acc):
+    rng = np.random.default_rng(2)
+    nblk = 1000
+    sizes = rng.choice([25, 169, 529, 676, 1024, 1], nblk).astype(np.int32)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32)
+    mat = rng.random(int(sizes.sum()))
+    d_m, d_o, d_n = acc.to_device(mat, acc.s), acc.to_device(offs, acc.s), acc.to_device(sizes, acc.s)
+    d_out = acc.dev_alloc(nblk * 4)
+    acc.norms(d_m.ptr, nblk, d_o.ptr, d_n.ptr, d_out.ptr, acc.s)
+    out = acc.to_host(d_out, (nblk,), np.float32, acc.s)
+    ref = orc.norms(mat, offs, sizes)
+    assert np.allclose(out, ref, rtol=2e-7, atol=0)
