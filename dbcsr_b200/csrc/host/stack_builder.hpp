@@ -1,0 +1,105 @@
+// dbcsr_b200/csrc/host/stack_builder.hpp -- host-side local multiply: recursive index sort, recursive (M,K,N) bisection,
+// CSR leaf traversal with C-block creation, (m,n,k)-binned parameter stacks and their dispatch order.
+//
+// In a real DBCSR build this work is done by the Fortran layer that stays in place
+//   (src/mm/dbcsr_mm_common.F:227-309, src/mm/dbcsr_mm_multrec.F:263-658, src/mm/dbcsr_mm_csr.F:178-795,
+//    src/mm/dbcsr_mm_accdrv.F:364-423, src/dist/dbcsr_dist_util.F:753-812).
+// This C++ implementation exists because the benchmark / test harness needs the same stacks without a Fortran compiler, and as
+// the basis of the multi-threaded builder.  It reproduces the reference's traversal so that the C block
+// index (order of first touch), the stack contents and the stack dispatch order are identical for one thread.
+// All block coordinates and element offsets are 1-based as in DBCSR.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <vector>
+
+namespace dbcsr_b200 {
+
+struct Config {
+  int mm_stack_size = 30000;       // DBCSR_MM_STACK_SIZE on accelerator builds (src/core/dbcsr_config.F:76-82)
+  int n_stacks = 3;                // DBCSR_N_STACKS: n^3 homogeneous stacks + 1 default
+  int multrec_limit = 512;         // DBCSR_MULTREC_LIMIT
+  int stack_sort = 1;              // DBCSR_ACCDRV_STACK_SORT
+  int min_flop_sort = 4000;        // DBCSR_ACCDRV_MIN_FLOP_SORT
+  int binning_nbins = 4096;        // DBCSR_ACCDRV_BINNING_NBINS
+  int binning_binsize = 16;        // DBCSR_ACCDRV_BINNING_BINSIZE
+};
+
+struct Idx3 {
+  int row, col, blk;  // (local row, local col, 1-based element offset)
+};
+
+struct StackDescr {
+  int m = 0, n = 0, k = 0, max_m = 0, max_n = 0, max_k = 0;
+  int defined_mnk = 0;
+};
+
+// rec_sort_index (src/mm/dbcsr_mm_common.F:227-309): quadtree-like ordering of a block list, in place.
+void rec_sort_index(int mi, int mf, int ni, int nf, Idx3* a, int nele, std::vector<Idx3>& tmp);
+
+// stack_sort / stack_binning (src/mm/dbcsr_mm_accdrv.F:364-423): 7-wide host stack -> 3-wide device stack.
+void stack_sort(const int* params7, int* out3, int stack_size);
+void stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize);
+// what dbcsr_mm_accdrv_process does to a stack before upload (:481-491)
+void accdrv_order_stack(const Config& cfg, const StackDescr& d, const int* params7, int* out3, int stack_size);
+
+// map_most_common (src/dist/dbcsr_dist_util.F:753-812)
+void map_most_common(const std::vector<int>& array, int nmost_common, std::vector<int>& map, std::vector<int>& elements, int& max_val);
+
+class LocalMultiply {
+ public:
+  // called for every dispatched stack, in dispatch order: (stack number 1-based, descriptor, 7-wide params, size)
+  using DispatchFn = std::function<void(int, const StackDescr&, const int*, int)>;
+
+  LocalMultiply(const Config& cfg, const std::vector<int>& m_sizes, const std::vector<int>& n_sizes, const std::vector<int>& k_sizes);
+
+  // Existing C blocks (beta != 0 / retain_sparsity flows): row, col, 1-based offsets; defines datasize.
+  void preset_c(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize);
+
+  // One Cannon tick: lists must already be rec-sorted (use sort_panel); [a_first, a_last] = this thread's slice of the
+  // left list (1-based, inclusive; the whole list for one thread).  Stacks still partially filled at the end are purged
+  // (dbcsr_mm_multrec_multiply -> dbcsr_mm_csr_purge_stacks, src/mm/dbcsr_mm_multrec.F:263-324).
+  void multiply(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, const DispatchFn& dispatch);
+
+  static void sort_panel(std::vector<Idx3>& list, int nrows, int ncols);
+
+  // product work matrix (pre-finalize index, order of first touch; src/mm/dbcsr_mm_csr.F:309-323)
+  const std::vector<int>& c_row() const { return c_row_; }
+  const std::vector<int>& c_col() const { return c_col_; }
+  const std::vector<int>& c_blk_p() const { return c_blk_p_; }
+  int datasize() const { return datasize_; }
+  int64_t flop() const { return flop_; }
+  int nstacks() const { return nstacks_; }
+  const StackDescr& descr(int istack) const { return descr_[istack]; }  // 1-based
+
+ private:
+  void init_stack_map();
+  void sparse_multrec(int mi, int mf, int ni, int nf, int ki, int kf, int ai, int af, const Idx3* a, int bi, int bf, const Idx3* b);
+  void csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int af, int bi, int bf, const Idx3* a, const Idx3* b);
+  void flush_stacks(bool purge);
+  int c_lookup_or_insert(int row, int col, int nze, bool& created);
+  void hash_grow();
+
+  Config cfg_;
+  std::vector<int> m_sizes_, n_sizes_, k_sizes_;
+  std::vector<int> m_map_, n_map_, k_map_;
+  int max_m_ = 0, max_n_ = 0, max_k_ = 0;
+  int nstacks_ = 0;
+  std::vector<int> stack_map_;  // [(m_map-1)*(n+1)*(n+1) + (k_map-1)*(n+1) + (n_map-1)] -> stack number
+  std::vector<StackDescr> descr_;
+  std::vector<std::vector<int>> stacks_;  // 7 ints per entry
+  std::vector<int> fill_;
+  const DispatchFn* dispatch_ = nullptr;
+  // C index + hash (open addressing over (row,col) -> c_blk_id)
+  std::vector<int> c_row_, c_col_, c_blk_p_;
+  std::vector<uint64_t> hkeys_;
+  std::vector<int> hvals_;
+  uint64_t hmask_ = 0;
+  size_t hcount_ = 0;
+  int datasize_ = 0;
+  int64_t flop_ = 0;
+  // scratch for the CSR leaves
+  std::vector<int> a_row_p_, b_row_p_, a_info_, b_info_, counts_;
+};
+
+}  // namespace dbcsr_b200

@@ -1,0 +1,93 @@
+/*
+ * include/dbcsr_b200_host.h -- C ABI of the host side of the local multiply (stack builder + accelerator driver).
+ *
+ * In a real DBCSR build this layer is DBCSR's own Fortran (it stays in place and only sees include/dbcsr_acc*.h):
+ *   multrec   src/mm/dbcsr_mm_multrec.F:263-658       csr stack builder  src/mm/dbcsr_mm_csr.F:178-795
+ *   scheduler src/mm/dbcsr_mm_sched.F:266-382          acc driver         src/mm/dbcsr_mm_accdrv.F:170-541
+ *   index sort src/mm/dbcsr_mm_common.F:227-309        transposes         src/mm/dbcsr_mm_common.F:346-496
+ * The functions below are the C++ stand-in used by bench.py / the tests (no Fortran compiler on the target boxes) and the
+ * multi-threaded builder of SURVEY.md 8(f) row 1.  They call the accelerator ONLY through the acc/libsmm C ABI above.
+ * Conventions as in DBCSR: block rows/cols and element offsets are 1-based; list index = (row, col, blk_p) triples.
+ */
+#ifndef DBCSR_B200_HOST_H
+#define DBCSR_B200_HOST_H
+
+#include <stddef.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* dbcsr_cfg knobs on this path (src/core/dbcsr_config.F:151-180); zero-initialise then call dbcsr_b200_cfg_default */
+typedef struct dbcsr_b200_cfg {
+  int mm_stack_size;   /* MM_STACK_SIZE, 30000 on accelerator builds */
+  int n_stacks;        /* N_STACKS, 3 */
+  int multrec_limit;   /* MULTREC_LIMIT, 512 */
+  int stack_sort;      /* ACCDRV_STACK_SORT, 1 */
+  int min_flop_sort;   /* ACCDRV_MIN_FLOP_SORT, 4000 */
+  int binning_nbins;   /* ACCDRV_BINNING_NBINS, 4096 */
+  int binning_binsize; /* ACCDRV_BINNING_BINSIZE, 16 */
+  int thread_buffers;  /* ACCDRV_THREAD_BUFFERS, 8 */
+} dbcsr_b200_cfg_t;
+void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg);
+
+/* rec_sort_index (src/mm/dbcsr_mm_common.F:227-309), in place on nblks (row,col,blk_p) triples */
+void dbcsr_b200_rec_sort_index(int nrows, int ncols, int nblks, int* list3);
+/* stack_sort / stack_binning (src/mm/dbcsr_mm_accdrv.F:364-423): params7 -> out3 */
+void dbcsr_b200_stack_sort(const int* params7, int* out3, int stack_size);
+void dbcsr_b200_stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize);
+
+/* ---- engine: multrec + csr + sched + accdrv of `nthreads` host threads for one rank --------------------------------- */
+typedef struct dbcsr_b200_engine dbcsr_b200_engine_t;
+
+/* mode bits */
+#define DBCSR_B200_LAUNCH 1 /* enqueue every dispatched stack on the accelerator (needs a device) */
+#define DBCSR_B200_RECORD 2 /* keep every dispatched stack (host 7-wide + device-order 3-wide) for inspection / replay */
+
+/* m_sizes/n_sizes/k_sizes: block sizes of the local C rows, C cols and the contraction index.
+ * c_capacity: elements of device C buffer per engine (0 = dense upper bound).  Returns NULL on failure. */
+dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const int* m_sizes, int nrows, const int* n_sizes,
+  int ncols, const int* k_sizes, int nk, int nthreads, int mode, size_t c_capacity);
+void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e);
+
+/* One Cannon tick (src/mm/dbcsr_mm_cannon.F:1622-1667 -> dbcsr_mm_multrec_multiply): a_list3/b_list3 are the panels' list
+ * indices in BCSR order with panel-local coordinates; a_dev/b_dev the device data areas (B blocks already transposed, see
+ * dbcsr_b200_transpose_panel).  Sorts the lists (rec_sort_index), splits the left list over the threads by block rows,
+ * builds the stacks and (LAUNCH) streams them to the device.  Returns 0, or a negative code of the failing call. */
+int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
+  const void* b_dev);
+/* wait for all enqueued stacks (dbcsr_mm_accdrv_barrier, src/mm/dbcsr_mm_accdrv.F:425-431) */
+int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e);
+
+/* product work matrices, one per thread (pre-finalize index in order of first touch) */
+int dbcsr_b200_engine_nthreads(const dbcsr_b200_engine_t* e);
+int dbcsr_b200_engine_c_nblks(const dbcsr_b200_engine_t* e, int thread);
+int dbcsr_b200_engine_c_datasize(const dbcsr_b200_engine_t* e, int thread);
+const int* dbcsr_b200_engine_c_rows(const dbcsr_b200_engine_t* e, int thread);
+const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int thread);
+const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int thread);
+void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int thread);
+/* D2H of thread's C buffer (datasize elements) into host memory (dbcsr_mm_accdrv_finalize, src/mm/dbcsr_mm_accdrv.F:340-362) */
+int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int thread, double* host);
+long long dbcsr_b200_engine_flop(const dbcsr_b200_engine_t* e);
+/* seconds the host threads spent building+ordering stacks / waiting for free stack buffers in the last multiply (max over threads) */
+double dbcsr_b200_engine_build_seconds(const dbcsr_b200_engine_t* e);
+
+/* recorded stacks (RECORD mode), in dispatch order per thread then concatenated thread by thread */
+int dbcsr_b200_engine_nstacks(const dbcsr_b200_engine_t* e);
+/* info[10] = m, n, k, max_m, max_n, max_k, defined_mnk, stack_size, thread, stack_number */
+void dbcsr_b200_engine_stack_info(const dbcsr_b200_engine_t* e, int i, int* info);
+const int* dbcsr_b200_engine_stack_host(const dbcsr_b200_engine_t* e, int i); /* 7 ints per entry */
+const int* dbcsr_b200_engine_stack_dev(const dbcsr_b200_engine_t* e, int i);  /* 3 ints per entry, accdrv order */
+
+/* acc_transpose_blocks (src/mm/dbcsr_mm_common.F:346-496): in-place transpose of every block of the right panel on the device,
+ * one libsmm_acc_transpose call per distinct (k,n) size pair.  b_list3 = (row=k index, col, blk_p). Synchronous w.r.t. `stream`
+ * ordering only (no host sync).  scratch_dev must hold nb ints. */
+int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+  void* scratch_dev, void* stream);
+
+#if defined(__cplusplus)
+}
+#endif
+
+#endif /* DBCSR_B200_HOST_H */
