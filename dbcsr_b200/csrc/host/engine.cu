@@ -1,0 +1,383 @@
+// dbcsr_b200/csrc/host/engine.cu -- host-side engine behind include/dbcsr_b200_host.h: per-thread multrec/csr stack builder
+// feeding the accelerator through the acc/libsmm C ABI exactly the way DBCSR's accdrv does
+// (src/mm/dbcsr_mm_accdrv.F:170-219 init, :433-541 process, :340-362 finalize): per-thread stream, ring of stack buffers
+// (pinned + device) guarded by events, stack ordered by C, async H2D, libsmm_acc_process, device-resident C buffer.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "../../../include/dbcsr_acc.h"
+#include "../../../include/dbcsr_acc_libsmm.h"
+#include "../../../include/dbcsr_b200_host.h"
+#include "stack_builder.hpp"
+
+using dbcsr_b200::Config;
+using dbcsr_b200::Idx3;
+using dbcsr_b200::LocalMultiply;
+using dbcsr_b200::StackDescr;
+
+namespace {
+
+constexpr int kMaxKernelDim = 80;  // src/core/dbcsr_config.F:185
+
+Config to_config(const dbcsr_b200_cfg_t& c) {
+  Config k;
+  k.mm_stack_size = c.mm_stack_size;
+  k.n_stacks = c.n_stacks;
+  k.multrec_limit = c.multrec_limit;
+  k.stack_sort = c.stack_sort;
+  k.min_flop_sort = c.min_flop_sort;
+  k.binning_nbins = c.binning_nbins;
+  k.binning_binsize = c.binning_binsize;
+  return k;
+}
+
+struct RecordedStack {
+  StackDescr d;
+  int thread = 0, stack_number = 0, size = 0;
+  std::vector<int> host, dev;
+};
+
+struct StackBuffer {  // stack_buffer_type, src/mm/dbcsr_mm_accdrv.F:63-72
+  int* host = nullptr;   // pinned, 3 x mm_stack_size
+  void* dev = nullptr;   // device, 3 x mm_stack_size
+  void* calculated = nullptr;  // event
+};
+
+struct ThreadState {
+  std::unique_ptr<LocalMultiply> mm;
+  void* stream = nullptr;
+  std::vector<StackBuffer> bufs;
+  void* c_dev = nullptr;
+  size_t c_capacity = 0;
+  std::vector<RecordedStack> recorded;
+  std::vector<int> order_scratch;
+  int a_first = 1, a_last = 0;
+  int rc = 0;
+  double build_seconds = 0.0;
+};
+
+}  // namespace
+
+struct dbcsr_b200_engine {
+  dbcsr_b200_cfg_t cfg;
+  Config kcfg;
+  int mode = 0;
+  int device = 0;
+  int nrows = 0, ncols = 0, nk = 0;
+  std::vector<int> m_sizes, n_sizes, k_sizes;
+  std::vector<ThreadState> th;
+  std::vector<Idx3> a_sorted, b_sorted;
+};
+
+extern "C" {
+
+void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg) {
+  cfg->mm_stack_size = 30000;
+  cfg->n_stacks = 3;
+  cfg->multrec_limit = 512;
+  cfg->stack_sort = 1;
+  cfg->min_flop_sort = 4000;
+  cfg->binning_nbins = 4096;
+  cfg->binning_binsize = 16;
+  cfg->thread_buffers = 8;
+}
+
+void dbcsr_b200_rec_sort_index(int nrows, int ncols, int nblks, int* list3) {
+  static_assert(sizeof(Idx3) == 3 * sizeof(int), "Idx3 must be three packed ints");
+  std::vector<Idx3> tmp((size_t)std::max(nblks, 0));
+  if (nblks > 0) dbcsr_b200::rec_sort_index(1, nrows, 1, ncols, reinterpret_cast<Idx3*>(list3), nblks, tmp);
+}
+void dbcsr_b200_stack_sort(const int* params7, int* out3, int stack_size) { dbcsr_b200::stack_sort(params7, out3, stack_size); }
+void dbcsr_b200_stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize) {
+  dbcsr_b200::stack_binning(params7, out3, stack_size, nbins, binsize);
+}
+
+dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const int* m_sizes, int nrows, const int* n_sizes, int ncols,
+                                              const int* k_sizes, int nk, int nthreads, int mode, size_t c_capacity) {
+  if (cfg == nullptr || nthreads < 1 || nrows < 0 || ncols < 0 || nk < 0) return nullptr;
+  auto* e = new dbcsr_b200_engine();
+  e->cfg = *cfg;
+  e->kcfg = to_config(*cfg);
+  e->mode = mode;
+  if (mode & DBCSR_B200_LAUNCH) cudaGetDevice(&e->device);
+  e->nrows = nrows;
+  e->ncols = ncols;
+  e->nk = nk;
+  e->m_sizes.assign(m_sizes, m_sizes + nrows);
+  e->n_sizes.assign(n_sizes, n_sizes + ncols);
+  e->k_sizes.assign(k_sizes, k_sizes + nk);
+  e->th.resize((size_t)nthreads);
+  size_t sum_n = 0;
+  for (int v : e->n_sizes) sum_n += (size_t)v;
+  for (int t = 0; t < nthreads; ++t) {
+    ThreadState& ts = e->th[t];
+    ts.mm.reset(new LocalMultiply(e->kcfg, e->m_sizes, e->n_sizes, e->k_sizes));
+    if (mode & DBCSR_B200_LAUNCH) {
+      // dbcsr_mm_accdrv_init (src/mm/dbcsr_mm_accdrv.F:170-219,279-307): stream, stack buffers; the C buffer is created
+      // lazily at the first multiply, when the rows owned by the thread are known
+      if (c_dbcsr_acc_stream_create(&ts.stream, "dbcsr_b200 thread", 0) != 0) goto fail;
+      ts.bufs.resize((size_t)std::max(1, cfg->thread_buffers));
+      for (auto& b : ts.bufs) {
+        const size_t bytes = sizeof(int) * 3 * (size_t)cfg->mm_stack_size;
+        if (c_dbcsr_acc_host_mem_allocate(reinterpret_cast<void**>(&b.host), bytes, ts.stream) != 0) goto fail;
+        if (c_dbcsr_acc_dev_mem_allocate(&b.dev, bytes) != 0) goto fail;
+        if (c_dbcsr_acc_event_create(&b.calculated) != 0) goto fail;
+      }
+      ts.c_capacity = c_capacity;
+    }
+  }
+  (void)sum_n;
+  return e;
+fail:
+  dbcsr_b200_engine_destroy(e);
+  return nullptr;
+}
+
+void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e) {
+  if (e == nullptr) return;
+  for (auto& ts : e->th) {
+    if (ts.stream != nullptr) c_dbcsr_acc_stream_sync(ts.stream);
+    for (auto& b : ts.bufs) {
+      if (b.host != nullptr) c_dbcsr_acc_host_mem_deallocate(b.host, ts.stream);
+      if (b.dev != nullptr) c_dbcsr_acc_dev_mem_deallocate(b.dev);
+      if (b.calculated != nullptr) c_dbcsr_acc_event_destroy(b.calculated);
+    }
+    if (ts.c_dev != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_dev);
+    if (ts.stream != nullptr) c_dbcsr_acc_stream_destroy(ts.stream);
+  }
+  delete e;
+}
+
+int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
+                               const void* b_dev) {
+  if (e == nullptr || na < 0 || nb < 0) return -1;
+  const int nthreads = (int)e->th.size();
+  // --- left panel: split the BCSR-ordered list over the threads by block rows (DBCSR: thr_c slices of coo_l, each slice
+  //     rec-sorted on its own with the full panel extents, src/mm/dbcsr_mm_cannon.F:2910-2967)
+  e->a_sorted.resize((size_t)na);
+  std::memcpy(e->a_sorted.data(), a_list3, sizeof(int) * 3 * (size_t)na);
+  e->b_sorted.resize((size_t)nb);
+  std::memcpy(e->b_sorted.data(), b_list3, sizeof(int) * 3 * (size_t)nb);
+  {
+    // static ownership: thread t owns block rows (t*nrows/T, (t+1)*nrows/T] in every tick, so that the C rows of different
+    // threads stay disjoint over a whole Cannon multiply; the BCSR-ordered list is sorted by row => contiguous slices
+    int pos = 0;
+    for (int t = 0; t < nthreads; ++t) {
+      const int row_hi = (int)(((long long)e->nrows * (t + 1)) / nthreads);
+      int end = pos;
+      while (end < na && e->a_sorted[(size_t)end].row <= row_hi) ++end;
+      if (t == nthreads - 1) end = na;
+      e->th[t].a_first = pos + 1;
+      e->th[t].a_last = end;
+      pos = end;
+    }
+  }
+  // --- sort panels
+  {
+    std::vector<std::thread> workers;
+    for (int t = 0; t < nthreads; ++t) {
+      workers.emplace_back([e, t]() {
+        ThreadState& ts = e->th[t];
+        const int cnt = ts.a_last - ts.a_first + 1;
+        std::vector<Idx3> tmp((size_t)std::max(cnt, 0));
+        if (cnt > 0) dbcsr_b200::rec_sort_index(1, e->nrows, 1, e->nk, e->a_sorted.data() + (ts.a_first - 1), cnt, tmp);
+      });
+    }
+    {
+      std::vector<Idx3> tmp((size_t)nb);
+      if (nb > 0) dbcsr_b200::rec_sort_index(1, e->nk, 1, e->ncols, e->b_sorted.data(), nb, tmp);
+    }
+    for (auto& w : workers) w.join();
+  }
+  // --- device C buffers (dbcsr_mm_accdrv_init: sized like the work area, zeroed asynchronously)
+  if (e->mode & DBCSR_B200_LAUNCH) {
+    size_t sum_n = 0;
+    for (int v : e->n_sizes) sum_n += (size_t)v;
+    for (int t = 0; t < nthreads; ++t) {
+      ThreadState& ts = e->th[t];
+      if (ts.c_dev != nullptr) continue;
+      size_t cap = ts.c_capacity;
+      if (cap == 0) {  // dense upper bound over the block rows this thread owns
+        std::vector<char> seen((size_t)e->nrows + 1, 0);
+        size_t sum_m = 0;
+        for (int i = ts.a_first; i <= ts.a_last; ++i) {
+          const int r = e->a_sorted[(size_t)i - 1].row;
+          if (!seen[r]) {
+            seen[r] = 1;
+            sum_m += (size_t)e->m_sizes[(size_t)r - 1];
+          }
+        }
+        cap = sum_m * sum_n;
+      }
+      if (cap == 0) cap = 1;
+      if (cap > 0x7fffffffull) cap = 0x7fffffffull;  // offsets are int32 (hard part 8)
+      ts.c_capacity = cap;
+      if (c_dbcsr_acc_dev_mem_allocate(&ts.c_dev, cap * sizeof(double)) != 0) return -40;
+      if (c_dbcsr_acc_memset_zero(ts.c_dev, 0, cap * sizeof(double), ts.stream) != 0) return -41;
+    }
+  }
+  // --- per-thread multrec -> csr -> sched -> accdrv
+  std::vector<std::thread> workers;
+  for (int t = 0; t < nthreads; ++t) {
+    workers.emplace_back([e, t, a_dev, b_dev, nb]() {
+      ThreadState& ts = e->th[t];
+      ts.rc = 0;
+      if (e->mode & DBCSR_B200_LAUNCH) cudaSetDevice(e->device);  // the active device is per host thread
+      const auto t0 = std::chrono::steady_clock::now();
+      int next_buf = 0;
+      auto dispatch = [&](int stack_number, const StackDescr& d, const int* params7, int size) {
+        if (ts.rc != 0) return;
+        if (e->mode & DBCSR_B200_RECORD) {
+          RecordedStack r;
+          r.d = d;
+          r.thread = t;
+          r.stack_number = stack_number;
+          r.size = size;
+          r.host.assign(params7, params7 + 7 * (size_t)size);
+          r.dev.resize(3 * (size_t)size);
+          dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, r.dev.data(), size);
+          ts.recorded.push_back(std::move(r));
+        }
+        if (!(e->mode & DBCSR_B200_LAUNCH)) return;
+        if ((size_t)ts.mm->datasize() > ts.c_capacity) {
+          ts.rc = -42;  // device C buffer too small (the reference would grow it, src/mm/dbcsr_mm_accdrv.F:471-473)
+          return;
+        }
+        // pick a stack buffer whose previous kernel has finished (round robin + event wait instead of the reference's busy poll)
+        StackBuffer& b = ts.bufs[(size_t)next_buf];
+        next_buf = (next_buf + 1) % (int)ts.bufs.size();
+        if (c_dbcsr_acc_event_synchronize(b.calculated) != 0) {
+          ts.rc = -43;
+          return;
+        }
+        dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, b.host, size);
+        if (c_dbcsr_acc_memcpy_h2d(b.host, b.dev, sizeof(int) * 3 * (size_t)size, ts.stream) != 0) {
+          ts.rc = -44;
+          return;
+        }
+        const int rc = libsmm_acc_process(params7, static_cast<const int*>(b.dev), size, dbcsr_type_real_8, a_dev, b_dev, ts.c_dev,
+                                          d.max_m, d.max_n, d.max_k, kMaxKernelDim, d.defined_mnk, ts.stream, ts.stream);
+        if (rc < 0) {
+          ts.rc = rc;  // the reference would now run this stack on the CPU; this engine has no CPU path and reports the code
+          return;
+        }
+        if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
+      };
+      ts.mm->multiply(e->a_sorted.data(), ts.a_first, ts.a_last, e->b_sorted.data(), nb, dispatch);
+      ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (auto& ts : e->th)
+    if (ts.rc != 0) return ts.rc;
+  return 0;
+}
+
+int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e) {
+  if (e == nullptr) return -1;
+  for (auto& ts : e->th)
+    if (ts.stream != nullptr && c_dbcsr_acc_stream_sync(ts.stream) != 0) return -1;
+  return 0;
+}
+
+int dbcsr_b200_engine_nthreads(const dbcsr_b200_engine_t* e) { return (int)e->th.size(); }
+int dbcsr_b200_engine_c_nblks(const dbcsr_b200_engine_t* e, int t) { return (int)e->th[(size_t)t].mm->c_row().size(); }
+int dbcsr_b200_engine_c_datasize(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->datasize(); }
+const int* dbcsr_b200_engine_c_rows(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_row().data(); }
+const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_col().data(); }
+const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_blk_p().data(); }
+void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].c_dev; }
+
+int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int t, double* host) {
+  ThreadState& ts = e->th[(size_t)t];
+  if (ts.c_dev == nullptr || ts.stream == nullptr) return -1;
+  const size_t n = (size_t)ts.mm->datasize();
+  if (n > 0 && c_dbcsr_acc_memcpy_d2h(ts.c_dev, host, n * sizeof(double), ts.stream) != 0) return -1;
+  return c_dbcsr_acc_stream_sync(ts.stream);
+}
+
+long long dbcsr_b200_engine_flop(const dbcsr_b200_engine_t* e) {
+  long long f = 0;
+  for (auto& ts : e->th) f += ts.mm->flop();
+  return f;
+}
+
+double dbcsr_b200_engine_build_seconds(const dbcsr_b200_engine_t* e) {
+  double s = 0;
+  for (auto& ts : e->th) s = std::max(s, ts.build_seconds);
+  return s;
+}
+
+int dbcsr_b200_engine_nstacks(const dbcsr_b200_engine_t* e) {
+  size_t n = 0;
+  for (auto& ts : e->th) n += ts.recorded.size();
+  return (int)n;
+}
+
+static const RecordedStack* find_stack(const dbcsr_b200_engine_t* e, int i) {
+  for (auto& ts : e->th) {
+    if (i < (int)ts.recorded.size()) return &ts.recorded[(size_t)i];
+    i -= (int)ts.recorded.size();
+  }
+  return nullptr;
+}
+
+void dbcsr_b200_engine_stack_info(const dbcsr_b200_engine_t* e, int i, int* info) {
+  const RecordedStack* r = find_stack(e, i);
+  if (r == nullptr) return;
+  info[0] = r->d.m;
+  info[1] = r->d.n;
+  info[2] = r->d.k;
+  info[3] = r->d.max_m;
+  info[4] = r->d.max_n;
+  info[5] = r->d.max_k;
+  info[6] = r->d.defined_mnk;
+  info[7] = r->size;
+  info[8] = r->thread;
+  info[9] = r->stack_number;
+}
+const int* dbcsr_b200_engine_stack_host(const dbcsr_b200_engine_t* e, int i) {
+  const RecordedStack* r = find_stack(e, i);
+  return r ? r->host.data() : nullptr;
+}
+const int* dbcsr_b200_engine_stack_dev(const dbcsr_b200_engine_t* e, int i) {
+  const RecordedStack* r = find_stack(e, i);
+  return r ? r->dev.data() : nullptr;
+}
+
+int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+                               void* scratch_dev, void* stream) {
+  // group the blocks by (k,n) size pair, 0-based offsets (blk_p - 1), one transpose stack per pair
+  // (src/mm/dbcsr_mm_common.F:346-496)
+  if (nb <= 0) return 0;
+  std::vector<int> order((size_t)nb);
+  for (int i = 0; i < nb; ++i) order[(size_t)i] = i;
+  auto key = [&](int i) {
+    const int k = k_sizes[b_list3[3 * (size_t)i] - 1], n = n_sizes[b_list3[3 * (size_t)i + 1] - 1];
+    return ((long long)k << 32) | (unsigned)n;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
+  for (int i = 0; i < nb; ++i) scratch_host[i] = b_list3[3 * (size_t)order[(size_t)i] + 2] - 1;
+  if (c_dbcsr_acc_memcpy_h2d(scratch_host, scratch_dev, sizeof(int) * (size_t)nb, stream) != 0) return -1;
+  int start = 0;
+  while (start < nb) {
+    int end = start;
+    const long long k0 = key(order[(size_t)start]);
+    while (end < nb && key(order[(size_t)end]) == k0) ++end;
+    const int k = (int)(k0 >> 32), n = (int)(k0 & 0xffffffff);
+    const int rc = libsmm_acc_transpose(static_cast<const int*>(scratch_dev), start, end - start, b_dev, dbcsr_type_real_8, k, n,
+                                        kMaxKernelDim, stream);
+    if (rc != 0) return rc;
+    start = end;
+  }
+  return 0;
+}
+
+}  // extern "C"

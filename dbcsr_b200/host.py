@@ -1,0 +1,176 @@
+"""
+dbcsr_b200/host.py -- ctypes binding of include/dbcsr_b200_host.h: the C++ stand-in for DBCSR's Fortran local-multiply layer
+(multrec / csr stack builder / sched / accdrv).  Used by bench.py and the tests; never imports anything from oracle/.
+"""
+import ctypes
+
+import numpy as np
+
+from . import lib as acclib
+
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+LAUNCH, RECORD = 1, 2
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [(n, _i) for n in ("mm_stack_size", "n_stacks", "multrec_limit", "stack_sort", "min_flop_sort", "binning_nbins",
+                                  "binning_binsize", "thread_buffers")]
+
+
+_bound = False
+
+
+def _L():
+    global _bound
+    L = acclib.load()
+    if not _bound:
+        ip = ctypes.POINTER(_i)
+        L.dbcsr_b200_cfg_default.argtypes = [ctypes.POINTER(Cfg)]
+        L.dbcsr_b200_rec_sort_index.argtypes = [_i, _i, _i, _vp]
+        L.dbcsr_b200_stack_sort.argtypes = [_vp, _vp, _i]
+        L.dbcsr_b200_stack_binning.argtypes = [_vp, _vp, _i, _i, _i]
+        L.dbcsr_b200_engine_create.argtypes = [ctypes.POINTER(Cfg), _vp, _i, _vp, _i, _vp, _i, _i, _i, ctypes.c_size_t]
+        L.dbcsr_b200_engine_create.restype = _vp
+        L.dbcsr_b200_engine_destroy.argtypes = [_vp]
+        L.dbcsr_b200_engine_multiply.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _vp]
+        L.dbcsr_b200_engine_sync.argtypes = [_vp]
+        for f in ("nthreads", "nstacks"):
+            getattr(L, "dbcsr_b200_engine_" + f).argtypes = [_vp]
+        for f in ("c_nblks", "c_datasize"):
+            getattr(L, "dbcsr_b200_engine_" + f).argtypes = [_vp, _i]
+        for f in ("c_rows", "c_cols", "c_blk_p"):
+            fn = getattr(L, "dbcsr_b200_engine_" + f)
+            fn.argtypes = [_vp, _i]
+            fn.restype = ip
+        L.dbcsr_b200_engine_c_dev.argtypes = [_vp, _i]
+        L.dbcsr_b200_engine_c_dev.restype = _vp
+        L.dbcsr_b200_engine_c_to_host.argtypes = [_vp, _i, _vp]
+        L.dbcsr_b200_engine_flop.argtypes = [_vp]
+        L.dbcsr_b200_engine_flop.restype = ctypes.c_longlong
+        L.dbcsr_b200_engine_build_seconds.argtypes = [_vp]
+        L.dbcsr_b200_engine_build_seconds.restype = ctypes.c_double
+        L.dbcsr_b200_engine_stack_info.argtypes = [_vp, _i, _vp]
+        for f in ("stack_host", "stack_dev"):
+            fn = getattr(L, "dbcsr_b200_engine_" + f)
+            fn.argtypes = [_vp, _i]
+            fn.restype = ip
+        L.dbcsr_b200_transpose_panel.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        _bound = True
+    return L
+
+
+def default_cfg(**kw):
+    c = Cfg()
+    _L().dbcsr_b200_cfg_default(ctypes.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def rec_sort_index(nrows, ncols, list3):
+    a = np.ascontiguousarray(list3, dtype=np.int32).reshape(-1, 3).copy()
+    _L().dbcsr_b200_rec_sort_index(nrows, ncols, a.shape[0], a.ctypes.data)
+    return a
+
+
+def stack_sort(params7):
+    p = np.ascontiguousarray(params7, dtype=np.int32).reshape(-1, 7)
+    out = np.empty((p.shape[0], 3), dtype=np.int32)
+    _L().dbcsr_b200_stack_sort(p.ctypes.data, out.ctypes.data, p.shape[0])
+    return out
+
+
+def stack_binning(params7, nbins=4096, binsize=16):
+    p = np.ascontiguousarray(params7, dtype=np.int32).reshape(-1, 7)
+    out = np.empty((p.shape[0], 3), dtype=np.int32)
+    _L().dbcsr_b200_stack_binning(p.ctypes.data, out.ctypes.data, p.shape[0], nbins, binsize)
+    return out
+
+
+class Engine:
+    """multrec + csr + sched + accdrv of `nthreads` host threads for one rank (see include/dbcsr_b200_host.h)."""
+
+    def __init__(self, m_sizes, n_sizes, k_sizes, nthreads=1, mode=RECORD, cfg=None, c_capacity=0):
+        self.L = _L()
+        self.cfg = cfg if cfg is not None else default_cfg()
+        self.m = np.ascontiguousarray(m_sizes, dtype=np.int32)
+        self.n = np.ascontiguousarray(n_sizes, dtype=np.int32)
+        self.k = np.ascontiguousarray(k_sizes, dtype=np.int32)
+        self.h = self.L.dbcsr_b200_engine_create(ctypes.byref(self.cfg), self.m.ctypes.data, self.m.size, self.n.ctypes.data, self.n.size,
+                                                 self.k.ctypes.data, self.k.size, nthreads, mode, c_capacity)
+        if not self.h:
+            raise acclib.AccError("dbcsr_b200_engine_create failed")
+
+    def multiply(self, a_list3, a_dev_ptr, b_list3, b_dev_ptr):
+        a = np.ascontiguousarray(a_list3, dtype=np.int32).reshape(-1, 3)
+        b = np.ascontiguousarray(b_list3, dtype=np.int32).reshape(-1, 3)
+        rc = self.L.dbcsr_b200_engine_multiply(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, b.ctypes.data, b.shape[0], b_dev_ptr)
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_multiply returned %d" % rc)
+
+    def sync(self):
+        if self.L.dbcsr_b200_engine_sync(self.h) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_sync failed")
+
+    @property
+    def nthreads(self):
+        return self.L.dbcsr_b200_engine_nthreads(self.h)
+
+    def c_index(self, t=0):
+        nb = self.L.dbcsr_b200_engine_c_nblks(self.h, t)
+        f = lambda fn: np.ctypeslib.as_array(fn(self.h, t), shape=(nb,)).copy() if nb else np.zeros(0, dtype=np.int32)
+        return (f(self.L.dbcsr_b200_engine_c_rows), f(self.L.dbcsr_b200_engine_c_cols), f(self.L.dbcsr_b200_engine_c_blk_p),
+                self.L.dbcsr_b200_engine_c_datasize(self.h, t))
+
+    def c_dev(self, t=0):
+        return self.L.dbcsr_b200_engine_c_dev(self.h, t)
+
+    def c_to_host(self, t, host_array):
+        if self.L.dbcsr_b200_engine_c_to_host(self.h, t, host_array.ctypes.data) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_c_to_host failed")
+
+    def flop(self):
+        return int(self.L.dbcsr_b200_engine_flop(self.h))
+
+    def build_seconds(self):
+        return float(self.L.dbcsr_b200_engine_build_seconds(self.h))
+
+    def stacks(self):
+        """Recorded stacks: list of dicts like the index oracle produces (host S x 7, dev S x 3)."""
+        out = []
+        info = np.zeros(10, dtype=np.int32)
+        for i in range(self.L.dbcsr_b200_engine_nstacks(self.h)):
+            self.L.dbcsr_b200_engine_stack_info(self.h, i, info.ctypes.data)
+            S = int(info[7])
+            host = np.ctypeslib.as_array(self.L.dbcsr_b200_engine_stack_host(self.h, i), shape=(S, 7)).copy()
+            dev = np.ctypeslib.as_array(self.L.dbcsr_b200_engine_stack_dev(self.h, i), shape=(S, 3)).copy()
+            out.append(dict(m=int(info[0]), n=int(info[1]), k=int(info[2]), max_m=int(info[3]), max_n=int(info[4]), max_k=int(info[5]),
+                            defined_mnk=bool(info[6]), thread=int(info[8]), stack_id=int(info[9]), host=host, dev=dev))
+        return out
+
+    def close(self):
+        if self.h:
+            self.L.dbcsr_b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def transpose_panel(acc, b_list3, k_sizes, n_sizes, b_dev_ptr, stream):
+    """acc_transpose_blocks: transposes every block of the right panel in place on the device."""
+    b = np.ascontiguousarray(b_list3, dtype=np.int32).reshape(-1, 3)
+    ks = np.ascontiguousarray(k_sizes, dtype=np.int32)
+    ns = np.ascontiguousarray(n_sizes, dtype=np.int32)
+    nb = b.shape[0]
+    scratch_h = acc.host_alloc((max(nb, 1),), np.int32)
+    scratch_d = acc.dev_alloc(4 * max(nb, 1))
+    rc = _L().dbcsr_b200_transpose_panel(b.ctypes.data, nb, ks.ctypes.data, ns.ctypes.data, b_dev_ptr, scratch_h.ptr, scratch_d.ptr, stream)
+    acc.stream_sync(stream)
+    scratch_h.free()
+    scratch_d.free()
+    if rc != 0:
+        raise acclib.AccError("dbcsr_b200_transpose_panel returned %d" % rc)

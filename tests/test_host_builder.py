@@ -1,0 +1,108 @@
+"""CPU tests of the host-side stack builder (dbcsr_b200/csrc/host, C++) against the pure-Python index oracle
+(oracle/index_oracle.py): identical rec_sort order, identical stacks (contents + dispatch order), identical C block index
+(order of first touch = "bit-identical block index structure"), identical flop count."""
+import numpy as np
+import pytest
+
+from dbcsr_b200 import host
+from oracle import index_oracle as io
+from oracle import oracle as orc
+
+
+def random_lists(nrow, ncol, nk, occ_a, occ_b, sizes, seed):
+    rng = np.random.default_rng(seed)
+    m_sizes = rng.choice(sizes, nrow)
+    n_sizes = rng.choice(sizes, ncol)
+    k_sizes = rng.choice(sizes, nk)
+    A = orc.BlockMatrix(m_sizes, k_sizes, *np.nonzero(rng.random((nrow, nk)) < occ_a))
+    A.rows += 1
+    A.cols += 1
+    B = orc.BlockMatrix(k_sizes, n_sizes, *np.nonzero(rng.random((nk, ncol)) < occ_b))
+    B.rows += 1
+    B.cols += 1
+    A = orc.BlockMatrix(m_sizes, k_sizes, A.rows, A.cols)
+    B = orc.BlockMatrix(k_sizes, n_sizes, B.rows, B.cols)
+    return m_sizes, n_sizes, k_sizes, A, B
+
+
+def test_rec_sort_index_matches_oracle():
+    rng = np.random.default_rng(0)
+    for (nr, nc, nb) in [(1, 1, 1), (7, 3, 12), (50, 60, 400), (64, 64, 1000), (100, 17, 900), (3, 200, 300)]:
+        cells = rng.choice(nr * nc, size=min(nb, nr * nc), replace=False)
+        cells.sort()
+        lst = [(int(c // nc) + 1, int(c % nc) + 1, i + 1) for i, c in enumerate(cells)]
+        exp = io.rec_sort_index(1, nr, 1, nc, list(lst)) if len(lst) > 1 else lst
+        got = host.rec_sort_index(nr, nc, np.array(lst, dtype=np.int32))
+        assert [tuple(int(v) for v in r) for r in got] == exp
+
+
+def test_stack_sort_and_binning_match_oracle():
+    rng = np.random.default_rng(1)
+    S = 5000
+    p = np.zeros((S, 7), dtype=np.int32)
+    p[:, 3:6] = rng.integers(1, 10000, (S, 3))
+    p[:, 5] = rng.integers(0, 300, S) * 25 + 1
+    o = io.LocalMultiplyOracle([5], [5], [5])
+    assert np.array_equal(host.stack_sort(p), np.array(o._stack_sort([tuple(r) for r in p.tolist()]), dtype=np.int32))
+    assert np.array_equal(host.stack_binning(p), np.array(o._stack_binning([tuple(r) for r in p.tolist()]), dtype=np.int32))
+
+
+CASES = [
+    # nrow, ncol, nk, occA, occB, sizes, stack_size, n_stacks, multrec_limit
+    (40, 40, 40, 0.3, 0.3, [23], 1000, 3, 512),
+    (60, 50, 70, 0.2, 0.25, [5, 13, 23, 26, 32], 300, 3, 64),
+    (60, 50, 70, 0.2, 0.25, [5, 13, 23, 26, 32], 300, 5, 64),
+    (30, 100, 20, 0.5, 0.1, [4, 5, 7], 200, 3, 32),
+    (128, 128, 128, 0.1, 0.1, [23], 4000, 3, 512),
+    (10, 10, 10, 1.0, 1.0, [1, 3, 4], 50, 3, 8),
+    (33, 1, 17, 0.6, 0.9, [5, 8, 9], 64, 3, 16),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_engine_matches_index_oracle(case):
+    nrow, ncol, nk, oa, ob, sizes, ssz, nst, lim = case
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(nrow, ncol, nk, oa, ob, sizes, seed=sum(case[:3]))
+    ora = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=ssz, n_stacks=nst, multrec_limit=lim)
+    exp = ora.multiply(A.index_list(), B.index_list())
+    eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD,
+                      cfg=host.default_cfg(mm_stack_size=ssz, n_stacks=nst, multrec_limit=lim))
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    got = eng.stacks()
+    assert len(got) == len(exp)
+    for g, x in zip(got, exp):
+        for key in ("m", "n", "k", "max_m", "max_n", "max_k", "defined_mnk", "stack_id"):
+            assert g[key] == x[key], key
+        assert np.array_equal(g["host"], x["host"])
+        assert np.array_equal(g["dev"], x["dev"])
+    rows, cols, blk_p, datasize = eng.c_index(0)
+    assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p
+    assert datasize == ora.datasize and eng.flop() == ora.flop
+    # every (A blk, B blk) pair with matching k appears exactly once over all stacks
+    n_products = sum(g["host"].shape[0] for g in got)
+    kb = {}
+    for r in B.rows:
+        kb[int(r)] = kb.get(int(r), 0) + 1
+    assert n_products == sum(kb.get(int(c), 0) for c in A.cols)
+    eng.close()
+
+
+def test_multithreaded_engine_same_products_disjoint_rows():
+    """T threads: same multiset of (a,b) products, C rows disjoint between threads, per-thread C index self-consistent."""
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(96, 80, 64, 0.2, 0.2, [5, 13, 23], seed=5)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    e1 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, cfg=host.default_cfg(mm_stack_size=500))
+    e1.multiply(a_l, None, b_l, None)
+    e4 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=4, cfg=host.default_cfg(mm_stack_size=500))
+    e4.multiply(a_l, None, b_l, None)
+    prod = lambda eng: sorted((int(r[3]), int(r[4])) for s in eng.stacks() for r in s["host"])
+    assert prod(e1) == prod(e4) and e1.flop() == e4.flop()
+    seen_rows = set()
+    for t in range(4):
+        rows, cols, blk_p, ds = e4.c_index(t)
+        assert not (set(rows.tolist()) & seen_rows)
+        seen_rows |= set(rows.tolist())
+        sizes = m_sizes[rows - 1] * n_sizes[cols - 1]
+        assert np.array_equal(blk_p, 1 + np.concatenate([[0], np.cumsum(sizes)[:-1]])) and ds == int(sizes.sum())
+    e1.close()
+    e4.close()
