@@ -280,6 +280,18 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
   return 0;
 }
 
+int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
+  // start a new multiply on pooled resources (streams, stack buffers, device C buffer stay allocated like DBCSR's memory pools,
+  // src/data/dbcsr_mem_methods.F:41-251): forget the product index, clear recorded stacks, zero the C buffer asynchronously
+  if (e == nullptr) return -1;
+  for (auto& ts : e->th) {
+    ts.mm.reset(new LocalMultiply(e->kcfg, e->m_sizes, e->n_sizes, e->k_sizes));
+    ts.recorded.clear();
+    if (ts.c_dev != nullptr && c_dbcsr_acc_memset_zero(ts.c_dev, 0, ts.c_capacity * sizeof(double), ts.stream) != 0) return -41;
+  }
+  return 0;
+}
+
 int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e) {
   if (e == nullptr) return -1;
   for (auto& ts : e->th)

@@ -34,6 +34,7 @@ def _L():
         L.dbcsr_b200_engine_destroy.argtypes = [_vp]
         L.dbcsr_b200_engine_multiply.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _vp]
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
+        L.dbcsr_b200_engine_reset.argtypes = [_vp]
         for f in ("nthreads", "nstacks"):
             getattr(L, "dbcsr_b200_engine_" + f).argtypes = [_vp]
         for f in ("c_nblks", "c_datasize"):
@@ -107,6 +108,10 @@ class Engine:
         rc = self.L.dbcsr_b200_engine_multiply(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, b.ctypes.data, b.shape[0], b_dev_ptr)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_multiply returned %d" % rc)
+
+    def reset(self):
+        if self.L.dbcsr_b200_engine_reset(self.h) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_reset failed")
 
     def sync(self):
         if self.L.dbcsr_b200_engine_sync(self.h) != 0:

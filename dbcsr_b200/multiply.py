@@ -1,0 +1,115 @@
+"""
+dbcsr_b200/multiply.py -- host-side mirror of the accelerator path of `dbcsr_multiply` for one rank and one Cannon tick
+(C = A * B, alpha = 1, beta = 0, no filtering): what multiply_cannon + accdrv do around the C ABI
+(src/mm/dbcsr_mm_cannon.F:1622-1667 host2dev of both panels + transpose of the right one; src/mm/dbcsr_mm_accdrv.F:340-362 D2H of C).
+
+Everything that touches the device goes through the drop-in C ABI (dbcsr_b200.lib / dbcsr_b200.host); no CPU compute path.
+"""
+import numpy as np
+
+from . import host
+from . import lib as acclib
+
+
+class ProductC:
+    """Per-thread product work matrices: (rows, cols, blk_p (1-based), data) in order of first touch (pre-finalize)."""
+
+    def __init__(self, m_sizes, n_sizes):
+        self.m_sizes, self.n_sizes = np.asarray(m_sizes), np.asarray(n_sizes)
+        self.parts = []
+
+    def add(self, rows, cols, blk_p, data):
+        self.parts.append((rows, cols, blk_p, data))
+
+    @property
+    def nblks(self):
+        return sum(p[0].size for p in self.parts)
+
+    def blocks(self):
+        """dict (row, col) -> (m, n) ndarray"""
+        out = {}
+        for rows, cols, blk_p, data in self.parts:
+            for r, c, o in zip(rows, cols, blk_p):
+                m, n = int(self.m_sizes[r - 1]), int(self.n_sizes[c - 1])
+                out[(int(r), int(c))] = data[o - 1:o - 1 + m * n].reshape(n, m).T
+        return out
+
+    def bcsr_index(self):
+        """The finalized (canonical) index: row_p + sorted col_i (what dbcsr_finalize produces, independent of traversal)."""
+        keys = sorted((int(r), int(c)) for rows, cols, _, _ in self.parts for r, c in zip(rows, cols))
+        nrows = self.m_sizes.size
+        row_p = np.zeros(nrows + 1, dtype=np.int64)
+        for r, _ in keys:
+            row_p[r] += 1
+        return np.cumsum(row_p), np.array([c for _, c in keys], dtype=np.int32)
+
+
+class DeviceMultiply:
+    """Pooled resources for repeated multiplies of same-shaped panels (DBCSR keeps these in memory pools)."""
+
+    def __init__(self, acc, m_sizes, n_sizes, k_sizes, a_nze_max, b_nze_max, nb_max, nthreads=1, cfg=None, c_capacity=0,
+                 mode=host.LAUNCH):
+        self.acc = acc
+        self.m_sizes, self.n_sizes, self.k_sizes = (np.ascontiguousarray(x, dtype=np.int32) for x in (m_sizes, n_sizes, k_sizes))
+        self.engine = host.Engine(self.m_sizes, self.n_sizes, self.k_sizes, nthreads=nthreads, mode=mode, cfg=cfg, c_capacity=c_capacity)
+        self.copy_stream = acc.stream_create("panels", 0)
+        self.d_a = acc.dev_alloc(8 * max(a_nze_max, 1))
+        self.d_b = acc.dev_alloc(8 * max(b_nze_max, 1))
+        self.trs_h = acc.host_alloc((max(nb_max, 1),), np.int32)
+        self.trs_d = acc.dev_alloc(4 * max(nb_max, 1))
+        self.first = True
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def upload_panels(self, a_data, b_data, b_list3):
+        """host2dev of both panels + acc_transpose_blocks of the right one; returns after the stream is drained
+        (multiply_cannon synchronises the device before the local multiply, src/mm/dbcsr_mm_cannon.F:1642-1646)."""
+        acc = self.acc
+        acc.h2d(a_data, self.d_a, self.copy_stream)
+        acc.h2d(b_data, self.d_b, self.copy_stream)
+        b = np.ascontiguousarray(b_list3, dtype=np.int32).reshape(-1, 3)
+        rc = acc.L.dbcsr_b200_transpose_panel(b.ctypes.data, b.shape[0], self.k_sizes.ctypes.data, self.n_sizes.ctypes.data, self.d_b.ptr,
+                                              self.trs_h.ptr, self.trs_d.ptr, self.copy_stream)
+        if rc != 0:
+            raise acclib.AccError("transpose_panel returned %d" % rc)
+        acc.stream_sync(self.copy_stream)
+        self.h2d_bytes = a_data.nbytes + b_data.nbytes + 4 * b.shape[0]
+
+    def multiply(self, a_list3, b_list3):
+        """One local multiply on the uploaded panels (stacks are built, ordered, uploaded and drained asynchronously)."""
+        if not self.first:
+            self.engine.reset()
+        self.first = False
+        self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
+
+    def download_c(self, out_arrays=None):
+        """D2H of every thread's C buffer (datasize elements each). out_arrays: optional list of (pinned) host arrays."""
+        self.engine.sync()
+        prod = ProductC(self.m_sizes, self.n_sizes)
+        self.d2h_bytes = 0
+        for t in range(self.engine.nthreads):
+            rows, cols, blk_p, ds = self.engine.c_index(t)
+            buf = out_arrays[t][:ds] if out_arrays is not None else np.empty(ds)
+            if ds:
+                self.engine.c_to_host(t, buf)
+            self.d2h_bytes += 8 * ds
+            prod.add(rows, cols, blk_p, buf)
+        return prod
+
+    def close(self):
+        self.engine.close()
+        for d in (self.d_a, self.d_b, self.trs_d):
+            d.free()
+        self.trs_h.free()
+        self.acc.stream_destroy(self.copy_stream)
+
+
+def multiply(acc, A, B, m_sizes, n_sizes, k_sizes, nthreads=1, cfg=None):
+    """Convenience one-shot: C = A*B for host panels A, B (dbcsr_b200.workload.Panel-like: .data, .list3())."""
+    dm = DeviceMultiply(acc, m_sizes, n_sizes, k_sizes, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg)
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        return dm.download_c(), dm.engine.flop()
+    finally:
+        dm.close()

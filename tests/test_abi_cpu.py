@@ -58,9 +58,12 @@ def test_thread_safety_flag_and_version():
 
 
 def test_product_does_not_reference_the_oracle():
-    """The shipped path must never route through oracle/ (CPU) code."""
+    """The shipped path must never route through oracle/ (CPU) code: no import, no dlopen, no link."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle|liboracle|oracle\.(lib|ref)\(|oracle/_ref|orc_\w+\(", re.M)
     for dirpath, _, files in os.walk(os.path.join(ROOT, "dbcsr_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f == "lib.py" and False, os.path.join(dirpath, f)
+                assert not pat.search(txt), os.path.join(dirpath, f)
+    out = subprocess.check_output(["nm", "-D", acclib.LIB_PATH]).decode()
+    assert "orc_" not in out

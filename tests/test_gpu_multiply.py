@@ -1,0 +1,138 @@
+"""End-to-end GPU parity of the local multiply (host panels -> C ABI -> C blocks on the host) against the oracle, modelled on
+the reference's tests/dbcsr_test_multiply.F:523-759 (random sparse A, B -> reference product -> normwise criterion :753-759)
+and tests/dbcsr_unittest3.F:76-118 (GPU-targeted block-size mixes).  Full BASELINE size is checked through size-independent
+properties (sum of all C elements = sum over products of colsum(A).rowsum(B); C index = boolean product of the patterns)."""
+import numpy as np
+import pytest
+
+from dbcsr_b200 import host, workload
+from dbcsr_b200.multiply import DeviceMultiply, multiply
+from oracle import index_oracle as io
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def acc():
+    from dbcsr_b200 import lib as acclib
+
+    a = acclib.Acc(0)
+    yield a
+    a.finalize()
+
+
+def to_oracle(P):
+    return orc.BlockMatrix(P.row_sizes, P.col_sizes, P.rows, P.cols, data=P.data)
+
+
+def check_against_oracle(A, B, prod, m_sizes, n_sizes):
+    Cref = orc.multiply_blocks(to_oracle(A), to_oracle(B))
+    got = prod.blocks()
+    ref_keys = set(zip(Cref.rows.tolist(), Cref.cols.tolist()))
+    assert set(got.keys()) == ref_keys  # identical block structure
+    num = den = 0.0
+    amax = np.abs(A.data).max() if A.data.size else 0.0
+    bmax = np.abs(B.data).max() if B.data.size else 0.0
+    cmax = 0.0
+    worst = 0.0
+    for (r, c, o) in zip(Cref.rows, Cref.cols, Cref.offsets):
+        m, n = int(m_sizes[r - 1]), int(n_sizes[c - 1])
+        ref = Cref.data[o:o + m * n].reshape(n, m).T
+        d = got[(int(r), int(c))] - ref
+        num += float((d * d).sum())
+        den += float((ref * ref).sum())
+        cmax = max(cmax, float(np.abs(ref).max()))
+        worst = max(worst, float(np.abs(d).max()))
+    rel = np.sqrt(num / den) if den > 0 else 0.0
+    assert rel <= 1e-10, rel  # north_star FP64 tolerance
+    # tests/dbcsr_test_multiply.F:753-759: |C - C_ref|_inf / ((|A|+|B|+|C|) * N * eps) <= 10  (element-wise max norms here)
+    N = int(np.sum(A.col_sizes))
+    assert worst / ((amax + bmax + cmax) * N * np.finfo(np.float64).eps) <= 10.0
+    # canonical BCSR index identical to the reference structure
+    row_p, col_i = prod.bcsr_index()
+    keys = sorted(ref_keys)
+    assert list(col_i) == [c for _, c in keys]
+    return rel
+
+
+# block-size mixes of tests/dbcsr_unittest3.F:76-118 plus the BASELINE ones
+MIXES = [[23], [5, 13, 23, 26, 32], [1, 3, 4], [4, 5, 7], [5, 8, 9], [4, 13, 25], [14, 29, 32], [45, 67, 78]]
+
+
+@pytest.mark.parametrize("sizes", MIXES, ids=[str(s) for s in MIXES])
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_multiply_block_mixes(acc, sizes, nthreads):
+    rng = np.random.default_rng(len(sizes) * 7 + sizes[0])
+    nr, nc, nk = 48, 40, 56
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (nr, nc, nk))
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    # n_stacks=3 => at most 3 sizes per dimension are homogeneous; the rest lands in the inhomogeneous default stack,
+    # which this library (like the reference, libsmm_acc.cpp:327) rejects with -1 => use enough stacks here
+    cfg = host.default_cfg(mm_stack_size=500, n_stacks=max(3, len(sizes)))
+    prod, flop = multiply(acc, A, B, ms, ns, ks, nthreads=nthreads, cfg=cfg)
+    assert flop == int(sum(2 * int(ms[r - 1]) * int(ks[c - 1]) * int((ns[B.cols[B.rows == c] - 1]).sum()) for r, c in zip(A.rows, A.cols)))
+    check_against_oracle(A, B, prod, ms, ns)
+
+
+def test_first_touch_order_matches_index_oracle(acc):
+    """One thread: the pre-finalize C index (order of first touch) equals the restated reference traversal."""
+    rng = np.random.default_rng(3)
+    ms = ns = ks = workload.block_sizes(64, [23], rng)
+    A = workload.random_panel(ms, ks, 0.2, rng)
+    B = workload.random_panel(ks, ns, 0.2, rng)
+    prod, _ = multiply(acc, A, B, ms, ns, ks, nthreads=1, cfg=host.default_cfg(mm_stack_size=1000))
+    ora = io.LocalMultiplyOracle(ms, ns, ks, mm_stack_size=1000)
+    ora.multiply([tuple(int(v) for v in r) for r in A.list3()], [tuple(int(v) for v in r) for r in B.list3()])
+    rows, cols, blk_p, _ = prod.parts[0]
+    assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p
+    check_against_oracle(A, B, prod, ms, ns)
+
+
+def test_repeated_multiplies_on_pooled_buffers(acc):
+    rng = np.random.default_rng(8)
+    ms = ns = ks = workload.block_sizes(40, [13, 23], rng)
+    A = workload.random_panel(ms, ks, 0.25, rng)
+    B = workload.random_panel(ks, ns, 0.25, rng)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=2, cfg=host.default_cfg(mm_stack_size=300))
+    for _ in range(3):
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        check_against_oracle(A, B, dm.download_c(), ms, ns)
+    dm.close()
+
+
+@pytest.mark.parametrize("cfgname,nblk", [("cfg2", 1000), ("cfg3", 400)])
+def test_full_size_properties(acc, cfgname, nblk):
+    """BASELINE.json sizes (cfg2: N=1000, 23x23, 10 %): sum(C) == sum_products colsum(A).rowsum(B) and the C block structure
+    == boolean pattern product; also the recorded stacks drain to the same sum (stack-kernel-only path)."""
+    w = workload.make_config(cfgname, nblk=nblk)
+    A, B, bs = w["A"], w["B"], w["m_sizes"]
+    n_st = 3 if cfgname == "cfg2" else 5
+    dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=4, cfg=host.default_cfg(n_stacks=n_st),
+                        mode=host.LAUNCH)
+    dm.upload_panels(A.data, B.data, B.list3())
+    dm.multiply(A.list3(), B.list3())
+    prod = dm.download_c()
+    flop = dm.engine.flop()
+    dm.close()
+    # expected number of products / flops from the patterns alone
+    nb = bs.size
+    amask = np.zeros((nb, nb), dtype=np.float32)
+    amask[A.rows - 1, A.cols - 1] = 1
+    bmask = np.zeros((nb, nb), dtype=np.float32)
+    bmask[B.rows - 1, B.cols - 1] = 1
+    cnt = amask @ bmask
+    assert prod.nblks == int((cnt > 0).sum())
+    w3 = (amask * bs[:, None].astype(np.float32) * bs[None, :]).astype(np.float64) @ (bmask * bs[None, :]).astype(np.float64)
+    assert flop == int(round(2 * w3.sum()))
+    # sum over all elements of C == sum over block pairs of colsum(A_ik) . rowsum(B_kj)
+    colsum_a = [A.block(i).sum(axis=0) for i in range(A.nblks)]  # length k each
+    rowsum_b = {}
+    for i in range(B.nblks):
+        rowsum_b.setdefault(int(B.rows[i]), []).append(B.block(i).sum(axis=1))
+    rb = {k: np.sum(v, axis=0) for k, v in rowsum_b.items()}  # sum over all B blocks in block row k
+    expected = sum(float(colsum_a[i] @ rb[int(A.cols[i])]) for i in range(A.nblks) if int(A.cols[i]) in rb)
+    got = sum(float(p[3].sum()) for p in prod.parts)
+    assert abs(got / expected - 1.0) <= 1e-10, (got, expected)
