@@ -1,0 +1,377 @@
+"""
+dbcsr_b200/cannon.py -- multi-GPU multiply: one process per GPU = one rank of DBCSR's 2-D process grid, Cannon schedule with
+virtual k-slices, panels moved by NCCL send/recv over NVLink (torch.distributed), local multiplies through the C ABI.
+
+Reference: multiply_cannon (src/mm/dbcsr_mm_cannon.F:839-1771): C(I_i, J_j) is owned by grid rank (i,j) and never reduced;
+nvirt_k = lcm-style virtual images handle pr != pc (:1119-1121); per tick the left/right panels (data + index) are exchanged with
+isend/irecv (:1453-1463,1576-1586) into double buffers (:1243-1244,1708-1715) while the previous tick is multiplied.
+B200-first differences: panels stay in HBM for the whole multiply (no per-tick PCIe H2D, :1623-1624), the right panels are
+transposed once at their home rank, data + index travel in ONE NCCL message, and a panel is fetched from its home rank directly
+(NVSwitch gives every pair full bandwidth, so ring-forwarding through neighbours buys nothing and would double the B traffic on
+non-square grids).
+
+Schedule: V = lcm(pr, pc) k-slices.  Home of A(I_i, K_s) = rank (i, s mod pc); home of B(K_s, J_j) = rank (s mod pr, j).
+Tick t = 0..V-1: rank (i,j) multiplies slice s = (i + j + t) mod V.  For pr = pc this is exactly Cannon's skew + shifts.
+"""
+import math
+import os
+import time
+
+import numpy as np
+
+GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}  # 8 -> 2x4
+
+
+def split_points(n, parts):
+    return [(n * p) // parts for p in range(parts + 1)]
+
+
+class Schedule:
+    """Pure index arithmetic of the Cannon schedule (no communication): who needs which slice when, and who sends what."""
+
+    def __init__(self, world, pr=None, pc=None):
+        if pr is None:
+            pr, pc = GRIDS[world]
+        assert pr * pc == world
+        self.world, self.pr, self.pc = world, pr, pc
+        self.V = pr * pc // math.gcd(pr, pc)
+
+    def coords(self, rank):
+        return rank // self.pc, rank % self.pc
+
+    def rank_of(self, i, j):
+        return i * self.pc + j
+
+    def slice_at(self, rank, t):
+        i, j = self.coords(rank)
+        return (i + j + t) % self.V
+
+    def home_a(self, i, s):
+        return self.rank_of(i, s % self.pc)
+
+    def home_b(self, s, j):
+        return self.rank_of(s % self.pr, j)
+
+    def home_slices_a(self, rank):
+        i, j = self.coords(rank)
+        return [s for s in range(self.V) if s % self.pc == j]
+
+    def home_slices_b(self, rank):
+        i, j = self.coords(rank)
+        return [s for s in range(self.V) if s % self.pr == i]
+
+    def transfers(self, rank, t):
+        """Messages of tick t seen from `rank`: (recv_a_from, recv_b_from, [(dst, 'a'|'b', s), ...]); None = local panel."""
+        i, j = self.coords(rank)
+        s = self.slice_at(rank, t)
+        ha, hb = self.home_a(i, s), self.home_b(s, j)
+        sends = []
+        for s2 in self.home_slices_a(rank):  # my A(I_i, K_s2) is needed by (i, j2) with (i + j2 + t) % V == s2
+            j2 = (s2 - i - t) % self.V
+            if j2 < self.pc and j2 != j:
+                sends.append((self.rank_of(i, j2), "a", s2))
+        for s2 in self.home_slices_b(rank):  # my B(K_s2, J_j) is needed by (i2, j) with (i2 + j + t) % V == s2
+            i2 = (s2 - j - t) % self.V
+            if i2 < self.pr and i2 != i:
+                sends.append((self.rank_of(i2, j), "b", s2))
+        return (None if ha == rank else ha), (None if hb == rank else hb), sends
+
+
+def pack_panel(panel):
+    """data (float64) followed by the list index (int32 x 3 per block) as one byte buffer (one message per panel)."""
+    idx = panel.list3()
+    buf = np.empty(panel.data.nbytes + idx.nbytes, dtype=np.uint8)
+    buf[:panel.data.nbytes] = panel.data.view(np.uint8)
+    buf[panel.data.nbytes:] = idx.reshape(-1).view(np.uint8)
+    return buf
+
+
+class CannonMultiply:
+    """One rank of the distributed multiply.  `device` = torch device of this rank ('cuda:N' with NCCL, 'cpu' with gloo for tests).
+    acc = dbcsr_b200.lib.Acc (None on CPU: stacks are only recorded, nothing is launched)."""
+
+    def __init__(self, w, rank, world, device, acc=None, nthreads=1, mode=None, cfg=None, pr=None, pc=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import host
+
+        self.torch, self.dist, self.host = torch, dist, host
+        self.w, self.rank, self.world, self.device, self.acc = w, rank, world, torch.device(device), acc
+        self.sched = Schedule(world, pr, pc)
+        sc = self.sched
+        self.i, self.j = sc.coords(rank)
+        nb = w["nblk"]
+        self.rsp, self.csp, self.ksp = split_points(nb, sc.pr), split_points(nb, sc.pc), split_points(nb, sc.V)
+        bs = w["m_sizes"]
+        self.m_sizes = bs[self.rsp[self.i]:self.rsp[self.i + 1]]
+        self.n_sizes = bs[self.csp[self.j]:self.csp[self.j + 1]]
+        self.k_sizes = [bs[self.ksp[s]:self.ksp[s + 1]] for s in range(sc.V)]
+        if mode is None:
+            mode = host.LAUNCH if acc is not None else host.RECORD
+        self.mode = mode
+        n_st = 3 if len(w["sizes"]) <= 3 else len(w["sizes"])
+        self.cfg = cfg if cfg is not None else host.default_cfg(n_stacks=n_st)
+        # stack map from the GLOBAL k block sizes (dbcsr_mm_csr_init uses right_row_blk_size, src/mm/dbcsr_mm_csr.F:428-432)
+        self.engine = host.Engine(self.m_sizes, self.n_sizes, bs, nthreads=nthreads, mode=mode, cfg=self.cfg)
+        # ---- home panels (initial distribution; excluded from timing like the reference's make_images)
+        self.home = {}
+        A, B = w["A"], w["B"]
+        for s in sc.home_slices_a(rank):
+            self.home[("a", s)] = A.sub(self.rsp[self.i], self.rsp[self.i + 1], self.ksp[s], self.ksp[s + 1])
+        for s in sc.home_slices_b(rank):
+            self.home[("b", s)] = B.sub(self.ksp[s], self.ksp[s + 1], self.csp[self.j], self.csp[self.j + 1])
+        self.home_buf, self.home_meta = {}, {}
+        for key, p in self.home.items():
+            t_ = torch.from_numpy(pack_panel(p)).to(self.device)
+            self.home_buf[key] = t_
+            self.home_meta[key] = (p.nblks, p.data.size)
+        if acc is not None:  # transpose the right panels once, at home, on the device
+            s0 = acc.stream_create("cannon setup", 0)
+            for key, p in self.home.items():
+                if key[0] == "b" and p.nblks:
+                    host.transpose_panel(acc, p.list3(), self.k_sizes[key[1]], self.n_sizes, self.home_buf[key].data_ptr(), s0)
+            acc.stream_destroy(s0)
+        # ---- exchange panel sizes (mp_allgather of the image sizes, src/mm/dbcsr_mm_cannon.F:1036)
+        meta = torch.zeros((world, 2, sc.V, 2), dtype=torch.int64)
+        for (kind, s), (nblk, nze) in self.home_meta.items():
+            meta[rank, 0 if kind == "a" else 1, s, 0] = nblk
+            meta[rank, 0 if kind == "a" else 1, s, 1] = nze
+        if world > 1:
+            meta = meta.to(self.device)
+            dist.all_reduce(meta)
+            meta = meta.cpu()
+        self.meta = meta.numpy()
+        max_bytes = int((self.meta[..., 1] * 8 + self.meta[..., 0] * 12).max())
+        self.recv = {kind: [torch.empty(max(max_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(2)] for kind in "ab"}
+        self.flop = 0
+        self.last_build_s = 0.0
+
+    # -------------------------------------------------------------------------------------------------------------
+    def panel_meta(self, kind, s, i, j):
+        src = self.sched.home_a(i, s) if kind == "a" else self.sched.home_b(s, j)
+        nblk, nze = self.meta[src, 0 if kind == "a" else 1, s]
+        return src, int(nblk), int(nze)
+
+    def post_exchange(self, t):
+        """Post the grouped send/recv of tick t's panels (returns the work handles); local panels need no message."""
+        dist = self.dist
+        ra, rb, sends = self.sched.transfers(self.rank, t)
+        ops = []
+        s = self.sched.slice_at(self.rank, t)
+        if ra is not None:
+            _, nblk, nze = self.panel_meta("a", s, self.i, self.j)
+            ops.append(dist.P2POp(dist.irecv, self.recv["a"][t % 2][:nze * 8 + nblk * 12], ra))
+        if rb is not None:
+            _, nblk, nze = self.panel_meta("b", s, self.i, self.j)
+            ops.append(dist.P2POp(dist.irecv, self.recv["b"][t % 2][:nze * 8 + nblk * 12], rb))
+        for dst, kind, s2 in sends:
+            ops.append(dist.P2POp(dist.isend, self.home_buf[(kind, s2)], dst))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def panel_of_tick(self, t, kind):
+        """(buffer tensor, nblks, nze) of the panel this rank multiplies at tick t (after its exchange completed)."""
+        s = self.sched.slice_at(self.rank, t)
+        src, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
+        buf = self.home_buf[(kind, s)] if src == self.rank else self.recv[kind][t % 2]
+        return buf, nblk, nze
+
+    def index_to_host(self, buf, nblk, nze):
+        idx = buf[nze * 8:nze * 8 + nblk * 12]
+        return idx.cpu().numpy().view(np.int32).reshape(-1, 3).copy()
+
+    def run(self):
+        """The whole multiply: V ticks; exchange of tick t+1 overlaps the local multiply of tick t.  Returns per-tick stack lists
+        when recording."""
+        V = self.sched.V
+        pending = self.post_exchange(0)
+        per_tick = []
+        n_before = 0
+        for t in range(V):
+            for wk in pending:
+                wk.wait()
+            if self.device.type == "cuda":
+                self.torch.cuda.current_stream().synchronize()
+            pending = self.post_exchange(t + 1) if t + 1 < V else []
+            (abuf, anb, anz), (bbuf, bnb, bnz) = self.panel_of_tick(t, "a"), self.panel_of_tick(t, "b")
+            a_idx, b_idx = self.index_to_host(abuf, anb, anz), self.index_to_host(bbuf, bnb, bnz)
+            s = self.sched.slice_at(self.rank, t)
+            self.engine.set_k_sizes(self.k_sizes[s])
+            a_ptr = abuf.data_ptr() if self.acc is not None else None
+            b_ptr = bbuf.data_ptr() if self.acc is not None else None
+            self.engine.multiply(a_idx, a_ptr, b_idx, b_ptr)
+            self.last_build_s += self.engine.build_seconds()
+            if self.mode & self.host.RECORD:
+                st = self.engine.stacks()
+                per_tick.append(st[n_before:])
+                n_before = len(st)
+            if self.acc is not None:
+                self.engine.sync()  # the recv buffers of tick t are reused at tick t+2
+        self.flop = self.engine.flop()
+        return per_tick
+
+    # ------------------------------------------------------------------------------------------------ replay (stack-kernel only)
+    def build_replay(self):
+        """Pre-build every tick's stacks on the host (one thread = the reference's traversal order), put them into HBM and
+        allocate the device C buffer: the multi-GPU counterpart of bench.py's single-GPU `value` (stack-kernel only + NCCL)."""
+        torch, host, acc = self.torch, self.host, self.acc
+        rec = CannonMultiply.__new__(CannonMultiply)
+        rec.__dict__.update(self.__dict__)
+        rec.acc, rec.mode = None, host.RECORD
+        rec.engine = host.Engine(self.m_sizes, self.n_sizes, self.w["m_sizes"], nthreads=1, mode=host.RECORD, cfg=self.cfg)
+        per_tick = rec.run()
+        self.flop = rec.engine.flop()
+        self.replay_datasize = rec.engine.c_index(0)[3]
+        rec.engine.close()
+        flat = [st["dev"].reshape(-1) for tick in per_tick for st in tick]
+        all_dev = np.concatenate(flat).astype(np.int32) if flat else np.zeros(3, dtype=np.int32)
+        self.replay_stacks = torch.from_numpy(all_dev).to(self.device)
+        self.replay = []
+        off = 0
+        for tick in per_tick:
+            lst = []
+            for st in tick:
+                lst.append((off, st["dev"].shape[0], st["max_m"], st["max_n"], st["max_k"], st["defined_mnk"]))
+                off += st["dev"].size
+            self.replay.append(lst)
+        self.replay_c = torch.zeros(max(self.replay_datasize, 1), dtype=torch.float64, device=self.device)
+        self.cs = acc.stream_create("cannon compute", 0)
+        from . import lib as acclib
+
+        self.cs_torch = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(self.cs).value)
+        self.comm_stream = torch.cuda.Stream()
+        self.n_replay_launches = sum(len(x) for x in self.replay)
+
+    def replay_step(self):
+        """One whole multiply, enqueued without any host synchronisation: C memset, then per tick the NCCL exchange of the next
+        panels (comm stream) overlapped with this tick's stack kernels (compute stream), ordered by events."""
+        torch, acc = self.torch, self.acc
+        V = self.sched.V
+        cs = self.cs_torch
+        with torch.cuda.stream(cs):
+            self.replay_c.zero_()
+        ev_comp = [None] * V
+
+        def exchange(t, after):
+            with torch.cuda.stream(self.comm_stream):
+                if after is not None:
+                    self.comm_stream.wait_event(after)  # recv buffer (t % 2) was read by the kernels of tick t-2
+                for wk in self.post_exchange(t):
+                    wk.wait()
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+            return ev
+
+        ev_comm = exchange(0, None)
+        for t in range(V):
+            nxt = exchange(t + 1, ev_comp[t - 1] if t >= 1 else None) if t + 1 < V else None
+            cs.wait_event(ev_comm)
+            (abuf, _, _), (bbuf, _, _) = self.panel_of_tick(t, "a"), self.panel_of_tick(t, "b")
+            base = self.replay_stacks.data_ptr()
+            for off, S, mm, nn, kk, dm in self.replay[t]:
+                rc = acc.process(None, base + 4 * off, S, abuf.data_ptr(), bbuf.data_ptr(), self.replay_c.data_ptr(), mm, nn, kk, dm,
+                                 self.cs, self.cs)
+                if rc < 0:
+                    raise RuntimeError("libsmm_acc_process returned %d" % rc)
+            ev_comp[t] = torch.cuda.Event()
+            ev_comp[t].record(cs)
+            ev_comm = nxt
+
+    def close(self):
+        self.engine.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------- bench
+def bench_main(args):
+    """bench.py --gpus N (N > 1): launched by torchrun, one rank per GPU."""
+    import json
+
+    import torch
+    import torch.distributed as dist
+
+    from . import host, workload
+    from . import lib as acclib
+    from bench import ClockSampler, measured_peaks, workload_config
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    acc = acclib.Acc(local)
+    w = workload.make_config(args.config, nblk=args.nblk)
+    nthreads = args.threads or max(1, min(16, (os.cpu_count() or 2) // (2 * world)))
+    cm = CannonMultiply(w, rank, world, "cuda:%d" % local, acc=acc, nthreads=nthreads)
+    sc = cm.sched
+
+    cm.build_replay()
+
+    def timed(fn, steps):
+        ts = []
+        for _ in range(steps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(cm.cs_torch):
+                e0.record(cm.cs_torch)
+            fn()
+            torch.cuda.synchronize()
+            with torch.cuda.stream(cm.cs_torch):
+                e1.record(cm.cs_torch)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return ts
+
+    for _ in range(args.warmup):
+        cm.replay_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = acc.launch_count()
+    times = timed(cm.replay_step, args.steps)
+    launches = acc.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: stacks built by the host threads every step and streamed to the device (engine path), C stays on the device
+    def one_multiply():
+        cm.engine.reset()
+        cm.last_build_s = 0.0
+        cm.run()
+
+    e2e_times = [0.0]
+    if not args.no_e2e:
+        cm.run()  # creates the engine's device C buffers
+        for _ in range(max(1, args.e2e_warmup)):
+            one_multiply()
+        e2e_times = timed(one_multiply, args.e2e_steps)
+    t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times))],
+                     dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(tmax[0])
+        flop = float(tsum[1])
+        value = flop / (ms * 1e-3) * 1e-9
+        peak, peak_src = measured_peaks()
+        out = {"metric": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
+               "config": workload_config(w, {"grid": "%dx%d" % (sc.pr, sc.pc), "k_slices": sc.V, "host_threads_per_rank": nthreads,
+                                             "flop": flop, "parallelism": "cannon %dx%d over NCCL send/recv" % (sc.pr, sc.pc),
+                                             "timed": "whole multiply per step: C memset, %d ticks of (NCCL panel exchange || stack kernels on pre-built device stacks); max over ranks of CUDA-event time; initial distribution excluded" % sc.V}),
+               "clocks": clocks, "gpu_launches": int(float(tsum[2])),
+               "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                            "note": "per-kernel roofline is reported by the N=1 run; this line is the distributed multiply"},
+               "e2e": ({"value": flop / (float(tmax[4]) * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": float(tmax[4]),
+                        "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": 0,
+                        "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
+                       if not args.no_e2e else None),
+               "cpu_baseline": None, "host_build_seconds_max": float(tmax[3])}
+        print(json.dumps(out))
+    dist.barrier()
+    cm.close()
+    dist.destroy_process_group()

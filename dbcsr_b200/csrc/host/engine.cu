@@ -280,6 +280,14 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
   return 0;
 }
 
+int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk) {
+  if (e == nullptr || nk < 0) return -1;
+  std::vector<int> ks(k_sizes, k_sizes + nk);
+  e->nk = nk;
+  for (auto& ts : e->th) ts.mm->set_k_sizes(ks);
+  return 0;
+}
+
 int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
   // start a new multiply on pooled resources (streams, stack buffers, device C buffer stay allocated like DBCSR's memory pools,
   // src/data/dbcsr_mem_methods.F:41-251): forget the product index, clear recorded stacks, zero the C buffer asynchronously

@@ -274,12 +274,12 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
   const int w = cfg_.n_stacks + 1;
   for (int a_row_l = mi; a_row_l <= mf; ++a_row_l) {
     const int m_size = m_sizes_[a_row_l - 1];
-    const int mapped_row = m_map_[m_size];
+    const int mapped_row = m_size < (int)m_map_.size() ? m_map_[m_size] : cfg_.n_stacks + 1;
     for (int a_blk = a_row_p_[a_row_l - mi]; a_blk < a_row_p_[a_row_l - mi + 1]; ++a_blk) {
       const int a_col_l = a_info_[2 * (size_t)a_blk];
       const int a_first = a_info_[2 * (size_t)a_blk + 1];
       const int k_size = k_sizes_[a_col_l - 1];
-      const int mapped_k = k_map_[k_size];
+      const int mapped_k = k_size < (int)k_map_.size() ? k_map_[k_size] : cfg_.n_stacks + 1;
       for (int b_blk = b_row_p_[a_col_l - ki]; b_blk < b_row_p_[a_col_l - ki + 1]; ++b_blk) {
         const int b_col_l = b_info_[2 * (size_t)b_blk];
         const int b_first = b_info_[2 * (size_t)b_blk + 1];
@@ -288,7 +288,7 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
         bool created = false;
         const int c_blk_id = c_lookup_or_insert(a_row_l, b_col_l, c_nze, created);
         const int offset = c_blk_p_[c_blk_id - 1];
-        const int mapped_col = n_map_[n_size];
+        const int mapped_col = n_size < (int)n_map_.size() ? n_map_[n_size] : cfg_.n_stacks + 1;
         const int ws = stack_map_[((size_t)(mapped_row - 1) * w + (mapped_k - 1)) * w + (mapped_col - 1)];
         int* p = stacks_[ws].data() + 7 * (size_t)fill_[ws];
         p[0] = m_size;

@@ -35,6 +35,7 @@ def _L():
         L.dbcsr_b200_engine_multiply.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _vp]
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
         L.dbcsr_b200_engine_reset.argtypes = [_vp]
+        L.dbcsr_b200_engine_set_k_sizes.argtypes = [_vp, _vp, _i]
         for f in ("nthreads", "nstacks"):
             getattr(L, "dbcsr_b200_engine_" + f).argtypes = [_vp]
         for f in ("c_nblks", "c_datasize"):
@@ -108,6 +109,11 @@ class Engine:
         rc = self.L.dbcsr_b200_engine_multiply(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, b.ctypes.data, b.shape[0], b_dev_ptr)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_multiply returned %d" % rc)
+
+    def set_k_sizes(self, k_sizes):
+        ks = np.ascontiguousarray(k_sizes, dtype=np.int32)
+        if self.L.dbcsr_b200_engine_set_k_sizes(self.h, ks.ctypes.data, ks.size) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_set_k_sizes failed")
 
     def reset(self):
         if self.L.dbcsr_b200_engine_reset(self.h) != 0:

@@ -56,6 +56,9 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e);
  * builds the stacks and (LAUNCH) streams them to the device.  Returns 0, or a negative code of the failing call. */
 int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
   const void* b_dev);
+/* block sizes of the contraction index of the NEXT panels (Cannon ticks bring different k-slices); the stack map built at
+ * creation (from the k_sizes given there: use the global right-matrix row block sizes) is kept */
+int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk);
 /* begin a new multiply on the same (pooled) buffers: clears the product index, zeroes the device C buffers asynchronously */
 int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e);
 /* wait for all enqueued stacks (dbcsr_mm_accdrv_barrier, src/mm/dbcsr_mm_accdrv.F:425-431) */

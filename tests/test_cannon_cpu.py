@@ -1,0 +1,133 @@
+"""CPU tests of the multi-GPU path (N>1): the Cannon schedule arithmetic, and the whole distributed multiply on the gloo backend
+(world_size 2, 4 and 8 = grids 1x2, 2x2, 2x4) with the recorded host stacks drained by the oracle and compared with the
+oracle's global block product."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from dbcsr_b200 import cannon, workload
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_schedule_covers_every_slice_once_and_messages_match(world):
+    sc = cannon.Schedule(world)
+    for r in range(world):
+        assert sorted(sc.slice_at(r, t) for t in range(sc.V)) == list(range(sc.V))
+    for t in range(sc.V):
+        sends = {}
+        for r in range(world):
+            _, _, snd = sc.transfers(r, t)
+            for dst, kind, s in snd:
+                assert (dst, kind) not in sends  # at most one panel of a kind per destination and tick
+                sends[(dst, kind)] = (r, s)
+        for r in range(world):
+            ra, rb, _ = sc.transfers(r, t)
+            s = sc.slice_at(r, t)
+            for kind, src in (("a", ra), ("b", rb)):
+                if src is None:
+                    assert (r, kind) not in sends
+                else:
+                    assert sends.pop((r, kind)) == (src, s)
+        assert not sends
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nblk, sizes, q):
+    import torch.distributed as dist
+
+    from oracle import oracle as orc
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)
+    bs = workload.block_sizes(nblk, sizes, rng)
+    A = workload.random_panel(bs, bs, 0.25, rng)
+    B = workload.random_panel(bs, bs, 0.25, rng)
+    w = dict(name="t", nblk=nblk, sizes=sizes, occupation=0.25, m_sizes=bs, n_sizes=bs, k_sizes=bs, A=A, B=B, seed=123)
+    from dbcsr_b200 import host
+
+    cm = cannon.CannonMultiply(w, rank, world, "cpu", acc=None, nthreads=1, cfg=host.default_cfg(mm_stack_size=200, n_stacks=max(3, len(sizes))))
+    # drain the recorded host stacks of every tick with the oracle's CPU path on the panels this rank held at that tick
+    sc = cm.sched
+    per_tick = []
+    V = sc.V
+    pending = cm.post_exchange(0)
+    rows, cols, blk_p, ds = None, None, None, 0
+    c = None
+    n_before = 0
+    for t in range(V):
+        for wk in pending:
+            wk.wait()
+        pending = cm.post_exchange(t + 1) if t + 1 < V else []
+        (abuf, anb, anz), (bbuf, bnb, bnz) = cm.panel_of_tick(t, "a"), cm.panel_of_tick(t, "b")
+        a_idx, b_idx = cm.index_to_host(abuf, anb, anz), cm.index_to_host(bbuf, bnb, bnz)
+        cm.engine.set_k_sizes(cm.k_sizes[sc.slice_at(rank, t)])
+        cm.engine.multiply(a_idx, None, b_idx, None)
+        st = cm.engine.stacks()
+        a_data = abuf[:anz * 8].numpy().view(np.float64).copy()
+        b_data = bbuf[:bnz * 8].numpy().view(np.float64).copy()
+        per_tick.append((st[n_before:], a_data, b_data))
+        n_before = len(st)
+    rows, cols, blk_p, ds = cm.engine.c_index(0)
+    c = np.zeros(max(ds, 1))
+    for stacks, a_data, b_data in per_tick:
+        for s_ in stacks:
+            orc.host_stack(s_["host"], a_data if a_data.size else np.zeros(1), b_data if b_data.size else np.zeros(1), c)
+    # global coordinates of this rank's C blocks
+    out = {}
+    for r, cc, o in zip(rows, cols, blk_p):
+        gr, gc = int(r) + cm.rsp[cm.i], int(cc) + cm.csp[cm.j]
+        m, n = int(bs[gr - 1]), int(bs[gc - 1])
+        out[(gr, gc)] = c[o - 1:o - 1 + m * n].copy()
+    q.put((rank, out, cm.engine.flop()))
+    dist.barrier()
+    cm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sizes", [(2, [23]), (4, [5, 13, 23]), (8, [23])])
+def test_distributed_multiply_gloo(world, sizes):
+    import torch.multiprocessing as mp
+
+    from oracle import oracle as orc
+
+    nblk = 24
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nblk, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(123)
+    bs = workload.block_sizes(nblk, sizes, rng)
+    A = workload.random_panel(bs, bs, 0.25, rng)
+    B = workload.random_panel(bs, bs, 0.25, rng)
+    Cref = orc.multiply_blocks(orc.BlockMatrix(bs, bs, A.rows, A.cols, data=A.data), orc.BlockMatrix(bs, bs, B.rows, B.cols, data=B.data))
+    got = {}
+    flop = 0
+    for rank, out, f in results:
+        assert not (set(out) & set(got))  # every C block is owned by exactly one rank
+        got.update(out)
+        flop += f
+    assert set(got) == set(zip(Cref.rows.tolist(), Cref.cols.tolist()))
+    num = den = 0.0
+    for r, c, o in zip(Cref.rows, Cref.cols, Cref.offsets):
+        m, n = int(bs[r - 1]), int(bs[c - 1])
+        ref = Cref.data[o:o + m * n]
+        num += float(((got[(int(r), int(c))] - ref) ** 2).sum())
+        den += float((ref ** 2).sum())
+    assert (num / den) ** 0.5 <= 1e-12
+    assert flop == sum(2 * int(bs[r - 1]) * int(bs[c - 1]) * int(bs[B.cols[B.rows == c] - 1].sum()) for r, c in zip(A.rows, A.cols))
