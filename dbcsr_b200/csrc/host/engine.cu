@@ -315,6 +315,23 @@ const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int t) { retur
 const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_blk_p().data(); }
 void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].c_dev; }
 
+int dbcsr_b200_engine_wait_event(dbcsr_b200_engine_t* e, void* event) {
+  // every thread stream waits for `event` (e.g. "panels uploaded and transposed") before running anything enqueued later
+  if (e == nullptr || event == nullptr) return -1;
+  for (auto& ts : e->th)
+    if (ts.stream != nullptr && c_dbcsr_acc_stream_wait_event(ts.stream, event) != 0) return -1;
+  return 0;
+}
+
+int dbcsr_b200_engine_c_to_host_async(dbcsr_b200_engine_t* e, int t, double* host) {
+  // D2H of the thread's C buffer enqueued behind its last stack; completes at dbcsr_b200_engine_sync
+  ThreadState& ts = e->th[(size_t)t];
+  if (ts.c_dev == nullptr || ts.stream == nullptr) return -1;
+  const size_t n = (size_t)ts.mm->datasize();
+  if (n > 0 && c_dbcsr_acc_memcpy_d2h(ts.c_dev, host, n * sizeof(double), ts.stream) != 0) return -1;
+  return 0;
+}
+
 int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int t, double* host) {
   ThreadState& ts = e->th[(size_t)t];
   if (ts.c_dev == nullptr || ts.stream == nullptr) return -1;

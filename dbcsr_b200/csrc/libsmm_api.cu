@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "../../include/dbcsr_acc_libsmm.h"
+#include "smm_bf16.cuh"
 #include "smm_generic.cuh"
 #include "smm_launch.h"
 
@@ -64,6 +65,29 @@ smm::launch_fn lookup(int m, int n, int k) {
   }
 }
 
+int launch_bf16(const int* dev_stack, int stack_size, const void* a_tiles, const void* b_tiles, void* c, int m, int n, int k,
+                cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  const smm::Bf16Geom g = smm::bf16_geom(m, n, k);
+  const size_t smem = smm::bf16_smem_bytes(g);
+  static std::atomic<size_t> smem_set{0};
+  if (smem_set.load(std::memory_order_acquire) < smem) {
+    if (cudaFuncSetAttribute(smm::smm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -30;
+    smem_set.store(smem, std::memory_order_release);
+  }
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm > 512 / smm::BF_TMEM_COLS) per_sm = 512 / smm::BF_TMEM_COLS;  // TMEM: 512 columns per SM
+  if (per_sm < 1) return -30;
+  const int max_grid = num_sms() * per_sm;
+  int grid = (stack_size + 15) / 16;
+  if (grid > max_grid) grid = max_grid;
+  const int chunk = (stack_size + grid - 1) / grid;
+  grid = (stack_size + chunk - 1) / chunk;
+  smm::smm_bf16_kernel<<<grid, smm::BF_THREADS, smem, stream>>>(dev_stack, stack_size, static_cast<const unsigned char*>(a_tiles),
+                                                               static_cast<const unsigned char*>(b_tiles), static_cast<float*>(c), m, n, k, chunk);
+  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+}
+
 int launch_generic(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k,
                    int b_transposed, cudaStream_t stream) {
   if (stack_size <= 0) return 0;
@@ -87,7 +111,25 @@ int libsmm_acc_gpu_warp_size(void) { return 32; }
 long long libsmm_acc_b200_launch_count(void) { return g_launches.load(); }
 const char* libsmm_acc_b200_version(void) { return "dbcsr_acc_b200 r1 (sm_100a, DMMA.8x8x4 + TMA bulk staging)"; }
 
+int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
+
+int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
+                              void* stream) {
+  if (nblks <= 0) return 0;
+  if (stream == nullptr || rows <= 0 || kdim <= 0 || rows > 32 || kdim > 32) return -2;
+  const int wpc = 8;
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::pack_bf16_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream)>>>(dev_src, nblks, rows, kdim, row_stride, k_stride,
+                                                                                 static_cast<unsigned char*>(dev_dst));
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype) {
+  if (datatype == dbcsr_type_bf16_ext) return (m > 0 && n > 0 && k > 0 && m <= 32 && n <= 32 && k <= 32) ? 3 : 0;
   if (datatype != dbcsr_type_real_8) return 0;
   if (m <= 0 || n <= 0 || k <= 0) return 0;
   return lookup(m, n, k) != nullptr ? 1 : 2;
@@ -98,9 +140,17 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
                        int max_kernel_dim, c_dbcsr_acc_bool_t def_mnk, void* stack_stream, void* c_stream) {
   (void)host_param_stack;
   if (def_mnk != 1) return -1;                      // inhomogeneous stack: not handled (reference: libsmm_acc.cpp:327)
-  if (datatype != dbcsr_type_real_8) return -10;    // reference: libsmm_acc.cpp:338
   if (stack_size < 0 || m_max <= 0 || n_max <= 0 || k_max <= 0) return -2;
   if (stack_stream == nullptr) return -2;
+  if (datatype == dbcsr_type_bf16_ext) {
+    // extension: A/B are BF16 tile panels made by libsmm_acc_b200_pack_bf16, C is FP32; tensor-core (tcgen05) kernel
+    if (m_max > 32 || n_max > 32 || k_max > 32) return -10;
+    const int rc = launch_bf16(dev_param_stack, stack_size, dev_a_data, dev_b_data, dev_c_data, m_max, n_max, k_max,
+                               *static_cast<cudaStream_t*>(stack_stream));
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
+  if (datatype != dbcsr_type_real_8) return -10;    // reference: libsmm_acc.cpp:338
   const double* a = static_cast<const double*>(dev_a_data);
   const double* b = static_cast<const double*>(dev_b_data);
   double* c = static_cast<double*>(dev_c_data);

@@ -156,7 +156,14 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
   const int gw = blockIdx.x * WPC + warp;
   const int e0 = gw * chunk;
   const int e1 = min(e0 + chunk, stack_size);
-  if (e0 >= e1) return;  // warps never synchronise with each other
+  // Programmatic dependent launch: let the next stack kernel of this stream start filling SMs as soon as our CTAs retire
+  // (stacks only accumulate into C with RED, so consecutive drains are independent); the matching wait sits at the very end so
+  // that a kernel never COMPLETES before its predecessor has (later memcpys / events keep plain stream-order semantics).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (e0 >= e1) {  // warps never synchronise with each other
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    return;
+  }
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * NST;
   unsigned char* wbase = smem_raw + round_up_c(WPC * NST * 8, 128) + (size_t)warp * NST * SH::STAGE;
@@ -169,25 +176,41 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
   __syncwarp();
 
 
-  auto issue = [&](int e) {  // lane 0 only
-    const int3 p = ld_entry(stack, e);
-    const int sidx = (e - e0) % NST;
-    unsigned char* stg = wbase + (size_t)sidx * SH::STAGE;
-    const uint64_t ga = reinterpret_cast<uint64_t>(a_data + (p.x - 1));
-    const uint64_t gb = reinterpret_cast<uint64_t>(b_data + (p.y - 1));
-    // expect first (the count must be known before the copies can complete), then copy
-    const uint32_t ba = stage_block(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], false);
-    const uint32_t bb = stage_block(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], false);
-    mbar_expect_tx(&bars[sidx], ba + bb);
-    stage_block(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], true);
-    stage_block(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], true);
+  // Stack entries are fetched 32 at a time, one per lane (coalesced), and handed out with warp shuffles, so that no global
+  // load sits on the per-entry critical path (ncu r01: long_scoreboard was the second largest stall). `cur` holds the entries
+  // [ebase, ebase+32), `nxt` the following 32 (loaded one batch ahead).
+  int ebase = e0;
+  int3 cur = make_int3(1, 1, 1), nxt = make_int3(1, 1, 1);
+  if (ebase + lane < e1) cur = ld_entry(stack, ebase + lane);
+  if (ebase + 32 + lane < e1) nxt = ld_entry(stack, ebase + 32 + lane);
+  auto entry = [&](int e) -> int3 {  // warp-uniform e in [ebase, ebase+64)
+    const int r = e - ebase;
+    const int3 a = make_int3(__shfl_sync(0xffffffffu, cur.x, r & 31), __shfl_sync(0xffffffffu, cur.y, r & 31),
+                             __shfl_sync(0xffffffffu, cur.z, r & 31));
+    const int3 b = make_int3(__shfl_sync(0xffffffffu, nxt.x, r & 31), __shfl_sync(0xffffffffu, nxt.y, r & 31),
+                             __shfl_sync(0xffffffffu, nxt.z, r & 31));
+    return r < 32 ? a : b;
   };
 
-  if (lane == 0) {
+  auto issue = [&](int e) {  // executed by the whole warp (uniform), the copies are issued by lane 0
+    const int3 p = entry(e);
+    if (lane == 0) {
+      const int sidx = (e - e0) % NST;
+      unsigned char* stg = wbase + (size_t)sidx * SH::STAGE;
+      const uint64_t ga = reinterpret_cast<uint64_t>(a_data + (p.x - 1));
+      const uint64_t gb = reinterpret_cast<uint64_t>(b_data + (p.y - 1));
+      // expect first (the count must be known before the copies can complete), then copy
+      const uint32_t ba = stage_block(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], false);
+      const uint32_t bb = stage_block(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], false);
+      mbar_expect_tx(&bars[sidx], ba + bb);
+      stage_block(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], true);
+      stage_block(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], true);
+    }
+  };
+
 #pragma unroll
-    for (int p = 0; p < NST - 1; ++p)
-      if (e0 + p < e1) issue(e0 + p);
-  }
+  for (int p = 0; p < NST - 1; ++p)
+    if (e0 + p < e1) issue(e0 + p);
 
   double acc[TM][TN][2];
 #pragma unroll
@@ -214,10 +237,16 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
 
   int cur_c = -1;
   for (int e = e0; e < e1; ++e) {
+    if (e - ebase >= 32) {  // roll the entry batches; the new `nxt` is needed 32 - (NST-1) entries from now at the earliest
+      ebase += 32;
+      cur = nxt;
+      nxt = make_int3(1, 1, 1);
+      if (ebase + 32 + lane < e1) nxt = ld_entry(stack, ebase + 32 + lane);
+    }
     // stage (e-1)%NST was consumed by the previous iteration (guarded by the __syncwarp at its end): refill it
-    if (lane == 0 && e + NST - 1 < e1) issue(e + NST - 1);
+    if (e + NST - 1 < e1) issue(e + NST - 1);
 
-    const int3 p = ld_entry(stack, e);
+    const int3 p = entry(e);
     if (p.z != cur_c) {
       if (cur_c >= 0) flush(cur_c);
       cur_c = p.z;
@@ -251,6 +280,7 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
     __syncwarp();  // every lane is done reading this stage before lane 0 refills it
   }
   if (cur_c >= 0) flush(cur_c);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 }  // namespace smm

@@ -3,6 +3,7 @@
 // This is the ahead-of-time replacement of the reference's NVRTC JIT + kernel cache (src/acc/libsmm_acc/libsmm_acc.cpp:90-253).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 #include "smm_dmma.cuh"
 #include "smm_launch.h"
@@ -15,13 +16,23 @@ namespace smm {
 namespace {
 
 int g_num_sms = 0;
+// DBCSR_B200_PDL=0 disables programmatic dependent launch (A/B experiments); default on
+const bool g_use_pdl = [] {
+  const char* e = getenv("DBCSR_B200_PDL");
+  return e == nullptr || atoi(e) != 0;
+}();
 
 template <int M, int N, int K>
 int launch(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
            cudaStream_t stream) {
   using SH = Shape<M, N, K>;
+#if defined(SMM_FORCE_NST) && defined(SMM_FORCE_WPC)
+  constexpr int NST = (SMM_FORCE_WPC * SMM_FORCE_NST * SH::STAGE <= 220 * 1024) ? SMM_FORCE_NST : pick_nst(SH::STAGE);
+  constexpr int WPC = (SMM_FORCE_WPC * SMM_FORCE_NST * SH::STAGE <= 220 * 1024) ? SMM_FORCE_WPC : pick_wpc(SH::STAGE);
+#else
   constexpr int NST = pick_nst(SH::STAGE);
   constexpr int WPC = pick_wpc(SH::STAGE);
+#endif
   constexpr int SMEM = round_up_c(WPC * NST * 8, 128) + WPC * NST * SH::STAGE;
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
   auto kern = smm_dmma_kernel<M, N, K, NST, WPC>;
@@ -43,8 +54,19 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
   if (grid > max_grid) grid = max_grid;
   const int warps = grid * WPC;
   const int chunk = (stack_size + warps - 1) / warps;
-  kern<<<grid, WPC * 32, SMEM, stream>>>(dev_stack, stack_size, a, b, c, a_limit, b_limit, chunk);
-  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WPC * 32);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const unsigned long long al = a_limit, bl = b_limit;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, dev_stack, stack_size, a, b, c, al, bl, chunk);
+  return (err == cudaSuccess) ? 0 : -31;
 }
 
 template <int M, int N>

@@ -47,6 +47,8 @@ def _L():
         L.dbcsr_b200_engine_c_dev.argtypes = [_vp, _i]
         L.dbcsr_b200_engine_c_dev.restype = _vp
         L.dbcsr_b200_engine_c_to_host.argtypes = [_vp, _i, _vp]
+        L.dbcsr_b200_engine_c_to_host_async.argtypes = [_vp, _i, _vp]
+        L.dbcsr_b200_engine_wait_event.argtypes = [_vp, _vp]
         L.dbcsr_b200_engine_flop.argtypes = [_vp]
         L.dbcsr_b200_engine_flop.restype = ctypes.c_longlong
         L.dbcsr_b200_engine_build_seconds.argtypes = [_vp]
@@ -139,6 +141,14 @@ class Engine:
     def c_to_host(self, t, host_array):
         if self.L.dbcsr_b200_engine_c_to_host(self.h, t, host_array.ctypes.data) != 0:
             raise acclib.AccError("dbcsr_b200_engine_c_to_host failed")
+
+    def c_to_host_async(self, t, host_array):
+        if self.L.dbcsr_b200_engine_c_to_host_async(self.h, t, host_array.ctypes.data) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_c_to_host_async failed")
+
+    def wait_event(self, event):
+        if self.L.dbcsr_b200_engine_wait_event(self.h, event) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_wait_event failed")
 
     def flop(self):
         return int(self.L.dbcsr_b200_engine_flop(self.h))

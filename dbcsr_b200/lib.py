@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdbcsr_acc_b200.so")
+# DBCSR_B200_LIB selects an alternative build of the same library (kernel-variant experiments); default = the in-tree build
+LIB_PATH = os.environ.get("DBCSR_B200_LIB") or os.path.join(_HERE, "lib", "libdbcsr_acc_b200.so")
 
 # every symbol include/*.h declares; tests check that the library exports all of them
 ACC_SYMBOLS = [
@@ -27,10 +28,11 @@ ACC_SYMBOLS = [
 SMM_SYMBOLS = [
     "libsmm_acc_init", "libsmm_acc_finalize", "libsmm_acc_is_thread_safe", "libsmm_acc_transpose", "libsmm_acc_process",
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
-    "libsmm_acc_b200_version",
+    "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
+DBCSR_TYPE_BF16_EXT = 9  # extension of this library: BF16 operand tiles, FP32 C
 MAX_KERNEL_DIM = 80  # src/core/dbcsr_config.F:185
 
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -77,6 +79,8 @@ def load():
     L.c_calculate_norms.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
     L.libsmm_acc_b200_kernel_kind.argtypes = [_i, _i, _i, _i]
     L.libsmm_acc_b200_launch_count.restype = ctypes.c_longlong
+    L.libsmm_acc_b200_pack_bf16.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp]
+    L.libsmm_acc_b200_bf16_tile_bytes.argtypes = [_i, _i]
     L.libsmm_acc_b200_version.restype = ctypes.c_char_p
     L.c_dbcsr_acc_clear_errors.restype = None
     _lib = L
@@ -217,6 +221,12 @@ class Acc:
 
     def norms(self, mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream):
         _ck(self.L.c_calculate_norms(mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream), "c_calculate_norms")
+
+    def pack_bf16(self, src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream):
+        _ck(self.L.libsmm_acc_b200_pack_bf16(src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream), "libsmm_acc_b200_pack_bf16")
+
+    def bf16_tile_bytes(self, rows, kdim):
+        return int(self.L.libsmm_acc_b200_bf16_tile_bytes(rows, kdim))
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())

@@ -58,12 +58,14 @@ class DeviceMultiply:
         self.trs_h = acc.host_alloc((max(nb_max, 1),), np.int32)
         self.trs_d = acc.dev_alloc(4 * max(nb_max, 1))
         self.first = True
+        self.panels_ready = acc.event_create()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
     def upload_panels(self, a_data, b_data, b_list3):
-        """host2dev of both panels + acc_transpose_blocks of the right one; returns after the stream is drained
-        (multiply_cannon synchronises the device before the local multiply, src/mm/dbcsr_mm_cannon.F:1642-1646)."""
+        """host2dev of both panels + acc_transpose_blocks of the right one, all asynchronous on the copy stream; the event
+        `panels_ready` orders the stack kernels behind them (the reference synchronises the whole device here,
+        src/mm/dbcsr_mm_cannon.F:1642-1646; an event lets the host build stacks while the panels are still in flight)."""
         acc = self.acc
         acc.h2d(a_data, self.d_a, self.copy_stream)
         acc.h2d(b_data, self.d_b, self.copy_stream)
@@ -72,7 +74,8 @@ class DeviceMultiply:
                                               self.trs_h.ptr, self.trs_d.ptr, self.copy_stream)
         if rc != 0:
             raise acclib.AccError("transpose_panel returned %d" % rc)
-        acc.stream_sync(self.copy_stream)
+        acc.event_record(self.panels_ready, self.copy_stream)
+        self._keep = (a_data, b_data, b)  # host buffers must stay alive until the copies ran
         self.h2d_bytes = a_data.nbytes + b_data.nbytes + 4 * b.shape[0]
 
     def multiply(self, a_list3, b_list3):
@@ -80,20 +83,22 @@ class DeviceMultiply:
         if not self.first:
             self.engine.reset()
         self.first = False
+        self.engine.wait_event(self.panels_ready)
         self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
 
     def download_c(self, out_arrays=None):
         """D2H of every thread's C buffer (datasize elements each). out_arrays: optional list of (pinned) host arrays."""
-        self.engine.sync()
         prod = ProductC(self.m_sizes, self.n_sizes)
         self.d2h_bytes = 0
+        # every thread's D2H is enqueued behind that thread's last stack, so early finishers copy while others still compute
         for t in range(self.engine.nthreads):
             rows, cols, blk_p, ds = self.engine.c_index(t)
             buf = out_arrays[t][:ds] if out_arrays is not None else np.empty(ds)
             if ds:
-                self.engine.c_to_host(t, buf)
+                self.engine.c_to_host_async(t, buf)
             self.d2h_bytes += 8 * ds
             prod.add(rows, cols, blk_p, buf)
+        self.engine.sync()
         return prod
 
     def close(self):
@@ -101,6 +106,7 @@ class DeviceMultiply:
         for d in (self.d_a, self.d_b, self.trs_d):
             d.free()
         self.trs_h.free()
+        self.acc.event_destroy(self.panels_ready)
         self.acc.stream_destroy(self.copy_stream)
 
 

@@ -59,7 +59,16 @@ int libsmm_acc_gpu_warp_size(void);
 
 /* ---- extensions of this library (not part of the reference ABI) -------------------------------------------------- */
 
-/* Which kernel would libsmm_acc_process use for (m,n,k)?  0 = none, 1 = specialised DMMA kernel, 2 = generic kernel. */
+/* BF16 extension (dbcsr_type_bf16_ext): convert nblks FP64 blocks, stored back to back (block b at dev_src + b*rows*kdim, element
+ * (row, kk) at [row*row_stride + kk*k_stride]), into BF16 operand tiles of libsmm_acc_b200_bf16_tile_bytes(rows, kdim) bytes each
+ * (canonical tcgen05 K-major layout, zero padded).  A panel: rows = m, kdim = k, row_stride = 1, k_stride = m.  Transposed B panel
+ * (n x k column-major, what libsmm_acc_transpose leaves behind): rows = n, kdim = k, row_stride = 1, k_stride = n.
+ * libsmm_acc_process(datatype = dbcsr_type_bf16_ext) then takes the tile panels as dev_a_data / dev_b_data, an FP32 C buffer, and
+ * the ordinary stack (element offsets of the ORIGINAL FP64 panels; all blocks of a panel must have the stack's (m,k) / (n,k)). */
+int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
+  void* stream);
+int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim);
+/* Which kernel would libsmm_acc_process use for (m,n,k)?  0 = none, 1 = specialised DMMA kernel, 2 = generic kernel, 3 = BF16 tcgen05. */
 int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype);
 /* Number of kernel launches this library has enqueued since load (all threads). */
 long long libsmm_acc_b200_launch_count(void);

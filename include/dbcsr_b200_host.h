@@ -74,6 +74,10 @@ const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int thread);
 void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int thread);
 /* D2H of thread's C buffer (datasize elements) into host memory (dbcsr_mm_accdrv_finalize, src/mm/dbcsr_mm_accdrv.F:340-362) */
 int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int thread, double* host);
+/* asynchronous variant: enqueued on the thread's stream behind its last stack; complete after dbcsr_b200_engine_sync */
+int dbcsr_b200_engine_c_to_host_async(dbcsr_b200_engine_t* e, int thread, double* host);
+/* all thread streams wait for an acc event (e.g. panels uploaded + transposed on another stream) */
+int dbcsr_b200_engine_wait_event(dbcsr_b200_engine_t* e, void* event);
 long long dbcsr_b200_engine_flop(const dbcsr_b200_engine_t* e);
 /* seconds the host threads spent building+ordering stacks / waiting for free stack buffers in the last multiply (max over threads) */
 double dbcsr_b200_engine_build_seconds(const dbcsr_b200_engine_t* e);
