@@ -176,9 +176,9 @@ def run_reference(args):
 
 
 def workload_config(w, extra=None):
-    c = {"workload": "%s: %dx%d block grid, blocks %s FP64, %.0f%% occupation, C=A*B (alpha=1, beta=0)"
+    c = {"workload": "%s: %dx%d block grid, blocks %s %s, %.0f%% occupation, C=A*B (alpha=1, beta=0)"
                      % (w["name"], w["nblk"], w["nblk"], "x".join(str(s) for s in w["sizes"]) if len(w["sizes"]) > 1 else "%dx%d" % (w["sizes"][0], w["sizes"][0]),
-                        100 * w["occupation"]),
+                        "BF16 (FP32 accumulate)" if w["name"] == "cfg4" else "FP64", 100 * w["occupation"]),
          "a_blocks": w["A"].nblks, "b_blocks": w["B"].nblks, "mm_stack_size": 30000,
          "l2_policy": "inputs (A+B %.0f MB, C rewritten every step) larger than L2; C memset each step" % ((w["A"].data.nbytes + w["B"].data.nbytes) / 1e6)}
     if extra:
@@ -219,13 +219,25 @@ def run_single(args):
     all_dev = np.concatenate([st["dev"].reshape(-1) for st in stacks]).astype(np.int32)
     d_st = acc.to_device(all_dev, s)
     offs = np.concatenate([[0], np.cumsum([st["dev"].size for st in stacks])]).astype(np.int64)
-    d_c = acc.dev_alloc(8 * max(c_datasize, 1))
+    bf16 = args.config == "cfg4"
+    dtype_id = acclib.DBCSR_TYPE_BF16_EXT if bf16 else acclib.DBCSR_TYPE_REAL_8
+    if bf16:  # pack both panels once into BF16 operand tiles (A: m x k col-major, B: transposed n x k col-major)
+        mm_ = int(w["sizes"][0])
+        ta_bytes = acc.bf16_tile_bytes(mm_, mm_)
+        p_a, p_b = acc.dev_alloc(A.nblks * ta_bytes), acc.dev_alloc(B.nblks * ta_bytes)
+        acc.pack_bf16(d_a.ptr, A.nblks, mm_, mm_, 1, mm_, p_a.ptr, s)
+        acc.pack_bf16(d_b.ptr, B.nblks, mm_, mm_, 1, mm_, p_b.ptr, s)
+        acc.stream_sync(s)
+        d_a.free()
+        d_b.free()
+        d_a, d_b = p_a, p_b
+    d_c = acc.dev_alloc((4 if bf16 else 8) * max(c_datasize, 1))
     alg_bytes = algorithmic_bytes(stacks)
 
     def drain():
         for i, st in enumerate(stacks):
             rc = acc.process(None, d_st.ptr + 4 * int(offs[i]), st["dev"].shape[0], d_a.ptr, d_b.ptr, d_c.ptr, st["max_m"], st["max_n"],
-                             st["max_k"], st["defined_mnk"], s, s)
+                             st["max_k"], st["defined_mnk"], s, s, datatype=dtype_id)
             if rc < 0:
                 raise RuntimeError("libsmm_acc_process returned %d for stack %d" % (rc, i))
 
@@ -266,14 +278,29 @@ def run_single(args):
             traffic = json.load(open(ncu_json)).get(args.config, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    if bf16:
+        tile = acc.bf16_tile_bytes(int(w["sizes"][0]), int(w["sizes"][0]))
+        runs = sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in stacks)
+        alg_bytes = n_entries * (2 * tile + 12) + runs * 2 * 4 * int(w["sizes"][0]) ** 2
+        achieved = alg_bytes / (float(np.mean(kern_ms)) * 1e-3) * 1e-9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": "smm_dmma_kernel<%s> (x%d launches/step)" % (",".join(str(x) for x in (stacks[0]["m"], stacks[0]["n"], stacks[0]["k"])), len(stacks)),
                 "algorithmic_bytes_per_launch": alg_bytes / max(len(stacks), 1), "avg_launch_us": float(np.mean(kern_ms)) * 1e3 / max(len(stacks), 1),
                 "kernel_only_gflops": flop / (float(np.mean(kern_ms)) * 1e-3) * 1e-9, "fp64_tensor_peak_gflops_measured": 37050.0}
+    if bf16:
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * 1e3
+        except Exception:
+            tpeak = 1590e3
+        useful = roofline["kernel_only_gflops"]
+        issued = useful * (128.0 * 32 * 32) / (23.0 ** 3)  # per entry two tcgen05.mma of M=128,N=32,K=16
+        roofline.update({"kernel": "smm_bf16_kernel (tcgen05.mma M128 N32 K16, x%d launches/step)" % len(stacks),
+                         "tensor": {"peak_gflops": tpeak, "useful_frac": useful / tpeak, "issued_frac": issued / tpeak,
+                                    "note": "useful = 2*23^3 per product; issued = padded MMA flops (M128 x N32 x K32 per product)"}})
 
     # ---- end to end through the host engine, host buffers pinned
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not bf16:
         nthreads = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2))
         d_c.free()
         pa = acc.host_alloc((A.data.size,), np.float64)
@@ -288,7 +315,9 @@ def run_single(args):
             acc.device_synchronize()
             t0 = time.perf_counter()
             dm.upload_panels(pa.array, pb.array, b_l)
+            t_up = time.perf_counter()
             dm.multiply(a_l, b_l)
+            t_mul = time.perf_counter()
             if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
                 dm.engine.sync()
                 pcs = [acc.host_alloc((max(dm.engine.c_index(t)[3], 1),), np.float64) for t in range(nthreads)]
@@ -296,21 +325,24 @@ def run_single(args):
             dt = time.perf_counter() - t0
             if it >= max(1, args.e2e_warmup):
                 times.append(dt)
+                phases = {"enqueue_upload_ms": (t_up - t0) * 1e3, "host_build_and_enqueue_ms": (t_mul - t_up) * 1e3,
+                          "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
         stack_bytes = 12 * n_entries
         e2e = {"value": flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
                "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads,
-               "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "timing": "wall clock around the public call, device synchronised on both sides"}
+               "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases, "timing": "wall clock around the public call, device synchronised on both sides"}
         dm.close()
         for p in [pa, pb] + pcs:
             p.free()
 
     cpu = None
-    if not args.no_cpu:
-        cpu = cpu_reference_sample(w, args.ref_entries)
+    if not args.no_cpu and not bf16:
+        cpu = cpu_reference_sample(w, args.ref_entries, n_stacks=n_st)
 
-    out = {"metric": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)" if args.config == "cfg2" else "block-sparse GEMM GFLOP/s (FP64, mixed blocks)",
+    out = {"metric": {"cfg2": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)", "cfg3": "block-sparse GEMM GFLOP/s (FP64, mixed blocks {5,13,23,26,32}, 5% occ)",
+                      "cfg4": "block-sparse GEMM GFLOP/s (BF16 operands / FP32 accumulate, 23^3 blocks, 50% occ)"}[args.config],
            "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if bf16 else "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
            "config": workload_config(w, {"products": n_entries, "flop": flop, "stacks": len(stacks), "c_blocks": int(c_nblks),
                                          "timed": "CUDA events on the launching stream; step = memset(C) + %d libsmm_acc_process calls" % len(stacks)}),
            "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
@@ -326,7 +358,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--nblk", type=int, default=None, help="override the block-grid size (default 1000)")
     ap.add_argument("--threads", type=int, default=0, help="host threads of the e2e engine (default: min(32, cpus/2))")
     ap.add_argument("--e2e-steps", type=int, default=3)

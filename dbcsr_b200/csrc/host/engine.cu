@@ -293,7 +293,8 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
   // src/data/dbcsr_mem_methods.F:41-251): forget the product index, clear recorded stacks, zero the C buffer asynchronously
   if (e == nullptr) return -1;
   for (auto& ts : e->th) {
-    ts.mm.reset(new LocalMultiply(e->kcfg, e->m_sizes, e->n_sizes, e->k_sizes));
+    ts.mm->reset();
+    ts.mm->set_k_sizes(e->k_sizes);
     ts.recorded.clear();
     if (ts.c_dev != nullptr && c_dbcsr_acc_memset_zero(ts.c_dev, 0, ts.c_capacity * sizeof(double), ts.stream) != 0) return -41;
   }

@@ -130,7 +130,7 @@ LocalMultiply::LocalMultiply(const Config& cfg, const std::vector<int>& m_sizes,
   init_stack_map();
   stacks_.resize((size_t)nstacks_ + 1);
   fill_.assign((size_t)nstacks_ + 1, 0);
-  for (int i = 1; i <= nstacks_; ++i) stacks_[i].resize((size_t)7 * cfg_.mm_stack_size);
+  // stack buffers (7 x mm_stack_size ints each) are allocated at first use: most of the n^3+1 stacks never see an entry
   hkeys_.assign(1u << 12, 0);
   hvals_.assign(1u << 12, 0);
   hmask_ = (1u << 12) - 1;
@@ -186,6 +186,17 @@ void LocalMultiply::init_stack_map() {
   descr_[nstacks_] = descr[nstacks_];
   newpos[nstacks_] = nstacks_;
   for (auto& s : stack_map_) s = newpos[s];
+}
+
+void LocalMultiply::reset() {
+  c_row_.clear();
+  c_col_.clear();
+  c_blk_p_.clear();
+  std::fill(hvals_.begin(), hvals_.end(), 0);
+  hcount_ = 0;
+  datasize_ = 0;
+  flop_ = 0;
+  std::fill(fill_.begin(), fill_.end(), 0);
 }
 
 void LocalMultiply::preset_c(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize) {
@@ -290,6 +301,7 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
         const int offset = c_blk_p_[c_blk_id - 1];
         const int mapped_col = n_size < (int)n_map_.size() ? n_map_[n_size] : cfg_.n_stacks + 1;
         const int ws = stack_map_[((size_t)(mapped_row - 1) * w + (mapped_k - 1)) * w + (mapped_col - 1)];
+        if (stacks_[ws].empty()) stacks_[ws].resize((size_t)7 * cfg_.mm_stack_size);
         int* p = stacks_[ws].data() + 7 * (size_t)fill_[ws];
         p[0] = m_size;
         p[1] = n_size;

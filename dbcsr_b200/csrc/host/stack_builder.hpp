@@ -67,6 +67,9 @@ class LocalMultiply {
   // (DBCSR passes k_sizes per dbcsr_mm_multrec_multiply call, src/mm/dbcsr_mm_multrec.F:263-296; the stack map stays as built).
   void set_k_sizes(const std::vector<int>& k_sizes) { k_sizes_ = k_sizes; }
 
+  // Forget the product index (new multiply) but keep every allocation (stack buffers, hash table, index capacity).
+  void reset();
+
   // product work matrix (pre-finalize index, order of first touch; src/mm/dbcsr_mm_csr.F:309-323)
   const std::vector<int>& c_row() const { return c_row_; }
   const std::vector<int>& c_col() const { return c_col_; }

@@ -194,7 +194,11 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
 
   auto issue = [&](int e) {  // executed by the whole warp (uniform), the copies are issued by lane 0
     const int3 p = entry(e);
+#if defined(SMM_ABL_NOTMA)
+    if (p.x < 0) {
+#else
     if (lane == 0) {
+#endif
       const int sidx = (e - e0) % NST;
       unsigned char* stg = wbase + (size_t)sidx * SH::STAGE;
       const uint64_t ga = reinterpret_cast<uint64_t>(a_data + (p.x - 1));
@@ -219,6 +223,16 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
     for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   auto flush = [&](int c_first) {
+#if defined(SMM_ABL_NOFLUSH)
+    if (c_first > 0) {  // ablation: no RED traffic (results wrong)
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          if (acc[i][j][0] == 1.2345e300) c_data[0] = acc[i][j][1];
+      return;
+    }
+#endif
     double* __restrict__ cb = c_data + (c_first - 1);
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -259,7 +273,9 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
     const double* __restrict__ As = reinterpret_cast<const double*>(stg + sha);
     const double* __restrict__ Bs = reinterpret_cast<const double*>(stg + SH::ABUF + shb);
 
+#if !defined(SMM_ABL_NOTMA)
     mbar_wait(&bars[sidx], (uint32_t)((i / NST) & 1));
+#endif
 
 #pragma unroll
     for (int s = 0; s < KS; ++s) {
@@ -269,9 +285,16 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
       const bool valid = all_valid || (k < K);
       double af[TM], bf[TN];
 #pragma unroll
+#if defined(SMM_ABL_NOLDS)
+      for (int ti = 0; ti < TM; ++ti) af[ti] = (double)(s + ti + sha);
+#pragma unroll
+      for (int tj = 0; tj < TN; ++tj) bf[tj] = (double)(s - tj + shb);
+      (void)As; (void)Bs; (void)valid;
+#else
       for (int ti = 0; ti < TM; ++ti) af[ti] = valid ? As[k * M + ti * 8 + g] : 0.0;
 #pragma unroll
       for (int tj = 0; tj < TN; ++tj) bf[tj] = valid ? Bs[k * N + tj * 8 + g] : 0.0;
+#endif
 #pragma unroll
       for (int ti = 0; ti < TM; ++ti)
 #pragma unroll

@@ -69,7 +69,7 @@ def random_panel(row_sizes, col_sizes, occupation, rng):
 
 def make_config(name, seed=42, nblk=None):
     """BASELINE.json configs: 'cfg2' = 23x23 FP64, N=1000 block rows/cols/k, 10 % occupation (configs[0..1], [4]);
-    'cfg3' = mixed {5,13,23,26,32}, 5 %. nblk overrides N (parity tests use small N)."""
+    'cfg3' = mixed {5,13,23,26,32}, 5 %; 'cfg4' = 23x23, 50 % (BF16 config). nblk overrides N (parity tests use small N)."""
     rng = np.random.default_rng(seed)
     if name == "cfg2":
         n = nblk or 1000
@@ -77,6 +77,9 @@ def make_config(name, seed=42, nblk=None):
     elif name == "cfg3":
         n = nblk or 1000
         sizes, occ = [5, 13, 23, 26, 32], 0.05
+    elif name == "cfg4":  # 23x23, 50 % occupation, BF16 operands / FP32 C on the tensor cores (extension dtype)
+        n = nblk or 1000
+        sizes, occ = [23], 0.50
     else:
         raise ValueError(name)
     bs = block_sizes(n, sizes, rng)  # same size vector for rows, cols and k
