@@ -320,8 +320,11 @@ def run_single(args):
             t_mul = time.perf_counter()
             if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
                 dm.engine.sync()
-                pcs = [acc.host_alloc((max(dm.engine.c_index(t)[3], 1),), np.float64) for t in range(nthreads)]
-            prod = dm.download_c([p.array for p in pcs])
+                pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
+                prod = dm.download_c([p.array for p in pcs])
+                dm.set_result_buffers([p.array for p in pcs])
+            else:
+                prod = dm.download_c()
             dt = time.perf_counter() - t0
             if it >= max(1, args.e2e_warmup):
                 times.append(dt)

@@ -59,6 +59,7 @@ struct ThreadState {
   std::vector<RecordedStack> recorded;
   std::vector<int> order_scratch;
   int a_first = 1, a_last = 0;
+  double* c_host = nullptr;  // optional: D2H target enqueued right behind this thread's last stack
   int rc = 0;
   double build_seconds = 0.0;
 };
@@ -271,6 +272,10 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
       ts.mm->multiply(e->a_sorted.data(), ts.a_first, ts.a_last, e->b_sorted.data(), nb, dispatch);
+      if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ts.mm->datasize() > 0) {
+        // this thread's part of C is final once its stream drains: start the D2H now, other threads are still building
+        if (c_dbcsr_acc_memcpy_d2h(ts.c_dev, ts.c_host, (size_t)ts.mm->datasize() * sizeof(double), ts.stream) != 0) ts.rc = -46;
+      }
       ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
   }
@@ -315,6 +320,14 @@ const int* dbcsr_b200_engine_c_rows(const dbcsr_b200_engine_t* e, int t) { retur
 const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_col().data(); }
 const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_blk_p().data(); }
 void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].c_dev; }
+
+int dbcsr_b200_engine_set_c_host(dbcsr_b200_engine_t* e, int t, double* host) {
+  if (e == nullptr || t < 0 || t >= (int)e->th.size()) return -1;
+  e->th[(size_t)t].c_host = host;
+  return 0;
+}
+
+size_t dbcsr_b200_engine_c_capacity(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].c_capacity; }
 
 int dbcsr_b200_engine_wait_event(dbcsr_b200_engine_t* e, void* event) {
   // every thread stream waits for `event` (e.g. "panels uploaded and transposed") before running anything enqueued later

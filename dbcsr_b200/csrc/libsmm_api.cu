@@ -81,11 +81,22 @@ int launch_bf16(const int* dev_stack, int stack_size, const void* a_tiles, const
   const int max_grid = num_sms() * per_sm;
   int grid = (stack_size + 15) / 16;
   if (grid > max_grid) grid = max_grid;
+  if (per_sm > 8) per_sm = 8;
   const int chunk = (stack_size + grid - 1) / grid;
   grid = (stack_size + chunk - 1) / chunk;
-  smm::smm_bf16_kernel<<<grid, smm::BF_THREADS, smem, stream>>>(dev_stack, stack_size, static_cast<const unsigned char*>(a_tiles),
-                                                               static_cast<const unsigned char*>(b_tiles), static_cast<float*>(c), m, n, k, chunk);
-  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(smm::BF_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_bf16_kernel, dev_stack, stack_size, static_cast<const unsigned char*>(a_tiles),
+                                             static_cast<const unsigned char*>(b_tiles), static_cast<float*>(c), m, n, k, chunk);
+  return (err == cudaSuccess) ? 0 : -31;
 }
 
 int launch_generic(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k,

@@ -25,8 +25,8 @@
 
 namespace smm {
 
-constexpr int BF_SLOTS = 16;   // ring slots (entries in flight) per CTA
-constexpr int BF_ACC = 4;      // TMEM accumulators per CTA, 32 columns each
+constexpr int BF_SLOTS = 8;    // ring slots (entries in flight) per CTA
+constexpr int BF_ACC = 2;      // TMEM accumulators per CTA, 32 columns each (64 columns => up to 8 CTAs per SM)
 constexpr int BF_TMEM_COLS = BF_ACC * 32;
 constexpr int BF_THREADS = 128;
 
@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e0 = blockIdx.x * chunk;
   const int e1 = min(e0 + chunk, stack_size);
-  if (e0 >= e1) return;  // whole CTA
+  if (e0 >= e1) {  // whole CTA
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    return;
+  }
   const int nent = e1 - e0;
   const Bf16Geom g = bf16_geom(m, n, k);
   const int mk = m * k, nk = n * k;
@@ -125,8 +129,22 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
   unsigned char* slots_b = slots_a + (size_t)BF_SLOTS * g.slot_a;
   const size_t ring_bytes = (size_t)BF_SLOTS * (g.slot_a + g.slot_b) + (size_t)g.kg_slot * 2048 + 2048;
 
-  // zero the ring once: the k padding group of every slot must read as zero, and no NaN patterns may sit in k positions
-  for (size_t i = threadIdx.x * 16; i < ring_bytes; i += BF_THREADS * 16) *reinterpret_cast<uint4*>(slots_a + i) = make_uint4(0, 0, 0, 0);
+  // Programmatic dependent launch, same protocol as the FP64 kernel (see smm_dmma.cuh)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // The k padding group of every slot must read as zero (tiles carry kg groups, a slot kg_slot): zero just those bytes and the
+  // slack behind the ring once; everything else is either overwritten by the TMA or only feeds discarded rows/columns.
+  {
+    const int pad_a = g.slot_a - g.tile_a, pad_b = g.slot_b - g.tile_b;
+    for (int s = 0; s < BF_SLOTS; ++s) {
+      for (int i = threadIdx.x * 16; i < pad_a; i += BF_THREADS * 16)
+        *reinterpret_cast<uint4*>(slots_a + (size_t)s * g.slot_a + g.tile_a + i) = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x * 16; i < pad_b; i += BF_THREADS * 16)
+        *reinterpret_cast<uint4*>(slots_b + (size_t)s * g.slot_b + g.tile_b + i) = make_uint4(0, 0, 0, 0);
+    }
+    const size_t ring_only = (size_t)BF_SLOTS * (g.slot_a + g.slot_b);
+    for (size_t i = ring_only + threadIdx.x * 16; i < ring_bytes; i += BF_THREADS * 16)
+      *reinterpret_cast<uint4*>(slots_a + i) = make_uint4(0, 0, 0, 0);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < BF_SLOTS; ++s) {
       mbar_init(&full[s], 1);
@@ -235,6 +253,7 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
     }
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // never complete before the predecessor kernel has
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BF_TMEM_COLS) : "memory");
   }

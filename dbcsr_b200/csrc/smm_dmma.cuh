@@ -73,15 +73,12 @@ struct Shape {
   static constexpr int STAGE = ABUF + BBUF;
 };
 
-// (warps per CTA, stages) for a given stage size: keep >= 2 stages, prefer 3, and as many warps as fit in 200 KB
-__host__ __device__ constexpr int pick_nst(int stage_bytes) { return (8 * 3 * stage_bytes <= 215 * 1024) ? 3 : 2; }
-__host__ __device__ constexpr int pick_wpc(int stage_bytes) {
-  const int nst = pick_nst(stage_bytes);
-  int w = (215 * 1024) / (nst * stage_bytes);
-  if (w > 16) w = 16;
-  if (w >= 8) w = (w / 4) * 4;  // multiples of 4: one or more warps per SM sub-partition
-  return w < 1 ? 1 : w;
-}
+// (warps per CTA, stages).  Sweep on B200 (profiles/variants_r01_*.txt, cfg2): with programmatic dependent launch the best
+// configurations use ONE stage per warp and many small CTAs per SM (8x1: 22.6, 12x1: 22.5, 4x1: 22.4 TFLOP/s) -- 24 resident
+// warps hide the TMA latency better than a deeper ring under fewer warps (8x3: 19.8), and small CTAs retire/launch
+// independently, which keeps the SMs busy across kernel boundaries.
+__host__ __device__ constexpr int pick_nst(int stage_bytes) { return stage_bytes > 0 ? 1 : 1; }
+__host__ __device__ constexpr int pick_wpc(int stage_bytes) { return (4 * stage_bytes <= 200 * 1024) ? 4 : ((2 * stage_bytes <= 200 * 1024) ? 2 : 1); }
 
 // stack entry e = (a_first, b_first, c_first), 1-based element offsets
 __device__ __forceinline__ int3 ld_entry(const int* __restrict__ stack, int e) {

@@ -96,3 +96,24 @@ launch_fn SMM_CAT(lookup_m, SMM_M)(int n, int k) {
 }
 
 }  // namespace smm
+
+#if defined(SMM_EXPERIMENT_ONLY_THIS_M)
+// kernel-variant experiments build only one M (small libraries travel faster to the GPU box); the other tables are empty
+namespace smm {
+#  if SMM_M != 5
+launch_fn lookup_m5(int, int) { return nullptr; }
+#  endif
+#  if SMM_M != 13
+launch_fn lookup_m13(int, int) { return nullptr; }
+#  endif
+#  if SMM_M != 23
+launch_fn lookup_m23(int, int) { return nullptr; }
+#  endif
+#  if SMM_M != 26
+launch_fn lookup_m26(int, int) { return nullptr; }
+#  endif
+#  if SMM_M != 32
+launch_fn lookup_m32(int, int) { return nullptr; }
+#  endif
+}  // namespace smm
+#endif

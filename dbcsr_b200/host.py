@@ -49,6 +49,9 @@ def _L():
         L.dbcsr_b200_engine_c_to_host.argtypes = [_vp, _i, _vp]
         L.dbcsr_b200_engine_c_to_host_async.argtypes = [_vp, _i, _vp]
         L.dbcsr_b200_engine_wait_event.argtypes = [_vp, _vp]
+        L.dbcsr_b200_engine_set_c_host.argtypes = [_vp, _i, _vp]
+        L.dbcsr_b200_engine_c_capacity.argtypes = [_vp, _i]
+        L.dbcsr_b200_engine_c_capacity.restype = ctypes.c_size_t
         L.dbcsr_b200_engine_flop.argtypes = [_vp]
         L.dbcsr_b200_engine_flop.restype = ctypes.c_longlong
         L.dbcsr_b200_engine_build_seconds.argtypes = [_vp]
@@ -145,6 +148,14 @@ class Engine:
     def c_to_host_async(self, t, host_array):
         if self.L.dbcsr_b200_engine_c_to_host_async(self.h, t, host_array.ctypes.data) != 0:
             raise acclib.AccError("dbcsr_b200_engine_c_to_host_async failed")
+
+    def set_c_host(self, t, host_array):
+        ptr = host_array.ctypes.data if host_array is not None else None
+        if self.L.dbcsr_b200_engine_set_c_host(self.h, t, ptr) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_set_c_host failed")
+
+    def c_capacity(self, t):
+        return int(self.L.dbcsr_b200_engine_c_capacity(self.h, t))
 
     def wait_event(self, event):
         if self.L.dbcsr_b200_engine_wait_event(self.h, event) != 0:

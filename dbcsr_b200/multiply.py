@@ -86,10 +86,25 @@ class DeviceMultiply:
         self.engine.wait_event(self.panels_ready)
         self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
 
+    def set_result_buffers(self, out_arrays):
+        """Pooled (pinned) host buffers for C, one per thread, each at least engine.c_capacity(t) elements: from now on every
+        thread enqueues its own D2H right behind its last stack (download_c then only waits)."""
+        self.early = list(out_arrays)
+        for t, arr in enumerate(self.early):
+            assert arr.size >= self.engine.c_capacity(t)
+            self.engine.set_c_host(t, arr)
+
     def download_c(self, out_arrays=None):
         """D2H of every thread's C buffer (datasize elements each). out_arrays: optional list of (pinned) host arrays."""
         prod = ProductC(self.m_sizes, self.n_sizes)
         self.d2h_bytes = 0
+        if getattr(self, "early", None) is not None:  # copies were enqueued by the engine threads themselves
+            self.engine.sync()
+            for t in range(self.engine.nthreads):
+                rows, cols, blk_p, ds = self.engine.c_index(t)
+                self.d2h_bytes += 8 * ds
+                prod.add(rows, cols, blk_p, self.early[t][:ds])
+            return prod
         # every thread's D2H is enqueued behind that thread's last stack, so early finishers copy while others still compute
         for t in range(self.engine.nthreads):
             rows, cols, blk_p, ds = self.engine.c_index(t)

@@ -76,6 +76,11 @@ void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int thread);
 int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int thread, double* host);
 /* asynchronous variant: enqueued on the thread's stream behind its last stack; complete after dbcsr_b200_engine_sync */
 int dbcsr_b200_engine_c_to_host_async(dbcsr_b200_engine_t* e, int thread, double* host);
+/* Optional: (pinned) host target for thread's C buffer; when set, the D2H of the thread's datasize elements is enqueued by the
+ * thread itself right behind its last stack of every multiply (single-tick multiplies only), overlapping other threads' work;
+ * complete after dbcsr_b200_engine_sync.  capacity (elements) of the thread's device C buffer is known after the first multiply. */
+int dbcsr_b200_engine_set_c_host(dbcsr_b200_engine_t* e, int thread, double* host);
+size_t dbcsr_b200_engine_c_capacity(const dbcsr_b200_engine_t* e, int thread);
 /* all thread streams wait for an acc event (e.g. panels uploaded + transposed on another stream) */
 int dbcsr_b200_engine_wait_event(dbcsr_b200_engine_t* e, void* event);
 long long dbcsr_b200_engine_flop(const dbcsr_b200_engine_t* e);
