@@ -305,19 +305,21 @@ def bench_main(args):
 
     cm.build_replay()
 
-    def timed(fn, steps):
+    def timed(fn, steps, ends_on_compute_stream):
+        """CUDA-event time of fn() on the compute stream, bracketed by barrier + device sync on both sides."""
         ts = []
         for _ in range(steps):
             dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(cm.cs_torch):
-                e0.record(cm.cs_torch)
+            e0.record(cm.cs_torch)
             fn()
-            torch.cuda.synchronize()
-            with torch.cuda.stream(cm.cs_torch):
-                e1.record(cm.cs_torch)
+            if not ends_on_compute_stream:
+                torch.cuda.synchronize()  # the engine path ends on the engine's own streams
+            e1.record(cm.cs_torch)
             e1.synchronize()
+            torch.cuda.synchronize()
+            dist.barrier()
             ts.append(e0.elapsed_time(e1))
         return ts
 
@@ -330,7 +332,7 @@ def bench_main(args):
         sampler.start()
         time.sleep(0.3)
     launches0 = acc.launch_count()
-    times = timed(cm.replay_step, args.steps)
+    times = timed(cm.replay_step, args.steps, True)
     launches = acc.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -345,7 +347,7 @@ def bench_main(args):
         cm.run()  # creates the engine's device C buffers
         for _ in range(max(1, args.e2e_warmup)):
             one_multiply()
-        e2e_times = timed(one_multiply, args.e2e_steps)
+        e2e_times = timed(one_multiply, args.e2e_steps, False)
     t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times))],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
