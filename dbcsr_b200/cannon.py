@@ -242,12 +242,16 @@ class CannonMultiply:
         self.comm_stream = torch.cuda.Stream()
         self.n_replay_launches = sum(len(x) for x in self.replay)
 
-    def replay_step(self):
+    def replay_step(self, fork_from_compute=False):
         """One whole multiply, enqueued without any host synchronisation: C memset, then per tick the NCCL exchange of the next
         panels (comm stream) overlapped with this tick's stack kernels (compute stream), ordered by events."""
         torch, acc = self.torch, self.acc
         V = self.sched.V
         cs = self.cs_torch
+        if fork_from_compute:  # graph capture: the comm stream has to branch off the capturing stream
+            ev0 = torch.cuda.Event()
+            ev0.record(cs)
+            self.comm_stream.wait_event(ev0)
         with torch.cuda.stream(cs):
             self.replay_c.zero_()
         ev_comp = [None] * V
@@ -276,6 +280,26 @@ class CannonMultiply:
             ev_comp[t] = torch.cuda.Event()
             ev_comp[t].record(cs)
             ev_comm = nxt
+
+    def capture_replay(self):
+        """Capture one whole replay step (C memset, all NCCL exchanges, all stack kernels, their cross-stream events) into a CUDA
+        graph: at 8 ranks a step is only ~45 short kernels + 8 messages per rank and Python/driver launch latency would otherwise
+        dominate.  Returns True when the graph was captured (replay_graph.replay() then runs a step)."""
+        torch = self.torch
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.cs_torch, capture_error_mode="thread_local"):
+                self.replay_step(fork_from_compute=True)
+            self.replay_graph = g
+            return True
+        except Exception as ex:  # capture not possible (e.g. NCCL/graph incompatibility): stay with eager launches
+            self.replay_graph = None
+            self.capture_error = repr(ex)[:300]
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+            return False
 
     def close(self):
         self.engine.close()
@@ -327,12 +351,27 @@ def bench_main(args):
         cm.replay_step()
     dist.barrier()
     torch.cuda.synchronize()
+    use_graph = os.environ.get("DBCSR_B200_GRAPH", "1") != "0" and cm.capture_replay()
+    flag = torch.tensor([1 if use_graph else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
+    use_graph = bool(flag.item())
+    def graph_step():
+        with torch.cuda.stream(cm.cs_torch):  # the graph runs on the stream the events are recorded on
+            cm.replay_graph.replay()
+
+    step_fn = graph_step if use_graph else cm.replay_step
+    for _ in range(2):
+        step_fn()
+    dist.barrier()
+    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
     launches0 = acc.launch_count()
-    times = timed(cm.replay_step, args.steps, True)
+    t_host0 = time.perf_counter()
+    times = timed(step_fn, args.steps, True)
+    t_host = (time.perf_counter() - t_host0) / max(1, args.steps)
     launches = acc.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -372,7 +411,8 @@ def bench_main(args):
                         "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": 0,
                         "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
                        if not args.no_e2e else None),
-               "cpu_baseline": None, "host_build_seconds_max": float(tmax[3])}
+               "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph,
+               "graph_capture_error": getattr(cm, "capture_error", None), "wall_ms_per_step_incl_barriers": t_host * 1e3}
         print(json.dumps(out))
     dist.barrier()
     cm.close()

@@ -45,12 +45,32 @@ void LocalMultiply::sort_panel(std::vector<Idx3>& list, int nrows, int ncols) {
 
 // ------------------------------------------------------------------------------------------------ stack ordering
 void stack_sort(const int* params7, int* out3, int stack_size) {
-  // DBCSR's sort() is a stable merge sort (src/utils/dbcsr_array_sort.F): stable order by c_first (params(6,:))
-  std::vector<int> idx((size_t)stack_size);
-  std::iota(idx.begin(), idx.end(), 0);
-  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return params7[7 * (size_t)x + 5] < params7[7 * (size_t)y + 5]; });
+  // DBCSR's sort() is a stable merge sort (src/utils/dbcsr_array_sort.F) by c_first (params(6,:)).  Same result with a stable
+  // LSD radix sort (3 passes of 11 bits over the non-negative 32-bit keys): the host-side sort is on the critical path of every
+  // stack (src/mm/dbcsr_mm_accdrv.F:476-478 flags it), a comparison sort of 30000 keys costs more than building the stack.
+  if (stack_size <= 0) return;
+  static thread_local std::vector<uint32_t> idx_a, idx_b;
+  idx_a.resize((size_t)stack_size);
+  idx_b.resize((size_t)stack_size);
+  uint32_t kmax = 0;
   for (int i = 0; i < stack_size; ++i) {
-    const int* p = params7 + 7 * (size_t)idx[i];
+    idx_a[(size_t)i] = (uint32_t)i;
+    kmax |= (uint32_t)params7[7 * (size_t)i + 5];
+  }
+  uint32_t* src = idx_a.data();
+  uint32_t* dst = idx_b.data();
+  for (int shift = 0; shift < 32 && (kmax >> shift) != 0; shift += 11) {
+    uint32_t count[2049] = {0};
+    for (int i = 0; i < stack_size; ++i) count[(((uint32_t)params7[7 * (size_t)src[i] + 5] >> shift) & 2047u) + 1]++;
+    for (int d = 0; d < 2048; ++d) count[d + 1] += count[d];
+    for (int i = 0; i < stack_size; ++i) {
+      const uint32_t d = ((uint32_t)params7[7 * (size_t)src[i] + 5] >> shift) & 2047u;
+      dst[count[d]++] = src[i];
+    }
+    std::swap(src, dst);
+  }
+  for (int i = 0; i < stack_size; ++i) {
+    const int* p = params7 + 7 * (size_t)src[i];
     out3[3 * (size_t)i] = p[3];
     out3[3 * (size_t)i + 1] = p[4];
     out3[3 * (size_t)i + 2] = p[5];
@@ -131,9 +151,7 @@ LocalMultiply::LocalMultiply(const Config& cfg, const std::vector<int>& m_sizes,
   stacks_.resize((size_t)nstacks_ + 1);
   fill_.assign((size_t)nstacks_ + 1, 0);
   // stack buffers (7 x mm_stack_size ints each) are allocated at first use: most of the n^3+1 stacks never see an entry
-  hkeys_.assign(1u << 12, 0);
-  hvals_.assign(1u << 12, 0);
-  hmask_ = (1u << 12) - 1;
+  rows_.resize(m_sizes_.size() + 1);
 }
 
 // src/mm/dbcsr_mm_csr.F:404-525
@@ -192,8 +210,10 @@ void LocalMultiply::reset() {
   c_row_.clear();
   c_col_.clear();
   c_blk_p_.clear();
-  std::fill(hvals_.begin(), hvals_.end(), 0);
-  hcount_ = 0;
+  for (auto& t : rows_) {
+    if (t.count > 0) std::fill(t.ids.begin(), t.ids.end(), 0);
+    t.count = 0;
+  }
   datasize_ = 0;
   flop_ = 0;
   std::fill(fill_.begin(), fill_.end(), 0);
@@ -208,37 +228,22 @@ void LocalMultiply::preset_c(const int* rows, const int* cols, const int* blk_p,
   datasize_ = datasize;
 }
 
-void LocalMultiply::hash_grow() {
-  const size_t ncap = (hmask_ + 1) * 4;
-  std::vector<uint64_t> nk(ncap, 0);
-  std::vector<int> nv(ncap, 0);
-  const uint64_t nmask = ncap - 1;
-  for (size_t i = 0; i <= hmask_; ++i) {
-    if (hvals_[i] != 0) {
-      uint64_t h = (hkeys_[i] * 0x9E3779B97F4A7C15ull) >> 20;
-      size_t p = h & nmask;
-      while (nv[p] != 0) p = (p + 1) & nmask;
-      nk[p] = hkeys_[i];
-      nv[p] = hvals_[i];
-    }
-  }
-  hkeys_.swap(nk);
-  hvals_.swap(nv);
-  hmask_ = nmask;
-}
-
 // hash_table_get / hash_table_add of the reference (src/utils/dbcsr_hash_table.f90) only affect speed, not results;
 // new block => offset = datasize + 1, appended to the work index (src/mm/dbcsr_mm_csr.F:309-323).
 int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created) {
-  const uint64_t key = ((uint64_t)(uint32_t)row << 32) | (uint32_t)col;
-  uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> 20;
-  size_t p = h & hmask_;
-  while (hvals_[p] != 0) {
-    if (hkeys_[p] == key) {
+  RowTable& t = rows_[(size_t)row];
+  if (t.mask == 0) {
+    t.cols.assign(16, 0);
+    t.ids.assign(16, 0);
+    t.mask = 15;
+  }
+  unsigned p = ((unsigned)col * 2654435761u >> 7) & (unsigned)t.mask;
+  while (t.ids[p] != 0) {
+    if (t.cols[p] == col) {
       created = false;
-      return hvals_[p];
+      return t.ids[p];
     }
-    p = (p + 1) & hmask_;
+    p = (p + 1) & (unsigned)t.mask;
   }
   created = true;
   c_row_.push_back(row);
@@ -246,9 +251,25 @@ int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created) 
   c_blk_p_.push_back(datasize_ + 1);
   datasize_ += nze;
   const int id = (int)c_blk_p_.size();
-  hkeys_[p] = key;
-  hvals_[p] = id;
-  if (++hcount_ * 2 > hmask_) hash_grow();
+  t.cols[p] = col;
+  t.ids[p] = id;
+  if (++t.count * 2 > t.mask) {  // grow x4 and re-insert
+    std::vector<int> oc, oi;
+    oc.swap(t.cols);
+    oi.swap(t.ids);
+    const int ncap = (t.mask + 1) * 4;
+    t.cols.assign((size_t)ncap, 0);
+    t.ids.assign((size_t)ncap, 0);
+    t.mask = ncap - 1;
+    for (size_t i = 0; i < oi.size(); ++i) {
+      if (oi[i] != 0) {
+        unsigned q = ((unsigned)oc[i] * 2654435761u >> 7) & (unsigned)t.mask;
+        while (t.ids[q] != 0) q = (q + 1) & (unsigned)t.mask;
+        t.cols[q] = oc[i];
+        t.ids[q] = oi[i];
+      }
+    }
+  }
   return id;
 }
 

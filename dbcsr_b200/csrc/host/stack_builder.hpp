@@ -85,7 +85,6 @@ class LocalMultiply {
   void csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int af, int bi, int bf, const Idx3* a, const Idx3* b);
   void flush_stacks(bool purge);
   int c_lookup_or_insert(int row, int col, int nze, bool& created);
-  void hash_grow();
 
   Config cfg_;
   std::vector<int> m_sizes_, n_sizes_, k_sizes_;
@@ -97,12 +96,14 @@ class LocalMultiply {
   std::vector<std::vector<int>> stacks_;  // 7 ints per entry
   std::vector<int> fill_;
   const DispatchFn* dispatch_ = nullptr;
-  // C index + hash (open addressing over (row,col) -> c_blk_id)
+  // C index + one small open-addressing table per C row (col -> c_blk_id), like the reference's c_hashes(a_row)
+  // (src/mm/dbcsr_mm_csr.F:294, src/utils/dbcsr_hash_table.f90): row-local tables stay cache resident during a CSR leaf
+  struct RowTable {
+    std::vector<int> cols, ids;  // ids == 0: empty slot
+    int mask = 0, count = 0;
+  };
   std::vector<int> c_row_, c_col_, c_blk_p_;
-  std::vector<uint64_t> hkeys_;
-  std::vector<int> hvals_;
-  uint64_t hmask_ = 0;
-  size_t hcount_ = 0;
+  std::vector<RowTable> rows_;
   int datasize_ = 0;
   int64_t flop_ = 0;
   // scratch for the CSR leaves

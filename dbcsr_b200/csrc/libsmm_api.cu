@@ -6,10 +6,14 @@
 // returns a negative code and leaves C untouched (DBCSR then runs the stack on its own CPU driver).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
 
 #include "../../include/dbcsr_acc_libsmm.h"
 #include "smm_bf16.cuh"
@@ -111,6 +115,100 @@ int launch_generic(const int* dev_stack, int stack_size, const double* a, const 
   return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
 }
 
+// ---- inhomogeneous stacks (def_mnk = 0) -------------------------------------------------------------------------------------
+// The reference rejects them (-1, libsmm_acc.cpp:327) and DBCSR drains them on the CPU.  Here the 7-wide HOST stack is binned by
+// (m,n,k), every bin ordered by c_first (stable), uploaded through a small per-thread ring of pinned/device scratch buffers and
+// drained by the kernel of its shape, all on stack_stream.  The host stack is consumed before the call returns.
+struct InhomoScratch {
+  int* host = nullptr;
+  int* dev = nullptr;
+  size_t cap = 0;  // ints
+  cudaEvent_t done = nullptr;
+};
+struct InhomoRing {
+  InhomoScratch buf[4];
+  int next = 0;
+  ~InhomoRing() {
+    for (auto& b : buf) {
+      if (b.done != nullptr) cudaEventDestroy(b.done);
+      if (b.host != nullptr) cudaFreeHost(b.host);
+      if (b.dev != nullptr) cudaFree(b.dev);
+    }
+  }
+};
+
+int process_inhomogeneous(const int* host7, int stack_size, const double* a, const double* b, double* c, int max_kernel_dim,
+                          cudaStream_t stream) {
+  if (host7 == nullptr) return -1;
+  if (stack_size <= 0) return 0;
+  static thread_local InhomoRing ring;
+  InhomoScratch& sc = ring.buf[ring.next];
+  ring.next = (ring.next + 1) % 4;
+  if (sc.done == nullptr && cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming) != cudaSuccess) return -30;
+  if (cudaEventSynchronize(sc.done) != cudaSuccess) return -30;  // previous user of this scratch has finished
+  const size_t need = 3 * (size_t)stack_size;
+  if (sc.cap < need) {
+    if (sc.host != nullptr) cudaFreeHost(sc.host);
+    if (sc.dev != nullptr) cudaFree(sc.dev);
+    sc.cap = std::max(need, (size_t)3 * 30000);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&sc.host), sc.cap * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return -30;
+    if (cudaMalloc(reinterpret_cast<void**>(&sc.dev), sc.cap * sizeof(int)) != cudaSuccess) return -30;
+  }
+  // order: by shape, then by c_first, stable
+  std::vector<int> order((size_t)stack_size);
+  std::iota(order.begin(), order.end(), 0);
+  auto shape = [&](int i) {
+    const int* p = host7 + 7 * (size_t)i;
+    return ((uint64_t)(uint32_t)p[0] << 42) | ((uint64_t)(uint32_t)p[1] << 21) | (uint64_t)(uint32_t)p[2];
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    const uint64_t sx = shape(x), sy = shape(y);
+    if (sx != sy) return sx < sy;
+    return host7[7 * (size_t)x + 5] < host7[7 * (size_t)y + 5];
+  });
+  for (int i = 0; i < stack_size; ++i) {
+    const int* p = host7 + 7 * (size_t)order[(size_t)i];
+    sc.host[3 * (size_t)i] = p[3];
+    sc.host[3 * (size_t)i + 1] = p[4];
+    sc.host[3 * (size_t)i + 2] = p[5];
+  }
+  if (cudaMemcpyAsync(sc.dev, sc.host, need * sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -31;
+  const uint64_t a_end = allocation_end(a), b_end = allocation_end(b);
+  int rc_all = 0;
+  int lo = 0;
+  while (lo < stack_size) {
+    int hi = lo;
+    const uint64_t sh = shape(order[(size_t)lo]);
+    while (hi < stack_size && shape(order[(size_t)hi]) == sh) ++hi;
+    const int* p = host7 + 7 * (size_t)order[(size_t)lo];
+    const int m = p[0], n = p[1], k = p[2];
+    int rc;
+    if (m <= 0 || n <= 0 || k <= 0) {
+      rc = 0;  // empty blocks: nothing to do
+    }
+    else if (m > max_kernel_dim || n > max_kernel_dim || k > max_kernel_dim) {
+      rc = launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, (n <= max_kernel_dim && k <= max_kernel_dim) ? 1 : 0, stream);
+      if (rc == 0) rc_all = 10;
+    }
+    else if (const smm::launch_fn fn = lookup(m, n, k)) {
+      rc = fn(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, a_end, b_end, stream);
+    }
+    else {
+      rc = launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
+      if (rc == 0) rc_all = 10;
+    }
+    if (rc < 0) {
+      // kernels of earlier bins are already enqueued: report a hard error instead of a "redo on the CPU" code
+      cudaEventRecord(sc.done, stream);
+      return -32;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    lo = hi;
+  }
+  if (cudaEventRecord(sc.done, stream) != cudaSuccess) return -31;
+  return rc_all;
+}
+
 }  // namespace
 
 extern "C" {
@@ -149,10 +247,20 @@ int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype)
 int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, int stack_size, libsmm_acc_data_t datatype,
                        const void* dev_a_data, const void* dev_b_data, void* dev_c_data, int m_max, int n_max, int k_max,
                        int max_kernel_dim, c_dbcsr_acc_bool_t def_mnk, void* stack_stream, void* c_stream) {
-  (void)host_param_stack;
-  if (def_mnk != 1) return -1;                      // inhomogeneous stack: not handled (reference: libsmm_acc.cpp:327)
   if (stack_size < 0 || m_max <= 0 || n_max <= 0 || k_max <= 0) return -2;
   if (stack_stream == nullptr) return -2;
+  if (def_mnk != 1) {
+    // inhomogeneous stack: the reference returns -1 here (libsmm_acc.cpp:327) and DBCSR falls back to the CPU; this library
+    // bins the host stack by shape and drains every bin on the GPU (DBCSR_B200_INHOMOGENEOUS=0 restores the reference behaviour)
+    static const bool enabled = [] {
+      const char* e = getenv("DBCSR_B200_INHOMOGENEOUS");
+      return e == nullptr || atoi(e) != 0;
+    }();
+    if (!enabled || datatype != dbcsr_type_real_8) return -1;
+    return process_inhomogeneous(host_param_stack, stack_size, static_cast<const double*>(dev_a_data),
+                                 static_cast<const double*>(dev_b_data), static_cast<double*>(dev_c_data), max_kernel_dim,
+                                 *static_cast<cudaStream_t*>(stack_stream));
+  }
   if (datatype == dbcsr_type_bf16_ext) {
     // extension: A/B are BF16 tile panels made by libsmm_acc_b200_pack_bf16, C is FP32; tensor-core (tcgen05) kernel
     if (m_max > 32 || n_max > 32 || k_max > 32) return -10;

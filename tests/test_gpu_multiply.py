@@ -76,6 +76,25 @@ def test_multiply_block_mixes(acc, sizes, nthreads):
     check_against_oracle(A, B, prod, ms, ns)
 
 
+@pytest.mark.parametrize("sizes,n_stacks", [([5, 13, 23, 26, 32], 3), ([4, 7, 9, 45, 67], 2), ([3, 100, 23], 1)])
+def test_inhomogeneous_stacks_run_on_the_gpu(acc, sizes, n_stacks):
+    """More block sizes than DBCSR_N_STACKS: the rest lands in the inhomogeneous default stack (def_mnk = 0).  The reference
+    returns -1 for it (CPU fall-back); this library bins it by shape and drains it on the GPU (incl. untuned and >80 shapes)."""
+    rng = np.random.default_rng(sum(sizes))
+    nr, nc, nk = 40, 36, 44
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (nr, nc, nk))
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=2,
+                        cfg=host.default_cfg(mm_stack_size=400, n_stacks=n_stacks), mode=host.LAUNCH | host.RECORD)
+    dm.upload_panels(A.data, B.data, B.list3())
+    dm.multiply(A.list3(), B.list3())
+    prod = dm.download_c()
+    assert any(not st["defined_mnk"] for st in dm.engine.stacks())  # the inhomogeneous path was really exercised
+    dm.close()
+    check_against_oracle(A, B, prod, ms, ns)
+
+
 def test_first_touch_order_matches_index_oracle(acc):
     """One thread: the pre-finalize C index (order of first touch) equals the restated reference traversal."""
     rng = np.random.default_rng(3)

@@ -190,11 +190,18 @@ def test_large_blocks_b_not_transposed(acc):
 
 
 def test_unsupported_requests_leave_c_untouched(acc):
-    """def_mnk=0 -> -1, dtype != real_8 -> -10 (reference return codes); C must not be modified so that DBCSR can redo the stack on the CPU."""
+    """dtype != real_8 -> -10 (reference return code); C must not be modified so that DBCSR can redo the stack on the CPU.
+    def_mnk=0 is handled on the GPU by this library (test_gpu_multiply.py); without a host stack it is rejected with -1."""
     m = n = k = 23
     a, b, stack, csz = ref_test_problem(m, n, k)
+    d_a0, d_b0, d_s0 = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
+    d_c0 = acc.dev_alloc(csz * 8)
+    acc.memset_zero(d_c0, acc.s)
+    assert acc.process(None, d_s0.ptr, stack.shape[0], d_a0.ptr, d_b0.ptr, d_c0.ptr, m, n, k, False, acc.s, acc.s) == -1
+    assert not acc.to_host(d_c0, (csz,), np.float64, acc.s).any()
+    # with the host stack the homogeneous problem gives the same result through the inhomogeneous path
     rc, c = run_process(acc, stack, a, b, csz, m, n, k, def_mnk=False)
-    assert rc == -1 and not c.any()
+    assert rc == 0 and np.array_equal(c, orc.stack_calc(stack, np.zeros(csz), a, b, m, n, k))
     d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
     d_c = acc.dev_alloc(csz * 8)
     acc.memset_zero(d_c, acc.s)
