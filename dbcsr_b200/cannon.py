@@ -15,6 +15,7 @@ Tick t = 0..V-1: rank (i,j) multiplies slice s = (i + j + t) mod V.  For pr = pc
 """
 import math
 import os
+import sys
 import time
 
 import numpy as np
@@ -387,7 +388,7 @@ def bench_main(args):
         for _ in range(max(1, args.e2e_warmup)):
             one_multiply()
         e2e_times = timed(one_multiply, args.e2e_steps, False)
-    t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times))],
+    t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times)), float(cm.n_replay_launches)],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -404,7 +405,8 @@ def bench_main(args):
                "config": workload_config(w, {"grid": "%dx%d" % (sc.pr, sc.pc), "k_slices": sc.V, "host_threads_per_rank": nthreads,
                                              "flop": flop, "parallelism": "cannon %dx%d over NCCL send/recv" % (sc.pr, sc.pc),
                                              "timed": "whole multiply per step: C memset, %d ticks of (NCCL panel exchange || stack kernels on pre-built device stacks); max over ranks of CUDA-event time; initial distribution excluded" % sc.V}),
-               "clocks": clocks, "gpu_launches": int(float(tsum[2])),
+               "clocks": clocks, "gpu_launches": int(float(tsum[2])) if not use_graph else int(args.steps * float(tsum[5])),
+               "gpu_launches_note": "kernels of this library per timed region, summed over ranks (graph replays counted from the captured launch list)",
                "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
                             "note": "per-kernel roofline is reported by the N=1 run; this line is the distributed multiply"},
                "e2e": ({"value": flop / (float(tmax[4]) * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": float(tmax[4]),
@@ -413,7 +415,11 @@ def bench_main(args):
                        if not args.no_e2e else None),
                "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph,
                "graph_capture_error": getattr(cm, "capture_error", None), "wall_ms_per_step_incl_barriers": t_host * 1e3}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     dist.barrier()
-    cm.close()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    # a captured graph holding NCCL work makes process-group teardown hang (observed on the 2-GPU box): everything that matters
+    # has been printed and synchronised, so leave without running the destructors
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)

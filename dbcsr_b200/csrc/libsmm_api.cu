@@ -209,6 +209,48 @@ int process_inhomogeneous(const int* host7, int stack_size, const double* a, con
   return rc_all;
 }
 
+template <typename T>
+int launch_generic_typed(const int* dev_stack, int stack_size, const void* a, const void* b, void* c, int m, int n, int k,
+                         int b_transposed, cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  const int max_grid = num_sms() * 8;
+  int grid = (stack_size + 15) / 16;
+  if (grid > max_grid) grid = max_grid;
+  const int warps = grid * 8;
+  const int chunk = (stack_size + warps - 1) / warps;
+  smm::smm_generic_typed_kernel<T><<<grid, 256, 0, stream>>>(dev_stack, stack_size, static_cast<const T*>(a), static_cast<const T*>(b),
+                                                            static_cast<T*>(c), m, n, k, b_transposed, chunk);
+  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+}
+
+template <typename T>
+int launch_transpose_typed(const int* dev_trs_stack, int nblks, void* data, int m, int n, cudaStream_t stream) {
+  const size_t blk_bytes = (size_t)m * n * sizeof(T);
+  int wpc = (int)((96 * 1024) / blk_bytes);
+  if (wpc > 8) wpc = 8;
+  if (wpc < 1) return -3;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(smm::transpose_typed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+      return -30;
+    attr_set.store(true, std::memory_order_release);
+  }
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::transpose_typed_kernel<T><<<grid, wpc * 32, blk_bytes * wpc, stream>>>(dev_trs_stack, nblks, static_cast<T*>(data), m, n);
+  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+}
+
+// DBCSR_B200_ALL_TYPES=0 restores the reference's behaviour for real_4 / complex types (process: -10, transpose: no-op)
+bool all_types_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("DBCSR_B200_ALL_TYPES");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return v;
+}
+
 }  // namespace
 
 extern "C" {
@@ -239,8 +281,10 @@ int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kd
 
 int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype) {
   if (datatype == dbcsr_type_bf16_ext) return (m > 0 && n > 0 && k > 0 && m <= 32 && n <= 32 && k <= 32) ? 3 : 0;
-  if (datatype != dbcsr_type_real_8) return 0;
   if (m <= 0 || n <= 0 || k <= 0) return 0;
+  if (datatype == dbcsr_type_real_4 || datatype == dbcsr_type_complex_4 || datatype == dbcsr_type_complex_8)
+    return all_types_enabled() ? 2 : 0;
+  if (datatype != dbcsr_type_real_8) return 0;
   return lookup(m, n, k) != nullptr ? 1 : 2;
 }
 
@@ -269,7 +313,25 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
-  if (datatype != dbcsr_type_real_8) return -10;    // reference: libsmm_acc.cpp:338
+  if (datatype != dbcsr_type_real_8) {
+    // real_4 / complex_4 / complex_8: rejected by the reference (-10, libsmm_acc.cpp:338 => CPU); drained here by the typed
+    // generic kernel.  B blocks of these types are transposed by libsmm_acc_transpose below under the same rule as real_8.
+    if (!all_types_enabled() || def_mnk != 1) return -10;
+    cudaStream_t st = *static_cast<cudaStream_t*>(stack_stream);
+    const int bt = (n_max <= max_kernel_dim && k_max <= max_kernel_dim) ? 1 : 0;
+    int rc = -10;
+    if (datatype == dbcsr_type_real_4)
+      rc = launch_generic_typed<float>(dev_param_stack, stack_size, dev_a_data, dev_b_data, dev_c_data, m_max, n_max, k_max, bt, st);
+    else if (datatype == dbcsr_type_complex_4)
+      rc = launch_generic_typed<float2>(dev_param_stack, stack_size, dev_a_data, dev_b_data, dev_c_data, m_max, n_max, k_max, bt, st);
+    else if (datatype == dbcsr_type_complex_8)
+      rc = launch_generic_typed<double2>(dev_param_stack, stack_size, dev_a_data, dev_b_data, dev_c_data, m_max, n_max, k_max, bt, st);
+    if (rc == 0) {
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      return 10;
+    }
+    return rc;
+  }
   const double* a = static_cast<const double*>(dev_a_data);
   const double* b = static_cast<const double*>(dev_b_data);
   double* c = static_cast<double*>(dev_c_data);
@@ -300,9 +362,23 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
 
 int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, void* dev_data, libsmm_acc_data_t datatype, int m,
                          int n, int max_kernel_dim, void* stream) {
-  if (datatype != dbcsr_type_real_8) return 0;               // transpose not needed (reference: libsmm_acc.cpp:484)
   if (m > max_kernel_dim || n > max_kernel_dim) return 0;    // reference: libsmm_acc.cpp:485
   if (stack_size <= 0 || m <= 0 || n <= 0) return 0;
+  if (datatype != dbcsr_type_real_8) {
+    // reference: "transpose not needed" (libsmm_acc.cpp:484) because it never multiplies these types on the device; this
+    // library does (typed generic kernel), so their right-panel blocks are transposed exactly like real_8 ones
+    if (!all_types_enabled() || stream == nullptr) return 0;
+    cudaStream_t st = *static_cast<cudaStream_t*>(stream);
+    int rc = 0;
+    if (datatype == dbcsr_type_real_4)
+      rc = launch_transpose_typed<float>(dev_trs_stack + offset, stack_size, dev_data, m, n, st);
+    else if (datatype == dbcsr_type_complex_4)
+      rc = launch_transpose_typed<float2>(dev_trs_stack + offset, stack_size, dev_data, m, n, st);
+    else if (datatype == dbcsr_type_complex_8)
+      rc = launch_transpose_typed<double2>(dev_trs_stack + offset, stack_size, dev_data, m, n, st);
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+    return rc;
+  }
   if (stream == nullptr) return -2;
   const size_t blk_bytes = (size_t)m * n * sizeof(double);
   int wpc = (int)((96 * 1024) / blk_bytes);

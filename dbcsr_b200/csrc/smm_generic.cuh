@@ -12,6 +12,104 @@
 
 namespace smm {
 
+// ---- element types of the ABI (libsmm_acc_data_t): real_4, real_8, complex_4, complex_8 ---------------------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<float> {
+  static __device__ __forceinline__ float zero() { return 0.f; }
+  static __device__ __forceinline__ void fma_(float& acc, float a, float b) { acc = fmaf(a, b, acc); }
+  static __device__ __forceinline__ void add(float& acc, float v) { acc += v; }
+  static __device__ __forceinline__ void red(float* p, float v) { atomicAdd(p, v); }
+};
+template <>
+struct Elem<double> {
+  static __device__ __forceinline__ double zero() { return 0.0; }
+  static __device__ __forceinline__ void fma_(double& acc, double a, double b) { acc = fma(a, b, acc); }
+  static __device__ __forceinline__ void add(double& acc, double v) { acc += v; }
+  static __device__ __forceinline__ void red(double* p, double v) { atomicAdd(p, v); }
+};
+template <>
+struct Elem<float2> {
+  static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+  static __device__ __forceinline__ void fma_(float2& acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, fmaf(-a.y, b.y, acc.x));
+    acc.y = fmaf(a.x, b.y, fmaf(a.y, b.x, acc.y));
+  }
+  static __device__ __forceinline__ void add(float2& acc, float2 v) {
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  static __device__ __forceinline__ void red(float2* p, float2 v) {
+    atomicAdd(&p->x, v.x);
+    atomicAdd(&p->y, v.y);
+  }
+};
+template <>
+struct Elem<double2> {
+  static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ void fma_(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, fma(-a.y, b.y, acc.x));
+    acc.y = fma(a.x, b.y, fma(a.y, b.x, acc.y));
+  }
+  static __device__ __forceinline__ void add(double2& acc, double2 v) {
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  static __device__ __forceinline__ void red(double2* p, double2 v) {
+    atomicAdd(&p->x, v.x);
+    atomicAdd(&p->y, v.y);
+  }
+};
+
+// Generic drain for the non-real_8 types (the reference rejects them with -10 and DBCSR computes them on the CPU,
+// src/acc/libsmm_acc/libsmm_acc.cpp:338): one warp per entry, lanes own C elements, plain C += A*B (no conjugation).
+template <typename T>
+__global__ void __launch_bounds__(256) smm_generic_typed_kernel(const int* __restrict__ stack, int stack_size, const T* __restrict__ a_data,
+                                                               const T* __restrict__ b_data, T* __restrict__ c_data, int m, int n, int k,
+                                                               int b_transposed, int chunk) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + warp;
+  const int e0 = gw * chunk;
+  const int e1 = min(e0 + chunk, stack_size);
+  const int mn = m * n;
+  for (int e = e0; e < e1; ++e) {
+    const int3 p = ld_entry(stack, e);
+    const T* __restrict__ A = a_data + (p.x - 1);
+    const T* __restrict__ B = b_data + (p.y - 1);
+    T* cb = c_data + (p.z - 1);
+    for (int idx = lane; idx < mn; idx += 32) {
+      const int col = idx / m, row = idx - col * m;
+      T s = Elem<T>::zero();
+      if (b_transposed) {
+        for (int l = 0; l < k; ++l) Elem<T>::fma_(s, A[l * m + row], B[l * n + col]);
+      }
+      else {
+        for (int l = 0; l < k; ++l) Elem<T>::fma_(s, A[l * m + row], B[col * k + l]);
+      }
+      Elem<T>::red(cb + idx, s);
+    }
+  }
+}
+
+// In-place transpose for any element type (one warp per block through shared memory), see transpose_kernel below.
+template <typename T>
+__global__ void transpose_typed_kernel(const int* __restrict__ trs_stack, int nblks, T* __restrict__ data, int m, int n) {
+  extern __shared__ unsigned char tr_raw[];
+  T* tr = reinterpret_cast<T*>(tr_raw);
+  const int wpc = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mn = m * n;
+  T* buf = tr + (size_t)warp * mn;
+  for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
+    T* blk = data + __ldg(trs_stack + b);
+    for (int i = lane; i < mn; i += 32) buf[i] = blk[i];
+    __syncwarp();
+    for (int i = lane; i < mn; i += 32) blk[i] = buf[(i % n) * m + i / n];
+    __syncwarp();
+  }
+}
+
 // One warp per stack entry (grid-stride over chunks of the C-sorted stack); lanes own C elements round-robin.
 // A and B are read straight from global memory (L1/L2 serve the reuse inside a block product); consecutive entries with the
 // same c_first are accumulated in registers when m*n <= 32*GEN_ACC, otherwise every entry is flushed on its own.

@@ -54,7 +54,9 @@ def test_thread_safety_flag_and_version():
     assert b"sm_100a" in L.libsmm_acc_b200_version()
     assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 3) == 1
     assert L.libsmm_acc_b200_kernel_kind(7, 9, 11, 3) == 2
-    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 1) == 0
+    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 1) == 2  # real_4: typed generic kernel (reference: -10)
+    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 9) == 3  # BF16 extension
+    assert L.libsmm_acc_b200_kernel_kind(23, 23, 23, 4) == 0
 
 
 def test_product_does_not_reference_the_oracle():

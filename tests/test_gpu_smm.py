@@ -190,24 +190,57 @@ def test_large_blocks_b_not_transposed(acc):
 
 
 def test_unsupported_requests_leave_c_untouched(acc):
-    """dtype != real_8 -> -10 (reference return code); C must not be modified so that DBCSR can redo the stack on the CPU.
-    def_mnk=0 is handled on the GPU by this library (test_gpu_multiply.py); without a host stack it is rejected with -1."""
+    """Unknown dtype -> -10 (reference return code, libsmm_acc.cpp:338); def_mnk=0 without a host stack -> -1.  C must not be
+    modified so that DBCSR can redo the stack on the CPU."""
     m = n = k = 23
     a, b, stack, csz = ref_test_problem(m, n, k)
     d_a0, d_b0, d_s0 = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
     d_c0 = acc.dev_alloc(csz * 8)
     acc.memset_zero(d_c0, acc.s)
     assert acc.process(None, d_s0.ptr, stack.shape[0], d_a0.ptr, d_b0.ptr, d_c0.ptr, m, n, k, False, acc.s, acc.s) == -1
+    for dt in (0, 2, 11):
+        assert acc.process(None, d_s0.ptr, stack.shape[0], d_a0.ptr, d_b0.ptr, d_c0.ptr, m, n, k, True, acc.s, acc.s, datatype=dt) == -10
     assert not acc.to_host(d_c0, (csz,), np.float64, acc.s).any()
     # with the host stack the homogeneous problem gives the same result through the inhomogeneous path
     rc, c = run_process(acc, stack, a, b, csz, m, n, k, def_mnk=False)
     assert rc == 0 and np.array_equal(c, orc.stack_calc(stack, np.zeros(csz), a, b, m, n, k))
-    d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
-    d_c = acc.dev_alloc(csz * 8)
-    acc.memset_zero(d_c, acc.s)
-    for dt in (1, 5, 7):
-        assert acc.process(None, d_s.ptr, stack.shape[0], d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s, datatype=dt) == -10
-    assert not acc.to_host(d_c, (csz,), np.float64, acc.s).any()
+
+
+@pytest.mark.parametrize("dt,npt,tol", [(1, np.float32, 2e-6), (5, np.complex64, 2e-6), (7, np.complex128, 1e-14)])
+def test_other_abi_types(acc, dt, npt, tol):
+    """real_4 / complex_4 / complex_8 (libsmm_acc_data_t 1/5/7): the reference answers -10 (CPU); here transpose + process run on the
+    device with the typed generic kernel and report 10 (untuned).  Checked against numpy in double precision."""
+    rng = np.random.default_rng(dt)
+    for (m, n, k) in [(23, 23, 23), (5, 13, 7), (32, 4, 9)]:
+        n_a = n_b = 30
+        n_c, S = 6, 120
+        def rnd(sz):
+            x = rng.random(sz)
+            return (x + 1j * rng.random(sz)).astype(npt) if np.issubdtype(npt, np.complexfloating) else x.astype(npt)
+        a, b = rnd(n_a * m * k), rnd(n_b * k * n)              # b: k x n col-major blocks (host layout)
+        stack = np.zeros((S, 3), dtype=np.int32)
+        ia, ib = rng.integers(0, n_a, S), rng.integers(0, n_b, S)
+        ic = np.sort(rng.integers(0, n_c, S))
+        stack[:, 0], stack[:, 1], stack[:, 2] = ia * m * k + 1, ib * k * n + 1, ic * m * n + 1
+        d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
+        d_t = acc.to_device(np.arange(n_b, dtype=np.int32) * k * n, acc.s)
+        acc.transpose(d_t.ptr, 0, n_b, d_b.ptr, k, n, acc.s, datatype=dt)
+        bt = acc.to_host(d_b, b.shape, npt, acc.s)
+        assert np.array_equal(bt.reshape(n_b, k, n), b.reshape(n_b, n, k).transpose(0, 2, 1))  # n x k col-major now
+        d_c = acc.dev_alloc(n_c * m * n * a.itemsize)
+        acc.memset_zero(d_c, acc.s)
+        assert acc.process(None, d_s.ptr, S, d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s, datatype=dt) == 10
+        c = acc.to_host(d_c, (n_c * m * n,), npt, acc.s)
+        hp = np.complex128 if np.issubdtype(npt, np.complexfloating) else np.float64
+        c_ref = np.zeros((n_c, n, m), dtype=hp)  # col-major blocks: [blk][col][row]
+        A = a.astype(hp).reshape(n_a, k, m)       # [blk][l][row]
+        B = b.astype(hp).reshape(n_b, n, k)       # [blk][col][l]
+        for e in range(S):
+            c_ref[ic[e]] += B[ib[e]] @ A[ia[e]]
+        err = np.linalg.norm(c.astype(hp) - c_ref.reshape(-1)) / np.linalg.norm(c_ref)
+        assert err <= tol, (dt, m, n, k, err)
+        for d in (d_a, d_b, d_s, d_t, d_c):
+            d.free()
 
 
 def test_transpose_all_tuned_pairs(acc):
