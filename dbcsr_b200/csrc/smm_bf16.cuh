@@ -11,7 +11,7 @@
 // with ONE cp.async.bulk and fed to the MMA without any shuffling; padding rows/k are stored as zeros by the pack kernel.
 //
 // Kernel structure (one CTA = 4 warps, several CTAs per SM share TMEM 128 columns each):
-//   warp 1 lane 0 : TMA producer  - per stack entry two bulk copies (A tile, B tile) into a ring of SLOTS slots
+//   warp 1        : TMA producers - lane s owns ring slot s: per stack entry two bulk copies (A tile, B tile)
 //   warp 2 lane 0 : MMA issuer    - per entry ceil(K/16) tcgen05.mma (M=128, N=32, K=16, D in TMEM); a run of equal c_first
 //                                    accumulates in one TMEM accumulator; tcgen05.commit releases the slot / publishes the run
 //   warp 0        : epilogue      - tcgen05.ld of the finished accumulator (row = lane), RED.ADD.F32 into the C block
@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 1) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int i = 0; i < nent; ++i) {
-        const int s = i % BF_SLOTS;
+    // ===== TMA producers: lane s owns ring slot s and the entries i = s, s + SLOTS, ... (issue latencies overlap) =====
+    if (lane < BF_SLOTS) {
+      const int s = lane;
+      for (int i = lane; i < nent; i += BF_SLOTS) {
         const int3 p = ld_entry(stack, e0 + i);
         mbar_wait(&empty[s], (uint32_t)(((i / BF_SLOTS) & 1) ^ 1));
         slot_c[s] = p.z;

@@ -299,3 +299,52 @@ def test_norms(acc):
     out = acc.to_host(d_out, (nblk,), np.float32, acc.s)
     ref = orc.norms(mat, offs, sizes)
     assert np.allclose(out, ref, rtol=2e-7, atol=0)
+
+
+def test_concurrent_threads_own_streams(acc):
+    """DBCSR calls libsmm_acc_process from every OpenMP thread on its own stream and C buffer (src/mm/dbcsr_mm_accdrv.F:229,300);
+    libsmm_acc_is_thread_safe() promises that works.  8 host threads x 20 stacks each, shared A/B, private C."""
+    import threading
+
+    m = n = k = 23
+    rng = np.random.default_rng(17)
+    n_a = n_b = 400
+    a, b = rng.random(n_a * m * k), rng.random(n_b * k * n)
+    d_a, d_b = acc.to_device(a, acc.s), acc.to_device(b, acc.s)
+    nthreads, nstacks, S, n_c = 8, 20, 3000, 60
+    results, errors = [None] * nthreads, []
+
+    def worker(t):
+        try:
+            r = np.random.default_rng(100 + t)
+            s = acc.stream_create("t%d" % t, 0)
+            d_c = acc.dev_alloc(n_c * m * n * 8)
+            acc.memset_zero(d_c, s)
+            c_ref = np.zeros(n_c * m * n)
+            keep = []
+            for _ in range(nstacks):
+                st = np.zeros((S, 3), dtype=np.int32)
+                st[:, 0] = r.integers(0, n_a, S) * m * k + 1
+                st[:, 1] = r.integers(0, n_b, S) * k * n + 1
+                st[:, 2] = np.sort(r.integers(0, n_c, S)) * m * n + 1
+                d_s = acc.dev_alloc(st.nbytes)
+                keep.append((d_s, acc.h2d(st, d_s, s)))
+                rc = acc.process(None, d_s.ptr, S, d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, s, s)
+                assert rc == 0
+                orc.stack_calc(st, c_ref, a, b, m, n, k)
+            c = acc.to_host(d_c, (n_c * m * n,), np.float64, s)
+            results[t] = np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref)
+            for d_s, _ in keep:
+                d_s.free()
+            d_c.free()
+            acc.stream_destroy(s)
+        except Exception as ex:  # pragma: no cover
+            errors.append(repr(ex))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
+    assert all(r is not None and r <= 1e-10 for r in results), results
