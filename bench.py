@@ -31,6 +31,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+METRIC_NAMES = {"cfg2": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)",
+                "cfg3": "block-sparse GEMM GFLOP/s (FP64, mixed blocks {5,13,23,26,32}, 5% occ)",
+                "cfg4": "block-sparse GEMM GFLOP/s (BF16 operands / FP32 accumulate, 23^3 blocks, 50% occ)"}
+
+
 # ------------------------------------------------------------------------------------------------ helpers
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -159,17 +164,19 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload.make_config(args.config, nblk=args.nblk)
-    vals = []
+    vals, ms = [], []
     info = None
     for i in range(args.warmup + args.steps):
-        info = cpu_reference_sample(w, args.ref_entries)
+        t0 = time.perf_counter()
+        info = cpu_reference_sample(w, args.ref_entries, n_stacks=3 if len(w["sizes"]) <= 3 else len(w["sizes"]))
         if i >= args.warmup:
             vals.append(info["value"])
+            ms.append((time.perf_counter() - t0) * 1e3)
     v = float(np.mean(vals))
     info["value"] = v
     sample_flop = None
-    print(json.dumps({"impl": "reference", "metric": "block-sparse GEMM GFLOP/s (FP64)", "value": v, "unit": "GFLOP/s", "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+    print(json.dumps({"impl": "reference", "metric": METRIC_NAMES[args.config], "value": v, "unit": "GFLOP/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic (seed 42)",
                       "config": workload_config(w), "cpu_baseline": info,
                       "e2e": {"value": v, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -342,8 +349,7 @@ def run_single(args):
     if not args.no_cpu and not bf16:
         cpu = cpu_reference_sample(w, args.ref_entries, n_stacks=n_st)
 
-    out = {"metric": {"cfg2": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)", "cfg3": "block-sparse GEMM GFLOP/s (FP64, mixed blocks {5,13,23,26,32}, 5% occ)",
-                      "cfg4": "block-sparse GEMM GFLOP/s (BF16 operands / FP32 accumulate, 23^3 blocks, 50% occ)"}[args.config],
+    out = {"metric": METRIC_NAMES[args.config],
            "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if bf16 else "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
            "config": workload_config(w, {"products": n_entries, "flop": flop, "stacks": len(stacks), "c_blocks": int(c_nblks),

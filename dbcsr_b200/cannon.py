@@ -147,6 +147,38 @@ class CannonMultiply:
         self.recv = {kind: [torch.empty(max(max_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(2)] for kind in "ab"}
         self.flop = 0
         self.last_build_s = 0.0
+        self.peer_buf = None
+        if self.device.type == "cuda" and world > 1 and os.environ.get("DBCSR_B200_EXCHANGE", "p2p") == "p2p":
+            self._setup_peer_access()
+
+    def _setup_peer_access(self):
+        """Map every rank's home panels into this process (CUDA IPC) so that a panel can be PULLED from its home rank with a
+        plain device-to-device copy over NVLink: copy engines instead of NCCL's SM-resident send/recv kernels (which compete with
+        the stack kernels for SMs and are limited to a few channels per peer), and no cross-process synchronisation at all during
+        the multiply - home panels are read-only.  NCCL stays the transport of the set-up collectives and the fall-back
+        (DBCSR_B200_EXCHANGE=nccl)."""
+        torch, dist = self.torch, self.dist
+        ok = 1
+        try:
+            from torch.multiprocessing.reductions import reduce_tensor
+
+            mine = {key: reduce_tensor(t) for key, t in self.home_buf.items()}
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+            peer = {}
+            for r, d in enumerate(everyone):
+                if r == self.rank:
+                    continue
+                for key, (fn, a) in d.items():
+                    peer[(r,) + key] = fn(*a)
+            self.peer_buf = peer
+        except Exception as ex:
+            ok = 0
+            self.peer_error = repr(ex)[:300]
+        flag = torch.tensor([ok], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            self.peer_buf = None
 
     # -------------------------------------------------------------------------------------------------------------
     def panel_meta(self, kind, s, i, j):
@@ -155,11 +187,19 @@ class CannonMultiply:
         return src, int(nblk), int(nze)
 
     def post_exchange(self, t):
-        """Post the grouped send/recv of tick t's panels (returns the work handles); local panels need no message."""
+        """Post the grouped send/recv of tick t's panels (returns the work handles); local panels need no message.
+        With peer access the panels are pulled by asynchronous device-to-device copies on the current stream instead."""
         dist = self.dist
         ra, rb, sends = self.sched.transfers(self.rank, t)
         ops = []
         s = self.sched.slice_at(self.rank, t)
+        if self.peer_buf is not None:
+            for kind, src in (("a", ra), ("b", rb)):
+                if src is not None:
+                    _, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
+                    n = nze * 8 + nblk * 12
+                    self.recv[kind][t % 2][:n].copy_(self.peer_buf[(src, kind, s)][:n], non_blocking=True)
+            return []
         if ra is not None:
             _, nblk, nze = self.panel_meta("a", s, self.i, self.j)
             ops.append(dist.P2POp(dist.irecv, self.recv["a"][t % 2][:nze * 8 + nblk * 12], ra))
@@ -257,20 +297,30 @@ class CannonMultiply:
             self.replay_c.zero_()
         ev_comp = [None] * V
 
+        trace = getattr(self, "trace", None)
+
         def exchange(t, after):
             with torch.cuda.stream(self.comm_stream):
                 if after is not None:
                     self.comm_stream.wait_event(after)  # recv buffer (t % 2) was read by the kernels of tick t-2
+                if trace is not None:
+                    b = torch.cuda.Event(enable_timing=True)
+                    b.record(self.comm_stream)
                 for wk in self.post_exchange(t):
                     wk.wait()
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=trace is not None)
                 ev.record(self.comm_stream)
+                if trace is not None:
+                    trace.append(("exchange", t, b, ev))
             return ev
 
         ev_comm = exchange(0, None)
         for t in range(V):
             nxt = exchange(t + 1, ev_comp[t - 1] if t >= 1 else None) if t + 1 < V else None
             cs.wait_event(ev_comm)
+            if trace is not None:
+                cb = torch.cuda.Event(enable_timing=True)
+                cb.record(cs)
             (abuf, _, _), (bbuf, _, _) = self.panel_of_tick(t, "a"), self.panel_of_tick(t, "b")
             base = self.replay_stacks.data_ptr()
             for off, S, mm, nn, kk, dm in self.replay[t]:
@@ -278,8 +328,10 @@ class CannonMultiply:
                                  self.cs, self.cs)
                 if rc < 0:
                     raise RuntimeError("libsmm_acc_process returned %d" % rc)
-            ev_comp[t] = torch.cuda.Event()
+            ev_comp[t] = torch.cuda.Event(enable_timing=trace is not None)
             ev_comp[t].record(cs)
+            if trace is not None:
+                trace.append(("compute", t, cb, ev_comp[t]))
             ev_comm = nxt
 
     def capture_replay(self):
@@ -321,6 +373,7 @@ def bench_main(args):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")  # one send/recv pair per panel must be able to fill NVLink
     # NCCL's send/recv kernels must get SMs while the stack kernels keep every SM busy: high-priority NCCL stream
     # (without it the exchange of tick t+1 only starts when the kernels of tick t drain: 8-GPU step 3.2 ms instead of ~2)
     try:
@@ -358,6 +411,17 @@ def bench_main(args):
         cm.replay_step()
     dist.barrier()
     torch.cuda.synchronize()
+    if os.environ.get("DBCSR_B200_CANNON_TRACE"):  # per-tick device timeline of one eager step (rank 0 prints it to stderr)
+        cm.trace = []
+        t0e = torch.cuda.Event(enable_timing=True)
+        t0e.record(cm.cs_torch)
+        cm.replay_step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            for kind, t, b, e in cm.trace:
+                print("trace %s tick %d: start %.3f ms, duration %.3f ms" % (kind, t, t0e.elapsed_time(b), b.elapsed_time(e)), file=sys.stderr)
+        cm.trace = None
+        dist.barrier()
     use_graph = os.environ.get("DBCSR_B200_GRAPH", "1") != "0" and cm.capture_replay()
     flag = torch.tensor([1 if use_graph else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
@@ -405,7 +469,8 @@ def bench_main(args):
         flop = float(tsum[1])
         value = flop / (ms * 1e-3) * 1e-9
         peak, peak_src = measured_peaks()
-        out = {"metric": "block-sparse GEMM GFLOP/s (FP64, 23^3 blocks, 10% occ)", "value": value, "unit": "GFLOP/s", "n_gpus": world,
+        from bench import METRIC_NAMES
+        out = {"metric": METRIC_NAMES[args.config], "value": value, "unit": "GFLOP/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
                "config": workload_config(w, {"grid": "%dx%d" % (sc.pr, sc.pc), "k_slices": sc.V, "host_threads_per_rank": nthreads,
