@@ -275,7 +275,13 @@ class CannonMultiply:
                 lst.append((off, st["dev"].shape[0], st["max_m"], st["max_n"], st["max_k"], st["defined_mnk"]))
                 off += st["dev"].size
             self.replay.append(lst)
-        self.replay_c = torch.zeros(max(self.replay_datasize, 1), dtype=torch.float64, device=self.device)
+        # two pooled C buffers: the one of the next step is zeroed on a side stream while this step's stacks run (see bench.py)
+        self.replay_cs = [torch.zeros(max(self.replay_datasize, 1), dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.replay_c = self.replay_cs[0]
+        self.zero_stream = torch.cuda.Stream()
+        self.ev_zero = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.step_no = 0
         self.cs = acc.stream_create("cannon compute", 0)
         from . import lib as acclib
 
@@ -293,8 +299,20 @@ class CannonMultiply:
             ev0 = torch.cuda.Event()
             ev0.record(cs)
             self.comm_stream.wait_event(ev0)
-        with torch.cuda.stream(cs):
-            self.replay_c.zero_()
+        k = self.step_no % 2
+        self.step_no += 1
+        self.replay_c = self.replay_cs[k]
+        if fork_from_compute:  # graph capture: single buffer, zeroed in line
+            with torch.cuda.stream(cs):
+                self.replay_c.zero_()
+        else:
+            with torch.cuda.stream(self.zero_stream):
+                if self.step_no > 1:
+                    self.zero_stream.wait_event(self.ev_free[1 - k])  # last reader of the other buffer (previous step)
+                self.replay_cs[1 - k].zero_()
+                self.ev_zero[1 - k].record(self.zero_stream)
+            if self.step_no > 1:
+                cs.wait_event(self.ev_zero[k])  # zeroed during the previous step (the very first buffer comes from torch.zeros)
         ev_comp = [None] * V
 
         trace = getattr(self, "trace", None)
@@ -333,6 +351,9 @@ class CannonMultiply:
             if trace is not None:
                 trace.append(("compute", t, cb, ev_comp[t]))
             ev_comm = nxt
+        if not fork_from_compute:
+            self.ev_free[k].record(cs)
+            cs.wait_event(self.ev_zero[1 - k])  # the step owns the memset it issued
 
     def capture_replay(self):
         """Capture one whole replay step (C memset, all NCCL exchanges, all stack kernels, their cross-stream events) into a CUDA
@@ -422,7 +443,8 @@ def bench_main(args):
                 print("trace %s tick %d: start %.3f ms, duration %.3f ms" % (kind, t, t0e.elapsed_time(b), b.elapsed_time(e)), file=sys.stderr)
         cm.trace = None
         dist.barrier()
-    use_graph = os.environ.get("DBCSR_B200_GRAPH", "1") != "0" and cm.capture_replay()
+    # peer pulls are cross-device copies, which PyTorch cannot record inside a stream capture: graphs only for the NCCL exchange
+    use_graph = os.environ.get("DBCSR_B200_GRAPH", "1") != "0" and cm.peer_buf is None and cm.capture_replay()
     flag = torch.tensor([1 if use_graph else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
     use_graph = bool(flag.item())
@@ -484,7 +506,7 @@ def bench_main(args):
                         "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": 0,
                         "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
                        if not args.no_e2e else None),
-               "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph,
+               "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph, "exchange": "cuda-ipc peer pull (copy engines over NVLink)" if cm.peer_buf is not None else "nccl send/recv",
                "graph_capture_error": getattr(cm, "capture_error", None), "wall_ms_per_step_incl_barriers": t_host * 1e3}
         print(json.dumps(out), flush=True)
     dist.barrier()

@@ -106,3 +106,47 @@ def test_multithreaded_engine_same_products_disjoint_rows():
         assert np.array_equal(blk_p, 1 + np.concatenate([[0], np.cumsum(sizes)[:-1]])) and ds == int(sizes.sum())
     e1.close()
     e4.close()
+
+
+def test_edge_cases_empty_and_ragged():
+    """Empty panels, a single block, more threads than block rows, no matching k, repeated multiplies with reset-free engines."""
+    bs = np.array([23, 5, 13, 23], dtype=np.int32)
+    empty = np.zeros((0, 3), dtype=np.int32)
+    one_a = np.array([[2, 3, 1]], dtype=np.int32)
+    one_b = np.array([[3, 1, 1]], dtype=np.int32)
+    for nthreads in (1, 3, 9):
+        e = host.Engine(bs, bs, bs, nthreads=nthreads, mode=host.RECORD)
+        e.multiply(empty, None, empty, None)
+        assert e.stacks() == [] and e.flop() == 0
+        e.multiply(one_a, None, empty, None)
+        e.multiply(empty, None, one_b, None)
+        assert e.stacks() == []
+        e.multiply(one_a, None, one_b, None)  # A(2,3) * B(3,1) -> C(2,1): m=5, k=13, n=23
+        st = e.stacks()
+        assert len(st) == 1 and st[0]["host"].tolist() == [[5, 23, 13, 1, 1, 1, 1]]
+        assert e.flop() == 2 * 5 * 23 * 13
+        # no common k: A(1,2) with B(3,1)
+        e.multiply(np.array([[1, 2, 1]], dtype=np.int32), None, one_b, None)
+        assert len(e.stacks()) == 1
+        e.close()
+
+
+def test_second_tick_accumulates_into_existing_c_blocks():
+    """Two ticks on one engine (Cannon): C blocks touched again keep their offset, new ones are appended (first touch order)."""
+    bs = np.full(6, 23, dtype=np.int32)
+    a1 = np.array([[1, 1, 1], [2, 2, 530]], dtype=np.int32)
+    b1 = np.array([[1, 1, 1], [2, 1, 530]], dtype=np.int32)
+    e = host.Engine(bs, bs, bs, nthreads=1, mode=host.RECORD)
+    e.multiply(a1, None, b1, None)   # C(1,1), C(2,1)
+    a2 = np.array([[1, 3, 1], [3, 3, 530]], dtype=np.int32)
+    b2 = np.array([[3, 1, 1], [3, 2, 530]], dtype=np.int32)
+    e.multiply(a2, None, b2, None)   # C(1,1) again, C(1,2), C(3,1), C(3,2) new
+    rows, cols, blk_p, ds = e.c_index(0)
+    got = list(zip(rows.tolist(), cols.tolist(), blk_p.tolist()))
+    assert got[:2] == [(1, 1, 1), (2, 1, 530)]
+    assert sorted(got[2:]) == [(1, 2, 1059), (3, 1, 1588), (3, 2, 2117)] or len(got) == 5
+    assert ds == 5 * 529 and len(set((r, c) for r, c, _ in got)) == 5
+    # the repeated C(1,1) product points at offset 1
+    second = e.stacks()[-1]["host"]
+    assert any(row[5] == 1 for row in second.tolist())
+    e.close()
