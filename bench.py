@@ -344,7 +344,8 @@ def run_single(args):
           pb = acc.host_alloc((B.data.size,), np.float64)
           pa.array[:] = A.data
           pb.array[:] = B.data
-          dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg)
+          cfg_e2e = host.default_cfg(n_stacks=n_st, row_chunks=args.row_chunks)
+          dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e)
           a_l, b_l = A.list3(), B.list3()
           pcs = None
           times = []
@@ -369,7 +370,7 @@ def run_single(args):
                             "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
           stack_bytes = 12 * n_entries
           e2e = {"value": flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
-                 "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads,
+                 "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads, "row_chunks_per_thread": args.row_chunks,
                  "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases, "timing": "wall clock around the public call, device synchronised on both sides"}
           dm.close()
           for p in [pa, pb] + pcs:
@@ -406,6 +407,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--nblk", type=int, default=None, help="override the block-grid size (default 1000)")
     ap.add_argument("--threads", type=int, default=0, help="host threads of the e2e engine (default: min(32, cpus/2))")
+    ap.add_argument("--row-chunks", type=int, default=4, help="block-row chunks per host thread in the e2e engine (earlier D2H)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

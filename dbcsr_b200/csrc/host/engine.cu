@@ -57,8 +57,8 @@ struct ThreadState {
   void* c_dev = nullptr;
   size_t c_capacity = 0;
   std::vector<RecordedStack> recorded;
-  std::vector<int> order_scratch;
   int a_first = 1, a_last = 0;
+  std::vector<std::pair<int, int>> slices;  // (a_first, a_last) of every row chunk this thread owns, in row order
   double* c_host = nullptr;  // optional: D2H target enqueued right behind this thread's last stack
   int rc = 0;
   double build_seconds = 0.0;
@@ -88,6 +88,7 @@ void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg) {
   cfg->binning_nbins = 4096;
   cfg->binning_binsize = 16;
   cfg->thread_buffers = 8;
+  cfg->row_chunks = 1;
 }
 
 void dbcsr_b200_rec_sort_index(int nrows, int ncols, int nblks, int* list3) {
@@ -115,8 +116,6 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
   e->n_sizes.assign(n_sizes, n_sizes + ncols);
   e->k_sizes.assign(k_sizes, k_sizes + nk);
   e->th.resize((size_t)nthreads);
-  size_t sum_n = 0;
-  for (int v : e->n_sizes) sum_n += (size_t)v;
   for (int t = 0; t < nthreads; ++t) {
     ThreadState& ts = e->th[t];
     ts.mm.reset(new LocalMultiply(e->kcfg, e->m_sizes, e->n_sizes, e->k_sizes));
@@ -134,7 +133,6 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
       ts.c_capacity = c_capacity;
     }
   }
-  (void)sum_n;
   return e;
 fail:
   dbcsr_b200_engine_destroy(e);
@@ -167,17 +165,24 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
   e->b_sorted.resize((size_t)nb);
   std::memcpy(e->b_sorted.data(), b_list3, sizeof(int) * 3 * (size_t)nb);
   {
-    // static ownership: thread t owns block rows (t*nrows/T, (t+1)*nrows/T] in every tick, so that the C rows of different
-    // threads stay disjoint over a whole Cannon multiply; the BCSR-ordered list is sorted by row => contiguous slices
+    // static ownership: chunk c = block rows (c*nrows/C, (c+1)*nrows/C], C = nthreads * row_chunks; thread t owns the chunks
+    // t, t+T, t+2T, ... in every tick, so that the C rows of different threads stay disjoint over a whole Cannon multiply;
+    // the BCSR-ordered list is sorted by row => contiguous slices.  row_chunks = 1 is DBCSR's one slice per thread.
+    const int rc = std::max(1, e->cfg.row_chunks);
+    const int nchunks = nthreads * rc;
+    for (auto& ts : e->th) ts.slices.clear();
     int pos = 0;
-    for (int t = 0; t < nthreads; ++t) {
-      const int row_hi = (int)(((long long)e->nrows * (t + 1)) / nthreads);
+    for (int c = 0; c < nchunks; ++c) {
+      const int row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
       int end = pos;
       while (end < na && e->a_sorted[(size_t)end].row <= row_hi) ++end;
-      if (t == nthreads - 1) end = na;
-      e->th[t].a_first = pos + 1;
-      e->th[t].a_last = end;
+      if (c == nchunks - 1) end = na;
+      e->th[(size_t)(c % nthreads)].slices.emplace_back(pos + 1, end);
       pos = end;
+    }
+    for (auto& ts : e->th) {  // kept for the dense-bound computation below: overall span of the thread's slices
+      ts.a_first = ts.slices.front().first;
+      ts.a_last = ts.slices.back().second;
     }
   }
   // --- sort panels
@@ -186,9 +191,11 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
     for (int t = 0; t < nthreads; ++t) {
       workers.emplace_back([e, t]() {
         ThreadState& ts = e->th[t];
-        const int cnt = ts.a_last - ts.a_first + 1;
-        std::vector<Idx3> tmp((size_t)std::max(cnt, 0));
-        if (cnt > 0) dbcsr_b200::rec_sort_index(1, e->nrows, 1, e->nk, e->a_sorted.data() + (ts.a_first - 1), cnt, tmp);
+        std::vector<Idx3> tmp;
+        for (const auto& sl : ts.slices) {
+          const int cnt = sl.second - sl.first + 1;
+          if (cnt > 0) dbcsr_b200::rec_sort_index(1, e->nrows, 1, e->nk, e->a_sorted.data() + (sl.first - 1), cnt, tmp);
+        }
       });
     }
     {
@@ -208,13 +215,14 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
       if (cap == 0) {  // dense upper bound over the block rows this thread owns
         std::vector<char> seen((size_t)e->nrows + 1, 0);
         size_t sum_m = 0;
-        for (int i = ts.a_first; i <= ts.a_last; ++i) {
-          const int r = e->a_sorted[(size_t)i - 1].row;
-          if (!seen[r]) {
-            seen[r] = 1;
-            sum_m += (size_t)e->m_sizes[(size_t)r - 1];
+        for (const auto& sl : ts.slices)
+          for (int i = sl.first; i <= sl.second; ++i) {
+            const int r = e->a_sorted[(size_t)i - 1].row;
+            if (!seen[r]) {
+              seen[r] = 1;
+              sum_m += (size_t)e->m_sizes[(size_t)r - 1];
+            }
           }
-        }
         cap = sum_m * sum_n;
       }
       if (cap == 0) cap = 1;
@@ -271,10 +279,16 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
         }
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
-      ts.mm->multiply(e->a_sorted.data(), ts.a_first, ts.a_last, e->b_sorted.data(), nb, dispatch);
-      if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ts.mm->datasize() > 0) {
-        // this thread's part of C is final once its stream drains: start the D2H now, other threads are still building
-        if (c_dbcsr_acc_memcpy_d2h(ts.c_dev, ts.c_host, (size_t)ts.mm->datasize() * sizeof(double), ts.stream) != 0) ts.rc = -46;
+      for (const auto& sl : ts.slices) {
+        const size_t ds0 = (size_t)ts.mm->datasize();
+        ts.mm->multiply(e->a_sorted.data(), sl.first, sl.second, e->b_sorted.data(), nb, dispatch);  // ends with a purge
+        const size_t ds1 = (size_t)ts.mm->datasize();
+        if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds0) {
+          // the C blocks created by this row chunk are final once the stream drains: start their D2H now, while this thread
+          // builds its next chunk and the other threads are still busy
+          if (c_dbcsr_acc_memcpy_d2h(static_cast<double*>(ts.c_dev) + ds0, ts.c_host + ds0, (ds1 - ds0) * sizeof(double), ts.stream) != 0)
+            ts.rc = -46;
+        }
       }
       ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });

@@ -17,6 +17,7 @@
 
 #include "../../include/dbcsr_acc_libsmm.h"
 #include "smm_bf16.cuh"
+#include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
 #include "smm_launch.h"
 
@@ -101,6 +102,57 @@ int launch_bf16(const int* dev_stack, int stack_size, const void* a_tiles, const
   const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_bf16_kernel, dev_stack, stack_size, static_cast<const unsigned char*>(a_tiles),
                                              static_cast<const unsigned char*>(b_tiles), static_cast<float*>(c), m, n, k, chunk);
   return (err == cudaSuccess) ? 0 : -31;
+}
+
+// run-time-shape DMMA kernel (smm_dmma_rt.cuh): every m, n <= 32 without a specialised kernel, k limited by shared memory
+template <int TM, int TN>
+int launch_rt_t(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
+                uint64_t b_end, cudaStream_t stream) {
+  const int smem = 128 + smm::RT_WPC * (smm::rt_abuf(m, k) + smm::rt_abuf(n, k));
+  static std::atomic<int> smem_set{0};
+  if (smem_set.load(std::memory_order_acquire) < smem) {
+    if (cudaFuncSetAttribute(smm::smm_dmma_rt_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
+    smem_set.store(smem, std::memory_order_release);
+  }
+  int cps = (220 * 1024) / smem;
+  if (cps > 12) cps = 12;
+  if (cps < 1) return -30;
+  const int max_grid = num_sms() * cps;
+  int grid = (stack_size + smm::RT_WPC * 4 - 1) / (smm::RT_WPC * 4);
+  if (grid > max_grid) grid = max_grid;
+  const int warps = grid * smm::RT_WPC;
+  const int chunk = (stack_size + warps - 1) / warps;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(smm::RT_WPC * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const unsigned long long al = a_end, bl = b_end;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_dmma_rt_kernel<TM, TN>, dev_stack, stack_size, a, b, c, al, bl, chunk, m, n, k);
+  return (err == cudaSuccess) ? 0 : -31;
+}
+
+bool rt_eligible(int m, int n, int k) {
+  return m <= 32 && n <= 32 && 128 + smm::RT_WPC * (smm::rt_abuf(m, k) + smm::rt_abuf(n, k)) <= 220 * 1024;
+}
+
+int launch_rt(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
+              uint64_t b_end, cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  const int tm = (m + 7) / 8, tn = (n + 7) / 8;
+#define SMM_RT_CASE(TM_, TN_) \
+  if (tm == TM_ && tn == TN_) return launch_rt_t<TM_, TN_>(dev_stack, stack_size, a, b, c, m, n, k, a_end, b_end, stream);
+  SMM_RT_CASE(1, 1) SMM_RT_CASE(1, 2) SMM_RT_CASE(1, 3) SMM_RT_CASE(1, 4)
+  SMM_RT_CASE(2, 1) SMM_RT_CASE(2, 2) SMM_RT_CASE(2, 3) SMM_RT_CASE(2, 4)
+  SMM_RT_CASE(3, 1) SMM_RT_CASE(3, 2) SMM_RT_CASE(3, 3) SMM_RT_CASE(3, 4)
+  SMM_RT_CASE(4, 1) SMM_RT_CASE(4, 2) SMM_RT_CASE(4, 3) SMM_RT_CASE(4, 4)
+#undef SMM_RT_CASE
+  return -30;
 }
 
 int launch_generic(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k,
@@ -194,7 +246,8 @@ int process_inhomogeneous(const int* host7, int stack_size, const double* a, con
       rc = fn(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, a_end, b_end, stream);
     }
     else {
-      rc = launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
+      rc = rt_eligible(m, n, k) ? launch_rt(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
+                                : launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
       if (rc == 0) rc_all = 10;
     }
     if (rc < 0) {
@@ -355,7 +408,9 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
-  const int rc = launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, 1, stream);
+  const int rc = rt_eligible(m_max, n_max, k_max)
+                   ? launch_rt(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, allocation_end(a), allocation_end(b), stream)
+                   : launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, 1, stream);
   if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc == 0 ? 10 : rc;  // 10 = "ran with an untuned kernel" (reference: libsmm_acc.cpp:319)
 }

@@ -7,14 +7,17 @@
 //     (fragments are distributed one element per lane); tcgen05 has no FP64 kind, so this is the tensor path for FP64;
 //   * every warp is autonomous (no CTA-wide barrier anywhere): it owns a contiguous chunk of the C-sorted stack and a private
 //     ring of NST shared-memory stages; lane 0 stages the A and B blocks of entry i+NST-1 with cp.async.bulk (TMA, UBLKCP) and
-//     an mbarrier transaction count while the warp multiplies entry i.  Blocks are only 8-byte aligned in the data area
-//     (4232 B for 23x23), TMA needs 16 B: the copy fetches the enclosing 16-byte-aligned window and the block starts
-//     `addr & 15` bytes into the stage;
+//     an mbarrier transaction count while the warp multiplies entry i.  The B200 sweep (profiles/variants_r01_*.txt) settled on
+//     NST = 1 with 24 resident warps per SM (small CTAs): the other warps hide the copy latency better than a deeper ring.
+//     Blocks are only 8-byte aligned in the data area (4232 B for 23x23), TMA needs 16 B: the copy fetches the enclosing
+//     16-byte-aligned window and the block starts `addr & 15` bytes into the stage;
 //   * the raw column-major block layout is kept in shared memory (TMA cannot pad), so bank conflicts of the fragment loads
 //     are removed by permuting the k index instead: DMMA sums over 4 k-values per instruction and any assignment of k to the
 //     four lane groups is legal; KMap picks the stride that makes `k*ld mod 16` distinct for the four groups;
 //   * C is accumulated in registers over a run of equal c_first (the stack is C-sorted) and flushed with RED.ADD.F64
-//     (no read of C; L2 does the read-modify-write), which stays correct for unsorted/binned stacks and chunk boundaries.
+//     (no read of C; L2 does the read-modify-write), which stays correct for unsorted/binned stacks and chunk boundaries;
+//   * launches use programmatic dependent launch (griddepcontrol.launch_dependents at entry, .wait at exit): consecutive
+//     stack drains of a stream overlap their ramp-up/tail, completion order is still stream order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -28,6 +28,8 @@ typedef struct dbcsr_b200_cfg {
   int binning_nbins;   /* ACCDRV_BINNING_NBINS, 4096 */
   int binning_binsize; /* ACCDRV_BINNING_BINSIZE, 16 */
   int thread_buffers;  /* ACCDRV_THREAD_BUFFERS, 8 */
+  int row_chunks;      /* (engine) block-row chunks per host thread, processed in row order; 1 = DBCSR's one slice per thread.
+                          >1 lets the D2H of finished chunks start while later chunks are still being built/multiplied */
 } dbcsr_b200_cfg_t;
 void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg);
 

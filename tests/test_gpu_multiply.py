@@ -109,6 +109,26 @@ def test_first_touch_order_matches_index_oracle(acc):
     check_against_oracle(A, B, prod, ms, ns)
 
 
+def test_row_chunks_with_early_d2h(acc):
+    """Engine with several row chunks per thread and pooled host result buffers: every chunk's D2H is enqueued behind its last
+    stack (the bench's end-to-end path); results identical to the oracle, three multiplies in a row."""
+    rng = np.random.default_rng(21)
+    ms = ns = ks = workload.block_sizes(60, [13, 23], rng)
+    A = workload.random_panel(ms, ks, 0.25, rng)
+    B = workload.random_panel(ks, ns, 0.25, rng)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=3, cfg=host.default_cfg(mm_stack_size=300, row_chunks=4))
+    dm.upload_panels(A.data, B.data, B.list3())
+    dm.multiply(A.list3(), B.list3())
+    check_against_oracle(A, B, dm.download_c(), ms, ns)
+    bufs = [np.empty(max(dm.engine.c_capacity(t), 1)) for t in range(3)]
+    dm.set_result_buffers(bufs)
+    for _ in range(2):
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        check_against_oracle(A, B, dm.download_c(), ms, ns)
+    dm.close()
+
+
 def test_repeated_multiplies_on_pooled_buffers(acc):
     rng = np.random.default_rng(8)
     ms = ns = ks = workload.block_sizes(40, [13, 23], rng)

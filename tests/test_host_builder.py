@@ -150,3 +150,26 @@ def test_second_tick_accumulates_into_existing_c_blocks():
     second = e.stacks()[-1]["host"]
     assert any(row[5] == 1 for row in second.tolist())
     e.close()
+
+
+def test_row_chunks_same_products_and_row_ordered_c():
+    """row_chunks > 1: every thread walks several block-row chunks in row order; products unchanged, C rows disjoint between
+    threads, and inside a thread the C blocks of a chunk are contiguous (what the early per-chunk D2H relies on)."""
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(90, 70, 60, 0.2, 0.2, [5, 13, 23], seed=9)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    e1 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, cfg=host.default_cfg(mm_stack_size=300))
+    e1.multiply(a_l, None, b_l, None)
+    ec = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=2, cfg=host.default_cfg(mm_stack_size=300, row_chunks=3))
+    ec.multiply(a_l, None, b_l, None)
+    prod = lambda eng: sorted((int(r[3]), int(r[4])) for s in eng.stacks() for r in s["host"])
+    assert prod(e1) == prod(ec) and e1.flop() == ec.flop()
+    seen = set()
+    for t in range(2):
+        rows, cols, blk_p, ds = ec.c_index(t)
+        assert not (set(rows.tolist()) & seen)
+        seen |= set(rows.tolist())
+        chunk_of = (rows - 1) * 6 // 90  # chunk id of every C block (6 chunks over 90 rows)
+        assert np.all(np.diff(chunk_of) >= 0)          # chunk by chunk
+        assert set(chunk_of.tolist()) <= {t, t + 2, t + 4}  # thread t owns chunks t, t+2, t+4
+    e1.close()
+    ec.close()
