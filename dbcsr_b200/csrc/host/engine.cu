@@ -212,17 +212,15 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
       ThreadState& ts = e->th[t];
       if (ts.c_dev != nullptr) continue;
       size_t cap = ts.c_capacity;
-      if (cap == 0) {  // dense upper bound over the block rows this thread owns
-        std::vector<char> seen((size_t)e->nrows + 1, 0);
+      if (cap == 0) {  // dense upper bound over ALL block rows this thread owns (later Cannon ticks may touch rows that have
+                       // no A block in the first panel)
+        const int rcn = std::max(1, e->cfg.row_chunks);
+        const int nchunks = nthreads * rcn;
         size_t sum_m = 0;
-        for (const auto& sl : ts.slices)
-          for (int i = sl.first; i <= sl.second; ++i) {
-            const int r = e->a_sorted[(size_t)i - 1].row;
-            if (!seen[r]) {
-              seen[r] = 1;
-              sum_m += (size_t)e->m_sizes[(size_t)r - 1];
-            }
-          }
+        for (int c = t; c < nchunks; c += nthreads) {
+          const int row_lo = (int)(((long long)e->nrows * c) / nchunks), row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
+          for (int r = row_lo; r < row_hi; ++r) sum_m += (size_t)e->m_sizes[(size_t)r];
+        }
         cap = sum_m * sum_n;
       }
       if (cap == 0) cap = 1;
