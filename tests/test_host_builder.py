@@ -173,3 +173,43 @@ def test_row_chunks_same_products_and_row_ordered_c():
         assert set(chunk_of.tolist()) <= {t, t + 2, t + 4}  # thread t owns chunks t, t+2, t+4
     e1.close()
     ec.close()
+
+
+MIXES = [[23], [5, 13, 23, 26, 32], [1, 3, 4], [4, 5, 7], [5, 8, 9], [4, 13, 25], [14, 29, 32], [45, 67, 78]]
+
+
+@pytest.mark.parametrize("sizes", MIXES, ids=[str(s) for s in MIXES])
+def test_recorded_host_stacks_reproduce_the_block_product(sizes):
+    """CPU end-to-end of the host side: stacks built by the C++ engine (block-size mixes of tests/dbcsr_unittest3.F:76-118, default
+    N_STACKS=3 so that inhomogeneous default stacks occur) and drained with the oracle's blas_process_mm_stack restatement give the
+    same C as the oracle's plain block product, and the same (row, col) structure."""
+    rng = np.random.default_rng(len(sizes) * 11 + sizes[0])
+    nr, nc, nk = 30, 26, 34
+    ms, ns, ks = (rng.choice(sizes, n).astype(np.int32) for n in (nr, nc, nk))
+    amask, bmask = rng.random((nr, nk)) < 0.3, rng.random((nk, nc)) < 0.3
+    ar, ac = np.nonzero(amask)
+    br, bc = np.nonzero(bmask)
+    A = orc.BlockMatrix(ms, ks, ar + 1, ac + 1)
+    B = orc.BlockMatrix(ks, ns, br + 1, bc + 1)
+    A.data[:] = rng.random(A.nze)
+    B.data[:] = rng.random(B.nze)
+    eng = host.Engine(ms, ns, ks, nthreads=2, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=150))
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    got = {}
+    for t in range(2):
+        rows, cols, blk_p, ds = eng.c_index(t)
+        c = np.zeros(max(ds, 1))
+        for st in eng.stacks():
+            if st["thread"] == t:
+                orc.host_stack(st["host"], A.data, B.data, c)
+        for r, cc, o in zip(rows, cols, blk_p):
+            got[(int(r), int(cc))] = c[o - 1:o - 1 + int(ms[r - 1]) * int(ns[cc - 1])]
+    Cref = orc.multiply_blocks(A, B)
+    assert set(got) == set(zip(Cref.rows.tolist(), Cref.cols.tolist()))
+    num = den = 0.0
+    for r, cc, o in zip(Cref.rows, Cref.cols, Cref.offsets):
+        ref = Cref.data[o:o + int(ms[r - 1]) * int(ns[cc - 1])]
+        num += float(((got[(int(r), int(cc))] - ref) ** 2).sum())
+        den += float((ref ** 2).sum())
+    assert (num / den) ** 0.5 <= 1e-13
+    eng.close()

@@ -139,3 +139,27 @@ def test_norms():
     out = orc.norms(mat, offs, ne)
     exp = np.array([np.sum(mat[o:o + e] ** 2) for o, e in zip(offs, ne)], dtype=np.float32)
     assert np.allclose(out, exp, rtol=1e-6)
+
+
+def test_h2o_statistics_from_reference_docs():
+    """Known answer from the reference's documentation (docs/guide/3-developer-guide/4-performance/1-insights.md:21-35): the DBCSR
+    STATISTICS table of `dbcsr_perf tests/inputs/test_H2O.perf` (2208^3, 23x23 blocks, sparsity 0.2, 50 multiplications, 1 rank):
+    flops 23x23x23 = 687272462200, matmuls total = 28243300, 1600 stacks of average size 17652.1 (= 32 threads x 1 stack x 50).
+    Reproduces the block patterns of the dlarnv/geometric-skipping generator, the product enumeration of the stack builder, the
+    flop count (src/mm/dbcsr_mm_csr.F:350) and the one-stack-per-thread purge behaviour."""
+    from dbcsr_b200 import host
+
+    sizes = orc.random_block_sizes(2208, [1, 23])
+    assert len(sizes) == 96
+    A = orc.random_matrix(sizes, sizes, 0.2, 12341315)  # generation order C, A, B after the seed reset
+    B = orc.random_matrix(sizes, sizes, 0.2, 12341316)
+    eng = host.Engine(sizes, sizes, sizes, nthreads=32, mode=host.RECORD)
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    stacks = eng.stacks()
+    matmuls = sum(s["host"].shape[0] for s in stacks)
+    assert matmuls * 50 == 28243300
+    assert eng.flop() * 50 == 687272462200
+    assert len(stacks) * 50 == 1600
+    assert abs(matmuls / len(stacks) - 17652.1) < 0.05
+    assert all(s["m"] == 23 and s["n"] == 23 and s["k"] == 23 and s["defined_mnk"] for s in stacks)
+    eng.close()
