@@ -75,6 +75,9 @@ struct dbcsr_b200_engine {
   std::vector<int> m_sizes, n_sizes, k_sizes;
   std::vector<ThreadState> th;
   std::vector<Idx3> a_sorted, b_sorted;
+  // on-the-fly filter: per-row thresholds, norms permuted like the sorted lists
+  std::vector<float> row_eps, a_norm_sorted, b_norm_sorted;
+  std::vector<int> blk_tmp;
 };
 
 extern "C" {
@@ -154,16 +157,23 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e) {
   delete e;
 }
 
-int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
-                               const void* b_dev) {
+static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
+                                const int* b_list3, int nb, const void* b_dev, const float* b_norms) {
   if (e == nullptr || na < 0 || nb < 0) return -1;
   const int nthreads = (int)e->th.size();
+  const bool filter = a_norms != nullptr && b_norms != nullptr && !e->row_eps.empty();
   // --- left panel: split the BCSR-ordered list over the threads by block rows (DBCSR: thr_c slices of coo_l, each slice
   //     rec-sorted on its own with the full panel extents, src/mm/dbcsr_mm_cannon.F:2910-2967)
   e->a_sorted.resize((size_t)na);
   std::memcpy(e->a_sorted.data(), a_list3, sizeof(int) * 3 * (size_t)na);
   e->b_sorted.resize((size_t)nb);
   std::memcpy(e->b_sorted.data(), b_list3, sizeof(int) * 3 * (size_t)nb);
+  if (filter) {
+    // the norms must follow their blocks through rec_sort_index: sort with the list position in the blk slot, then put the
+    // element offsets back (the reference computes the norms after the sort, src/mm/dbcsr_mm_cannon.F:1127-1160)
+    for (int i = 0; i < na; ++i) e->a_sorted[(size_t)i].blk = i;
+    for (int i = 0; i < nb; ++i) e->b_sorted[(size_t)i].blk = i;
+  }
   {
     // static ownership: chunk c = block rows (c*nrows/C, (c+1)*nrows/C], C = nthreads * row_chunks; thread t owns the chunks
     // t, t+T, t+2T, ... in every tick, so that the C rows of different threads stay disjoint over a whole Cannon multiply;
@@ -204,6 +214,20 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
     }
     for (auto& w : workers) w.join();
   }
+  if (filter) {
+    e->a_norm_sorted.resize((size_t)na);
+    e->b_norm_sorted.resize((size_t)nb);
+    for (int j = 0; j < na; ++j) {
+      const int i = e->a_sorted[(size_t)j].blk;
+      e->a_norm_sorted[(size_t)j] = a_norms[i];
+      e->a_sorted[(size_t)j].blk = a_list3[3 * (size_t)i + 2];
+    }
+    for (int j = 0; j < nb; ++j) {
+      const int i = e->b_sorted[(size_t)j].blk;
+      e->b_norm_sorted[(size_t)j] = b_norms[i];
+      e->b_sorted[(size_t)j].blk = b_list3[3 * (size_t)i + 2];
+    }
+  }
   // --- device C buffers (dbcsr_mm_accdrv_init: sized like the work area, zeroed asynchronously)
   if (e->mode & DBCSR_B200_LAUNCH) {
     size_t sum_n = 0;
@@ -233,7 +257,7 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
   // --- per-thread multrec -> csr -> sched -> accdrv
   std::vector<std::thread> workers;
   for (int t = 0; t < nthreads; ++t) {
-    workers.emplace_back([e, t, a_dev, b_dev, nb]() {
+    workers.emplace_back([e, t, a_dev, b_dev, nb, filter]() {
       ThreadState& ts = e->th[t];
       ts.rc = 0;
       if (e->mode & DBCSR_B200_LAUNCH) cudaSetDevice(e->device);  // the active device is per host thread
@@ -279,7 +303,8 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
       };
       for (const auto& sl : ts.slices) {
         const size_t ds0 = (size_t)ts.mm->datasize();
-        ts.mm->multiply(e->a_sorted.data(), sl.first, sl.second, e->b_sorted.data(), nb, dispatch);  // ends with a purge
+        ts.mm->multiply(e->a_sorted.data(), sl.first, sl.second, e->b_sorted.data(), nb, dispatch,  // ends with a purge
+                        filter ? e->a_norm_sorted.data() : nullptr, filter ? e->b_norm_sorted.data() : nullptr);
         const size_t ds1 = (size_t)ts.mm->datasize();
         if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds0) {
           // the C blocks created by this row chunk are final once the stream drains: start their D2H now, while this thread
@@ -295,6 +320,36 @@ int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int n
   for (auto& ts : e->th)
     if (ts.rc != 0) return ts.rc;
   return 0;
+}
+
+int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
+                               const void* b_dev) {
+  return engine_multiply_impl(e, a_list3, na, a_dev, nullptr, b_list3, nb, b_dev, nullptr);
+}
+
+int dbcsr_b200_engine_multiply_filtered(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
+                                        const int* b_list3, int nb, const void* b_dev, const float* b_norms) {
+  if (a_norms == nullptr || b_norms == nullptr) return -1;
+  return engine_multiply_impl(e, a_list3, na, a_dev, a_norms, b_list3, nb, b_dev, b_norms);
+}
+
+int dbcsr_b200_engine_set_filter(dbcsr_b200_engine_t* e, const float* row_max_epss) {
+  if (e == nullptr) return -1;
+  if (row_max_epss == nullptr)
+    e->row_eps.clear();
+  else
+    e->row_eps.assign(row_max_epss, row_max_epss + e->nrows);
+  for (auto& ts : e->th) ts.mm->set_row_eps(e->row_eps);
+  return 0;
+}
+
+void dbcsr_b200_row_max_epss(double filter_eps, const int* total_row_counts, int nrows, float* row_max_epss) {
+  // src/mm/dbcsr_mm_cannon.F:1098-1107: everything in single precision
+  const float eps_sp = (float)filter_eps;
+  for (int r = 0; r < nrows; ++r) {
+    const float q = eps_sp / (float)std::max(1, total_row_counts[r]);
+    row_max_epss[r] = q * q;
+  }
 }
 
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk) {

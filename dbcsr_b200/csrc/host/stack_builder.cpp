@@ -284,35 +284,45 @@ void LocalMultiply::flush_stacks(bool purge) {
   }
 }
 
-// src/mm/dbcsr_mm_csr.F:178-359 with build_csr_index :741-795 (no norm filter, no symmetry: BASELINE configs use neither)
+// src/mm/dbcsr_mm_csr.F:178-359 with build_csr_index :741-795 (optional norm filter; no symmetry: BASELINE configs have none)
 void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int af, int bi, int bf, const Idx3* a, const Idx3* b) {
   const int nrow = mf - mi + 1, nk = kf - ki + 1, na = af - ai + 1, nb = bf - bi + 1;
-  auto build = [&](int lo, int n_rows, int first, int count, const Idx3* lst, std::vector<int>& row_p, std::vector<int>& info) {
+  const bool use_eps = a_norms_ != nullptr && b_norms_ != nullptr && !row_eps_.empty();
+  auto build = [&](int lo, int n_rows, int first, int count, const Idx3* lst, std::vector<int>& row_p, std::vector<int>& info,
+                   const float* list_norms, std::vector<float>& csr_norms) {
     row_p.assign((size_t)n_rows + 1, 0);
     counts_.assign((size_t)n_rows, 0);
     for (int i = first; i < first + count; ++i) counts_[lst[i - 1].row - lo]++;
     for (int r = 1; r <= n_rows; ++r) row_p[r] = row_p[r - 1] + counts_[r - 1];
     info.resize((size_t)2 * count);
+    if (use_eps) csr_norms.resize((size_t)count);
     std::fill(counts_.begin(), counts_.end(), 0);
     for (int i = first; i < first + count; ++i) {
       const int r = lst[i - 1].row - lo;
       const int pos = row_p[r] + counts_[r]++;
       info[2 * (size_t)pos] = lst[i - 1].col;
       info[2 * (size_t)pos + 1] = lst[i - 1].blk;
+      if (use_eps) csr_norms[(size_t)pos] = list_norms[i - 1];
     }
   };
-  build(mi, nrow, ai, na, a, a_row_p_, a_info_);
-  build(ki, nk, bi, nb, b, b_row_p_, b_info_);
+  build(mi, nrow, ai, na, a, a_row_p_, a_info_, a_norms_, a_csr_norms_);
+  build(ki, nk, bi, nb, b, b_row_p_, b_info_, b_norms_, b_csr_norms_);
   const int w = cfg_.n_stacks + 1;
   for (int a_row_l = mi; a_row_l <= mf; ++a_row_l) {
     const int m_size = m_sizes_[a_row_l - 1];
     const int mapped_row = m_size < (int)m_map_.size() ? m_map_[m_size] : cfg_.n_stacks + 1;
+    const float a_row_eps = use_eps ? row_eps_[(size_t)a_row_l - 1] : 0.0f;
     for (int a_blk = a_row_p_[a_row_l - mi]; a_blk < a_row_p_[a_row_l - mi + 1]; ++a_blk) {
       const int a_col_l = a_info_[2 * (size_t)a_blk];
       const int a_first = a_info_[2 * (size_t)a_blk + 1];
       const int k_size = k_sizes_[a_col_l - 1];
       const int mapped_k = k_size < (int)k_map_.size() ? k_map_[k_size] : cfg_.n_stacks + 1;
+      const float a_norm = use_eps ? a_csr_norms_[(size_t)a_blk] : 0.0f;
       for (int b_blk = b_row_p_[a_col_l - ki]; b_blk < b_row_p_[a_col_l - ki + 1]; ++b_blk) {
+        if (use_eps) {  // single-precision product and compare, like the reference
+          const float prod = a_norm * b_csr_norms_[(size_t)b_blk];
+          if (prod < a_row_eps) continue;
+        }
         const int b_col_l = b_info_[2 * (size_t)b_blk];
         const int b_first = b_info_[2 * (size_t)b_blk + 1];
         const int n_size = n_sizes_[b_col_l - 1];
@@ -394,11 +404,15 @@ void LocalMultiply::sparse_multrec(int mi, int mf, int ni, int nf, int ki, int k
   }
 }
 
-void LocalMultiply::multiply(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, const DispatchFn& dispatch) {
+void LocalMultiply::multiply(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, const DispatchFn& dispatch,
+                             const float* a_norms, const float* b_norms) {
   dispatch_ = &dispatch;
+  a_norms_ = a_norms;
+  b_norms_ = b_norms;
   sparse_multrec(1, (int)m_sizes_.size(), 1, (int)n_sizes_.size(), 1, (int)k_sizes_.size(), a_first, a_last, a_index, 1, nb, b_index);
   flush_stacks(true);
   dispatch_ = nullptr;
+  a_norms_ = b_norms_ = nullptr;
 }
 
 }  // namespace dbcsr_b200

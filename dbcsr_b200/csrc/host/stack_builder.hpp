@@ -59,13 +59,20 @@ class LocalMultiply {
   // One Cannon tick: lists must already be rec-sorted (use sort_panel); [a_first, a_last] = this thread's slice of the
   // left list (1-based, inclusive; the whole list for one thread).  Stacks still partially filled at the end are purged
   // (dbcsr_mm_multrec_multiply -> dbcsr_mm_csr_purge_stacks, src/mm/dbcsr_mm_multrec.F:263-324).
-  void multiply(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, const DispatchFn& dispatch);
+  // a_norms / b_norms (optional, both or neither): per-block norms (sum of squares, single precision, c_calculate_norms /
+  // calculate_norms src/mm/dbcsr_mm_common.F:629-670) aligned with a_index / b_index; with set_row_eps they switch on the
+  // on-the-fly filter of the CSR leaf (src/mm/dbcsr_mm_csr.F:270-278): product skipped when a_norm*b_norm < row_eps(a_row).
+  void multiply(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, const DispatchFn& dispatch,
+                const float* a_norms = nullptr, const float* b_norms = nullptr);
 
   static void sort_panel(std::vector<Idx3>& list, int nrows, int ncols);
 
   // Cannon ticks bring panels with different k-slices: block sizes of the contraction index of the CURRENT panels
   // (DBCSR passes k_sizes per dbcsr_mm_multrec_multiply call, src/mm/dbcsr_mm_multrec.F:263-296; the stack map stays as built).
   void set_k_sizes(const std::vector<int>& k_sizes) { k_sizes_ = k_sizes; }
+
+  // per-C-row threshold row_max_epss (src/mm/dbcsr_mm_cannon.F:1100-1107); empty = no filtering
+  void set_row_eps(const std::vector<float>& eps) { row_eps_ = eps; }
 
   // Forget the product index (new multiply) but keep every allocation (stack buffers, hash table, index capacity).
   void reset();
@@ -108,6 +115,10 @@ class LocalMultiply {
   int64_t flop_ = 0;
   // scratch for the CSR leaves
   std::vector<int> a_row_p_, b_row_p_, a_info_, b_info_, counts_;
+  // on-the-fly filter (optional)
+  std::vector<float> row_eps_, a_csr_norms_, b_csr_norms_;
+  const float* a_norms_ = nullptr;
+  const float* b_norms_ = nullptr;
 };
 
 }  // namespace dbcsr_b200

@@ -33,6 +33,10 @@ def _L():
         L.dbcsr_b200_engine_create.restype = _vp
         L.dbcsr_b200_engine_destroy.argtypes = [_vp]
         L.dbcsr_b200_engine_multiply.argtypes = [_vp, _vp, _i, _vp, _vp, _i, _vp]
+        L.dbcsr_b200_engine_multiply_filtered.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp]
+        L.dbcsr_b200_engine_set_filter.argtypes = [_vp, _vp]
+        L.dbcsr_b200_row_max_epss.argtypes = [ctypes.c_double, _vp, _i, _vp]
+        L.dbcsr_b200_row_max_epss.restype = None
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
         L.dbcsr_b200_engine_reset.argtypes = [_vp]
         L.dbcsr_b200_engine_set_k_sizes.argtypes = [_vp, _vp, _i]
@@ -94,6 +98,14 @@ def stack_binning(params7, nbins=4096, binsize=16):
     return out
 
 
+def row_max_epss(filter_eps, total_row_counts):
+    """row_max_epss of dbcsr_multiply's on-the-fly filter (src/mm/dbcsr_mm_cannon.F:1098-1107), float32 per block row."""
+    cnt = np.ascontiguousarray(total_row_counts, dtype=np.int32)
+    out = np.empty(cnt.size, dtype=np.float32)
+    _L().dbcsr_b200_row_max_epss(float(filter_eps), cnt.ctypes.data, cnt.size, out.ctypes.data)
+    return out
+
+
 class Engine:
     """multrec + csr + sched + accdrv of `nthreads` host threads for one rank (see include/dbcsr_b200_host.h)."""
 
@@ -108,12 +120,32 @@ class Engine:
         if not self.h:
             raise acclib.AccError("dbcsr_b200_engine_create failed")
 
-    def multiply(self, a_list3, a_dev_ptr, b_list3, b_dev_ptr):
+    def multiply(self, a_list3, a_dev_ptr, b_list3, b_dev_ptr, a_norms=None, b_norms=None):
         a = np.ascontiguousarray(a_list3, dtype=np.int32).reshape(-1, 3)
         b = np.ascontiguousarray(b_list3, dtype=np.int32).reshape(-1, 3)
-        rc = self.L.dbcsr_b200_engine_multiply(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, b.ctypes.data, b.shape[0], b_dev_ptr)
+        if a_norms is None and b_norms is None:
+            rc = self.L.dbcsr_b200_engine_multiply(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, b.ctypes.data, b.shape[0], b_dev_ptr)
+        else:
+            an = np.ascontiguousarray(a_norms, dtype=np.float32)
+            bn = np.ascontiguousarray(b_norms, dtype=np.float32)
+            if an.size != a.shape[0] or bn.size != b.shape[0]:
+                raise ValueError("one norm per block of each panel")
+            rc = self.L.dbcsr_b200_engine_multiply_filtered(self.h, a.ctypes.data, a.shape[0], a_dev_ptr, an.ctypes.data,
+                                                            b.ctypes.data, b.shape[0], b_dev_ptr, bn.ctypes.data)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_multiply returned %d" % rc)
+
+    def set_filter(self, row_eps):
+        """row_eps: float32 per local block row (see row_max_epss) or None to switch the on-the-fly filter off."""
+        if row_eps is None:
+            rc = self.L.dbcsr_b200_engine_set_filter(self.h, None)
+        else:
+            r = np.ascontiguousarray(row_eps, dtype=np.float32)
+            if r.size != self.m.size:
+                raise ValueError("one threshold per block row")
+            rc = self.L.dbcsr_b200_engine_set_filter(self.h, r.ctypes.data)
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_set_filter failed")
 
     def set_k_sizes(self, k_sizes):
         ks = np.ascontiguousarray(k_sizes, dtype=np.int32)

@@ -1,6 +1,6 @@
 """
 dbcsr_b200/multiply.py -- host-side mirror of the accelerator path of `dbcsr_multiply` for one rank and one Cannon tick
-(C = A * B, alpha = 1, beta = 0, no filtering): what multiply_cannon + accdrv do around the C ABI
+(C = A * B, alpha = 1, beta = 0, optional on-the-fly norm filter): what multiply_cannon + accdrv do around the C ABI
 (src/mm/dbcsr_mm_cannon.F:1622-1667 host2dev of both panels + transpose of the right one; src/mm/dbcsr_mm_accdrv.F:340-362 D2H of C).
 
 Everything that touches the device goes through the drop-in C ABI (dbcsr_b200.lib / dbcsr_b200.host); no CPU compute path.
@@ -78,13 +78,49 @@ class DeviceMultiply:
         self._keep = (a_data, b_data, b)  # host buffers must stay alive until the copies ran
         self.h2d_bytes = a_data.nbytes + b_data.nbytes + 4 * b.shape[0]
 
-    def multiply(self, a_list3, b_list3):
-        """One local multiply on the uploaded panels (stacks are built, ordered, uploaded and drained asynchronously)."""
+    def panel_norms(self, list3, row_sizes, col_sizes, d_data):
+        """acc_calculate_norms (src/mm/dbcsr_mm_common.F:498-591): offsets (blk_p - 1) and element counts go up, c_calculate_norms
+        runs on the device data area, the squared single-precision block norms come back.  Runs on the copy stream behind the
+        panel upload; the in-place transpose of the right panel does not change a block's sum of squares."""
+        acc = self.acc
+        l3 = np.ascontiguousarray(list3, dtype=np.int32).reshape(-1, 3)
+        nb = l3.shape[0]
+        if nb == 0:
+            return np.zeros(0, dtype=np.float32)
+        offs = np.ascontiguousarray(l3[:, 2] - 1, dtype=np.int32)
+        nel = np.ascontiguousarray(np.asarray(row_sizes)[l3[:, 0] - 1] * np.asarray(col_sizes)[l3[:, 1] - 1], dtype=np.int32)
+        d_o, d_n, d_out = acc.dev_alloc(4 * nb), acc.dev_alloc(4 * nb), acc.dev_alloc(4 * nb)
+        out = np.empty(nb, dtype=np.float32)
+        try:
+            acc.h2d(offs, d_o, self.copy_stream)
+            acc.h2d(nel, d_n, self.copy_stream)
+            acc.norms(d_data.ptr, nb, d_o.ptr, d_n.ptr, d_out.ptr, self.copy_stream)
+            acc.d2h(d_out, out, self.copy_stream)
+            acc.stream_sync(self.copy_stream)
+        finally:
+            for d in (d_o, d_n, d_out):
+                d.free()
+        return out
+
+    def multiply(self, a_list3, b_list3, filter_eps=None, total_row_counts=None):
+        """One local multiply on the uploaded panels (stacks are built, ordered, uploaded and drained asynchronously).
+        filter_eps: dbcsr_multiply's on-the-fly filter; total_row_counts = A blocks per block row over the whole process row
+        (default: of this panel, i.e. a 1-column process grid)."""
         if not self.first:
             self.engine.reset()
         self.first = False
         self.engine.wait_event(self.panels_ready)
-        self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
+        if filter_eps is None:
+            self.engine.set_filter(None)
+            self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
+            return
+        a = np.ascontiguousarray(a_list3, dtype=np.int32).reshape(-1, 3)
+        if total_row_counts is None:
+            total_row_counts = np.bincount(a[:, 0] - 1, minlength=self.m_sizes.size)
+        self.a_norms = self.panel_norms(a, self.m_sizes, self.k_sizes, self.d_a)
+        self.b_norms = self.panel_norms(b_list3, self.k_sizes, self.n_sizes, self.d_b)
+        self.engine.set_filter(host.row_max_epss(filter_eps, total_row_counts))
+        self.engine.multiply(a, self.d_a.ptr, b_list3, self.d_b.ptr, a_norms=self.a_norms, b_norms=self.b_norms)
 
     def set_result_buffers(self, out_arrays):
         """Pooled (pinned) host buffers for C, one per thread, each at least engine.c_capacity(t) elements: from now on every

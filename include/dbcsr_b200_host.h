@@ -58,6 +58,17 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e);
  * builds the stacks and (LAUNCH) streams them to the device.  Returns 0, or a negative code of the failing call. */
 int dbcsr_b200_engine_multiply(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const int* b_list3, int nb,
   const void* b_dev);
+/* On-the-fly norm filter (filter_eps of dbcsr_multiply; src/mm/dbcsr_mm_cannon.F:1038-1107, src/mm/dbcsr_mm_csr.F:270-278).
+ * dbcsr_b200_row_max_epss: row_max_epss(r) = (filter_eps / max(1, total_row_counts(r)))^2 in single precision, where
+ *   total_row_counts(r) = number of A blocks in block row r over the whole process row.
+ * dbcsr_b200_engine_set_filter: thresholds for the engine's nrows local block rows (NULL switches the filter off).
+ * dbcsr_b200_engine_multiply_filtered: like _multiply, with the per-block norms (sum of squares, single precision; what
+ *   c_calculate_norms writes) of the panels, aligned with a_list3 / b_list3; a product is skipped when
+ *   a_norm * b_norm < row_max_epss(a_row).  Without a preceding set_filter it behaves like _multiply. */
+void dbcsr_b200_row_max_epss(double filter_eps, const int* total_row_counts, int nrows, float* row_max_epss);
+int dbcsr_b200_engine_set_filter(dbcsr_b200_engine_t* e, const float* row_max_epss);
+int dbcsr_b200_engine_multiply_filtered(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
+  const int* b_list3, int nb, const void* b_dev, const float* b_norms);
 /* block sizes of the contraction index of the NEXT panels (Cannon ticks bring different k-slices); the stack map built at
  * creation (from the k_sizes given there: use the global right-matrix row block sizes) is kept */
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk);

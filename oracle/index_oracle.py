@@ -111,8 +111,31 @@ def find_cut(lst, ai, af, which, val):
     return ihigh
 
 
+def row_max_epss(filter_eps, total_row_counts):
+    """src/mm/dbcsr_mm_cannon.F:1098-1107: (filter_eps_sp / REAL(MAX(1, count)))**2, all in single precision."""
+    eps_sp = np.float32(filter_eps)
+    out = np.empty(len(total_row_counts), dtype=np.float32)
+    for r, c in enumerate(total_row_counts):
+        q = np.float32(eps_sp / np.float32(max(1, int(c))))
+        out[r] = np.float32(q * q)
+    return out
+
+
+def block_norms(list3, row_sizes, col_sizes, data):
+    """calc_norms_d, src/mm/dbcsr_mm_common.F:700-730: norms(blk) = REAL(SUM(DATA(bp:bpe)**2), KIND=sp) -- the SQUARED
+    Frobenius norm accumulated in double, rounded to single.  list3: (row, col, blk_p) 1-based."""
+    out = np.zeros(len(list3), dtype=np.float32)
+    for i, (row, col, bp) in enumerate(list3):
+        if bp != 0:
+            nze = row_sizes[row - 1] * col_sizes[col - 1]
+            blk = np.asarray(data[abs(bp) - 1:abs(bp) - 1 + nze], dtype=np.float64)
+            out[i] = np.float32(np.sum(blk * blk))
+    return out
+
+
 def build_csr_index(mi, mf, ai, af, lst):
-    """src/mm/dbcsr_mm_csr.F:741-795. Returns row_p dict-like list (offset by mi) and blk_info list of (col, blk_p)."""
+    """src/mm/dbcsr_mm_csr.F:741-795. Returns row_p dict-like list (offset by mi) and blk_info list of (col, blk_p)
+    (plus the list position of each CSR entry as a third component, which is how csr_norms(:) follows list_norms(:))."""
     counts = [0] * (mf - mi + 1)
     for i in range(ai, af + 1):
         counts[lst[i - 1][0] - mi] += 1
@@ -124,7 +147,7 @@ def build_csr_index(mi, mf, ai, af, lst):
     for i in range(ai, af + 1):
         row = lst[i - 1][0]
         counts[row - mi] += 1
-        blk_info[row_p[row - mi] + counts[row - mi] - 1] = (lst[i - 1][1], lst[i - 1][2])
+        blk_info[row_p[row - mi] + counts[row - mi] - 1] = (lst[i - 1][1], lst[i - 1][2], i)
     return row_p, blk_info
 
 
@@ -155,6 +178,10 @@ class LocalMultiplyOracle:
         self.c_hash = {}
         self.flop = 0
         self.dispatched = []
+        # on-the-fly filter (use_eps): thresholds per C row and norms aligned with the SORTED lists (set by multiply)
+        self.row_eps = None
+        self.a_norms = self.b_norms = None
+        self.skipped = 0
 
     # src/mm/dbcsr_mm_csr.F:404-525
     def _init_stack_map(self):
@@ -241,12 +268,18 @@ class LocalMultiplyOracle:
         for a_row_l in range(mi, mf + 1):
             m_size = self.m_sizes[a_row_l - 1]
             mapped_row_size = self.m_map[m_size]
+            use_eps = self.row_eps is not None and self.a_norms is not None
+            a_row_eps = np.float32(self.row_eps[a_row_l - 1]) if use_eps else None
             for a_blk in range(a_row_p[a_row_l - mi] + 1, a_row_p[a_row_l - mi + 1] + 1):
-                a_col_l, a_first = a_blk_info[a_blk - 1]
+                a_col_l, a_first, a_pos = a_blk_info[a_blk - 1]
                 k_size = self.k_sizes[a_col_l - 1]
                 mapped_k_size = self.k_map[k_size]
                 for b_blk in range(b_row_p[a_col_l - ki] + 1, b_row_p[a_col_l - ki + 1] + 1):
-                    b_col_l, b_first = b_blk_info[b_blk - 1]
+                    b_col_l, b_first, b_pos = b_blk_info[b_blk - 1]
+                    if use_eps:  # src/mm/dbcsr_mm_csr.F:270-278, single precision
+                        if np.float32(np.float32(self.a_norms[a_pos - 1]) * np.float32(self.b_norms[b_pos - 1])) < a_row_eps:
+                            self.skipped += 1
+                            continue
                     c_blk_id = self.c_hash.get((a_row_l, b_col_l), 0)
                     n_size = self.n_sizes[b_col_l - 1]
                     c_nze = m_size * n_size
@@ -301,10 +334,23 @@ class LocalMultiplyOracle:
             self.sparse_multrec(mi, mf, ni + s1, nf, ki, kf, ai, af, a_index, bcut, bf, b_index)
 
     # src/mm/dbcsr_mm_multrec.F:263-324 (+ setup_rec_index_2d, src/mm/dbcsr_mm_cannon.F:2910-2967)
-    def multiply(self, a_list, b_list):
+    def multiply(self, a_list, b_list, a_norms=None, b_norms=None, row_eps=None):
+        """a_norms/b_norms (aligned with a_list/b_list) + row_eps (per C row) switch the on-the-fly filter on."""
         nrow, ncol, nk = len(self.m_sizes), len(self.n_sizes), len(self.k_sizes)
+        if a_norms is not None:
+            # carry the norm with its block through the sort (the reference computes norms on the sorted images)
+            a_list = [tuple(e[:3]) + (float(a_norms[i]),) for i, e in enumerate(a_list)]
+            b_list = [tuple(e[:3]) + (float(b_norms[i]),) for i, e in enumerate(b_list)]
         a_index = rec_sort_index(1, nrow, 1, nk, list(a_list)) if len(a_list) > 1 else list(a_list)
         b_index = rec_sort_index(1, nk, 1, ncol, list(b_list)) if len(b_list) > 1 else list(b_list)
+        if a_norms is not None:
+            self.a_norms = np.array([e[3] for e in a_index], dtype=np.float32)
+            self.b_norms = np.array([e[3] for e in b_index], dtype=np.float32)
+            self.row_eps = None if row_eps is None else np.asarray(row_eps, dtype=np.float32)
+            a_index = [e[:3] for e in a_index]
+            b_index = [e[:3] for e in b_index]
+        else:
+            self.a_norms = self.b_norms = self.row_eps = None
         self.a_index, self.b_index = a_index, b_index
         self.sparse_multrec(1, nrow, 1, ncol, 1, nk, 1, len(a_index), a_index, 1, len(b_index), b_index)
         self.flush_stacks(purge=True)

@@ -26,6 +26,17 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), "missing export: " + s
 
 
+def test_host_stand_in_header_symbols_are_exported():
+    """include/dbcsr_b200_host.h (the C++ stand-in for DBCSR's Fortran local-multiply layer) is part of the same library."""
+    txt = open(os.path.join(ROOT, "include", "dbcsr_b200_host.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    declared = set(re.findall(r"\b(dbcsr_b200_\w+)\s*\(", txt))
+    assert len(declared) >= 30
+    out = subprocess.check_output(["nm", "-D", "--defined-only", acclib.LIB_PATH]).decode()
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    assert not (declared - exported), declared - exported
+
+
 def test_reference_abi_symbol_names_are_all_present():
     """The 26 + 6 names of the reference's src/acc/acc.h:34-71 and src/acc/acc_libsmm.h:38-49 (hard-coded list)."""
     ref = """c_dbcsr_acc_init c_dbcsr_acc_finalize c_dbcsr_acc_clear_errors c_dbcsr_acc_get_ndevices c_dbcsr_acc_set_active_device

@@ -175,3 +175,54 @@ def test_full_size_properties(acc, cfgname, nblk):
     expected = sum(float(colsum_a[i] @ rb[int(A.cols[i])]) for i in range(A.nblks) if int(A.cols[i]) in rb)
     got = sum(float(p[3].sum()) for p in prod.parts)
     assert abs(got / expected - 1.0) <= 1e-10, (got, expected)
+
+
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_on_the_fly_filter(acc, nthreads):
+    """dbcsr_multiply(filter_eps=...): block norms from c_calculate_norms on the device (src/mm/dbcsr_mm_common.F:498-591),
+    thresholds row_max_epss (src/mm/dbcsr_mm_cannon.F:1098-1107), products with a_norm*b_norm < row_eps skipped
+    (src/mm/dbcsr_mm_csr.F:270-278).  Expected C = sum over exactly the surviving products, computed on the CPU."""
+    rng = np.random.default_rng(77)
+    sizes = [5, 13, 23]
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (40, 36, 44))
+    A = workload.random_panel(ms, ks, 0.35, rng)
+    B = workload.random_panel(ks, ns, 0.35, rng)
+    for P in (A, B):  # block magnitudes over four decades so that a mid-range eps cuts a good part of the products
+        for i in range(P.nblks):
+            P.block(i)[...] *= 10.0 ** rng.uniform(-4, 0)
+    eps = 0.5
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=400))
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3(), filter_eps=eps)
+        prod = dm.download_c()
+        a_n, b_n = dm.a_norms, dm.b_norms
+        flop = dm.engine.flop()
+    finally:
+        dm.close()
+    # device norms = the oracle's (squared Frobenius norm, single precision), up to summation order
+    ref_an = orc.norms(A.data, A.offsets, ms[A.rows - 1] * ks[A.cols - 1])
+    ref_bn = orc.norms(B.data, B.offsets, ks[B.rows - 1] * ns[B.cols - 1])
+    assert np.allclose(a_n, ref_an, rtol=1e-5, atol=0) and np.allclose(b_n, ref_bn, rtol=1e-5, atol=0)
+    row_eps = io.row_max_epss(eps, np.bincount(A.rows - 1, minlength=ms.size))
+    by_k = {}
+    for j in range(B.nblks):
+        by_k.setdefault(int(B.rows[j]), []).append(j)
+    exp, kept, total, exp_flop = {}, 0, 0, 0
+    for i in range(A.nblks):
+        r = int(A.rows[i])
+        for j in by_k.get(int(A.cols[i]), []):
+            total += 1
+            if np.float32(a_n[i] * b_n[j]) < row_eps[r - 1]:
+                continue
+            kept += 1
+            key = (r, int(B.cols[j]))
+            blk = A.block(i) @ B.block(j)
+            exp[key] = exp[key] + blk if key in exp else blk
+            exp_flop += 2 * blk.shape[0] * blk.shape[1] * A.block(i).shape[1]
+    assert 0 < kept < total and flop == exp_flop
+    got = prod.blocks()
+    assert set(got.keys()) == set(exp.keys())
+    num = sum(float(((got[k] - exp[k]) ** 2).sum()) for k in exp)
+    den = sum(float((exp[k] ** 2).sum()) for k in exp)
+    assert np.sqrt(num / den) <= 1e-10

@@ -213,3 +213,84 @@ def test_recorded_host_stacks_reproduce_the_block_product(sizes):
         den += float((ref ** 2).sum())
     assert (num / den) ** 0.5 <= 1e-13
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------- on-the-fly norm filter
+def _filter_case(seed, nrow=48, ncol=40, nk=56, sizes=(5, 13, 23)):
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(nrow, ncol, nk, 0.3, 0.3, list(sizes), seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    # squared block norms spread over 8 decades so that a mid-range eps removes a good part of the products
+    a_n = (10.0 ** rng.uniform(-8, 0, a_l.shape[0])).astype(np.float32)
+    b_n = (10.0 ** rng.uniform(-8, 0, b_l.shape[0])).astype(np.float32)
+    counts = np.bincount(a_l[:, 0] - 1, minlength=nrow)
+    return m_sizes, n_sizes, k_sizes, A, B, a_l, b_l, a_n, b_n, counts
+
+
+def test_row_max_epss_matches_oracle_single_precision():
+    counts = np.array([0, 1, 2, 3, 7, 100, 12345], dtype=np.int32)
+    for eps in (1e-5, 1e-7, 3.3e-10, 0.0):
+        got = host.row_max_epss(eps, counts)
+        assert got.dtype == np.float32 and np.array_equal(got, io.row_max_epss(eps, counts))
+
+
+@pytest.mark.parametrize("eps", [1e-2, 1e-1, 1.0])
+def test_filtered_engine_matches_index_oracle(eps):
+    """filter_eps: product skipped when a_norm*b_norm < row_max_epss(row) (src/mm/dbcsr_mm_csr.F:270-278); same stacks and
+    the same C index as the restated reference traversal, and strictly fewer products than without the filter."""
+    m_sizes, n_sizes, k_sizes, A, B, a_l, b_l, a_n, b_n, counts = _filter_case(seed=11)
+    row_eps = io.row_max_epss(eps, counts)
+    ora = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=400, multrec_limit=64)
+    exp = ora.multiply(A.index_list(), B.index_list(), a_norms=a_n, b_norms=b_n, row_eps=row_eps)
+    assert ora.skipped > 0
+    eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=400, multrec_limit=64))
+    eng.set_filter(host.row_max_epss(eps, counts))
+    eng.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+    got = eng.stacks()
+    assert len(got) == len(exp)
+    for g, x in zip(got, exp):
+        assert g["stack_id"] == x["stack_id"] and np.array_equal(g["host"], x["host"]) and np.array_equal(g["dev"], x["dev"])
+    rows, cols, blk_p, datasize = eng.c_index(0)
+    assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p and datasize == ora.datasize
+    assert eng.flop() == ora.flop
+    # unfiltered run on the same engine type has more products
+    e0 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=400, multrec_limit=64))
+    e0.multiply(a_l, None, b_l, None)
+    assert e0.flop() > eng.flop()
+    n_kept = sum(g["host"].shape[0] for g in got)
+    assert n_kept + ora.skipped == sum(s["host"].shape[0] for s in e0.stacks())
+    e0.close()
+    eng.close()
+
+
+def test_filter_keeps_exactly_the_products_above_threshold_multithreaded():
+    """Independent of the traversal: the set of surviving (a_blk, b_blk) pairs is {a_norm*b_norm >= row_eps(row)} in float32,
+    for 1 and 4 threads and with row chunks; filter off (set_filter(None) or eps = 0) gives the unfiltered product set."""
+    m_sizes, n_sizes, k_sizes, A, B, a_l, b_l, a_n, b_n, counts = _filter_case(seed=23, nrow=64)
+    row_eps = host.row_max_epss(0.2, counts)
+    by_k = {}
+    for j in range(b_l.shape[0]):
+        by_k.setdefault(int(b_l[j, 0]), []).append(j)
+    want, everything = set(), set()
+    for i in range(a_l.shape[0]):
+        for j in by_k.get(int(a_l[i, 1]), []):
+            everything.add((int(a_l[i, 2]), int(b_l[j, 2])))
+            if not (np.float32(a_n[i] * b_n[j]) < row_eps[a_l[i, 0] - 1]):
+                want.add((int(a_l[i, 2]), int(b_l[j, 2])))
+    assert 0 < len(want) < len(everything)
+    prod = lambda eng: sorted((int(r[3]), int(r[4])) for s in eng.stacks() for r in s["host"])
+    for nthreads, chunks in ((1, 1), (4, 1), (3, 2)):
+        e = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=nthreads, mode=host.RECORD,
+                        cfg=host.default_cfg(mm_stack_size=300, row_chunks=chunks))
+        e.set_filter(row_eps)
+        e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+        assert prod(e) == sorted(want)
+        e.reset()
+        e.set_filter(None)
+        e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+        assert prod(e) == sorted(everything)
+        e.reset()
+        e.set_filter(host.row_max_epss(0.0, counts))
+        e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+        assert prod(e) == sorted(everything)
+        e.close()
