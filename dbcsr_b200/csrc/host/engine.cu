@@ -60,6 +60,13 @@ struct ThreadState {
   int a_first = 1, a_last = 0;
   std::vector<std::pair<int, int>> slices;  // (a_first, a_last) of every row chunk this thread owns, in row order
   double* c_host = nullptr;  // optional: D2H target enqueued right behind this thread's last stack
+  bool has_preset = false;   // work matrix started from existing C blocks (beta != 0 / retain_sparsity)
+  // result of dbcsr_b200_engine_filter_c: compacted index + compacted device data area
+  bool filtered = false;
+  std::vector<int> f_rows, f_cols, f_blk_p;
+  int f_datasize = 0;
+  void* c_final = nullptr;
+  size_t c_final_capacity = 0;
   int rc = 0;
   double build_seconds = 0.0;
 };
@@ -152,9 +159,50 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e) {
       if (b.calculated != nullptr) c_dbcsr_acc_event_destroy(b.calculated);
     }
     if (ts.c_dev != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_dev);
+    if (ts.c_final != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_final);
     if (ts.stream != nullptr) c_dbcsr_acc_stream_destroy(ts.stream);
   }
   delete e;
+}
+
+// device C buffers (dbcsr_mm_accdrv_init: sized like the work area, zeroed asynchronously); created at first use
+static int ensure_c_buffers(dbcsr_b200_engine_t* e) {
+  if (!(e->mode & DBCSR_B200_LAUNCH)) return 0;
+  const int nthreads = (int)e->th.size();
+  size_t sum_n = 0;
+  for (int v : e->n_sizes) sum_n += (size_t)v;
+  for (int t = 0; t < nthreads; ++t) {
+    ThreadState& ts = e->th[t];
+    if (ts.c_dev != nullptr) continue;
+    size_t cap = ts.c_capacity;
+    if (cap == 0) {  // dense upper bound over ALL block rows this thread owns (later Cannon ticks may touch rows that have
+                     // no A block in the first panel)
+      const int rcn = std::max(1, e->cfg.row_chunks);
+      const int nchunks = nthreads * rcn;
+      size_t sum_m = 0;
+      for (int c = t; c < nchunks; c += nthreads) {
+        const int row_lo = (int)(((long long)e->nrows * c) / nchunks), row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
+        for (int r = row_lo; r < row_hi; ++r) sum_m += (size_t)e->m_sizes[(size_t)r];
+      }
+      cap = sum_m * sum_n;
+    }
+    if (cap == 0) cap = 1;
+    if (cap > 0x7fffffffull) cap = 0x7fffffffull;  // offsets are int32 (hard part 8)
+    ts.c_capacity = cap;
+    if (c_dbcsr_acc_dev_mem_allocate(&ts.c_dev, cap * sizeof(double)) != 0) return -40;
+    if (c_dbcsr_acc_memset_zero(ts.c_dev, 0, cap * sizeof(double), ts.stream) != 0) return -41;
+  }
+  return 0;
+}
+
+// owner thread of a (1-based) block row: chunk c = rows (c*nrows/C, (c+1)*nrows/C], C = nthreads*row_chunks, thread = c mod nthreads
+static int owner_of_row(const dbcsr_b200_engine_t* e, int row) {
+  const int nthreads = (int)e->th.size();
+  const int nchunks = nthreads * std::max(1, e->cfg.row_chunks);
+  int c = (int)(((long long)(row - 1) * nchunks) / std::max(1, e->nrows));
+  while (c > 0 && row <= (int)(((long long)e->nrows * c) / nchunks)) --c;
+  while (c < nchunks - 1 && row > (int)(((long long)e->nrows * (c + 1)) / nchunks)) ++c;
+  return c % nthreads;
 }
 
 static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
@@ -162,6 +210,7 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
   if (e == nullptr || na < 0 || nb < 0) return -1;
   const int nthreads = (int)e->th.size();
   const bool filter = a_norms != nullptr && b_norms != nullptr && !e->row_eps.empty();
+  for (auto& ts : e->th) ts.filtered = false;
   // --- left panel: split the BCSR-ordered list over the threads by block rows (DBCSR: thr_c slices of coo_l, each slice
   //     rec-sorted on its own with the full panel extents, src/mm/dbcsr_mm_cannon.F:2910-2967)
   e->a_sorted.resize((size_t)na);
@@ -228,31 +277,9 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
       e->b_sorted[(size_t)j].blk = b_list3[3 * (size_t)i + 2];
     }
   }
-  // --- device C buffers (dbcsr_mm_accdrv_init: sized like the work area, zeroed asynchronously)
-  if (e->mode & DBCSR_B200_LAUNCH) {
-    size_t sum_n = 0;
-    for (int v : e->n_sizes) sum_n += (size_t)v;
-    for (int t = 0; t < nthreads; ++t) {
-      ThreadState& ts = e->th[t];
-      if (ts.c_dev != nullptr) continue;
-      size_t cap = ts.c_capacity;
-      if (cap == 0) {  // dense upper bound over ALL block rows this thread owns (later Cannon ticks may touch rows that have
-                       // no A block in the first panel)
-        const int rcn = std::max(1, e->cfg.row_chunks);
-        const int nchunks = nthreads * rcn;
-        size_t sum_m = 0;
-        for (int c = t; c < nchunks; c += nthreads) {
-          const int row_lo = (int)(((long long)e->nrows * c) / nchunks), row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
-          for (int r = row_lo; r < row_hi; ++r) sum_m += (size_t)e->m_sizes[(size_t)r];
-        }
-        cap = sum_m * sum_n;
-      }
-      if (cap == 0) cap = 1;
-      if (cap > 0x7fffffffull) cap = 0x7fffffffull;  // offsets are int32 (hard part 8)
-      ts.c_capacity = cap;
-      if (c_dbcsr_acc_dev_mem_allocate(&ts.c_dev, cap * sizeof(double)) != 0) return -40;
-      if (c_dbcsr_acc_memset_zero(ts.c_dev, 0, cap * sizeof(double), ts.stream) != 0) return -41;
-    }
+  {
+    const int rc_alloc = ensure_c_buffers(e);
+    if (rc_alloc != 0) return rc_alloc;
   }
   // --- per-thread multrec -> csr -> sched -> accdrv
   std::vector<std::thread> workers;
@@ -306,12 +333,16 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
         ts.mm->multiply(e->a_sorted.data(), sl.first, sl.second, e->b_sorted.data(), nb, dispatch,  // ends with a purge
                         filter ? e->a_norm_sorted.data() : nullptr, filter ? e->b_norm_sorted.data() : nullptr);
         const size_t ds1 = (size_t)ts.mm->datasize();
-        if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds0) {
+        if (ts.rc == 0 && ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds0 && !ts.has_preset) {
           // the C blocks created by this row chunk are final once the stream drains: start their D2H now, while this thread
           // builds its next chunk and the other threads are still busy
           if (c_dbcsr_acc_memcpy_d2h(static_cast<double*>(ts.c_dev) + ds0, ts.c_host + ds0, (ds1 - ds0) * sizeof(double), ts.stream) != 0)
             ts.rc = -46;
         }
+      }
+      if (ts.rc == 0 && ts.has_preset && ts.c_host != nullptr && ts.c_dev != nullptr && ts.mm->datasize() > 0) {
+        // products accumulate into the pre-existing blocks too: one D2H of the whole work area behind the last stack
+        if (c_dbcsr_acc_memcpy_d2h(ts.c_dev, ts.c_host, (size_t)ts.mm->datasize() * sizeof(double), ts.stream) != 0) ts.rc = -46;
       }
       ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     });
@@ -352,6 +383,184 @@ void dbcsr_b200_row_max_epss(double filter_eps, const int* total_row_counts, int
   }
 }
 
+int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const int* cols, int nblks, const double* host_data,
+                               int keep_sparsity) {
+  // The work matrices start from the existing C blocks (dbcsr_mm_csr_init -> fill_hash_tables, src/mm/dbcsr_mm_csr.F:526-576):
+  // block i goes to the thread that owns its block row, in list order, at the next free offset of that thread's work area.
+  if (e == nullptr || nblks < 0) return -1;
+  const int nthreads = (int)e->th.size();
+  for (auto& ts : e->th)
+    if (!ts.mm->c_row().empty()) return -2;  // must come before the first tick of a multiply (after create / reset)
+  std::vector<std::vector<int>> r((size_t)nthreads), c((size_t)nthreads), p((size_t)nthreads);
+  std::vector<std::vector<double>> data((size_t)nthreads);
+  std::vector<long long> ds((size_t)nthreads, 0);
+  size_t src = 0;
+  for (int i = 0; i < nblks; ++i) {
+    if (rows[i] < 1 || rows[i] > e->nrows || cols[i] < 1 || cols[i] > e->ncols) return -3;
+    const int t = owner_of_row(e, rows[i]);
+    const size_t nze = (size_t)e->m_sizes[(size_t)rows[i] - 1] * (size_t)e->n_sizes[(size_t)cols[i] - 1];
+    r[(size_t)t].push_back(rows[i]);
+    c[(size_t)t].push_back(cols[i]);
+    p[(size_t)t].push_back((int)(ds[(size_t)t] + 1));
+    ds[(size_t)t] += (long long)nze;
+    if (ds[(size_t)t] > 0x7fffffffLL) return -4;
+    if (host_data != nullptr && (e->mode & DBCSR_B200_LAUNCH)) data[(size_t)t].insert(data[(size_t)t].end(), host_data + src, host_data + src + nze);
+    src += nze;
+  }
+  const int rc_alloc = ensure_c_buffers(e);
+  if (rc_alloc != 0) return rc_alloc;
+  for (int t = 0; t < nthreads; ++t) {
+    ThreadState& ts = e->th[(size_t)t];
+    ts.mm->preset_c(r[(size_t)t].data(), c[(size_t)t].data(), p[(size_t)t].data(), (int)r[(size_t)t].size(), (int)ds[(size_t)t]);
+    ts.mm->set_keep_sparsity(keep_sparsity != 0);
+    ts.has_preset = true;
+    if ((e->mode & DBCSR_B200_LAUNCH) && !data[(size_t)t].empty()) {
+      if ((size_t)ds[(size_t)t] > ts.c_capacity) return -42;
+      if (c_dbcsr_acc_memcpy_h2d(data[(size_t)t].data(), ts.c_dev, data[(size_t)t].size() * sizeof(double), ts.stream) != 0) return -44;
+    }
+  }
+  for (int t = 0; t < nthreads; ++t)  // the staging vectors die here
+    if (e->th[(size_t)t].stream != nullptr && c_dbcsr_acc_stream_sync(e->th[(size_t)t].stream) != 0) return -1;
+  return 0;
+}
+
+int dbcsr_b200_filter_index(double filter_eps, const double* norms2, int nblks, int* rows, int* cols, int* blk_p, const int* nelems,
+                            long long* nze_after) {
+  // multrec_filtering_d, src/mm/dbcsr_mm_multrec.F:700-758: keep a block iff DDOT(blk, blk) >= filter_eps**2; kept entries move
+  // to the front in order, their blk_p values are unchanged (the data area keeps its holes)
+  const double eps2 = filter_eps * filter_eps;
+  int last = 0;
+  long long nze = 0;
+  for (int b = 0; b < nblks; ++b) {
+    if (blk_p[b] == 0 || nelems[b] == 0) continue;
+    if (norms2[b] >= eps2) {
+      if (last < b) {
+        rows[last] = rows[b];
+        cols[last] = cols[b];
+        blk_p[last] = blk_p[b];
+      }
+      ++last;
+      nze += nelems[b];
+    }
+  }
+  if (nze_after != nullptr) *nze_after = nze;
+  return last;
+}
+
+int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
+  // Final filter of the product (dbcsr_mm_multrec_finalize -> multrec_filtering) BEFORE the download: squared block norms in
+  // double on the device, 8 B per block to the host, index compaction there, then the surviving blocks are gathered into a
+  // contiguous device area in index order -- only those travel over PCIe.
+  if (e == nullptr || !(e->mode & DBCSR_B200_LAUNCH)) return -1;
+  struct Scratch {
+    std::vector<int> offs, nel;
+    std::vector<double> norms;
+    void *d_offs = nullptr, *d_nel = nullptr, *d_norms = nullptr, *d_dst = nullptr;
+  };
+  const int nthreads = (int)e->th.size();
+  std::vector<Scratch> sc((size_t)nthreads);
+  int rc = 0;
+  auto release = [&]() {
+    for (auto& x : sc)
+      for (void* d : {x.d_offs, x.d_nel, x.d_norms, x.d_dst})
+        if (d != nullptr) c_dbcsr_acc_dev_mem_deallocate(d);
+  };
+  // phase 1: norms of every thread's blocks, all streams busy at once
+  for (int t = 0; t < nthreads && rc == 0; ++t) {
+    ThreadState& ts = e->th[(size_t)t];
+    Scratch& x = sc[(size_t)t];
+    ts.filtered = false;
+    const int nb = (int)ts.mm->c_row().size();
+    if (nb == 0 || ts.c_dev == nullptr) continue;
+    x.offs.resize((size_t)nb);
+    x.nel.resize((size_t)nb);
+    x.norms.resize((size_t)nb);
+    for (int b = 0; b < nb; ++b) {
+      x.offs[(size_t)b] = ts.mm->c_blk_p()[(size_t)b] - 1;
+      x.nel[(size_t)b] = e->m_sizes[(size_t)ts.mm->c_row()[(size_t)b] - 1] * e->n_sizes[(size_t)ts.mm->c_col()[(size_t)b] - 1];
+    }
+    const size_t ib = sizeof(int) * (size_t)nb;
+    if (c_dbcsr_acc_dev_mem_allocate(&x.d_offs, ib) != 0 || c_dbcsr_acc_dev_mem_allocate(&x.d_nel, ib) != 0 ||
+        c_dbcsr_acc_dev_mem_allocate(&x.d_dst, ib) != 0 || c_dbcsr_acc_dev_mem_allocate(&x.d_norms, sizeof(double) * (size_t)nb) != 0) {
+      rc = -40;
+      break;
+    }
+    if (c_dbcsr_acc_memcpy_h2d(x.offs.data(), x.d_offs, ib, ts.stream) != 0 || c_dbcsr_acc_memcpy_h2d(x.nel.data(), x.d_nel, ib, ts.stream) != 0 ||
+        libsmm_acc_b200_block_norms_f64(static_cast<const double*>(ts.c_dev), nb, static_cast<const int*>(x.d_offs),
+                                        static_cast<const int*>(x.d_nel), static_cast<double*>(x.d_norms), ts.stream) != 0 ||
+        c_dbcsr_acc_memcpy_d2h(x.d_norms, x.norms.data(), sizeof(double) * (size_t)nb, ts.stream) != 0)
+      rc = -47;
+  }
+  // phase 2: compaction of the index on the host, gather of the kept blocks on the device
+  for (int t = 0; t < nthreads && rc == 0; ++t) {
+    ThreadState& ts = e->th[(size_t)t];
+    Scratch& x = sc[(size_t)t];
+    const int nb = (int)ts.mm->c_row().size();
+    ts.f_rows = ts.mm->c_row();
+    ts.f_cols = ts.mm->c_col();
+    ts.f_blk_p = ts.mm->c_blk_p();
+    ts.f_datasize = 0;
+    if (nb == 0 || ts.c_dev == nullptr) {
+      ts.filtered = true;
+      continue;
+    }
+    if (c_dbcsr_acc_stream_sync(ts.stream) != 0) {
+      rc = -1;
+      break;
+    }
+    long long nze = 0;
+    const int kept = dbcsr_b200_filter_index(filter_eps, x.norms.data(), nb, ts.f_rows.data(), ts.f_cols.data(), ts.f_blk_p.data(),
+                                             x.nel.data(), &nze);
+    ts.f_rows.resize((size_t)kept);
+    ts.f_cols.resize((size_t)kept);
+    ts.f_blk_p.resize((size_t)kept);
+    // gather plan: kept block j moves from its work-area offset to the next free offset of the compact area
+    std::vector<int>& src_off = x.offs;  // reuse
+    std::vector<int> dst_off((size_t)kept);
+    int run = 0;
+    for (int j = 0; j < kept; ++j) {
+      src_off[(size_t)j] = ts.f_blk_p[(size_t)j] - 1;
+      x.nel[(size_t)j] = e->m_sizes[(size_t)ts.f_rows[(size_t)j] - 1] * e->n_sizes[(size_t)ts.f_cols[(size_t)j] - 1];
+      dst_off[(size_t)j] = run;
+      ts.f_blk_p[(size_t)j] = run + 1;
+      run += x.nel[(size_t)j];
+    }
+    ts.f_datasize = run;
+    if ((size_t)run > ts.c_final_capacity) {
+      if (ts.c_final != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_final);
+      ts.c_final = nullptr;
+      ts.c_final_capacity = 0;
+      if (c_dbcsr_acc_dev_mem_allocate(&ts.c_final, (size_t)run * sizeof(double)) != 0) {
+        rc = -40;
+        break;
+      }
+      ts.c_final_capacity = (size_t)run;
+    }
+    if (kept > 0) {
+      const size_t kb = sizeof(int) * (size_t)kept;
+      if (c_dbcsr_acc_memcpy_h2d(src_off.data(), x.d_offs, kb, ts.stream) != 0 || c_dbcsr_acc_memcpy_h2d(x.nel.data(), x.d_nel, kb, ts.stream) != 0 ||
+          c_dbcsr_acc_memcpy_h2d(dst_off.data(), x.d_dst, kb, ts.stream) != 0 ||
+          libsmm_acc_b200_gather_blocks(static_cast<const double*>(ts.c_dev), static_cast<double*>(ts.c_final), kept,
+                                        static_cast<const int*>(x.d_offs), static_cast<const int*>(x.d_dst), static_cast<const int*>(x.d_nel),
+                                        ts.stream) != 0) {
+        rc = -48;
+        break;
+      }
+      // dst_off lives in this scope only: the H2D from pageable memory has been staged when memcpy_h2d returns, but make the
+      // lifetime explicit
+      if (c_dbcsr_acc_stream_sync(ts.stream) != 0) {
+        rc = -1;
+        break;
+      }
+    }
+    ts.filtered = true;
+  }
+  for (auto& ts : e->th)
+    if (ts.stream != nullptr) c_dbcsr_acc_stream_sync(ts.stream);
+  release();
+  return rc;
+}
+
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk) {
   if (e == nullptr || nk < 0) return -1;
   std::vector<int> ks(k_sizes, k_sizes + nk);
@@ -368,6 +577,8 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
     ts.mm->reset();
     ts.mm->set_k_sizes(e->k_sizes);
     ts.recorded.clear();
+    ts.has_preset = false;
+    ts.filtered = false;
     if (ts.c_dev != nullptr && c_dbcsr_acc_memset_zero(ts.c_dev, 0, ts.c_capacity * sizeof(double), ts.stream) != 0) return -41;
   }
   return 0;
@@ -381,12 +592,30 @@ int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e) {
 }
 
 int dbcsr_b200_engine_nthreads(const dbcsr_b200_engine_t* e) { return (int)e->th.size(); }
-int dbcsr_b200_engine_c_nblks(const dbcsr_b200_engine_t* e, int t) { return (int)e->th[(size_t)t].mm->c_row().size(); }
-int dbcsr_b200_engine_c_datasize(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->datasize(); }
-const int* dbcsr_b200_engine_c_rows(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_row().data(); }
-const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_col().data(); }
-const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].mm->c_blk_p().data(); }
-void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int t) { return e->th[(size_t)t].c_dev; }
+int dbcsr_b200_engine_c_nblks(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? (int)ts.f_rows.size() : (int)ts.mm->c_row().size();
+}
+int dbcsr_b200_engine_c_datasize(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? ts.f_datasize : ts.mm->datasize();
+}
+const int* dbcsr_b200_engine_c_rows(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? ts.f_rows.data() : ts.mm->c_row().data();
+}
+const int* dbcsr_b200_engine_c_cols(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? ts.f_cols.data() : ts.mm->c_col().data();
+}
+const int* dbcsr_b200_engine_c_blk_p(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? ts.f_blk_p.data() : ts.mm->c_blk_p().data();
+}
+void* dbcsr_b200_engine_c_dev(const dbcsr_b200_engine_t* e, int t) {
+  const ThreadState& ts = e->th[(size_t)t];
+  return ts.filtered ? ts.c_final : ts.c_dev;
+}
 
 int dbcsr_b200_engine_set_c_host(dbcsr_b200_engine_t* e, int t, double* host) {
   if (e == nullptr || t < 0 || t >= (int)e->th.size()) return -1;
@@ -408,16 +637,18 @@ int dbcsr_b200_engine_c_to_host_async(dbcsr_b200_engine_t* e, int t, double* hos
   // D2H of the thread's C buffer enqueued behind its last stack; completes at dbcsr_b200_engine_sync
   ThreadState& ts = e->th[(size_t)t];
   if (ts.c_dev == nullptr || ts.stream == nullptr) return -1;
-  const size_t n = (size_t)ts.mm->datasize();
-  if (n > 0 && c_dbcsr_acc_memcpy_d2h(ts.c_dev, host, n * sizeof(double), ts.stream) != 0) return -1;
+  const size_t n = ts.filtered ? (size_t)ts.f_datasize : (size_t)ts.mm->datasize();
+  const void* src = ts.filtered ? ts.c_final : ts.c_dev;
+  if (n > 0 && c_dbcsr_acc_memcpy_d2h(src, host, n * sizeof(double), ts.stream) != 0) return -1;
   return 0;
 }
 
 int dbcsr_b200_engine_c_to_host(dbcsr_b200_engine_t* e, int t, double* host) {
   ThreadState& ts = e->th[(size_t)t];
   if (ts.c_dev == nullptr || ts.stream == nullptr) return -1;
-  const size_t n = (size_t)ts.mm->datasize();
-  if (n > 0 && c_dbcsr_acc_memcpy_d2h(ts.c_dev, host, n * sizeof(double), ts.stream) != 0) return -1;
+  const size_t n = ts.filtered ? (size_t)ts.f_datasize : (size_t)ts.mm->datasize();
+  const void* src = ts.filtered ? ts.c_final : ts.c_dev;
+  if (n > 0 && c_dbcsr_acc_memcpy_d2h(src, host, n * sizeof(double), ts.stream) != 0) return -1;
   return c_dbcsr_acc_stream_sync(ts.stream);
 }
 

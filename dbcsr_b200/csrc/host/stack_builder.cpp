@@ -216,6 +216,7 @@ void LocalMultiply::reset() {
   }
   datasize_ = 0;
   flop_ = 0;
+  keep_sparsity_ = false;
   std::fill(fill_.begin(), fill_.end(), 0);
 }
 
@@ -230,7 +231,7 @@ void LocalMultiply::preset_c(const int* rows, const int* cols, const int* blk_p,
 
 // hash_table_get / hash_table_add of the reference (src/utils/dbcsr_hash_table.f90) only affect speed, not results;
 // new block => offset = datasize + 1, appended to the work index (src/mm/dbcsr_mm_csr.F:309-323).
-int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created) {
+int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created, bool insert) {
   RowTable& t = rows_[(size_t)row];
   if (t.mask == 0) {
     t.cols.assign(16, 0);
@@ -244,6 +245,10 @@ int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created) 
       return t.ids[p];
     }
     p = (p + 1) & (unsigned)t.mask;
+  }
+  if (!insert) {
+    created = false;
+    return 0;
   }
   created = true;
   c_row_.push_back(row);
@@ -328,7 +333,8 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
         const int n_size = n_sizes_[b_col_l - 1];
         const int c_nze = m_size * n_size;
         bool created = false;
-        const int c_blk_id = c_lookup_or_insert(a_row_l, b_col_l, c_nze, created);
+        const int c_blk_id = c_lookup_or_insert(a_row_l, b_col_l, c_nze, created, !keep_sparsity_);
+        if (c_blk_id == 0) continue;  // keep_sparsity: no new blocks
         const int offset = c_blk_p_[c_blk_id - 1];
         const int mapped_col = n_size < (int)n_map_.size() ? n_map_[n_size] : cfg_.n_stacks + 1;
         const int ws = stack_map_[((size_t)(mapped_row - 1) * w + (mapped_k - 1)) * w + (mapped_col - 1)];

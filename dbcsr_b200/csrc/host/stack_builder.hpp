@@ -53,8 +53,11 @@ class LocalMultiply {
 
   LocalMultiply(const Config& cfg, const std::vector<int>& m_sizes, const std::vector<int>& n_sizes, const std::vector<int>& k_sizes);
 
-  // Existing C blocks (beta != 0 / retain_sparsity flows): row, col, 1-based offsets; defines datasize.
+  // Existing C blocks (beta != 0 / retain_sparsity flows): row, col, 1-based offsets; defines datasize
+  // (the work matrix starts from the existing blocks: fill_hash_tables, src/mm/dbcsr_mm_csr.F:540-576).
   void preset_c(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize);
+  // retain_sparsity of dbcsr_multiply: products whose C block does not exist yet are skipped (src/mm/dbcsr_mm_csr.F:307)
+  void set_keep_sparsity(bool keep) { keep_sparsity_ = keep; }
 
   // One Cannon tick: lists must already be rec-sorted (use sort_panel); [a_first, a_last] = this thread's slice of the
   // left list (1-based, inclusive; the whole list for one thread).  Stacks still partially filled at the end are purged
@@ -91,7 +94,7 @@ class LocalMultiply {
   void sparse_multrec(int mi, int mf, int ni, int nf, int ki, int kf, int ai, int af, const Idx3* a, int bi, int bf, const Idx3* b);
   void csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int af, int bi, int bf, const Idx3* a, const Idx3* b);
   void flush_stacks(bool purge);
-  int c_lookup_or_insert(int row, int col, int nze, bool& created);
+  int c_lookup_or_insert(int row, int col, int nze, bool& created, bool insert = true);  // 0: absent and !insert
 
   Config cfg_;
   std::vector<int> m_sizes_, n_sizes_, k_sizes_;
@@ -113,6 +116,7 @@ class LocalMultiply {
   std::vector<RowTable> rows_;
   int datasize_ = 0;
   int64_t flop_ = 0;
+  bool keep_sparsity_ = false;
   // scratch for the CSR leaves
   std::vector<int> a_row_p_, b_row_p_, a_info_, b_info_, counts_;
   // on-the-fly filter (optional)

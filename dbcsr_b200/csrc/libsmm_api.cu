@@ -462,8 +462,35 @@ int c_calculate_norms(const double* mat, int nblks, const int* offsets, const in
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
   if (grid > max_grid) grid = max_grid;
-  smm::norms_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream_ptr)>>>(mat, nblks, offsets, nelems, norms);
+  smm::norms_kernel<float><<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream_ptr)>>>(mat, nblks, offsets, nelems, norms);
   if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int libsmm_acc_b200_block_norms_f64(const double* mat, int nblks, const int* offsets, const int* nelems, double* norms, void* stream_ptr) {
+  if (nblks <= 0) return 0;
+  if (stream_ptr == nullptr) return -2;
+  const int wpc = 8;
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::norms_kernel<double><<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream_ptr)>>>(mat, nblks, offsets, nelems, norms);
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int libsmm_acc_b200_gather_blocks(const double* src, double* dst, int nblks, const int* src_offsets, const int* dst_offsets,
+                                  const int* nelems, void* stream_ptr) {
+  if (nblks <= 0) return 0;
+  if (stream_ptr == nullptr) return -2;
+  const int wpc = 8;
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::gather_blocks_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream_ptr)>>>(src, dst, nblks, src_offsets, dst_offsets, nelems);
+  if (cudaPeekAtLastError() != cudaSuccess) return -32;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
 }

@@ -208,9 +208,11 @@ __global__ void transpose_kernel(const int* __restrict__ trs_stack, int nblks, d
   }
 }
 
-// norms[b] = sum_i mat[offsets[b] + i]^2 as float; one warp per block, grid-stride.
+// norms[b] = sum_i mat[offsets[b] + i]^2 (accumulated in double, stored as OUT = float for c_calculate_norms, double for the
+// final filter); one warp per block, grid-stride.
+template <typename OUT>
 __global__ void norms_kernel(const double* __restrict__ mat, int nblks, const int* __restrict__ offsets, const int* __restrict__ nelems,
-                             float* __restrict__ norms) {
+                             OUT* __restrict__ norms) {
   const int wpc = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
@@ -223,7 +225,21 @@ __global__ void norms_kernel(const double* __restrict__ mat, int nblks, const in
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) norms[b] = (float)s;
+    if (lane == 0) norms[b] = (OUT)s;
+  }
+}
+
+// dst[dst_off[b] + i] = src[src_off[b] + i], i < nelems[b]: compaction of the C blocks that survive the final filter (and any
+// other block-wise re-packing of a data area).  One warp per block, grid-stride; pure HBM streaming (16 B/element).
+__global__ void gather_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int nblks, const int* __restrict__ src_off,
+                                     const int* __restrict__ dst_off, const int* __restrict__ nelems) {
+  const int wpc = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
+    const double* __restrict__ p = src + __ldg(src_off + b);
+    double* __restrict__ q = dst + __ldg(dst_off + b);
+    const int ne = __ldg(nelems + b);
+    for (int i = lane; i < ne; i += 32) q[i] = __ldg(p + i);
   }
 }
 

@@ -37,6 +37,9 @@ def _L():
         L.dbcsr_b200_engine_set_filter.argtypes = [_vp, _vp]
         L.dbcsr_b200_row_max_epss.argtypes = [ctypes.c_double, _vp, _i, _vp]
         L.dbcsr_b200_row_max_epss.restype = None
+        L.dbcsr_b200_engine_preset_c.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
+        L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
+        L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
         L.dbcsr_b200_engine_reset.argtypes = [_vp]
         L.dbcsr_b200_engine_set_k_sizes.argtypes = [_vp, _vp, _i]
@@ -106,6 +109,17 @@ def row_max_epss(filter_eps, total_row_counts):
     return out
 
 
+def filter_index(filter_eps, norms2, rows, cols, blk_p, nelems):
+    """multrec_filtering, index part (see include/dbcsr_b200_host.h).  Returns (rows, cols, blk_p, nze_after) of the kept blocks."""
+    n2 = np.ascontiguousarray(norms2, dtype=np.float64)
+    r, c, p = (np.ascontiguousarray(x, dtype=np.int32).copy() for x in (rows, cols, blk_p))
+    ne = np.ascontiguousarray(nelems, dtype=np.int32)
+    nze = ctypes.c_longlong(0)
+    kept = _L().dbcsr_b200_filter_index(float(filter_eps), n2.ctypes.data, r.size, r.ctypes.data, c.ctypes.data, p.ctypes.data, ne.ctypes.data,
+                                        ctypes.byref(nze))
+    return r[:kept], c[:kept], p[:kept], int(nze.value)
+
+
 class Engine:
     """multrec + csr + sched + accdrv of `nthreads` host threads for one rank (see include/dbcsr_b200_host.h)."""
 
@@ -146,6 +160,23 @@ class Engine:
             rc = self.L.dbcsr_b200_engine_set_filter(self.h, r.ctypes.data)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_set_filter failed")
+
+    def preset_c(self, rows, cols, data=None, keep_sparsity=False):
+        """Existing C blocks (beta*C_old, or zeros when data is None) the product accumulates onto; keep_sparsity = retain_sparsity."""
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        d = None if data is None else np.ascontiguousarray(data, dtype=np.float64)
+        if d is not None and d.size != int((self.m[r - 1].astype(np.int64) * self.n[c - 1]).sum()):
+            raise ValueError("data must hold exactly the listed blocks")
+        rc = self.L.dbcsr_b200_engine_preset_c(self.h, r.ctypes.data, c.ctypes.data, r.size, None if d is None else d.ctypes.data,
+                                               1 if keep_sparsity else 0)
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_preset_c returned %d" % rc)
+
+    def filter_c(self, filter_eps):
+        rc = self.L.dbcsr_b200_engine_filter_c(self.h, float(filter_eps))
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_filter_c returned %d" % rc)
 
     def set_k_sizes(self, k_sizes):
         ks = np.ascontiguousarray(k_sizes, dtype=np.int32)

@@ -29,6 +29,7 @@ SMM_SYMBOLS = [
     "libsmm_acc_init", "libsmm_acc_finalize", "libsmm_acc_is_thread_safe", "libsmm_acc_transpose", "libsmm_acc_process",
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
+    "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
@@ -77,6 +78,8 @@ def load():
     L.libsmm_acc_transpose.argtypes = [_vp, _i, _i, _vp, _i, _i, _i, _i, _vp]
     L.libsmm_acc_process.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
     L.c_calculate_norms.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+    L.libsmm_acc_b200_block_norms_f64.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+    L.libsmm_acc_b200_gather_blocks.argtypes = [_vp, _vp, _i, _vp, _vp, _vp, _vp]
     L.libsmm_acc_b200_kernel_kind.argtypes = [_i, _i, _i, _i]
     L.libsmm_acc_b200_launch_count.restype = ctypes.c_longlong
     L.libsmm_acc_b200_pack_bf16.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp]
@@ -221,6 +224,12 @@ class Acc:
 
     def norms(self, mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream):
         _ck(self.L.c_calculate_norms(mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream), "c_calculate_norms")
+
+    def block_norms_f64(self, mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream):
+        _ck(self.L.libsmm_acc_b200_block_norms_f64(mat_ptr, nblks, offsets_ptr, nelems_ptr, norms_ptr, stream), "block_norms_f64")
+
+    def gather_blocks(self, src_ptr, dst_ptr, nblks, src_off_ptr, dst_off_ptr, nelems_ptr, stream):
+        _ck(self.L.libsmm_acc_b200_gather_blocks(src_ptr, dst_ptr, nblks, src_off_ptr, dst_off_ptr, nelems_ptr, stream), "gather_blocks")
 
     def pack_bf16(self, src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream):
         _ck(self.L.libsmm_acc_b200_pack_bf16(src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream), "libsmm_acc_b200_pack_bf16")

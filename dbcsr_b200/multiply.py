@@ -102,13 +102,18 @@ class DeviceMultiply:
                 d.free()
         return out
 
-    def multiply(self, a_list3, b_list3, filter_eps=None, total_row_counts=None):
+    def multiply(self, a_list3, b_list3, filter_eps=None, total_row_counts=None, c_preset=None, retain_sparsity=False):
         """One local multiply on the uploaded panels (stacks are built, ordered, uploaded and drained asynchronously).
         filter_eps: dbcsr_multiply's on-the-fly filter; total_row_counts = A blocks per block row over the whole process row
-        (default: of this panel, i.e. a 1-column process grid)."""
+        (default: of this panel, i.e. a 1-column process grid).
+        c_preset = (rows, cols, data): existing C blocks, data already scaled by beta (C = A*B + beta*C_old); with
+        retain_sparsity only products landing in those blocks are computed."""
         if not self.first:
             self.engine.reset()
         self.first = False
+        if c_preset is not None:
+            self.engine.preset_c(c_preset[0], c_preset[1], c_preset[2], keep_sparsity=retain_sparsity)
+            self.h2d_bytes += 0 if c_preset[2] is None else 8 * int(np.asarray(c_preset[2]).size)
         self.engine.wait_event(self.panels_ready)
         if filter_eps is None:
             self.engine.set_filter(None)
@@ -121,6 +126,12 @@ class DeviceMultiply:
         self.b_norms = self.panel_norms(b_list3, self.k_sizes, self.n_sizes, self.d_b)
         self.engine.set_filter(host.row_max_epss(filter_eps, total_row_counts))
         self.engine.multiply(a, self.d_a.ptr, b_list3, self.d_b.ptr, a_norms=self.a_norms, b_norms=self.b_norms)
+
+    def filter_c(self, filter_eps):
+        """Final filter of the product on the device before the download (multrec_filtering, src/mm/dbcsr_mm_multrec.F:700-758):
+        blocks with sum(x^2) < filter_eps^2 are dropped, the survivors are packed contiguously (less PCIe traffic)."""
+        assert getattr(self, "early", None) is None, "early per-thread D2H and the final filter exclude each other"
+        self.engine.filter_c(filter_eps)
 
     def set_result_buffers(self, out_arrays):
         """Pooled (pinned) host buffers for C, one per thread, each at least engine.c_capacity(t) elements: from now on every

@@ -54,6 +54,14 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
  * offsets 0-based, all pointers device memory. */
 int c_calculate_norms(const double* mat, int nblks, const int* offsets, const int* nelems, float* norms, void* stream_ptr);
 
+/* Extensions for the product's finalize step on the device (the reference does both on the host after the D2H of C):
+ * block_norms_f64: norms[b] = sum_i mat[offsets[b]+i]^2 in double - the quantity multrec_filtering compares with filter_eps^2
+ *   (src/mm/dbcsr_mm_multrec.F:700-758: DDOT(blk,blk) >= filter_eps**2 keeps the block).  0-based offsets like c_calculate_norms.
+ * gather_blocks: dst[dst_offsets[b]+i] = src[src_offsets[b]+i], i < nelems[b]; src and dst must not overlap. */
+int libsmm_acc_b200_block_norms_f64(const double* mat, int nblks, const int* offsets, const int* nelems, double* norms, void* stream_ptr);
+int libsmm_acc_b200_gather_blocks(const double* src, double* dst, int nblks, const int* src_offsets, const int* dst_offsets,
+  const int* nelems, void* stream_ptr);
+
 /* Declared by DBCSR (interface in src/core/dbcsr_lib.F:111-116) but never defined by the reference; exported for safety. */
 int libsmm_acc_gpu_warp_size(void);
 

@@ -69,6 +69,25 @@ void dbcsr_b200_row_max_epss(double filter_eps, const int* total_row_counts, int
 int dbcsr_b200_engine_set_filter(dbcsr_b200_engine_t* e, const float* row_max_epss);
 int dbcsr_b200_engine_multiply_filtered(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
   const int* b_list3, int nb, const void* b_dev, const float* b_norms);
+/* beta != 0 / retain_sparsity flows of dbcsr_multiply (src/mm/dbcsr_mm.F:706-709 scales C by beta first; the work matrices then start
+ * from the existing blocks, src/mm/dbcsr_mm_csr.F:526-576).  rows/cols: block coordinates (1-based) of the existing C blocks;
+ * host_data: their elements (col-major blocks, concatenated in list order, ALREADY scaled by beta) or NULL for zeros.
+ * Block i is placed in the work area of the thread owning its block row, in list order; with LAUNCH its data is uploaded so that
+ * the stack kernels accumulate onto it (the reference keeps a zeroed device buffer and block_adds on the host afterwards,
+ * src/mm/dbcsr_mm_accdrv.F:340-362).  keep_sparsity != 0: products whose C block is not in the list are skipped
+ * (src/mm/dbcsr_mm_csr.F:307).  Call after create/reset and before the first tick.  Both settings end with the next reset. */
+int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const int* cols, int nblks, const double* host_data,
+  int keep_sparsity);
+/* Final filter of the product, multrec_filtering (src/mm/dbcsr_mm_multrec.F:700-758), index part: block b is kept iff blk_p[b] != 0,
+ * nelems[b] != 0 and norms2[b] (= sum of squares of its elements, double) >= filter_eps^2.  Kept entries are moved to the front of
+ * rows/cols/blk_p in order (blk_p values unchanged).  Returns the number kept; *nze_after = their element count. */
+int dbcsr_b200_filter_index(double filter_eps, const double* norms2, int nblks, int* rows, int* cols, int* blk_p, const int* nelems,
+  long long* nze_after);
+/* The same filter run on the device BEFORE the download (LAUNCH engines, after the last tick): block norms by
+ * libsmm_acc_b200_block_norms_f64, index compaction on the host, surviving blocks gathered into a contiguous device area in index
+ * order.  Afterwards the c_* accessors, c_dev and c_to_host(_async) describe the filtered product (blk_p = compact offsets);
+ * the next multiply/reset returns to the work matrices.  Not applied by DBCSR when retain_sparsity is set. */
+int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps);
 /* block sizes of the contraction index of the NEXT panels (Cannon ticks bring different k-slices); the stack map built at
  * creation (from the k_sizes given there: use the global right-matrix row block sizes) is kept */
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk);

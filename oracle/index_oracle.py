@@ -9,6 +9,9 @@ product's C++ stack builder (dbcsr_b200/csrc/host) entry by entry on small cases
   build_csr_index              src/mm/dbcsr_mm_csr.F:741-795
   dbcsr_mm_csr_multiply_low    src/mm/dbcsr_mm_csr.F:178-359
   dbcsr_mm_csr_init stack map  src/mm/dbcsr_mm_csr.F:361-538
+  fill_hash_tables (preset C)  src/mm/dbcsr_mm_csr.F:540-576
+  multrec_filtering            src/mm/dbcsr_mm_multrec.F:700-758
+  row_max_epss, norm filter    src/mm/dbcsr_mm_cannon.F:1098-1107, src/mm/dbcsr_mm_csr.F:270-278
   flush_stacks / purge         src/mm/dbcsr_mm_csr.F:696-739
   map_most_common              src/dist/dbcsr_dist_util.F:753-812
   stack_sort / stack_binning   src/mm/dbcsr_mm_accdrv.F:364-423
@@ -133,6 +136,27 @@ def block_norms(list3, row_sizes, col_sizes, data):
     return out
 
 
+def multrec_filtering(filter_eps, rowi, coli, blkp, rbs, cbs, data):
+    """multrec_filtering_d, src/mm/dbcsr_mm_multrec.F:700-758: keep block iff DDOT(blk, blk) >= filter_eps**2 (double); kept
+    entries move to the front in order, blk_p unchanged.  Returns (rowi, coli, blkp, nze) of the kept blocks and the norms used."""
+    eps_opt = float(filter_eps) ** 2
+    out_r, out_c, out_p, nze, norms = [], [], [], 0, []
+    for r, c, bp in zip(rowi, coli, blkp):
+        blk_nze = int(rbs[r - 1]) * int(cbs[c - 1])
+        if bp == 0 or blk_nze == 0:
+            norms.append(0.0)
+            continue
+        blk = np.asarray(data[bp - 1:bp - 1 + blk_nze], dtype=np.float64)
+        nrm = float(np.dot(blk, blk))
+        norms.append(nrm)
+        if nrm >= eps_opt:
+            out_r.append(int(r))
+            out_c.append(int(c))
+            out_p.append(int(bp))
+            nze += blk_nze
+    return out_r, out_c, out_p, nze, norms
+
+
 def build_csr_index(mi, mf, ai, af, lst):
     """src/mm/dbcsr_mm_csr.F:741-795. Returns row_p dict-like list (offset by mi) and blk_info list of (col, blk_p)
     (plus the list position of each CSR entry as a third component, which is how csr_norms(:) follows list_norms(:))."""
@@ -182,6 +206,18 @@ class LocalMultiplyOracle:
         self.row_eps = None
         self.a_norms = self.b_norms = None
         self.skipped = 0
+        self.keep_sparsity = False
+
+    def preset_c(self, rows, cols, keep_sparsity=False):
+        """Work matrix starts from existing C blocks in list order (fill_hash_tables, src/mm/dbcsr_mm_csr.F:540-576; offsets are
+        the running sum of the block sizes); keep_sparsity = retain_sparsity of dbcsr_multiply (src/mm/dbcsr_mm_csr.F:307)."""
+        for r, c in zip(rows, cols):
+            self.c_row_i.append(int(r))
+            self.c_col_i.append(int(c))
+            self.c_blk_p.append(self.datasize + 1)
+            self.datasize += int(self.m_sizes[r - 1]) * int(self.n_sizes[c - 1])
+            self.c_hash[(int(r), int(c))] = len(self.c_blk_p)
+        self.keep_sparsity = keep_sparsity
 
     # src/mm/dbcsr_mm_csr.F:404-525
     def _init_stack_map(self):
@@ -286,6 +322,8 @@ class LocalMultiplyOracle:
                     if c_blk_id > 0:
                         offset = self.c_blk_p[c_blk_id - 1]
                     else:
+                        if self.keep_sparsity:
+                            continue
                         offset = self.datasize + 1
                         self.datasize += c_nze
                         self.c_row_i.append(a_row_l)

@@ -226,3 +226,97 @@ def test_on_the_fly_filter(acc, nthreads):
     num = sum(float(((got[k] - exp[k]) ** 2).sum()) for k in exp)
     den = sum(float((exp[k] ** 2).sum()) for k in exp)
     assert np.sqrt(num / den) <= 1e-10
+
+
+def _preset_case(seed):
+    rng = np.random.default_rng(seed)
+    sizes = [5, 13, 23]
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (40, 36, 44))
+    A = workload.random_panel(ms, ks, 0.25, rng)
+    B = workload.random_panel(ks, ns, 0.25, rng)
+    C0 = workload.random_panel(ms, ns, 0.3, rng)
+    return ms, ns, ks, A, B, C0
+
+
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_beta_flow_accumulates_onto_existing_c(acc, nthreads):
+    """C = A*B + beta*C_old (dbcsr_multiply with beta != 0): the existing blocks are uploaded into the device work area and the
+    stack kernels accumulate onto them (reference: zeroed device buffer + host block_add, src/mm/dbcsr_mm_accdrv.F:340-362)."""
+    ms, ns, ks, A, B, C0 = _preset_case(5)
+    beta = -0.75
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=400))
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3(), c_preset=(C0.rows, C0.cols, beta * C0.data))
+        prod = dm.download_c()
+    finally:
+        dm.close()
+    C_in = orc.BlockMatrix(ms, ns, C0.rows, C0.cols, data=beta * C0.data)
+    Cref = orc.multiply_blocks(to_oracle(A), to_oracle(B), C_in=C_in)
+    got = prod.blocks()
+    assert set(got.keys()) == set(zip(Cref.rows.tolist(), Cref.cols.tolist()))
+    num = den = 0.0
+    for (r, c, o) in zip(Cref.rows, Cref.cols, Cref.offsets):
+        m, n = int(ms[r - 1]), int(ns[c - 1])
+        ref = Cref.data[o:o + m * n].reshape(n, m).T
+        num += float(((got[(int(r), int(c))] - ref) ** 2).sum())
+        den += float((ref ** 2).sum())
+    assert np.sqrt(num / den) <= 1e-10
+
+
+def test_retain_sparsity(acc):
+    """retain_sparsity: only the listed C blocks exist afterwards; each equals beta*C_old + sum of its products."""
+    ms, ns, ks, A, B, C0 = _preset_case(6)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=2, cfg=host.default_cfg(mm_stack_size=400))
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3(), c_preset=(C0.rows, C0.cols, C0.data), retain_sparsity=True)
+        prod = dm.download_c()
+    finally:
+        dm.close()
+    Cfull = orc.multiply_blocks(to_oracle(A), to_oracle(B), C_in=orc.BlockMatrix(ms, ns, C0.rows, C0.cols, data=C0.data))
+    full = {(int(r), int(c)): Cfull.data[o:o + int(ms[r - 1]) * int(ns[c - 1])].reshape(int(ns[c - 1]), int(ms[r - 1])).T
+            for r, c, o in zip(Cfull.rows, Cfull.cols, Cfull.offsets)}
+    got = prod.blocks()
+    listed = set(zip(C0.rows.tolist(), C0.cols.tolist()))
+    assert set(got.keys()) == listed and len(listed) < len(full)
+    num = sum(float(((got[k] - full[k]) ** 2).sum()) for k in listed)
+    den = sum(float((full[k] ** 2).sum()) for k in listed)
+    assert np.sqrt(num / den) <= 1e-10
+
+
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_final_filter_on_device(acc, nthreads):
+    """multrec_filtering on the device before the download: same surviving block set as the restated reference filter applied
+    to the unfiltered product, data of the survivors untouched and packed contiguously in index order."""
+    rng = np.random.default_rng(9)
+    sizes = [5, 13, 23]
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (40, 36, 44))
+    A = workload.random_panel(ms, ks, 0.2, rng)
+    B = workload.random_panel(ks, ns, 0.2, rng)
+    for i in range(A.nblks):  # row-dependent magnitudes => C block norms spread over many decades
+        A.block(i)[...] *= 10.0 ** (-6.0 * (A.rows[i] % 7) / 6.0)
+    eps = 1e-2
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=400))
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        full = dm.download_c()
+        dm.filter_c(eps)
+        filt = dm.download_c()
+        d2h_full, d2h_filt = sum(8 * p[3].size for p in full.parts), dm.d2h_bytes
+    finally:
+        dm.close()
+    assert len(filt.parts) == len(full.parts) == nthreads
+    kept_total = 0
+    for (rows, cols, blk_p, data), (frows, fcols, fblk_p, fdata) in zip(full.parts, filt.parts):
+        er, ec, ep, enze, norms = io.multrec_filtering(eps, rows, cols, blk_p, ms, ns, data)
+        # blocks whose norm sits within rounding of the threshold may legitimately differ (device summation order)
+        assert all(abs(n2 - eps * eps) > 1e-9 * eps * eps for n2 in norms)
+        assert frows.tolist() == er and fcols.tolist() == ec and fdata.size == enze
+        nel = ms[frows - 1] * ns[fcols - 1]
+        assert np.array_equal(fblk_p, 1 + np.concatenate([[0], np.cumsum(nel)[:-1]]).astype(np.int64)) if frows.size else True
+        for j in range(frows.size):
+            assert np.array_equal(fdata[fblk_p[j] - 1:fblk_p[j] - 1 + nel[j]], data[ep[j] - 1:ep[j] - 1 + nel[j]])
+        kept_total += frows.size
+    assert 0 < kept_total < full.nblks and d2h_filt < d2h_full

@@ -294,3 +294,88 @@ def test_filter_keeps_exactly_the_products_above_threshold_multithreaded():
         e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
         assert prod(e) == sorted(everything)
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------- beta != 0, retain_sparsity, final filter
+@pytest.mark.parametrize("keep", [False, True])
+def test_preset_c_and_retain_sparsity_match_index_oracle(keep):
+    """Work matrix starting from existing C blocks (beta != 0) and retain_sparsity: same stacks and C index as the restatement
+    of fill_hash_tables + dbcsr_mm_csr_multiply_low (src/mm/dbcsr_mm_csr.F:300-323,540-576)."""
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(40, 36, 44, 0.25, 0.25, [5, 13, 23], seed=31)
+    rng = np.random.default_rng(3)
+    pres = np.nonzero(rng.random((40, 36)) < 0.3)
+    c_rows, c_cols = pres[0] + 1, pres[1] + 1
+    ora = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=300, multrec_limit=64)
+    ora.preset_c(c_rows, c_cols, keep_sparsity=keep)
+    exp = ora.multiply(A.index_list(), B.index_list())
+    eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=300, multrec_limit=64))
+    eng.preset_c(c_rows, c_cols, keep_sparsity=keep)
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    got = eng.stacks()
+    assert len(got) == len(exp) and len(got) > 0
+    for g, x in zip(got, exp):
+        assert g["stack_id"] == x["stack_id"] and np.array_equal(g["host"], x["host"]) and np.array_equal(g["dev"], x["dev"])
+    rows, cols, blk_p, datasize = eng.c_index(0)
+    assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p and datasize == ora.datasize
+    assert eng.flop() == ora.flop
+    if keep:  # no new blocks, every product lands in a listed block
+        assert rows.size == c_rows.size
+        listed = set(zip(c_rows.tolist(), c_cols.tolist()))
+        assert all((int(rows[r[6] - 1]), int(cols[r[6] - 1])) in listed for s in got for r in s["host"])
+    else:
+        assert rows.size > c_rows.size and list(rows[:c_rows.size]) == c_rows.tolist()
+    with pytest.raises(Exception):  # only before the first tick
+        eng.preset_c(c_rows, c_cols)
+    eng.reset()  # both settings end with the multiply
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    ora2 = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=300, multrec_limit=64)
+    ora2.multiply(A.index_list(), B.index_list())
+    assert list(eng.c_index(0)[0]) == ora2.c_row_i and eng.flop() == ora2.flop
+    eng.close()
+
+
+def test_preset_c_multithreaded_blocks_go_to_row_owners():
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(50, 30, 40, 0.25, 0.25, [5, 13], seed=41)
+    rng = np.random.default_rng(4)
+    pres = np.nonzero(rng.random((50, 30)) < 0.4)
+    perm = rng.permutation(pres[0].size)  # arbitrary list order
+    c_rows, c_cols = pres[0][perm] + 1, pres[1][perm] + 1
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    e1 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, cfg=host.default_cfg(mm_stack_size=300))
+    e1.preset_c(c_rows, c_cols, keep_sparsity=True)
+    e1.multiply(a_l, None, b_l, None)
+    e3 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=3, cfg=host.default_cfg(mm_stack_size=300, row_chunks=2))
+    e3.preset_c(c_rows, c_cols, keep_sparsity=True)
+    e3.multiply(a_l, None, b_l, None)
+    prod = lambda eng: sorted((int(r[3]), int(r[4])) for s in eng.stacks() for r in s["host"])
+    assert prod(e1) == prod(e3) and e1.flop() == e3.flop()
+    seen, total = set(), 0
+    for t in range(3):
+        rows, cols, blk_p, ds = e3.c_index(t)
+        total += rows.size
+        assert not (set(rows.tolist()) & seen)
+        seen |= set(rows.tolist())
+        sizes = m_sizes[rows - 1] * n_sizes[cols - 1]
+        assert np.array_equal(blk_p, 1 + np.concatenate([[0], np.cumsum(sizes)[:-1]])) and ds == int(sizes.sum())
+    assert total == c_rows.size
+    e1.close()
+    e3.close()
+
+
+def test_filter_index_matches_multrec_filtering_restatement():
+    rng = np.random.default_rng(8)
+    rbs, cbs = rng.choice([5, 13, 23], 30), rng.choice([5, 13, 23], 25)
+    rows, cols = (x + 1 for x in np.nonzero(rng.random((30, 25)) < 0.5))
+    perm = rng.permutation(rows.size)
+    rows, cols = rows[perm], cols[perm]
+    nel = rbs[rows - 1] * cbs[cols - 1]
+    blk_p = 1 + np.concatenate([[0], np.cumsum(nel)[:-1]])
+    data = rng.standard_normal(int(nel.sum()))
+    for i in range(rows.size):
+        data[blk_p[i] - 1:blk_p[i] - 1 + nel[i]] *= 10.0 ** rng.uniform(-6, 0)
+    blk_p[5] = 0  # deleted block: skipped
+    for eps in (0.0, 1e-4, 1e-2, 1.0, 1e3):
+        er, ec, ep, enze, norms = io.multrec_filtering(eps, rows, cols, blk_p, rbs, cbs, data)
+        gr, gc, gp, gnze = host.filter_index(eps, norms, rows, cols, blk_p, nel)
+        assert gr.tolist() == er and gc.tolist() == ec and gp.tolist() == ep and gnze == enze
+    assert len(io.multrec_filtering(1e-2, rows, cols, blk_p, rbs, cbs, data)[0]) not in (0, rows.size - 1)
