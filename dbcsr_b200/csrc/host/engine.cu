@@ -85,6 +85,8 @@ struct dbcsr_b200_engine {
   // on-the-fly filter: per-row thresholds, norms permuted like the sorted lists
   std::vector<float> row_eps, a_norm_sorted, b_norm_sorted;
   std::vector<int> blk_tmp;
+  // optional: events[c] = "the A rows of chunk c are on the device" (pipelined panel upload); consumed by the next multiply
+  std::vector<void*> chunk_events;
 };
 
 extern "C" {
@@ -328,7 +330,13 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
         }
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
+      int slice_no = 0;
       for (const auto& sl : ts.slices) {
+        const int chunk = t + (slice_no++) * (int)e->th.size();
+        if ((e->mode & DBCSR_B200_LAUNCH) && chunk < (int)e->chunk_events.size() && e->chunk_events[(size_t)chunk] != nullptr && ts.rc == 0) {
+          // the stacks of this row chunk read A blocks that may still be in flight: order them behind the chunk's upload
+          if (c_dbcsr_acc_stream_wait_event(ts.stream, e->chunk_events[(size_t)chunk]) != 0) ts.rc = -49;
+        }
         const size_t ds0 = (size_t)ts.mm->datasize();
         ts.mm->multiply(e->a_sorted.data(), sl.first, sl.second, e->b_sorted.data(), nb, dispatch,  // ends with a purge
                         filter ? e->a_norm_sorted.data() : nullptr, filter ? e->b_norm_sorted.data() : nullptr);
@@ -348,6 +356,7 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
     });
   }
   for (auto& w : workers) w.join();
+  e->chunk_events.clear();  // one-shot
   for (auto& ts : e->th)
     if (ts.rc != 0) return ts.rc;
   return 0;
@@ -559,6 +568,24 @@ int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
     if (ts.stream != nullptr) c_dbcsr_acc_stream_sync(ts.stream);
   release();
   return rc;
+}
+
+int dbcsr_b200_engine_nchunks(const dbcsr_b200_engine_t* e) {
+  return e == nullptr ? 0 : (int)e->th.size() * std::max(1, e->cfg.row_chunks);
+}
+
+int dbcsr_b200_engine_chunk_rows(const dbcsr_b200_engine_t* e, int chunk, int* row_lo, int* row_hi) {
+  const int nchunks = dbcsr_b200_engine_nchunks(e);
+  if (e == nullptr || chunk < 0 || chunk >= nchunks) return -1;
+  *row_lo = (int)(((long long)e->nrows * chunk) / nchunks);        // chunk = block rows (row_lo, row_hi], 1-based
+  *row_hi = (int)(((long long)e->nrows * (chunk + 1)) / nchunks);
+  return 0;
+}
+
+int dbcsr_b200_engine_set_chunk_events(dbcsr_b200_engine_t* e, void* const* events, int nevents) {
+  if (e == nullptr || nevents < 0 || nevents > dbcsr_b200_engine_nchunks(e)) return -1;
+  e->chunk_events.assign(events, events + nevents);
+  return 0;
 }
 
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk) {

@@ -37,6 +37,9 @@ def _L():
         L.dbcsr_b200_engine_set_filter.argtypes = [_vp, _vp]
         L.dbcsr_b200_row_max_epss.argtypes = [ctypes.c_double, _vp, _i, _vp]
         L.dbcsr_b200_row_max_epss.restype = None
+        L.dbcsr_b200_engine_nchunks.argtypes = [_vp]
+        L.dbcsr_b200_engine_chunk_rows.argtypes = [_vp, _i, ip, ip]
+        L.dbcsr_b200_engine_set_chunk_events.argtypes = [_vp, _vp, _i]
         L.dbcsr_b200_engine_preset_c.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
         L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
@@ -160,6 +163,23 @@ class Engine:
             rc = self.L.dbcsr_b200_engine_set_filter(self.h, r.ctypes.data)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_set_filter failed")
+
+    @property
+    def nchunks(self):
+        return self.L.dbcsr_b200_engine_nchunks(self.h)
+
+    def chunk_rows(self, chunk):
+        """Block rows (row_lo, row_hi] (1-based) of row chunk `chunk`; thread chunk % nthreads owns it."""
+        lo, hi = _i(0), _i(0)
+        if self.L.dbcsr_b200_engine_chunk_rows(self.h, chunk, ctypes.byref(lo), ctypes.byref(hi)) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_chunk_rows failed")
+        return lo.value, hi.value
+
+    def set_chunk_events(self, events):
+        """events[c]: acc event recorded behind the upload of chunk c's A rows (None = no wait); used by the next multiply."""
+        arr = (_vp * len(events))(*[e if e else None for e in events])
+        if self.L.dbcsr_b200_engine_set_chunk_events(self.h, arr, len(events)) != 0:
+            raise acclib.AccError("dbcsr_b200_engine_set_chunk_events failed")
 
     def preset_c(self, rows, cols, data=None, keep_sparsity=False):
         """Existing C blocks (beta*C_old, or zeros when data is None) the product accumulates onto; keep_sparsity = retain_sparsity."""

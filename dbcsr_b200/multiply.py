@@ -62,19 +62,44 @@ class DeviceMultiply:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def upload_panels(self, a_data, b_data, b_list3):
+    def upload_panels(self, a_data, b_data, b_list3, a_list3=None):
         """host2dev of both panels + acc_transpose_blocks of the right one, all asynchronous on the copy stream; the event
         `panels_ready` orders the stack kernels behind them (the reference synchronises the whole device here,
-        src/mm/dbcsr_mm_cannon.F:1642-1646; an event lets the host build stacks while the panels are still in flight)."""
+        src/mm/dbcsr_mm_cannon.F:1642-1646; an event lets the host build stacks while the panels are still in flight).
+        With a_list3 (BCSR-ordered left list, data offsets ascending in list order) the upload is pipelined: right panel and its
+        transpose first (`panels_ready`), then the left panel in the engine's block-row chunks, one event per chunk - the stacks
+        of the first rows start (and their C blocks travel back) while later rows are still going up."""
         acc = self.acc
-        acc.h2d(a_data, self.d_a, self.copy_stream)
-        acc.h2d(b_data, self.d_b, self.copy_stream)
         b = np.ascontiguousarray(b_list3, dtype=np.int32).reshape(-1, 3)
+        pipelined = a_list3 is not None and self.engine.nchunks > 1
+        if not pipelined:
+            acc.h2d(a_data, self.d_a, self.copy_stream)
+        acc.h2d(b_data, self.d_b, self.copy_stream)
         rc = acc.L.dbcsr_b200_transpose_panel(b.ctypes.data, b.shape[0], self.k_sizes.ctypes.data, self.n_sizes.ctypes.data, self.d_b.ptr,
                                               self.trs_h.ptr, self.trs_d.ptr, self.copy_stream)
         if rc != 0:
             raise acclib.AccError("transpose_panel returned %d" % rc)
         acc.event_record(self.panels_ready, self.copy_stream)
+        self._chunk_events_armed = None
+        if pipelined:
+            a = np.ascontiguousarray(a_list3, dtype=np.int32).reshape(-1, 3)
+            nch = self.engine.nchunks
+            if getattr(self, "_chunk_events", None) is None or len(self._chunk_events) != nch:
+                self._chunk_events = [acc.event_create() for _ in range(nch)]
+            # element range of every chunk in the left data area: blocks of rows (row_lo, row_hi] are contiguous in BCSR order
+            row_hi = np.array([self.engine.chunk_rows(c)[1] for c in range(nch)], dtype=np.int64)
+            blk_end = np.searchsorted(a[:, 0], row_hi, side="right")  # first list position beyond the chunk
+            ends = np.where(blk_end < a.shape[0], a[np.minimum(blk_end, a.shape[0] - 1), 2].astype(np.int64) - 1, a_data.size) \
+                if a.shape[0] else np.zeros(nch, dtype=np.int64)
+            ends[-1] = a_data.size
+            lo = 0
+            for c in range(nch):
+                hi = int(ends[c])
+                if hi > lo:
+                    acc.h2d(a_data[lo:hi], self.d_a, self.copy_stream, offset_bytes=8 * lo)
+                    lo = hi
+                acc.event_record(self._chunk_events[c], self.copy_stream)
+            self._chunk_events_armed = list(self._chunk_events)
         self._keep = (a_data, b_data, b)  # host buffers must stay alive until the copies ran
         self.h2d_bytes = a_data.nbytes + b_data.nbytes + 4 * b.shape[0]
 
@@ -115,6 +140,9 @@ class DeviceMultiply:
             self.engine.preset_c(c_preset[0], c_preset[1], c_preset[2], keep_sparsity=retain_sparsity)
             self.h2d_bytes += 0 if c_preset[2] is None else 8 * int(np.asarray(c_preset[2]).size)
         self.engine.wait_event(self.panels_ready)
+        if getattr(self, "_chunk_events_armed", None):
+            self.engine.set_chunk_events(self._chunk_events_armed)
+            self._chunk_events_armed = None
         if filter_eps is None:
             self.engine.set_filter(None)
             self.engine.multiply(a_list3, self.d_a.ptr, b_list3, self.d_b.ptr)
@@ -169,14 +197,16 @@ class DeviceMultiply:
             d.free()
         self.trs_h.free()
         self.acc.event_destroy(self.panels_ready)
+        for ev in getattr(self, "_chunk_events", None) or []:
+            self.acc.event_destroy(ev)
         self.acc.stream_destroy(self.copy_stream)
 
 
-def multiply(acc, A, B, m_sizes, n_sizes, k_sizes, nthreads=1, cfg=None):
+def multiply(acc, A, B, m_sizes, n_sizes, k_sizes, nthreads=1, cfg=None, pipelined=False):
     """Convenience one-shot: C = A*B for host panels A, B (dbcsr_b200.workload.Panel-like: .data, .list3())."""
     dm = DeviceMultiply(acc, m_sizes, n_sizes, k_sizes, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg)
     try:
-        dm.upload_panels(A.data, B.data, B.list3())
+        dm.upload_panels(A.data, B.data, B.list3(), a_list3=A.list3() if pipelined else None)
         dm.multiply(A.list3(), B.list3())
         return dm.download_c(), dm.engine.flop()
     finally:

@@ -69,6 +69,14 @@ void dbcsr_b200_row_max_epss(double filter_eps, const int* total_row_counts, int
 int dbcsr_b200_engine_set_filter(dbcsr_b200_engine_t* e, const float* row_max_epss);
 int dbcsr_b200_engine_multiply_filtered(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
   const int* b_list3, int nb, const void* b_dev, const float* b_norms);
+/* Pipelined panel upload: the left panel can be uploaded in block-row pieces while earlier rows are already being multiplied and
+ * their C blocks downloaded (PCIe is full duplex).  The engine's static row ownership: chunk c = block rows (row_lo, row_hi]
+ * (1-based, dbcsr_b200_engine_chunk_rows), c < nchunks = nthreads * row_chunks, processed by thread c mod nthreads in chunk order.
+ * events[c] (acc events, NULL = no wait): recorded by the caller behind the upload of the A blocks of chunk c; the next
+ * dbcsr_b200_engine_multiply orders the stacks of chunk c behind events[c] and then forgets the list (single-tick multiplies). */
+int dbcsr_b200_engine_nchunks(const dbcsr_b200_engine_t* e);
+int dbcsr_b200_engine_chunk_rows(const dbcsr_b200_engine_t* e, int chunk, int* row_lo, int* row_hi);
+int dbcsr_b200_engine_set_chunk_events(dbcsr_b200_engine_t* e, void* const* events, int nevents);
 /* beta != 0 / retain_sparsity flows of dbcsr_multiply (src/mm/dbcsr_mm.F:706-709 scales C by beta first; the work matrices then start
  * from the existing blocks, src/mm/dbcsr_mm_csr.F:526-576).  rows/cols: block coordinates (1-based) of the existing C blocks;
  * host_data: their elements (col-major blocks, concatenated in list order, ALREADY scaled by beta) or NULL for zeros.

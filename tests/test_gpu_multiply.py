@@ -320,3 +320,17 @@ def test_final_filter_on_device(acc, nthreads):
             assert np.array_equal(fdata[fblk_p[j] - 1:fblk_p[j] - 1 + nel[j]], data[ep[j] - 1:ep[j] - 1 + nel[j]])
         kept_total += frows.size
     assert 0 < kept_total < full.nblks and d2h_filt < d2h_full
+
+
+@pytest.mark.parametrize("nthreads,row_chunks", [(1, 1), (3, 2), (4, 4), (7, 3)])
+def test_pipelined_left_panel_upload(acc, nthreads, row_chunks):
+    """Left panel uploaded in the engine's block-row chunks with one event per chunk (stacks of a chunk wait only for their own
+    rows): same product as the one-shot upload, including chunks without any A block and more chunks than block rows."""
+    rng = np.random.default_rng(123 + nthreads)
+    sizes = [5, 13, 23]
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (20 if nthreads == 7 else 48, 40, 56))
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    cfg = host.default_cfg(mm_stack_size=500, row_chunks=row_chunks)
+    prod, flop = multiply(acc, A, B, ms, ns, ks, nthreads=nthreads, cfg=cfg, pipelined=True)
+    check_against_oracle(A, B, prod, ms, ns)
