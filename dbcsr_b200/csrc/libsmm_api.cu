@@ -20,8 +20,22 @@
 #include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
 #include "smm_launch.h"
+#include "smm_tune.h"
+
+namespace smm {
+Tunables g_tune;
+}
 
 namespace {
+
+// environment defaults of the run-time knobs (smm_tune.h), read once when the library is loaded
+const bool g_tune_env_read = [] {
+  if (const char* e = getenv("DBCSR_B200_BALANCE")) smm::g_tune.balance.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_CHUNK")) smm::g_tune.chunk.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_ALIGN")) smm::g_tune.align.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_VARIANT")) smm::g_tune.variant.store(atoi(e));
+  return true;
+}();
 
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_num_sms{0};
@@ -314,6 +328,41 @@ c_dbcsr_acc_bool_t libsmm_acc_is_thread_safe(void) { return 1; }
 int libsmm_acc_gpu_warp_size(void) { return 32; }
 long long libsmm_acc_b200_launch_count(void) { return g_launches.load(); }
 const char* libsmm_acc_b200_version(void) { return "dbcsr_acc_b200 r1 (sm_100a, DMMA.8x8x4 + TMA bulk staging)"; }
+
+// Run-time knobs of the FP64 stack kernels (smm_tune.h).  Names: "balance", "align", "chunk", "variant", "trace_first", "trace_count",
+// "seq" (launch sequence counter).  Returns 0, or -1 for an unknown name.  libsmm_acc_b200_set_trace installs a device buffer of
+// trace_count * 4096 * 128 64-bit words (NULL switches tracing off); only TRACE kernel variants of experiment builds write to it.
+int libsmm_acc_b200_set_tunable(const char* name, long long value) {
+  if (name == nullptr) return -1;
+  if (strcmp(name, "balance") == 0) smm::g_tune.balance.store((int)value);
+  else if (strcmp(name, "chunk") == 0) smm::g_tune.chunk.store((int)value);
+  else if (strcmp(name, "align") == 0) smm::g_tune.align.store((int)value);
+  else if (strcmp(name, "variant") == 0) smm::g_tune.variant.store((int)value);
+  else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
+  else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
+  else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
+  else return -1;
+  return 0;
+}
+long long libsmm_acc_b200_get_tunable(const char* name) {
+  if (name == nullptr) return -1;
+  if (strcmp(name, "balance") == 0) return smm::g_tune.balance.load();
+  if (strcmp(name, "chunk") == 0) return smm::g_tune.chunk.load();
+  if (strcmp(name, "align") == 0) return smm::g_tune.align.load();
+  if (strcmp(name, "variant") == 0) return smm::g_tune.variant.load();
+  if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
+  if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
+  if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
+  if (strcmp(name, "experiment") == 0) {
+#if defined(SMM_EXPERIMENT)
+    return 1;
+#else
+    return 0;
+#endif
+  }
+  return -1;
+}
+void libsmm_acc_b200_set_trace(void* dev_words) { smm::g_tune.trace.store(static_cast<unsigned long long*>(dev_words)); }
 
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
 

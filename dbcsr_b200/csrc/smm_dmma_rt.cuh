@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(RT_WPC * 32) smm_dmma_rt_kernel(const int* __r
     const uint64_t ga = reinterpret_cast<uint64_t>(a_data + (p.x - 1));
     const uint64_t gb = reinterpret_cast<uint64_t>(b_data + (p.y - 1));
     if (lane == 0) {  // the single stage was released by the __syncwarp at the end of the previous iteration
-      const uint32_t ba = stage_block(stg, ga, a_bytes, a_limit, bar, false);
-      const uint32_t bb = stage_block(stg + abuf, gb, b_bytes, b_limit, bar, false);
+      const uint32_t ba = stage_block<0>(stg, ga, a_bytes, a_limit, bar, false, 0ull);
+      const uint32_t bb = stage_block<0>(stg + abuf, gb, b_bytes, b_limit, bar, false, 0ull);
       mbar_expect_tx(bar, ba + bb);
-      stage_block(stg, ga, a_bytes, a_limit, bar, true);
-      stage_block(stg + abuf, gb, b_bytes, b_limit, bar, true);
+      stage_block<0>(stg, ga, a_bytes, a_limit, bar, true, 0ull);
+      stage_block<0>(stg + abuf, gb, b_bytes, b_limit, bar, true, 0ull);
     }
     if (p.z != cur_c) {
       if (cur_c >= 0) flush(cur_c);

@@ -6,13 +6,34 @@
 #include <cstdlib>
 
 #include "smm_dmma.cuh"
+#include "smm_dmma_ws.cuh"
 #include "smm_launch.h"
+#include "smm_tune.h"
 
 #ifndef SMM_M
 #  error "compile with -DSMM_M=<block rows>"
 #endif
 
 namespace smm {
+// Per-shape launch policy of the warp-autonomous kernel, from the B200 sweeps with tools/kbench (profiles/r01_kbench_sweep*.txt,
+// cfg2-like stacks of 30000 entries, TFLOP/s kernel-only):
+//   23x23x23: RED flush, one wave of 9-entry chunks 22.6 | run-aligned chunks 23.1 | bulk flush from a scratch buffer (16 warps
+//             per SM) 24.5 | bulk flush from the operand stage (24 warps) 25.2 | + run-aligned 25.6 | + 12-entry chunks 26.2
+//   32^3, 26^3, 13^3, 5^3: the bulk flush and the aligned chunks are neutral or slower (few resident warps / tiny blocks), so
+//             they keep the RED flush and one wave of equal chunks.
+// FLUSH: see smm_dmma.cuh; CHUNK: entries per warp when the stack is large enough to give every SM a CTA (0 = one resident
+// wave); ALIGN: chunk boundaries moved to changes of c_first.  The run-time knobs (smm_tune.h) override CHUNK / ALIGN when >= 0.
+template <int M, int N, int K>
+struct Policy {
+  static constexpr int FLUSH = 0, CHUNK = 0;
+  static constexpr bool ALIGN = false;
+};
+template <>
+struct Policy<23, 23, 23> {
+  static constexpr int FLUSH = 2, CHUNK = 12;
+  static constexpr bool ALIGN = true;
+};
+
 namespace {
 
 int g_num_sms = 0;
@@ -21,6 +42,116 @@ const bool g_use_pdl = [] {
   const char* e = getenv("DBCSR_B200_PDL");
   return e == nullptr || atoi(e) != 0;
 }();
+
+// trace slot of this launch (TRACE kernels only): nullptr outside the recording window set by libsmm_acc_b200_set_tunable
+unsigned long long* trace_slot() {
+  const int seq = g_tune.seq.fetch_add(1, std::memory_order_relaxed);
+  unsigned long long* t = g_tune.trace.load(std::memory_order_relaxed);
+  if (t == nullptr) return nullptr;
+  const int first = g_tune.trace_first.load(std::memory_order_relaxed), cnt = g_tune.trace_count.load(std::memory_order_relaxed);
+  if (seq < first || seq >= first + cnt) return nullptr;
+  return t + (size_t)(seq - first) * TRACE_WARPS * TRACE_REC;
+}
+
+template <typename Kern>
+int occupancy(Kern kern, int threads, int smem, std::atomic<int>& cache) {
+  int cps = cache.load(std::memory_order_acquire);
+  if (cps == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
+    int dev = 0, nb = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -30;
+    if (g_num_sms == 0) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) return -30;
+    cps = nb;
+    cache.store(cps, std::memory_order_release);
+  }
+  return cps;
+}
+
+template <typename Kern, typename... Args>
+int launch_pdl(Kern kern, int grid, int threads, int smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, args...);
+  return (err == cudaSuccess) ? 0 : -31;
+}
+
+// warp-autonomous kernel (smm_dmma.cuh): NST stages per warp, WPC warps per CTA
+template <int M, int N, int K, int NST, int WPC, int HINT, bool TRACE, int FLUSH = 0, int ABL = 0>
+int launch_base(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
+                cudaStream_t stream) {
+  using G = BaseGeom<M, N, K, NST, WPC, FLUSH>;
+  constexpr int SMEM = G::SMEM;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+  auto kern = smm_dmma_kernel<M, N, K, NST, WPC, HINT, TRACE, FLUSH, ABL>;
+  static std::atomic<int> ctas_per_sm{0};
+  const int cps = occupancy(kern, WPC * 32, SMEM, ctas_per_sm);
+  if (cps < 0) return cps;
+  if (stack_size <= 0) return 0;
+  const int max_grid = g_num_sms * cps;
+  // at least 4 entries per warp so that the pipeline prologue and the C flush are amortised
+  int grid = (stack_size + WPC * 4 - 1) / (WPC * 4);
+  int max_chunk = g_tune.chunk.load(std::memory_order_relaxed);
+  if (max_chunk < 0) {
+    // per-shape policy: CHUNK entries per warp when that leaves part of the resident wave free for the next launch (programmatic
+    // dependent launch) and still gives every SM at least one CTA; otherwise one wave
+    max_chunk = 0;
+    if (Policy<M, N, K>::CHUNK > 0 && (long long)Policy<M, N, K>::CHUNK * max_grid * WPC > stack_size &&
+        (long long)Policy<M, N, K>::CHUNK * g_num_sms * WPC <= stack_size)
+      max_chunk = Policy<M, N, K>::CHUNK;
+  }
+  if (max_chunk > 0)
+    grid = (stack_size + WPC * max_chunk - 1) / (WPC * max_chunk);  // may exceed one resident wave
+  else if (grid > max_grid)
+    grid = max_grid;
+  const int warps = grid * WPC;
+  int chunk = (stack_size + warps - 1) / warps, extra = -1;
+  if (g_tune.balance.load(std::memory_order_relaxed) > 0) {
+    chunk = stack_size / warps;
+    extra = stack_size % warps;
+  }
+  const int align = g_tune.align.load(std::memory_order_relaxed);
+  const int flags = (align < 0 ? Policy<M, N, K>::ALIGN : align != 0) ? FLAG_ALIGN_RUNS : 0;
+  unsigned long long* trace = TRACE ? trace_slot() : nullptr;
+  const unsigned long long al = a_limit, bl = b_limit;
+  return launch_pdl(kern, grid, WPC * 32, SMEM, stream, dev_stack, stack_size, a, b, c, al, bl, chunk, extra, flags, trace);
+}
+
+// warp-specialised kernel (smm_dmma_ws.cuh): NC consumer warps with D stages each + one producer warp per CTA
+template <int M, int N, int K, int NC, int D, int HINT, bool TRACE, int FLUSH = 0, bool STAG = false>
+int launch_ws(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
+              cudaStream_t stream) {
+  using G = WsGeom<M, N, K, NC, D>;
+  static_assert(G::SMEM <= 227 * 1024, "shared memory budget exceeded");
+  auto kern = smm_dmma_ws_kernel<M, N, K, NC, D, HINT, TRACE, FLUSH, STAG>;
+  static std::atomic<int> ctas_per_sm{0};
+  const int cps = occupancy(kern, G::THREADS, G::SMEM, ctas_per_sm);
+  if (cps < 0) return cps;
+  if (stack_size <= 0) return 0;
+  const int max_grid = g_num_sms * cps;
+  int grid = (stack_size + NC * 4 - 1) / (NC * 4);
+  const int max_chunk = g_tune.chunk.load(std::memory_order_relaxed);
+  if (max_chunk > 0)
+    grid = (stack_size + NC * max_chunk - 1) / (NC * max_chunk);
+  else if (grid > max_grid)
+    grid = max_grid;
+  // a CTA keeps its slice of the stack (at most stack_size / grid + NC entries) in shared memory
+  const int min_grid = (stack_size + (WS_ENT_CAP - NC) - 1) / (WS_ENT_CAP - NC);
+  if (grid < min_grid) grid = min_grid;
+  const int consumers = grid * NC;
+  const int base = stack_size / consumers, extra = stack_size % consumers;
+  unsigned long long* trace = TRACE ? trace_slot() : nullptr;
+  const unsigned long long al = a_limit, bl = b_limit;
+  return launch_pdl(kern, grid, G::THREADS, G::SMEM, stream, dev_stack, stack_size, a, b, c, al, bl, base, extra, trace);
+}
 
 template <int M, int N, int K>
 int launch(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
@@ -33,40 +164,105 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
   constexpr int NST = pick_nst(SH::STAGE);
   constexpr int WPC = pick_wpc(SH::STAGE);
 #endif
-  constexpr int SMEM = round_up_c(WPC * NST * 8, 128) + WPC * NST * SH::STAGE;
-  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
-  auto kern = smm_dmma_kernel<M, N, K, NST, WPC>;
-  static std::atomic<int> ctas_per_sm{0};
-  int cps = ctas_per_sm.load(std::memory_order_acquire);
-  if (cps == 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -30;
-    int dev = 0, nb = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -30;
-    if (g_num_sms == 0) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WPC * 32, SMEM) != cudaSuccess || nb < 1) return -30;
-    cps = nb;
-    ctas_per_sm.store(cps, std::memory_order_release);
+#if defined(SMM_EXPERIMENT)
+  // kernel variants for tools/kbench (one experiment library, run-time switch); only the cubic shape carries them
+  if constexpr (N == M && K == M) {
+#  define SMM_ARGS dev_stack, stack_size, a, b, c, a_limit, b_limit, stream
+    switch (g_tune.variant.load(std::memory_order_relaxed)) {
+      case 9: return launch_base<M, N, K, NST, WPC, 0, false, 0>(SMM_ARGS);  // RED flush whatever the policy says
+      case 1: return launch_base<M, N, K, NST, WPC, 1, false>(SMM_ARGS);
+      case 2: return launch_base<M, N, K, NST, WPC, 2, false>(SMM_ARGS);
+      case 3: return launch_base<M, N, K, NST, WPC, 0, true>(SMM_ARGS);
+      case 4: return launch_base<M, N, K, 1, 8, 0, false>(SMM_ARGS);
+      case 5: return launch_base<M, N, K, 2, 4, 0, false>(SMM_ARGS);
+      case 6:
+        if constexpr (4 * 6 * SH::STAGE <= 220 * 1024) return launch_base<M, N, K, 6, 4, 0, false>(SMM_ARGS);
+        break;
+      case 10:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, false>(SMM_ARGS);
+        break;
+      case 11:
+        if constexpr (WsGeom<M, N, K, 4, 3>::SMEM <= 113 * 1024) return launch_ws<M, N, K, 4, 3, 0, false>(SMM_ARGS);
+        break;
+      case 12:
+        if constexpr (WsGeom<M, N, K, 12, 2>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 12, 2, 0, false>(SMM_ARGS);
+        break;
+      case 13:
+        if constexpr (WsGeom<M, N, K, 4, 6>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 4, 6, 0, false>(SMM_ARGS);
+        break;
+      case 14:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 2, false>(SMM_ARGS);
+        break;
+      case 15:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, true>(SMM_ARGS);
+        break;
+      case 16:
+        if constexpr (WsGeom<M, N, K, 6, 4>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 6, 4, 0, false>(SMM_ARGS);
+        break;
+      case 17:
+        if constexpr (WsGeom<M, N, K, 4, 3>::SMEM <= 113 * 1024) return launch_ws<M, N, K, 4, 3, 2, false>(SMM_ARGS);
+        break;
+      case 18:
+        if constexpr (WsGeom<M, N, K, 2, 4>::SMEM <= 75 * 1024) return launch_ws<M, N, K, 2, 4, 0, false>(SMM_ARGS);
+        break;
+      case 30: return launch_base<M, N, K, 1, 4, 0, false, 1>(SMM_ARGS);
+      case 31: return launch_base<M, N, K, 1, 8, 0, false, 1>(SMM_ARGS);
+      case 32: return launch_base<M, N, K, 1, 4, 0, true, 1>(SMM_ARGS);
+      case 33:
+        if constexpr (BaseGeom<M, N, K, 2, 4, 1>::SMEM <= 113 * 1024) return launch_base<M, N, K, 2, 4, 0, false, 1>(SMM_ARGS);
+        break;
+      case 60: return launch_base<M, N, K, 1, 4, 0, false, 2>(SMM_ARGS);
+      case 61: return launch_base<M, N, K, 1, 8, 0, false, 2>(SMM_ARGS);
+      case 62: return launch_base<M, N, K, 1, 4, 0, true, 2>(SMM_ARGS);
+      case 63: return launch_base<M, N, K, 1, 12, 0, false, 2>(SMM_ARGS);
+      case 64:
+        if constexpr (BaseGeom<M, N, K, 1, 16, 1>::SMEM <= 227 * 1024) return launch_base<M, N, K, 1, 16, 0, false, 1>(SMM_ARGS);
+        break;
+      case 40: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH>(SMM_ARGS);
+      case 41: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOLDS>(SMM_ARGS);
+      case 42: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOTMA>(SMM_ARGS);
+      case 43: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH | ABL_NOLDS | ABL_NOTMA>(SMM_ARGS);
+      case 50:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, false, 2, false>(SMM_ARGS);
+        break;
+      case 51:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, false, 2, true>(SMM_ARGS);
+        break;
+      case 52:
+        if constexpr (WsGeom<M, N, K, 4, 3>::SMEM <= 113 * 1024) return launch_ws<M, N, K, 4, 3, 0, false, 2, false>(SMM_ARGS);
+        break;
+      case 53:
+        if constexpr (WsGeom<M, N, K, 4, 3>::SMEM <= 113 * 1024) return launch_ws<M, N, K, 4, 3, 0, false, 2, true>(SMM_ARGS);
+        break;
+      case 54:
+        if constexpr (WsGeom<M, N, K, 12, 2>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 12, 2, 0, false, 2, false>(SMM_ARGS);
+        break;
+      case 55:
+        if constexpr (WsGeom<M, N, K, 12, 2>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 12, 2, 0, false, 2, true>(SMM_ARGS);
+        break;
+      case 56:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, false, 0, true>(SMM_ARGS);
+        break;
+      case 57:
+        if constexpr (WsGeom<M, N, K, 8, 3>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 3, 0, true, 2, true>(SMM_ARGS);
+        break;
+      case 58:
+        if constexpr (WsGeom<M, N, K, 8, 2>::SMEM <= 227 * 1024) return launch_ws<M, N, K, 8, 2, 0, false, 2, true>(SMM_ARGS);
+        break;
+      case 59:
+        if constexpr (WsGeom<M, N, K, 2, 4>::SMEM <= 75 * 1024) return launch_ws<M, N, K, 2, 4, 0, false, 2, false>(SMM_ARGS);
+        break;
+      case 20: return launch_ws<M, N, K, WsPick<M, N, K>::NC, WsPick<M, N, K>::D, 0, false>(SMM_ARGS);
+      case 21: return launch_ws<M, N, K, WsPick<M, N, K>::NC, WsPick<M, N, K>::D, 2, false>(SMM_ARGS);
+      default: break;
+    }
+#  undef SMM_ARGS
   }
-  if (stack_size <= 0) return 0;
-  const int max_grid = g_num_sms * cps;
-  // at least 4 entries per warp so that the pipeline prologue and the C flush are amortised
-  int grid = (stack_size + WPC * 4 - 1) / (WPC * 4);
-  if (grid > max_grid) grid = max_grid;
-  const int warps = grid * WPC;
-  const int chunk = (stack_size + warps - 1) / warps;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(WPC * 32);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const unsigned long long al = a_limit, bl = b_limit;
-  const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, dev_stack, stack_size, a, b, c, al, bl, chunk);
-  return (err == cudaSuccess) ? 0 : -31;
+#endif
+  if constexpr (Policy<M, N, K>::FLUSH == 2 && NST == 1)
+    return launch_base<M, N, K, NST, WPC, 0, false, 2>(dev_stack, stack_size, a, b, c, a_limit, b_limit, stream);
+  else
+    return launch_base<M, N, K, NST, WPC, 0, false, 0>(dev_stack, stack_size, a, b, c, a_limit, b_limit, stream);
 }
 
 template <int M, int N>

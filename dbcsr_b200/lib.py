@@ -29,7 +29,8 @@ SMM_SYMBOLS = [
     "libsmm_acc_init", "libsmm_acc_finalize", "libsmm_acc_is_thread_safe", "libsmm_acc_transpose", "libsmm_acc_process",
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
-    "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks",
+    "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
+    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
@@ -85,6 +86,11 @@ def load():
     L.libsmm_acc_b200_pack_bf16.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp]
     L.libsmm_acc_b200_bf16_tile_bytes.argtypes = [_i, _i]
     L.libsmm_acc_b200_version.restype = ctypes.c_char_p
+    L.libsmm_acc_b200_set_tunable.argtypes = [ctypes.c_char_p, ctypes.c_longlong]
+    L.libsmm_acc_b200_get_tunable.argtypes = [ctypes.c_char_p]
+    L.libsmm_acc_b200_get_tunable.restype = ctypes.c_longlong
+    L.libsmm_acc_b200_set_trace.argtypes = [_vp]
+    L.libsmm_acc_b200_set_trace.restype = None
     L.c_dbcsr_acc_clear_errors.restype = None
     _lib = L
     return L
@@ -239,6 +245,13 @@ class Acc:
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())
+
+    def set_tunable(self, name, value):
+        """Run-time knob of the FP64 stack kernels (include/dbcsr_acc_libsmm.h): "balance", "align", "chunk", "variant", ..."""
+        _ck(self.L.libsmm_acc_b200_set_tunable(name.encode(), int(value)), "libsmm_acc_b200_set_tunable(%s)" % name)
+
+    def get_tunable(self, name):
+        return int(self.L.libsmm_acc_b200_get_tunable(name.encode()))
 
     def finalize(self):
         _ck(self.L.c_dbcsr_acc_finalize(), "finalize")

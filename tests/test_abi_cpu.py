@@ -80,3 +80,23 @@ def test_product_does_not_reference_the_oracle():
                 assert not pat.search(txt), os.path.join(dirpath, f)
     out = subprocess.check_output(["nm", "-D", acclib.LIB_PATH]).decode()
     assert "orc_" not in out
+
+
+def test_tunables_round_trip():
+    """Run-time knobs of the FP64 stack kernels (dbcsr_b200/csrc/smm_tune.h): host-side state only, no device needed."""
+    from dbcsr_b200 import lib as acclib
+
+    L = acclib.load()
+    assert L.libsmm_acc_b200_get_tunable(b"no such knob") == -1
+    assert L.libsmm_acc_b200_set_tunable(b"no such knob", 1) == -1
+    defaults = {}
+    for name, val in (("balance", 1), ("align", 0), ("chunk", 7), ("trace_first", 3), ("trace_count", 2)):
+        defaults[name] = L.libsmm_acc_b200_get_tunable(name.encode())
+        assert L.libsmm_acc_b200_set_tunable(name.encode(), val) == 0
+        assert L.libsmm_acc_b200_get_tunable(name.encode()) == val
+    for name, val in defaults.items():
+        assert L.libsmm_acc_b200_set_tunable(name.encode(), val) == 0
+    # shipped defaults: per-shape launch policy (-1) for chunk and align, equal chunks off; production library has no variant table
+    if "DBCSR_B200_CHUNK" not in os.environ and "DBCSR_B200_ALIGN" not in os.environ:
+        assert defaults["chunk"] == -1 and defaults["align"] == -1
+    assert L.libsmm_acc_b200_get_tunable(b"experiment") in (0, 1)

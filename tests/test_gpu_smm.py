@@ -348,3 +348,36 @@ def test_concurrent_threads_own_streams(acc):
         t.join()
     assert not errors, errors
     assert all(r is not None and r <= 1e-10 for r in results), results
+
+
+@pytest.mark.parametrize("mnk", [(23, 23, 23), (13, 13, 13), (23, 13, 5)])
+def test_launch_knobs_keep_results(acc, mnk):
+    """Run-time launch knobs (chunk size, run-aligned chunk boundaries, equal chunks; include/dbcsr_acc_libsmm.h) only change
+    how a stack is split over the warps -- and, for 23^3, the flush of a run goes through one TMA bulk reduction
+    (cp.reduce.async.bulk.add.f64) instead of per-element REDs: every combination must give the oracle's result exactly on
+    integer-valued inputs, for C-sorted stacks with short and long runs, unsorted stacks and stacks smaller than the grid."""
+    m, n, k = mnk
+    rng = np.random.default_rng(17)
+    n_a = n_b = 300
+    a = rng.integers(0, 4, n_a * m * k).astype(np.float64)
+    b = rng.integers(0, 4, n_b * k * n).astype(np.float64)
+    saved = {name: acc.get_tunable(name) for name in ("balance", "align", "chunk")}
+    try:
+        for S, n_c, shuffle in [(3, 2, False), (200, 120, False), (4000, 37, False), (30000, 17000, False), (9000, 300, True)]:
+            stack = np.zeros((S, 3), dtype=np.int32)
+            stack[:, 0] = rng.integers(0, n_a, S) * m * k + 1
+            stack[:, 1] = rng.integers(0, n_b, S) * k * n + 1
+            stack[:, 2] = np.sort(rng.integers(0, n_c, S)) * m * n + 1
+            if shuffle:
+                stack = stack[rng.permutation(S)]
+            c_ref = orc.stack_calc(stack, np.zeros(n_c * m * n), a, b, m, n, k)
+            for balance, align, chunk in [(0, -1, -1), (0, 0, 0), (0, 1, 0), (1, 1, 0), (0, 1, 5), (1, 0, 12), (0, 1, 40)]:
+                acc.set_tunable("balance", balance)
+                acc.set_tunable("align", align)
+                acc.set_tunable("chunk", chunk)
+                rc, c = run_process(acc, stack, a, b, n_c * m * n, m, n, k, pad_elems=1 if chunk == 5 else 0)
+                assert rc == 0
+                assert np.array_equal(c, c_ref), (mnk, S, n_c, shuffle, balance, align, chunk, float(np.abs(c - c_ref).max()))
+    finally:
+        for name, v in saved.items():
+            acc.set_tunable(name, v)
