@@ -322,6 +322,15 @@ def run_single(args):
                 "peak_source": peak_src, "kernel": "smm_dmma_kernel<%s> (x%d launches/step)" % (",".join(str(x) for x in (stacks[0]["m"], stacks[0]["n"], stacks[0]["k"])), len(stacks)),
                 "algorithmic_bytes_per_launch": alg_bytes / max(len(stacks), 1), "avg_launch_us": float(np.mean(kern_ms)) * 1e3 / max(len(stacks), 1),
                 "kernel_only_gflops": flop / (float(np.mean(kern_ms)) * 1e-3) * 1e-9, "fp64_tensor_peak_gflops_measured": 37050.0}
+    if not bf16:
+        # the streaming-HBM model is not what binds this kernel (operands are re-used out of L2: frac > 1); the FP64 tensor pipe
+        # (DMMA.8x8x4, measured 37.05 TFLOP/s, profiles/microbench_r01.txt) and its padded ceiling (tiles of 8x8x4) are quoted beside it
+        m0, n0, k0 = stacks[0]["m"], stacks[0]["n"], stacks[0]["k"]
+        pad = (m0 * n0 * k0) / float(((m0 + 7) // 8 * 8) * ((n0 + 7) // 8 * 8) * ((k0 + 3) // 4 * 4))
+        roofline["alt_bounds"] = {"frac_of_fp64_tensor_peak": roofline["kernel_only_gflops"] / 37050.0,
+                                  "frac_of_padded_fp64_tensor_ceiling": roofline["kernel_only_gflops"] / (37050.0 * pad),
+                                  "mean_run_length": n_entries / max(1, sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in stacks)),
+                                  "traffic_note": "dram bytes per launch from the ncu --set full capture of the RED-flush kernel (profiles/ncu_summary.json)"}
     if bf16:
         try:
             tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * 1e3

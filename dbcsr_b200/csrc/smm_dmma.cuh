@@ -14,8 +14,11 @@
 //   * the raw column-major block layout is kept in shared memory (TMA cannot pad), so bank conflicts of the fragment loads
 //     are removed by permuting the k index instead: DMMA sums over 4 k-values per instruction and any assignment of k to the
 //     four lane groups is legal; KMap picks the stride that makes `k*ld mod 16` distinct for the four groups;
-//   * C is accumulated in registers over a run of equal c_first (the stack is C-sorted) and flushed with RED.ADD.F64
-//     (no read of C; L2 does the read-modify-write), which stays correct for unsorted/binned stacks and chunk boundaries;
+//   * C is accumulated in registers over a run of equal c_first (the stack is C-sorted) and flushed by an L2-side reduction
+//     (no read of C), which stays correct for unsorted/binned stacks, chunk boundaries and overlapping launches: either one
+//     RED.ADD.F64 per element, or -- FLUSH 2, shipped for 23^3 -- an image of the run in the warp's free operand stage that ONE
+//     cp.reduce.async.bulk.add.f64 (TMA, UBLKRED) adds into C.  Runs are short on real stacks (1.7 entries on the 23^3/10 %
+//     workload), so the flush is on the critical resource list: per-element REDs leave an SM at ~1 element per cycle;
 //   * launches use programmatic dependent launch (griddepcontrol.launch_dependents at entry, .wait at exit): consecutive
 //     stack drains of a stream overlap their ramp-up/tail, completion order is still stream order.
 #pragma once
