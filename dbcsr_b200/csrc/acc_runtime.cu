@@ -228,12 +228,14 @@ int c_dbcsr_acc_host_mem_deallocate(void* host_mem, void* stream) {
 
 int c_dbcsr_acc_memcpy_h2d(const void* host_mem, void* dev_mem, size_t nbytes, void* stream) {
   if (stream == nullptr) return -1;
+  if (nbytes == 0) return 0;  // empty panels / stacks: nothing to enqueue
   ACC_TRY(cudaMemcpyAsync(dev_mem, host_mem, nbytes, cudaMemcpyHostToDevice, as_stream(stream)));
   return 0;
 }
 
 int c_dbcsr_acc_memcpy_d2h(const void* dev_mem, void* host_mem, size_t nbytes, void* stream) {
   if (stream == nullptr) return -1;
+  if (nbytes == 0) return 0;
   ACC_TRY(cudaMemcpyAsync(host_mem, dev_mem, nbytes, cudaMemcpyDeviceToHost, as_stream(stream)));
   return 0;
 }

@@ -433,6 +433,17 @@ int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const in
   return 0;
 }
 
+int dbcsr_b200_engine_set_c_symmetry(dbcsr_b200_engine_t* e, int on, const int* global_rows, const int* global_cols) {
+  // product with symmetry: skip the half of the off-diagonal blocks that the checkerboard rule stores transposed
+  // (src/mm/dbcsr_mm_csr.F:280-292; c_local_rows / c_local_cols of the reference = global_rows / global_cols here)
+  if (e == nullptr) return -1;
+  std::vector<int> gr, gc;
+  if (global_rows != nullptr) gr.assign(global_rows, global_rows + e->nrows);
+  if (global_cols != nullptr) gc.assign(global_cols, global_cols + e->ncols);
+  for (auto& ts : e->th) ts.mm->set_c_symmetry(on != 0, gr, gc);
+  return 0;
+}
+
 int dbcsr_b200_filter_index(double filter_eps, const double* norms2, int nblks, int* rows, int* cols, int* blk_p, const int* nelems,
                             long long* nze_after) {
   // multrec_filtering_d, src/mm/dbcsr_mm_multrec.F:700-758: keep a block iff DDOT(blk, blk) >= filter_eps**2; kept entries move

@@ -217,6 +217,9 @@ void LocalMultiply::reset() {
   datasize_ = 0;
   flop_ = 0;
   keep_sparsity_ = false;
+  c_sym_ = false;
+  c_grow_.clear();
+  c_gcol_.clear();
   std::fill(fill_.begin(), fill_.end(), 0);
 }
 
@@ -289,7 +292,7 @@ void LocalMultiply::flush_stacks(bool purge) {
   }
 }
 
-// src/mm/dbcsr_mm_csr.F:178-359 with build_csr_index :741-795 (optional norm filter; no symmetry: BASELINE configs have none)
+// src/mm/dbcsr_mm_csr.F:178-359 with build_csr_index :741-795 (optional norm filter, optional symmetric-product skipping)
 void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int af, int bi, int bf, const Idx3* a, const Idx3* b) {
   const int nrow = mf - mi + 1, nk = kf - ki + 1, na = af - ai + 1, nb = bf - bi + 1;
   const bool use_eps = a_norms_ != nullptr && b_norms_ != nullptr && !row_eps_.empty();
@@ -329,6 +332,11 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
           if (prod < a_row_eps) continue;
         }
         const int b_col_l = b_info_[2 * (size_t)b_blk];
+        if (c_sym_) {  // don't calculate symmetric blocks (src/mm/dbcsr_mm_csr.F:280-292)
+          const int cr = c_grow_.empty() ? a_row_l : c_grow_[(size_t)a_row_l - 1];
+          const int cc = c_gcol_.empty() ? b_col_l : c_gcol_[(size_t)b_col_l - 1];
+          if (cr != cc && checker_tr(cr, cc)) continue;
+        }
         const int b_first = b_info_[2 * (size_t)b_blk + 1];
         const int n_size = n_sizes_[b_col_l - 1];
         const int c_nze = m_size * n_size;
@@ -336,6 +344,9 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
         const int c_blk_id = c_lookup_or_insert(a_row_l, b_col_l, c_nze, created, !keep_sparsity_);
         if (c_blk_id == 0) continue;  // keep_sparsity: no new blocks
         const int offset = c_blk_p_[c_blk_id - 1];
+        // zero-sized blocks (DBCSR allows block size 0): the C block exists from here on (src/mm/dbcsr_mm_csr.F:325-333 "we
+        // still need to get to here to get new blocks"), but there is nothing to multiply: no stack entry (kernels need m,n,k >= 1)
+        if (c_nze == 0 || k_size == 0) continue;
         const int mapped_col = n_size < (int)n_map_.size() ? n_map_[n_size] : cfg_.n_stacks + 1;
         const int ws = stack_map_[((size_t)(mapped_row - 1) * w + (mapped_k - 1)) * w + (mapped_col - 1)];
         if (stacks_[ws].empty()) stacks_[ws].resize((size_t)7 * cfg_.mm_stack_size);

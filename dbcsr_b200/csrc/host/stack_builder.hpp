@@ -58,6 +58,16 @@ class LocalMultiply {
   void preset_c(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize);
   // retain_sparsity of dbcsr_multiply: products whose C block does not exist yet are skipped (src/mm/dbcsr_mm_csr.F:307)
   void set_keep_sparsity(bool keep) { keep_sparsity_ = keep; }
+  // Product matrix with symmetry (src/mm/dbcsr_mm_csr.F:280-292): of every off-diagonal pair {(r,c),(c,r)} only the block whose
+  // GLOBAL coordinates do not need a transpose under the checkerboard rule (checker_tr, src/dist/dbcsr_dist_operations.F:65-75)
+  // is computed.  global_rows / global_cols map the local C rows / cols to global block indices (empty = identity).
+  // Ends with the next reset(), like keep_sparsity.
+  void set_c_symmetry(bool on, const std::vector<int>& global_rows = {}, const std::vector<int>& global_cols = {}) {
+    c_sym_ = on;
+    c_grow_ = global_rows;
+    c_gcol_ = global_cols;
+  }
+  static bool checker_tr(int row, int col) { return (((row + col) & 1) != 0) == (col >= row); }
 
   // One Cannon tick: lists must already be rec-sorted (use sort_panel); [a_first, a_last] = this thread's slice of the
   // left list (1-based, inclusive; the whole list for one thread).  Stacks still partially filled at the end are purged
@@ -117,6 +127,8 @@ class LocalMultiply {
   int datasize_ = 0;
   int64_t flop_ = 0;
   bool keep_sparsity_ = false;
+  bool c_sym_ = false;
+  std::vector<int> c_grow_, c_gcol_;
   // scratch for the CSR leaves
   std::vector<int> a_row_p_, b_row_p_, a_info_, b_info_, counts_;
   // on-the-fly filter (optional)

@@ -41,6 +41,7 @@ def _L():
         L.dbcsr_b200_engine_chunk_rows.argtypes = [_vp, _i, ip, ip]
         L.dbcsr_b200_engine_set_chunk_events.argtypes = [_vp, _vp, _i]
         L.dbcsr_b200_engine_preset_c.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
+        L.dbcsr_b200_engine_set_c_symmetry.argtypes = [_vp, _i, _vp, _vp]
         L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
@@ -192,6 +193,19 @@ class Engine:
                                                1 if keep_sparsity else 0)
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_preset_c returned %d" % rc)
+
+    def set_c_symmetry(self, on, global_rows=None, global_cols=None):
+        """Product with symmetry: compute only the blocks the checkerboard rule does not store transposed
+        (src/mm/dbcsr_mm_csr.F:280-292); global_rows/global_cols map local C rows/cols to global block indices (None = identity).
+        Ends with the next reset()."""
+        gr = None if global_rows is None else np.ascontiguousarray(global_rows, dtype=np.int32)
+        gc = None if global_cols is None else np.ascontiguousarray(global_cols, dtype=np.int32)
+        if (gr is not None and gr.size != self.m.size) or (gc is not None and gc.size != self.n.size):
+            raise ValueError("one global index per local block row / col")
+        rc = self.L.dbcsr_b200_engine_set_c_symmetry(self.h, 1 if on else 0, None if gr is None else gr.ctypes.data,
+                                                     None if gc is None else gc.ctypes.data)
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_set_c_symmetry returned %d" % rc)
 
     def filter_c(self, filter_eps):
         rc = self.L.dbcsr_b200_engine_filter_c(self.h, float(filter_eps))

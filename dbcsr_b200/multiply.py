@@ -127,18 +127,23 @@ class DeviceMultiply:
                 d.free()
         return out
 
-    def multiply(self, a_list3, b_list3, filter_eps=None, total_row_counts=None, c_preset=None, retain_sparsity=False):
+    def multiply(self, a_list3, b_list3, filter_eps=None, total_row_counts=None, c_preset=None, retain_sparsity=False,
+                 c_symmetry=False):
         """One local multiply on the uploaded panels (stacks are built, ordered, uploaded and drained asynchronously).
         filter_eps: dbcsr_multiply's on-the-fly filter; total_row_counts = A blocks per block row over the whole process row
         (default: of this panel, i.e. a 1-column process grid).
         c_preset = (rows, cols, data): existing C blocks, data already scaled by beta (C = A*B + beta*C_old); with
-        retain_sparsity only products landing in those blocks are computed."""
+        retain_sparsity only products landing in those blocks are computed.
+        c_symmetry: the product has symmetry - the mirrored half of the off-diagonal blocks is not computed
+        (checkerboard rule, src/mm/dbcsr_mm_csr.F:280-292)."""
         if not self.first:
             self.engine.reset()
         self.first = False
         if c_preset is not None:
             self.engine.preset_c(c_preset[0], c_preset[1], c_preset[2], keep_sparsity=retain_sparsity)
             self.h2d_bytes += 0 if c_preset[2] is None else 8 * int(np.asarray(c_preset[2]).size)
+        if c_symmetry:
+            self.engine.set_c_symmetry(True)
         self.engine.wait_event(self.panels_ready)
         if getattr(self, "_chunk_events_armed", None):
             self.engine.set_chunk_events(self._chunk_events_armed)

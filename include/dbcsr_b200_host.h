@@ -86,6 +86,11 @@ int dbcsr_b200_engine_set_chunk_events(dbcsr_b200_engine_t* e, void* const* even
  * (src/mm/dbcsr_mm_csr.F:307).  Call after create/reset and before the first tick.  Both settings end with the next reset. */
 int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const int* cols, int nblks, const double* host_data,
   int keep_sparsity);
+/* Product matrix with symmetry (dbcsr_multiply with a symmetric / antisymmetric C; src/mm/dbcsr_mm_csr.F:280-292): of every
+ * off-diagonal pair {(r,c),(c,r)} only the block whose GLOBAL coordinates need no transpose under DBCSR's checkerboard rule
+ * checker_tr(row, col) = (odd(row + col) == (col >= row)) (src/dist/dbcsr_dist_operations.F:65-75) is computed.
+ * global_rows / global_cols: global block index of every local C row / col (NULL = identity).  Ends with the next reset. */
+int dbcsr_b200_engine_set_c_symmetry(dbcsr_b200_engine_t* e, int on, const int* global_rows, const int* global_cols);
 /* Final filter of the product, multrec_filtering (src/mm/dbcsr_mm_multrec.F:700-758), index part: block b is kept iff blk_p[b] != 0,
  * nelems[b] != 0 and norms2[b] (= sum of squares of its elements, double) >= filter_eps^2.  Kept entries are moved to the front of
  * rows/cols/blk_p in order (blk_p values unchanged).  Returns the number kept; *nze_after = their element count. */

@@ -25,6 +25,11 @@ import numpy as np
 
 
 # --------------------------------------------------------------------------- rec_sort_index
+
+def checker_tr(row, column):
+    """src/dist/dbcsr_dist_operations.F:65-75 (copied to src/mm/dbcsr_mm_csr.F:797-810): BTEST(column + row, 0) .EQV. column >= row"""
+    return bool((column + row) & 1) == (column >= row)
+
 def rec_split(a, row_or_col, mi, half):
     """src/mm/dbcsr_mm_common.F:283-309: low part in order, high part filled from the END (i.e. reversed)."""
     nele = len(a)
@@ -207,6 +212,13 @@ class LocalMultiplyOracle:
         self.a_norms = self.b_norms = None
         self.skipped = 0
         self.keep_sparsity = False
+        # product with symmetry (src/mm/dbcsr_mm_csr.F:280-292): global block index of the local C rows / cols, or None
+        self.c_has_symmetry = False
+        self.c_local_rows = self.c_local_cols = None
+
+    def set_c_symmetry(self, on, global_rows=None, global_cols=None):
+        self.c_has_symmetry = bool(on)
+        self.c_local_rows, self.c_local_cols = global_rows, global_cols
 
     def preset_c(self, rows, cols, keep_sparsity=False):
         """Work matrix starts from existing C blocks in list order (fill_hash_tables, src/mm/dbcsr_mm_csr.F:540-576; offsets are
@@ -316,6 +328,11 @@ class LocalMultiplyOracle:
                         if np.float32(np.float32(self.a_norms[a_pos - 1]) * np.float32(self.b_norms[b_pos - 1])) < a_row_eps:
                             self.skipped += 1
                             continue
+                    if self.c_has_symmetry:  # "Don't calculate symmetric blocks", src/mm/dbcsr_mm_csr.F:280-292
+                        c_row_logical = a_row_l if self.c_local_rows is None else int(self.c_local_rows[a_row_l - 1])
+                        c_col_logical = b_col_l if self.c_local_cols is None else int(self.c_local_cols[b_col_l - 1])
+                        if c_row_logical != c_col_logical and checker_tr(c_row_logical, c_col_logical):
+                            continue
                     c_blk_id = self.c_hash.get((a_row_l, b_col_l), 0)
                     n_size = self.n_sizes[b_col_l - 1]
                     c_nze = m_size * n_size
@@ -331,6 +348,8 @@ class LocalMultiplyOracle:
                         self.c_blk_p.append(offset)
                         c_blk_id = len(self.c_blk_p)
                         self.c_hash[(a_row_l, b_col_l)] = c_blk_id
+                    if c_nze == 0 or k_size == 0:
+                        continue  # zero-sized block: C block created, nothing to multiply (the reference lets BLAS no-op it)
                     mapped_col_size = self.n_map[n_size]
                     ws = self.stack_map[(mapped_col_size, mapped_k_size, mapped_row_size)]
                     self.stacks[ws - 1].append((m_size, n_size, k_size, a_first, b_first, offset, c_blk_id))

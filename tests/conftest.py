@@ -6,6 +6,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+TESTS = os.path.dirname(os.path.abspath(__file__))
+if TESTS not in sys.path:  # shared test drivers (tests/dbcsr_multiply_cases.py)
+    sys.path.insert(0, TESTS)
 
 
 def pytest_configure(config):

@@ -1,0 +1,59 @@
+"""GPU twin of tests/test_dbcsr_multiply.py: the reference's dbcsr_multiply unit-test cases (tests/dbcsr_unittest1.F:95-330,
+driver tests/dbcsr_test_multiply.F) through the dbcsr_multiply mirror with the DEVICE backend: panels on the GPU, stacks by the
+host engine, drained by libsmm_acc_process (tuned DMMA kernels for 5/13/23 blocks, run-time-shape / generic kernels and
+inhomogeneous stacks for the 1..4-sized blocks of the reference's cases).  Criterion of dbcsr_check_multiply:
+||C_dbcsr - C_dense||_oo / ((||A||_oo + ||B||_oo + ||C_in||_oo) * n * eps) <= 10."""
+import numpy as np
+import pytest
+
+from dbcsr_b200 import dbcsr as D
+
+from dbcsr_multiply_cases import UNITTEST1_CASES, random_matrix, run_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def backend():
+    from dbcsr_b200 import lib as acclib
+
+    acc = acclib.Acc(0)
+    yield D.DeviceBackend(acc, nthreads=2)
+    acc.finalize()
+
+
+@pytest.mark.parametrize("case", UNITTEST1_CASES, ids=[c[0] for c in UNITTEST1_CASES])
+def test_dbcsr_multiply_unittest1_cases_on_device(case, backend):
+    rng = np.random.default_rng(abs(hash(case[0])) % (2 ** 31))
+    n = 0
+    for desc, eps_norm, flop in run_case(case, backend, rng):
+        assert eps_norm <= 10.0, (desc, eps_norm)
+        n += 1
+    assert n >= 4, n
+
+
+def test_filter_eps_on_device(backend):
+    """filter_eps through the device path: device norms (c_calculate_norms), on-the-fly filter in the host engine, final filter +
+    compaction of C on the device before the download."""
+    from oracle import oracle as orc
+
+    rng = np.random.default_rng(5)
+    sizes = orc.random_block_sizes(92, [1, 5, 1, 13, 1, 23])
+    a = random_matrix("A", sizes, sizes, 0.6, "N", rng)
+    b = random_matrix("B", sizes, sizes, 0.6, "N", rng)
+    for i in range(0, a.nblks, 3):
+        a.block(i)[...] *= 1e-7
+    exact = a.to_dense() @ b.to_dense()
+    c = D.DbcsrMatrix("C", sizes, sizes)
+    eps = 1e-4
+    D.dbcsr_multiply("N", "N", 1.0, a, b, 0.0, c, filter_eps=eps, backend=backend)
+    ro, co = c.row_blk_offset - 1, c.col_blk_offset - 1
+    got = c.blocks()
+    assert 0 < len(got) < len(sizes) ** 2
+    for (r, cc), blk in got.items():
+        assert np.linalg.norm(blk) >= eps
+        assert np.abs(blk - exact[ro[r - 1]:ro[r], co[cc - 1]:co[cc]]).max() <= 1e-3 * eps * len(sizes) + 1e-12
+    for r in range(1, len(sizes) + 1):
+        for cc in range(1, len(sizes) + 1):
+            if (r, cc) not in got:
+                assert np.linalg.norm(exact[ro[r - 1]:ro[r], co[cc - 1]:co[cc]]) < 2 * eps

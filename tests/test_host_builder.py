@@ -379,3 +379,55 @@ def test_filter_index_matches_multrec_filtering_restatement():
         gr, gc, gp, gnze = host.filter_index(eps, norms, rows, cols, blk_p, nel)
         assert gr.tolist() == er and gc.tolist() == ec and gp.tolist() == ep and gnze == enze
     assert len(io.multrec_filtering(1e-2, rows, cols, blk_p, rbs, cbs, data)[0]) not in (0, rows.size - 1)
+
+
+@pytest.mark.parametrize("use_maps", [False, True])
+def test_symmetric_product_skipping_matches_index_oracle(use_maps):
+    """Product matrix with symmetry (src/mm/dbcsr_mm_csr.F:280-292): only the blocks for which the checkerboard rule
+    checker_tr(global row, global col) is false are computed (plus the diagonal); stacks, C index and flop equal the oracle's,
+    for 1 and 4 threads the surviving product set is exactly {(i,j): i == j or not checker_tr(i,j)}."""
+    n, nk = 36, 40
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(n, n, nk, 0.3, 0.3, [5, 13, 23], seed=77)
+    rng = np.random.default_rng(3)
+    grows = gcols = None
+    if use_maps:  # local -> global block indices of a 2-column process grid (every second global row/col is local)
+        grows = 2 * np.arange(n, dtype=np.int32) + 1
+        gcols = 2 * np.arange(n, dtype=np.int32) + 2
+    ora = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=500, n_stacks=3, multrec_limit=64)
+    ora.set_c_symmetry(True, grows, gcols)
+    exp = ora.multiply(A.index_list(), B.index_list())
+    cfg = host.default_cfg(mm_stack_size=500, n_stacks=3, multrec_limit=64)
+    eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD, cfg=cfg)
+    eng.set_c_symmetry(True, grows, gcols)
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    got = eng.stacks()
+    assert len(got) == len(exp) and len(exp) > 0
+    for g, x in zip(got, exp):
+        assert np.array_equal(g["host"], x["host"]) and np.array_equal(g["dev"], x["dev"])
+    rows, cols, blk_p, datasize = eng.c_index(0)
+    assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p
+    assert eng.flop() == ora.flop
+    gr = np.arange(1, n + 1) if grows is None else grows
+    gc = np.arange(1, n + 1) if gcols is None else gcols
+    for r, c in zip(rows, cols):
+        assert gr[r - 1] == gc[c - 1] or not io.checker_tr(int(gr[r - 1]), int(gc[c - 1]))
+    # the skipped half is really skipped, the kept half complete: compare with the unrestricted product pattern
+    full = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD, cfg=cfg)
+    full.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    fr, fc, _, _ = full.c_index(0)
+    want = {(int(r), int(c)) for r, c in zip(fr, fc) if gr[r - 1] == gc[c - 1] or not io.checker_tr(int(gr[r - 1]), int(gc[c - 1]))}
+    assert {(int(r), int(c)) for r, c in zip(rows, cols)} == want
+    eng4 = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=4, mode=host.RECORD, cfg=cfg)
+    eng4.set_c_symmetry(True, grows, gcols)
+    eng4.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    got4 = set()
+    for t in range(4):
+        r4, c4, _, _ = eng4.c_index(t)
+        got4 |= {(int(r), int(c)) for r, c in zip(r4, c4)}
+    assert got4 == want and eng4.flop() == eng.flop()
+    # the setting ends with reset(): the next multiply computes everything again
+    eng.reset()
+    eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    assert eng.flop() == full.flop()
+    for e in (eng, full, eng4):
+        e.close()
