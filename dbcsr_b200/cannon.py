@@ -144,12 +144,18 @@ class CannonMultiply:
             meta = meta.cpu()
         self.meta = meta.numpy()
         max_bytes = int((self.meta[..., 1] * 8 + self.meta[..., 0] * 12).max())
-        self.recv = {kind: [torch.empty(max(max_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(2)] for kind in "ab"}
         self.flop = 0
         self.last_build_s = 0.0
         self.peer_buf = None
         if self.device.type == "cuda" and world > 1 and os.environ.get("DBCSR_B200_EXCHANGE", "p2p") == "p2p":
             self._setup_peer_access()
+        # Receive buffers.  Two per panel kind (double buffering, like the reference's two image buffers) for the NCCL exchange;
+        # with peer pull one per tick: a rank's panels of ALL ticks fit easily into HBM (cfg2 at 2x4: 4 x 106 MB), so every pull
+        # of a multiply can be issued up front and no exchange ever waits for the kernels of an earlier tick to release a buffer
+        # (the replay trace showed compute ticks waiting for exactly that, profiles/r01_cannon_trace_n8_p2p.txt).
+        self.prefetch_all = self.peer_buf is not None and os.environ.get("DBCSR_B200_PREFETCH_ALL", "1") != "0"
+        self.nbuf = sc.V if self.prefetch_all else 2
+        self.recv = {kind: [torch.empty(max(max_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(self.nbuf)] for kind in "ab"}
 
     def _setup_peer_access(self):
         """Map every rank's home panels into this process (CUDA IPC) so that a panel can be PULLED from its home rank with a
@@ -198,14 +204,14 @@ class CannonMultiply:
                 if src is not None:
                     _, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
                     n = nze * 8 + nblk * 12
-                    self.recv[kind][t % 2][:n].copy_(self.peer_buf[(src, kind, s)][:n], non_blocking=True)
+                    self.recv[kind][t % self.nbuf][:n].copy_(self.peer_buf[(src, kind, s)][:n], non_blocking=True)
             return []
         if ra is not None:
             _, nblk, nze = self.panel_meta("a", s, self.i, self.j)
-            ops.append(dist.P2POp(dist.irecv, self.recv["a"][t % 2][:nze * 8 + nblk * 12], ra))
+            ops.append(dist.P2POp(dist.irecv, self.recv["a"][t % self.nbuf][:nze * 8 + nblk * 12], ra))
         if rb is not None:
             _, nblk, nze = self.panel_meta("b", s, self.i, self.j)
-            ops.append(dist.P2POp(dist.irecv, self.recv["b"][t % 2][:nze * 8 + nblk * 12], rb))
+            ops.append(dist.P2POp(dist.irecv, self.recv["b"][t % self.nbuf][:nze * 8 + nblk * 12], rb))
         for dst, kind, s2 in sends:
             ops.append(dist.P2POp(dist.isend, self.home_buf[(kind, s2)], dst))
         return dist.batch_isend_irecv(ops) if ops else []
@@ -214,7 +220,7 @@ class CannonMultiply:
         """(buffer tensor, nblks, nze) of the panel this rank multiplies at tick t (after its exchange completed)."""
         s = self.sched.slice_at(self.rank, t)
         src, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
-        buf = self.home_buf[(kind, s)] if src == self.rank else self.recv[kind][t % 2]
+        buf = self.home_buf[(kind, s)] if src == self.rank else self.recv[kind][t % self.nbuf]
         return buf, nblk, nze
 
     def index_to_host(self, buf, nblk, nze):
@@ -332,9 +338,21 @@ class CannonMultiply:
                     trace.append(("exchange", t, b, ev))
             return ev
 
-        ev_comm = exchange(0, None)
+        prefetch_all = self.prefetch_all and not fork_from_compute
+        if prefetch_all:
+            # one receive buffer per tick: the pull of tick t only has to wait for the PREVIOUS multiply's kernels of tick t
+            prev = getattr(self, "prev_ev_comp", None) or [None] * V
+            ev_comms = [exchange(0, prev[0])] + [None] * (V - 1)
+        else:
+            ev_comm = exchange(0, None)
         for t in range(V):
-            nxt = exchange(t + 1, ev_comp[t - 1] if t >= 1 else None) if t + 1 < V else None
+            if prefetch_all:
+                if t == 1:  # the kernels of tick 0 are enqueued: now post every remaining pull of this multiply
+                    for u in range(1, V):
+                        ev_comms[u] = exchange(u, prev[u])
+                ev_comm, nxt = ev_comms[t], None
+            else:
+                nxt = exchange(t + 1, ev_comp[t - 1] if t >= 1 else None) if t + 1 < V else None
             cs.wait_event(ev_comm)
             if trace is not None:
                 cb = torch.cuda.Event(enable_timing=True)
@@ -351,6 +369,8 @@ class CannonMultiply:
             if trace is not None:
                 trace.append(("compute", t, cb, ev_comp[t]))
             ev_comm = nxt
+        if prefetch_all:
+            self.prev_ev_comp = ev_comp
         if not fork_from_compute:
             self.ev_free[k].record(cs)
             cs.wait_event(self.ev_zero[1 - k])  # the step owns the memset it issued
@@ -377,6 +397,29 @@ class CannonMultiply:
 
     def close(self):
         self.engine.close()
+
+
+def _axis_sums(panel, lo, hi, axis):
+    """Element-level sums of the blocks of `panel` whose block row (axis 0: lo < row <= hi, result indexed by full COLUMN) or
+    block col (axis 1: lo < col <= hi, result indexed by full ROW) lies in the given range."""
+    sizes = panel.col_sizes if axis == 0 else panel.row_sizes
+    off = np.concatenate([[0], np.cumsum(sizes, dtype=np.int64)])
+    out = np.zeros(int(off[-1]))
+    key = panel.rows if axis == 0 else panel.cols
+    other = panel.cols if axis == 0 else panel.rows
+    for i in np.nonzero((key > lo) & (key <= hi))[0]:
+        o = int(other[i]) - 1
+        out[off[o]:off[o + 1]] += panel.block(int(i)).sum(axis=axis)
+    return out
+
+
+def expected_local_c_sum(cm):
+    """Size-independent property of the product (tests/test_gpu_multiply.py uses the same one): the sum of all elements of this
+    rank's C(I, J) = A(I, :) B(:, J) equals colsum(A(I, :)) . rowsum(B(:, J))."""
+    A, B = cm.w["A"], cm.w["B"]
+    a = _axis_sums(A, cm.rsp[cm.i], cm.rsp[cm.i + 1], 0)
+    b = _axis_sums(B, cm.csp[cm.j], cm.csp[cm.j + 1], 1)
+    return float(np.dot(a, b))
 
 
 # ---------------------------------------------------------------------------------------------------------------- bench
@@ -432,6 +475,27 @@ def bench_main(args):
         cm.replay_step()
     dist.barrier()
     torch.cuda.synchronize()
+
+    # self-check of the replayed multiply (every rank, before anything is timed): sum(C_local) against the host expectation.
+    # If the prefetch-everything exchange order fails it, fall back to the double-buffered order and check again.
+    def selfcheck():
+        cm.replay_step()
+        torch.cuda.synchronize()
+        got = float(cm.replay_c.sum().item())
+        exp = expected_local_c_sum(cm)
+        err = torch.tensor([abs(got - exp) / max(abs(exp), 1e-300)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        return float(err.item())
+
+    selfcheck_err = selfcheck()
+    selfcheck_mode = "prefetch_all" if cm.prefetch_all else "double_buffered"
+    if selfcheck_err > 1e-9 and cm.prefetch_all:
+        cm.prefetch_all = False
+        cm.prev_ev_comp = None
+        # nbuf stays V: the double-buffered order only needs t % nbuf to be a valid buffer whose last reader (tick t-2 or
+        # earlier) has finished, which the `after` events of that order guarantee for any nbuf >= 2
+        selfcheck_err = selfcheck()
+        selfcheck_mode = "double_buffered (prefetch_all failed the self-check)"
     if os.environ.get("DBCSR_B200_CANNON_TRACE"):  # per-tick device timeline of one eager step (rank 0 prints it to stderr)
         cm.trace = []
         t0e = torch.cuda.Event(enable_timing=True)
@@ -507,6 +571,8 @@ def bench_main(args):
                         "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
                        if not args.no_e2e else None),
                "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph, "exchange": "cuda-ipc peer pull (copy engines over NVLink)" if cm.peer_buf is not None else "nccl send/recv",
+               "selfcheck": {"property": "sum(C_local) == colsum(A(I,:)) . rowsum(B(:,J)), max relative error over ranks", "rel_err": selfcheck_err,
+                             "exchange_order": selfcheck_mode},
                "graph_capture_error": getattr(cm, "capture_error", None), "wall_ms_per_step_incl_barriers": t_host * 1e3}
         print(json.dumps(out), flush=True)
     dist.barrier()
