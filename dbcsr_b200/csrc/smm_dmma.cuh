@@ -353,6 +353,8 @@ constexpr int TRACE_ENTRIES = 30;
 // FLUSH: 0 = per-element RED (flush_acc), 1 = bulk reduction through the TMA (flush_acc_bulk) from a scratch buffer per warp,
 //        2 = bulk reduction from the warp's (single) operand stage, which is free between two entries: no extra shared memory,
 //            but the copies of the next entry are issued only after the bulk engine has read the stage
+//        3 = like 2 with the image confined to the A half of the stage, so that the B copy of the next entry is issued BEFORE
+//            the flush and only the A copy waits for the bulk engine (experiment variant, not yet measured)
 template <int M, int N, int K, int NST, int WPC, int FLUSH>
 struct BaseGeom {
   using SH = Shape<M, N, K>;
@@ -371,6 +373,7 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
   using G = BaseGeom<M, N, K, NST, WPC, FLUSH>;
   constexpr int TM = SH::TM, TN = SH::TN;
   static_assert(FLUSH != 2 || (NST == 1 && SH::STAGE >= scratch_bytes(M, N)), "FLUSH 2 stages the C image in the single operand stage");
+  static_assert(FLUSH != 3 || (NST == 1 && SH::ABUF >= scratch_bytes(M, N)), "FLUSH 3 stages the C image in the A half of the stage");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -455,24 +458,30 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
     return r < 32 ? a : b;
   };
 
-  auto issue = [&](int e) {  // executed by the whole warp (uniform), the copies are issued by lane 0
+  // parts: 1 = arm the barrier with the byte count of both blocks + copy the B block, 2 = copy the A block, 3 = both
+  auto issue_parts = [&](int e, int parts) {  // executed by the whole warp (uniform), the copies are issued by lane 0
     const int3 p = entry(e);
     if (((ABL & ABL_NOTMA) != 0) ? (p.x < 0) : (lane == 0)) {
       const int sidx = (e - e0) % NST;
       unsigned char* stg = wbase + (size_t)sidx * SH::STAGE;
       const uint64_t ga = reinterpret_cast<uint64_t>(a_data + (p.x - 1));
       const uint64_t gb = reinterpret_cast<uint64_t>(b_data + (p.y - 1));
-      // expect first (the count must be known before the copies can complete), then copy
-      const uint32_t ba = stage_block<HINT>(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], false, pol_ab);
-      const uint32_t bb = stage_block<HINT>(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], false, pol_ab);
-      mbar_expect_tx(&bars[sidx], ba + bb);
-      stage_block<HINT>(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], true, pol_ab);
-      stage_block<HINT>(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], true, pol_ab);
-      if (TRACE) {
-        if (rec != nullptr && e - e0 < TRACE_ENTRIES) rec[4 + 4 * (e - e0)] = clock_now();
+      if ((parts & 1) != 0) {
+        // expect first (the count must be known before the copies can complete), then copy
+        const uint32_t ba = stage_block<HINT>(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], false, pol_ab);
+        const uint32_t bb = stage_block<HINT>(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], false, pol_ab);
+        mbar_expect_tx(&bars[sidx], ba + bb);
+        stage_block<HINT>(stg + SH::ABUF, gb, SH::B_BYTES, b_limit, &bars[sidx], true, pol_ab);
+      }
+      if ((parts & 2) != 0) {
+        stage_block<HINT>(stg, ga, SH::A_BYTES, a_limit, &bars[sidx], true, pol_ab);
+        if (TRACE) {
+          if (rec != nullptr && e - e0 < TRACE_ENTRIES) rec[4 + 4 * (e - e0)] = clock_now();
+        }
       }
     }
   };
+  auto issue = [&](int e) { issue_parts(e, 3); };
 
 #pragma unroll
   for (int p = 0; p < NST - 1; ++p)
@@ -493,7 +502,7 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
       __syncwarp();
       flush_acc_bulk<M, N, K>(c_data, c_first, acc, g, t, lane, scratch);
     }
-    else if constexpr (FLUSH == 2) {
+    else if constexpr (FLUSH == 2 || FLUSH == 3) {
       flush_acc_bulk<M, N, K>(c_data, c_first, acc, g, t, lane, wbase);
       // lane 0 issues the next entry's copies into this stage: only after the bulk engine has read the C image
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -516,15 +525,30 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
       if (ebase + 32 + lane < stack_size) nxt = ld_entry(stack, ebase + 32 + lane);
     }
     // stage (e-1)%NST was consumed by the previous iteration (guarded by the __syncwarp at its end): refill it
-    if constexpr (FLUSH != 2) {
+    if constexpr (FLUSH != 2 && FLUSH != 3) {
       if (e + NST - 1 < e1) issue(e + NST - 1);
     }
     const int3 p = entry(e);
-    if (p.z != cur_c) {
-      if (cur_c >= 0) flush(cur_c);
+    if constexpr (FLUSH == 3) {
+      // the C image only occupies the A half of the stage: the B block of this entry is already on its way while the bulk
+      // engine reads the image; only the A copy has to wait for it
+      if (p.z != cur_c && cur_c >= 0) {
+        issue_parts(e, 1);
+        flush(cur_c);
+        issue_parts(e, 2);
+      }
+      else {
+        issue(e);
+      }
       cur_c = p.z;
     }
-    if constexpr (FLUSH == 2) issue(e);  // after the flush, which borrows the stage
+    else {
+      if (p.z != cur_c) {
+        if (cur_c >= 0) flush(cur_c);
+        cur_c = p.z;
+      }
+      if constexpr (FLUSH == 2) issue(e);  // after the flush, which borrows the stage
+    }
     const int i = e - e0;
     const int sidx = i % NST;
     const unsigned char* stg = wbase + (size_t)sidx * SH::STAGE;

@@ -218,6 +218,15 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
       case 64:
         if constexpr (BaseGeom<M, N, K, 1, 16, 1>::SMEM <= 227 * 1024) return launch_base<M, N, K, 1, 16, 0, false, 1>(SMM_ARGS);
         break;
+      case 70:
+        if constexpr (Shape<M, N, K>::ABUF >= scratch_bytes(M, N)) return launch_base<M, N, K, 1, 4, 0, false, 3>(SMM_ARGS);
+        break;
+      case 71:
+        if constexpr (Shape<M, N, K>::ABUF >= scratch_bytes(M, N)) return launch_base<M, N, K, 1, 8, 0, false, 3>(SMM_ARGS);
+        break;
+      case 72:
+        if constexpr (Shape<M, N, K>::ABUF >= scratch_bytes(M, N)) return launch_base<M, N, K, 1, 4, 0, true, 3>(SMM_ARGS);
+        break;
       case 40: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH>(SMM_ARGS);
       case 41: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOLDS>(SMM_ARGS);
       case 42: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOTMA>(SMM_ARGS);
