@@ -227,6 +227,17 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
       case 72:
         if constexpr (Shape<M, N, K>::ABUF >= scratch_bytes(M, N)) return launch_base<M, N, K, 1, 4, 0, true, 3>(SMM_ARGS);
         break;
+      // autotune grid for every cubic shape: 100 + 10 * (index of warps per CTA in {2,4,8,12,16}) + FLUSH (0 or 2), one stage
+#  define SMM_TUNE_CASE(ID, WPC_, FLUSH_)                                                                      \
+  case ID:                                                                                                    \
+    if constexpr (BaseGeom<M, N, K, 1, WPC_, FLUSH_>::SMEM <= 227 * 1024 &&                                    \
+                  (FLUSH_ != 2 || Shape<M, N, K>::STAGE >= scratch_bytes(M, N)))                               \
+      return launch_base<M, N, K, 1, WPC_, 0, false, FLUSH_>(SMM_ARGS);                                        \
+    break;
+        SMM_TUNE_CASE(100, 2, 0) SMM_TUNE_CASE(102, 2, 2) SMM_TUNE_CASE(110, 4, 0) SMM_TUNE_CASE(112, 4, 2)
+        SMM_TUNE_CASE(120, 8, 0) SMM_TUNE_CASE(122, 8, 2) SMM_TUNE_CASE(130, 12, 0) SMM_TUNE_CASE(132, 12, 2)
+        SMM_TUNE_CASE(140, 16, 0) SMM_TUNE_CASE(142, 16, 2)
+#  undef SMM_TUNE_CASE
       case 40: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH>(SMM_ARGS);
       case 41: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOLDS>(SMM_ARGS);
       case 42: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOTMA>(SMM_ARGS);
