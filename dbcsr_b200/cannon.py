@@ -47,19 +47,23 @@ class Schedule:
         i, j = self.coords(rank)
         return (i + j + t) % self.V
 
+    # Home layout = Cannon's initial alignment (the skew the reference applies when it builds the images, make_images
+    # src/mm/dbcsr_mm_cannon.F:292-740): rank (i,j) is home to the k-slices it multiplies at tick 0, s = (i+j) mod V (and, when
+    # V > pc or V > pr, to the further slices congruent to it), so the first tick of every rank needs no message at all and tick t
+    # takes A from the t-th neighbour to the right and B from the t-th neighbour below.
     def home_a(self, i, s):
-        return self.rank_of(i, s % self.pc)
+        return self.rank_of(i, (s - i) % self.pc)
 
     def home_b(self, s, j):
-        return self.rank_of(s % self.pr, j)
+        return self.rank_of((s - j) % self.pr, j)
 
     def home_slices_a(self, rank):
         i, j = self.coords(rank)
-        return [s for s in range(self.V) if s % self.pc == j]
+        return [s for s in range(self.V) if (s - i) % self.pc == j]
 
     def home_slices_b(self, rank):
         i, j = self.coords(rank)
-        return [s for s in range(self.V) if s % self.pr == i]
+        return [s for s in range(self.V) if (s - j) % self.pr == i]
 
     def transfers(self, rank, t):
         """Messages of tick t seen from `rank`: (recv_a_from, recv_b_from, [(dst, 'a'|'b', s), ...]); None = local panel."""
@@ -216,6 +220,25 @@ class CannonMultiply:
             ops.append(dist.P2POp(dist.isend, self.home_buf[(kind, s2)], dst))
         return dist.batch_isend_irecv(ops) if ops else []
 
+    def tick_order(self):
+        """Order in which this rank takes its V ticks when every panel is pulled from read-only home buffers: rotated so that
+        the first tick is the one with the fewest bytes to pull."""
+        if getattr(self, "_tick_order", None) is None:
+            V = self.sched.V
+            cost = []
+            for t in range(V):
+                ra, rb, _ = self.sched.transfers(self.rank, t)
+                s = self.sched.slice_at(self.rank, t)
+                c = 0
+                for kind, src in (("a", ra), ("b", rb)):
+                    if src is not None:
+                        _, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
+                        c += nze * 8 + nblk * 12
+                cost.append(c)
+            t0 = int(np.argmin(cost))
+            self._tick_order = [(t0 + u) % V for u in range(V)]
+        return self._tick_order
+
     def panel_of_tick(self, t, kind):
         """(buffer tensor, nblks, nze) of the panel this rank multiplies at tick t (after its exchange completed)."""
         s = self.sched.slice_at(self.rank, t)
@@ -339,16 +362,21 @@ class CannonMultiply:
             return ev
 
         prefetch_all = self.prefetch_all and not fork_from_compute
+        order = list(range(V))
         if prefetch_all:
-            # one receive buffer per tick: the pull of tick t only has to wait for the PREVIOUS multiply's kernels of tick t
+            # one receive buffer per tick: the pull of tick t only has to wait for the PREVIOUS multiply's kernels of tick t.
+            # Pulled panels come from read-only home buffers, so a rank may take its ticks in any order: it starts with the tick
+            # that needs the fewest bytes from peers (usually none), the k-slices are still all visited exactly once.
+            order = self.tick_order()
             prev = getattr(self, "prev_ev_comp", None) or [None] * V
-            ev_comms = [exchange(0, prev[0])] + [None] * (V - 1)
+            ev_comms = [None] * V
+            ev_comms[order[0]] = exchange(order[0], prev[order[0]])
         else:
             ev_comm = exchange(0, None)
-        for t in range(V):
+        for it, t in enumerate(order):
             if prefetch_all:
-                if t == 1:  # the kernels of tick 0 are enqueued: now post every remaining pull of this multiply
-                    for u in range(1, V):
+                if it == 1:  # the kernels of the first tick are enqueued: now post every remaining pull of this multiply
+                    for u in order[1:]:
                         ev_comms[u] = exchange(u, prev[u])
                 ev_comm, nxt = ev_comms[t], None
             else:
