@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <thread>
+#include <numeric>
 #include <vector>
 
 #include "../../../include/dbcsr_acc.h"
@@ -467,10 +468,41 @@ int dbcsr_b200_filter_index(double filter_eps, const double* norms2, int nblks, 
   return last;
 }
 
-int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
-  // Final filter of the product (dbcsr_mm_multrec_finalize -> multrec_filtering) BEFORE the download: squared block norms in
-  // double on the device, 8 B per block to the host, index compaction there, then the surviving blocks are gathered into a
-  // contiguous device area in index order -- only those travel over PCIe.
+int dbcsr_b200_finalize_index(int nblks, int* rows, int* cols, const int* nelems, int* perm, int* blk_p_new, long long* nze) {
+  // dbcsr_finalize / dbcsr_merge_all, index part (work/dbcsr_work_operations.F:749-958): the work index (order of first touch)
+  // becomes BCSR order -- rows ascending, columns ascending within a row -- and the data area is compacted in that order.
+  if (nblks < 0) return -1;
+  std::vector<int> order((size_t)nblks);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    if (rows[x] != rows[y]) return rows[x] < rows[y];
+    return cols[x] < cols[y];
+  });
+  std::vector<int> r((size_t)nblks), c((size_t)nblks);
+  long long run = 0;
+  for (int i = 0; i < nblks; ++i) {
+    const int o = order[(size_t)i];
+    r[(size_t)i] = rows[o];
+    c[(size_t)i] = cols[o];
+    perm[i] = o;
+    if (run + 1 > 0x7fffffffLL) return -4;
+    blk_p_new[i] = (int)(run + 1);
+    run += nelems[o];
+  }
+  for (int i = 1; i < nblks; ++i)
+    if (r[(size_t)i] == r[(size_t)i - 1] && c[(size_t)i] == c[(size_t)i - 1]) return -5;  // a block may exist once only
+  std::copy(r.begin(), r.end(), rows);
+  std::copy(c.begin(), c.end(), cols);
+  if (nze != nullptr) *nze = run;
+  return 0;
+}
+
+namespace {
+// Final filter (do_filter; dbcsr_mm_multrec_finalize -> multrec_filtering) and/or BCSR ordering (bcsr_order; dbcsr_finalize) of
+// every thread's product BEFORE the download: squared block norms in double on the device, 8 B per block to the host, index
+// compaction / sort there, then the kept blocks are gathered into a contiguous device area in index order -- only those travel
+// over PCIe, and they arrive in their final place.
+int finalize_impl(dbcsr_b200_engine_t* e, double filter_eps, bool do_filter, bool bcsr_order) {
   if (e == nullptr || !(e->mode & DBCSR_B200_LAUNCH)) return -1;
   struct Scratch {
     std::vector<int> offs, nel;
@@ -505,10 +537,11 @@ int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
       rc = -40;
       break;
     }
-    if (c_dbcsr_acc_memcpy_h2d(x.offs.data(), x.d_offs, ib, ts.stream) != 0 || c_dbcsr_acc_memcpy_h2d(x.nel.data(), x.d_nel, ib, ts.stream) != 0 ||
-        libsmm_acc_b200_block_norms_f64(static_cast<const double*>(ts.c_dev), nb, static_cast<const int*>(x.d_offs),
-                                        static_cast<const int*>(x.d_nel), static_cast<double*>(x.d_norms), ts.stream) != 0 ||
-        c_dbcsr_acc_memcpy_d2h(x.d_norms, x.norms.data(), sizeof(double) * (size_t)nb, ts.stream) != 0)
+    if (do_filter &&
+        (c_dbcsr_acc_memcpy_h2d(x.offs.data(), x.d_offs, ib, ts.stream) != 0 || c_dbcsr_acc_memcpy_h2d(x.nel.data(), x.d_nel, ib, ts.stream) != 0 ||
+         libsmm_acc_b200_block_norms_f64(static_cast<const double*>(ts.c_dev), nb, static_cast<const int*>(x.d_offs),
+                                         static_cast<const int*>(x.d_nel), static_cast<double*>(x.d_norms), ts.stream) != 0 ||
+         c_dbcsr_acc_memcpy_d2h(x.d_norms, x.norms.data(), sizeof(double) * (size_t)nb, ts.stream) != 0))
       rc = -47;
   }
   // phase 2: compaction of the index on the host, gather of the kept blocks on the device
@@ -529,11 +562,30 @@ int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
       break;
     }
     long long nze = 0;
-    const int kept = dbcsr_b200_filter_index(filter_eps, x.norms.data(), nb, ts.f_rows.data(), ts.f_cols.data(), ts.f_blk_p.data(),
-                                             x.nel.data(), &nze);
+    int kept = nb;
+    if (do_filter)
+      kept = dbcsr_b200_filter_index(filter_eps, x.norms.data(), nb, ts.f_rows.data(), ts.f_cols.data(), ts.f_blk_p.data(), x.nel.data(),
+                                     &nze);
     ts.f_rows.resize((size_t)kept);
     ts.f_cols.resize((size_t)kept);
     ts.f_blk_p.resize((size_t)kept);
+    if (bcsr_order && kept > 1) {  // rows ascending, columns ascending within a row (dbcsr_finalize); blk_p follows its block
+      std::vector<int> order((size_t)kept);
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int p, int q) {
+        if (ts.f_rows[(size_t)p] != ts.f_rows[(size_t)q]) return ts.f_rows[(size_t)p] < ts.f_rows[(size_t)q];
+        return ts.f_cols[(size_t)p] < ts.f_cols[(size_t)q];
+      });
+      std::vector<int> r2((size_t)kept), c2((size_t)kept), p2((size_t)kept);
+      for (int j = 0; j < kept; ++j) {
+        r2[(size_t)j] = ts.f_rows[(size_t)order[(size_t)j]];
+        c2[(size_t)j] = ts.f_cols[(size_t)order[(size_t)j]];
+        p2[(size_t)j] = ts.f_blk_p[(size_t)order[(size_t)j]];
+      }
+      ts.f_rows.swap(r2);
+      ts.f_cols.swap(c2);
+      ts.f_blk_p.swap(p2);
+    }
     // gather plan: kept block j moves from its work-area offset to the next free offset of the compact area
     std::vector<int>& src_off = x.offs;  // reuse
     std::vector<int> dst_off((size_t)kept);
@@ -579,6 +631,14 @@ int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) {
     if (ts.stream != nullptr) c_dbcsr_acc_stream_sync(ts.stream);
   release();
   return rc;
+}
+}  // namespace
+
+int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps) { return finalize_impl(e, filter_eps, true, false); }
+
+int dbcsr_b200_engine_finalize_c(dbcsr_b200_engine_t* e, double filter_eps) {
+  // dbcsr_finalize on the device: optional final filter (filter_eps >= 0), then every thread's blocks in BCSR order, compacted
+  return finalize_impl(e, filter_eps, filter_eps >= 0.0, true);
 }
 
 int dbcsr_b200_engine_nchunks(const dbcsr_b200_engine_t* e) {

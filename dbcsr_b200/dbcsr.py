@@ -257,10 +257,18 @@ def dbcsr_finalize(row_blk_size, col_blk_size, parts, matrix_type=dbcsr_type_no_
         raise DbcsrAbort("Duplicate blocks in the work matrices")
     nze = out.row_blk_size[rows - 1].astype(np.int64) * out.col_blk_size[cols - 1]
     new_p = np.concatenate([[1], 1 + np.cumsum(nze)])
-    data = np.empty(int(new_p[-1] - 1))
-    for i in range(rows.size):
-        src = parts[int(part[i])][3]
-        data[new_p[i] - 1:new_p[i + 1] - 1] = src[blk_p[i] - 1:blk_p[i] - 1 + nze[i]]
+    # one vectorised gather: element e of sorted block i comes from (start of its part) + blk_p - 1 + e
+    sizes = np.array([np.asarray(p[3]).size for p in parts], dtype=np.int64)
+    base = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    data_all = np.concatenate([np.asarray(p[3], dtype=np.float64).reshape(-1) for p in parts])
+    src0 = base[part] + blk_p - 1
+    if np.any(src0 + nze > base[part] + sizes[part]):
+        raise DbcsrAbort("Work matrix index points outside its data area")
+    total = int(new_p[-1] - 1)
+    if np.array_equal(src0, new_p[:-1] - 1) and data_all.size == total:
+        data = data_all  # already in BCSR order and compact (finalized on the device)
+    else:
+        data = data_all[np.repeat(src0 - (new_p[:-1] - 1), nze) + np.arange(total, dtype=np.int64)]
     out.row_p = np.concatenate([[0], np.cumsum(np.bincount(rows - 1, minlength=out.nblkrows_total))])
     out.col_i = cols.astype(np.int32)
     out.blk_p = new_p[:-1].astype(np.int32)
@@ -286,8 +294,8 @@ class DeviceBackend:
             dm.upload_panels(np.ascontiguousarray(left.data), np.ascontiguousarray(right.data), b_list)
             dm.multiply(left.list3(), b_list, filter_eps=filter_eps, c_preset=c_preset, retain_sparsity=keep_sparsity,
                         c_symmetry=c_symmetry)
-            if final_filter:
-                dm.filter_c(filter_eps)
+            # dbcsr_finalize on the device: final filter (if any), BCSR order, compaction; the download is the final data area
+            dm.finalize_c(filter_eps if final_filter else None)
             prod = dm.download_c()
             return [(r, c, p, np.array(d, copy=True)) for (r, c, p, d) in prod.parts], dm.engine.flop()
         finally:

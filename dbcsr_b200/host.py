@@ -44,6 +44,8 @@ def _L():
         L.dbcsr_b200_engine_set_c_symmetry.argtypes = [_vp, _i, _vp, _vp]
         L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
+        L.dbcsr_b200_engine_finalize_c.argtypes = [_vp, ctypes.c_double]
+        L.dbcsr_b200_finalize_index.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_sync.argtypes = [_vp]
         L.dbcsr_b200_engine_reset.argtypes = [_vp]
         L.dbcsr_b200_engine_set_k_sizes.argtypes = [_vp, _vp, _i]
@@ -212,6 +214,12 @@ class Engine:
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_filter_c returned %d" % rc)
 
+    def finalize_c(self, filter_eps=None):
+        """dbcsr_finalize on the device: optional final filter, every thread's blocks in BCSR order, data compacted."""
+        rc = self.L.dbcsr_b200_engine_finalize_c(self.h, -1.0 if filter_eps is None else float(filter_eps))
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_engine_finalize_c returned %d" % rc)
+
     def set_k_sizes(self, k_sizes):
         ks = np.ascontiguousarray(k_sizes, dtype=np.int32)
         if self.L.dbcsr_b200_engine_set_k_sizes(self.h, ks.ctypes.data, ks.size) != 0:
@@ -303,3 +311,18 @@ def transpose_panel(acc, b_list3, k_sizes, n_sizes, b_dev_ptr, stream):
     scratch_d.free()
     if rc != 0:
         raise acclib.AccError("dbcsr_b200_transpose_panel returned %d" % rc)
+
+
+def finalize_index(rows, cols, nelems):
+    """dbcsr_finalize, index part (C++): returns (rows, cols, blk_p_new, perm, nze) of the BCSR-ordered index."""
+    L = _L()
+    r = np.ascontiguousarray(rows, dtype=np.int32).copy()
+    c = np.ascontiguousarray(cols, dtype=np.int32).copy()
+    ne = np.ascontiguousarray(nelems, dtype=np.int32)
+    perm = np.empty(r.size, dtype=np.int32)
+    bp = np.empty(r.size, dtype=np.int32)
+    nze = ctypes.c_longlong(0)
+    rc = L.dbcsr_b200_finalize_index(r.size, r.ctypes.data, c.ctypes.data, ne.ctypes.data, perm.ctypes.data, bp.ctypes.data, ctypes.byref(nze))
+    if rc != 0:
+        raise acclib.AccError("dbcsr_b200_finalize_index returned %d" % rc)
+    return r, c, bp, perm, int(nze.value)

@@ -166,6 +166,12 @@ class DeviceMultiply:
         assert getattr(self, "early", None) is None, "early per-thread D2H and the final filter exclude each other"
         self.engine.filter_c(filter_eps)
 
+    def finalize_c(self, filter_eps=None):
+        """dbcsr_finalize on the device before the download (work/dbcsr_work_operations.F:749-958 + the final filter when
+        filter_eps is given): every thread's blocks in BCSR order, data compacted - what comes over PCIe is final."""
+        assert getattr(self, "early", None) is None, "early per-thread D2H and the device finalize exclude each other"
+        self.engine.finalize_c(filter_eps)
+
     def set_result_buffers(self, out_arrays):
         """Pooled (pinned) host buffers for C, one per thread, each at least engine.c_capacity(t) elements: from now on every
         thread enqueues its own D2H right behind its last stack (download_c then only waits)."""

@@ -101,6 +101,15 @@ int dbcsr_b200_filter_index(double filter_eps, const double* norms2, int nblks, 
  * order.  Afterwards the c_* accessors, c_dev and c_to_host(_async) describe the filtered product (blk_p = compact offsets);
  * the next multiply/reset returns to the work matrices.  Not applied by DBCSR when retain_sparsity is set. */
 int dbcsr_b200_engine_filter_c(dbcsr_b200_engine_t* e, double filter_eps);
+/* dbcsr_finalize (work/dbcsr_work_operations.F:749-958), index part: sorts the nblks work-index entries (rows, cols; order of
+ * first touch) into BCSR order - rows ascending, columns ascending within a row - in place, returns perm (sorted position ->
+ * original position) and blk_p_new (1-based offsets of the data area compacted in that order; nelems = elements per ORIGINAL
+ * entry) and *nze.  Returns 0, -5 if a block appears twice. */
+int dbcsr_b200_finalize_index(int nblks, int* rows, int* cols, const int* nelems, int* perm, int* blk_p_new, long long* nze);
+/* dbcsr_finalize on the device (LAUNCH engines, after the last tick): like dbcsr_b200_engine_filter_c - the final filter is
+ * applied when filter_eps >= 0 - and in addition every thread's blocks are put into BCSR order before they are gathered, so the
+ * downloaded data area of a thread is the final data area of its block rows.  Accessors as after filter_c. */
+int dbcsr_b200_engine_finalize_c(dbcsr_b200_engine_t* e, double filter_eps);
 /* block sizes of the contraction index of the NEXT panels (Cannon ticks bring different k-slices); the stack map built at
  * creation (from the k_sizes given there: use the global right-matrix row block sizes) is kept */
 int dbcsr_b200_engine_set_k_sizes(dbcsr_b200_engine_t* e, const int* k_sizes, int nk);

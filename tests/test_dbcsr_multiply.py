@@ -120,3 +120,25 @@ def test_finalize_merges_work_matrices_into_bcsr():
     assert b[(3, 2)].T.reshape(-1).tolist() == [1.0, 2.0, 3.0, 4.0] and b[(1, 2)].shape == (2, 4)
     with pytest.raises(D.DbcsrAbort):
         D.dbcsr_finalize(rs, cs, [p0, (np.array([3]), np.array([2]), np.array([1]), np.zeros(4))])
+
+
+def test_finalize_index_cpp_matches_python_finalize():
+    """dbcsr_b200_finalize_index (C++, used by the device-side finalize) against dbcsr_finalize (Python) on random work indices."""
+    from dbcsr_b200 import host
+
+    rng = np.random.default_rng(0)
+    for nr, nc, nb in [(20, 15, 120), (1, 1, 1), (7, 9, 0), (50, 3, 150)]:
+        rs, cs = rng.integers(0, 6, nr), rng.integers(1, 6, nc)
+        cells = rng.choice(nr * nc, nb, replace=False)
+        rows, cols = (cells // nc + 1).astype(np.int32), (cells % nc + 1).astype(np.int32)
+        ne = (rs[rows - 1] * cs[cols - 1]).astype(np.int32)
+        blk_p = (1 + np.concatenate([[0], np.cumsum(ne)[:-1]])).astype(np.int32) if nb else np.zeros(0, dtype=np.int32)
+        data = rng.random(int(ne.sum()))
+        r, c, bp, perm, nze = host.finalize_index(rows, cols, ne)
+        m = D.dbcsr_finalize(rs, cs, [(rows, cols, blk_p, data)])
+        assert np.array_equal(c, m.col_i) and np.array_equal(bp, m.blk_p) and nze == data.size
+        assert np.array_equal(r, m.block_rows())
+        gathered = np.concatenate([data[blk_p[o] - 1:blk_p[o] - 1 + ne[o]] for o in perm]) if nb else np.zeros(0)
+        assert np.array_equal(gathered, m.data)
+    with pytest.raises(Exception):
+        host.finalize_index([1, 1], [2, 2], [4, 4])

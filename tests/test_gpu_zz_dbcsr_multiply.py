@@ -57,3 +57,40 @@ def test_filter_eps_on_device(backend):
         for cc in range(1, len(sizes) + 1):
             if (r, cc) not in got:
                 assert np.linalg.norm(exact[ro[r - 1]:ro[r], co[cc - 1]:co[cc]]) < 2 * eps
+
+
+def test_device_finalize_gives_bcsr_order_and_same_blocks(backend):
+    """dbcsr_b200_engine_finalize_c: after it every thread's index is in BCSR order with compact offsets, and the merged product
+    equals the one merged on the host from the first-touch-ordered work matrices (bit for bit)."""
+    from dbcsr_b200 import host, workload
+    from dbcsr_b200.multiply import DeviceMultiply
+
+    rng = np.random.default_rng(9)
+    bs = workload.block_sizes(40, [5, 13, 23], rng)
+    A = workload.random_panel(bs, bs, 0.3, rng)
+    B = workload.random_panel(bs, bs, 0.3, rng)
+    dm = DeviceMultiply(backend.acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=3, cfg=host.default_cfg(mm_stack_size=300))
+    try:
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        raw = dm.download_c()
+        ref = D.dbcsr_finalize(bs, bs, [(r, c, p, np.array(d, copy=True)) for (r, c, p, d) in raw.parts])
+        dm.finalize_c()
+        fin = dm.download_c()
+        for rows, cols, blk_p, data in fin.parts:
+            key = rows.astype(np.int64) * 100000 + cols
+            assert np.all(key[1:] > key[:-1])
+            nze = bs[rows - 1].astype(np.int64) * bs[cols - 1]
+            assert np.array_equal(blk_p, 1 + np.concatenate([[0], np.cumsum(nze)[:-1]])) and data.size == int(nze.sum())
+        got = D.dbcsr_finalize(bs, bs, [(r, c, p, np.array(d, copy=True)) for (r, c, p, d) in fin.parts])
+        assert np.array_equal(got.row_p, ref.row_p) and np.array_equal(got.col_i, ref.col_i) and np.array_equal(got.blk_p, ref.blk_p)
+        assert np.array_equal(got.data, ref.data)
+        # with the final filter: survivors only, still sorted
+        dm.multiply(A.list3(), B.list3())
+        dm.finalize_c(filter_eps=3.0)
+        flt = dm.download_c()
+        kept = D.dbcsr_finalize(bs, bs, [(r, c, p, np.array(d, copy=True)) for (r, c, p, d) in flt.parts])
+        want = {k for k, b in ref.blocks().items() if float((b * b).sum()) >= 9.0}
+        assert set(kept.blocks()) == want and 0 < len(want) < ref.nblks
+    finally:
+        dm.close()
