@@ -250,9 +250,58 @@ class CannonMultiply:
         idx = buf[nze * 8:nze * 8 + nblk * 12]
         return idx.cpu().numpy().view(np.int32).reshape(-1, 3).copy()
 
+    def _run_prefetch_all(self):
+        """run() with peer pull and one receive buffer per tick: every pull of the multiply (and the small D2H of each panel's
+        list index into a pinned buffer) is posted up front on a side stream, the host then builds and launches tick after tick
+        as the panels arrive - no device synchronisation between ticks, so the stacks of tick t+1 are built while the device
+        drains tick t (the pipelined multi-tick engine of SURVEY.md 8f)."""
+        torch = self.torch
+        V = self.sched.V
+        if getattr(self, "pull_stream", None) is None:
+            self.pull_stream = torch.cuda.Stream()  # non-blocking: the engine's streams never wait for it implicitly
+            self.idx_pinned = {}
+        order = self.tick_order()
+        evs, idx_host = {}, {}
+        with torch.cuda.stream(self.pull_stream):
+            for t in order:
+                self.post_exchange(t)
+                for kind in "ab":
+                    buf, nblk, nze = self.panel_of_tick(t, kind)
+                    nbytes = nblk * 12
+                    pin = self.idx_pinned.get((t, kind))
+                    if pin is None or pin.numel() < nbytes:
+                        pin = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
+                        self.idx_pinned[(t, kind)] = pin
+                    if nbytes:
+                        pin[:nbytes].copy_(buf[nze * 8:nze * 8 + nbytes], non_blocking=True)
+                    idx_host[(t, kind)] = (pin, nblk)
+                ev = torch.cuda.Event()
+                ev.record(self.pull_stream)
+                evs[t] = ev
+        per_tick = []
+        n_before = 0
+        for t in order:
+            evs[t].synchronize()  # panels and list indices of tick t have arrived
+            (abuf, _, _), (bbuf, _, _) = self.panel_of_tick(t, "a"), self.panel_of_tick(t, "b")
+            a_idx = idx_host[(t, "a")][0][:idx_host[(t, "a")][1] * 12].numpy().view(np.int32).reshape(-1, 3).copy()
+            b_idx = idx_host[(t, "b")][0][:idx_host[(t, "b")][1] * 12].numpy().view(np.int32).reshape(-1, 3).copy()
+            s = self.sched.slice_at(self.rank, t)
+            self.engine.set_k_sizes(self.k_sizes[s])
+            self.engine.multiply(a_idx, abuf.data_ptr(), b_idx, bbuf.data_ptr())
+            self.last_build_s += self.engine.build_seconds()
+            if self.mode & self.host.RECORD:
+                st = self.engine.stacks()
+                per_tick.append(st[n_before:])
+                n_before = len(st)
+        self.engine.sync()  # the next multiply pulls into the same receive buffers
+        self.flop = self.engine.flop()
+        return per_tick
+
     def run(self):
         """The whole multiply: V ticks; exchange of tick t+1 overlaps the local multiply of tick t.  Returns per-tick stack lists
         when recording."""
+        if self.prefetch_all and self.acc is not None and getattr(self, "run_prefetch", True):
+            return self._run_prefetch_all()
         V = self.sched.V
         pending = self.post_exchange(0)
         per_tick = []
@@ -444,10 +493,12 @@ def _axis_sums(panel, lo, hi, axis):
 def expected_local_c_sum(cm):
     """Size-independent property of the product (tests/test_gpu_multiply.py uses the same one): the sum of all elements of this
     rank's C(I, J) = A(I, :) B(:, J) equals colsum(A(I, :)) . rowsum(B(:, J))."""
-    A, B = cm.w["A"], cm.w["B"]
-    a = _axis_sums(A, cm.rsp[cm.i], cm.rsp[cm.i + 1], 0)
-    b = _axis_sums(B, cm.csp[cm.j], cm.csp[cm.j + 1], 1)
-    return float(np.dot(a, b))
+    if getattr(cm, "_expected_c_sum", None) is None:
+        A, B = cm.w["A"], cm.w["B"]
+        a = _axis_sums(A, cm.rsp[cm.i], cm.rsp[cm.i + 1], 0)
+        b = _axis_sums(B, cm.csp[cm.j], cm.csp[cm.j + 1], 1)
+        cm._expected_c_sum = float(np.dot(a, b))
+    return cm._expected_c_sum
 
 
 # ---------------------------------------------------------------------------------------------------------------- bench
@@ -566,9 +617,33 @@ def bench_main(args):
         cm.last_build_s = 0.0
         cm.run()
 
+    def engine_c_sum():
+        tot = 0.0
+        for th in range(cm.engine.nthreads):
+            ds = cm.engine.c_index(th)[3]
+            if ds:
+                buf = np.empty(ds)
+                cm.engine.c_to_host(th, buf)
+                tot += float(buf.sum())
+        return tot
+
+    def e2e_selfcheck():
+        exp = expected_local_c_sum(cm)
+        err = torch.tensor([abs(engine_c_sum() - exp) / max(abs(exp), 1e-300)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        return float(err.item())
+
     e2e_times = [0.0]
+    e2e_check = None
     if not args.no_e2e:
         cm.run()  # creates the engine's device C buffers
+        torch.cuda.synchronize()
+        e2e_check = {"rel_err": e2e_selfcheck(), "order": "all pulls posted up front, no sync between ticks" if cm.prefetch_all else "double buffered"}
+        if e2e_check["rel_err"] > 1e-9 and cm.prefetch_all:
+            cm.run_prefetch = False  # fall back to the tick-by-tick loop and check again
+            one_multiply()
+            torch.cuda.synchronize()
+            e2e_check = {"rel_err": e2e_selfcheck(), "order": "double buffered (pipelined order failed the self-check)"}
         for _ in range(max(1, args.e2e_warmup)):
             one_multiply()
         e2e_times = timed(one_multiply, args.e2e_steps, False)
@@ -596,6 +671,7 @@ def bench_main(args):
                             "note": "per-kernel roofline is reported by the N=1 run; this line is the distributed multiply"},
                "e2e": ({"value": flop / (float(tmax[4]) * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": float(tmax[4]),
                         "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": 0,
+                        "selfcheck": e2e_check,
                         "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
                        if not args.no_e2e else None),
                "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph, "exchange": "cuda-ipc peer pull (copy engines over NVLink)" if cm.peer_buf is not None else "nccl send/recv",
