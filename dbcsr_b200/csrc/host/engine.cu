@@ -303,7 +303,7 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
           r.size = size;
           r.host.assign(params7, params7 + 7 * (size_t)size);
           r.dev.resize(3 * (size_t)size);
-          dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, r.dev.data(), size);
+          dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, r.dev.data(), size, true);
           ts.recorded.push_back(std::move(r));
         }
         if (!(e->mode & DBCSR_B200_LAUNCH)) return;
@@ -318,7 +318,7 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
           ts.rc = -43;
           return;
         }
-        dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, b.host, size);
+        dbcsr_b200::accdrv_order_stack(e->kcfg, d, params7, b.host, size, true);
         if (c_dbcsr_acc_memcpy_h2d(b.host, b.dev, sizeof(int) * 3 * (size_t)size, ts.stream) != 0) {
           ts.rc = -44;
           return;

@@ -2,6 +2,7 @@
 #include "stack_builder.hpp"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <numeric>
 
@@ -77,6 +78,59 @@ void stack_sort(const int* params7, int* out3, int stack_size) {
   }
 }
 
+// Same order as stack_sort when c_first is strictly increasing in the C block id params(7,:) over the entries of the stack --
+// true for every stack LocalMultiply builds (a new block gets offset datasize + 1, existing blocks were laid out in index order):
+// ONE counting-sort pass over the (narrow) id range of the stack instead of three radix passes over random 28-byte records.
+bool stack_sort_by_block_id(const int* params7, int* out3, int stack_size, int id_lo, int id_hi) {
+  if (stack_size <= 0) return true;
+  int lo = id_lo, hi = id_hi;
+  if (lo <= 0 || hi < lo) {  // range not tracked by the builder: one more pass
+    lo = hi = params7[6];
+    for (int i = 1; i < stack_size; ++i) {
+      const int id = params7[7 * (size_t)i + 6];
+      lo = std::min(lo, id);
+      hi = std::max(hi, id);
+    }
+  }
+  const long long range = (long long)hi - lo + 1;
+  if (range > 4LL * stack_size + 4096) {
+    // ids scattered (the stack revisits old C tiles): stable LSD radix sort of compact (key, position) pairs, 11 bits per pass --
+    // two passes cover 4M blocks -- then one gather; the 28-byte records are read once sequentially and once by position
+    static thread_local std::vector<uint64_t> pa, pb;
+    pa.resize((size_t)stack_size);
+    pb.resize((size_t)stack_size);
+    for (int i = 0; i < stack_size; ++i) pa[(size_t)i] = ((uint64_t)(uint32_t)(params7[7 * (size_t)i + 6] - lo) << 32) | (uint32_t)i;
+    uint64_t* src = pa.data();
+    uint64_t* dst = pb.data();
+    for (int shift = 0; shift < 32 && ((uint64_t)(range - 1) >> shift) != 0; shift += 11) {
+      uint32_t cnt[2049] = {0};
+      for (int i = 0; i < stack_size; ++i) cnt[((src[i] >> (32 + shift)) & 2047u) + 1]++;
+      for (int d = 0; d < 2048; ++d) cnt[d + 1] += cnt[d];
+      for (int i = 0; i < stack_size; ++i) dst[cnt[(src[i] >> (32 + shift)) & 2047u]++] = src[i];
+      std::swap(src, dst);
+    }
+    for (int i = 0; i < stack_size; ++i) {
+      const int* p = params7 + 7 * (size_t)(uint32_t)src[i];
+      out3[3 * (size_t)i] = p[3];
+      out3[3 * (size_t)i + 1] = p[4];
+      out3[3 * (size_t)i + 2] = p[5];
+    }
+    return true;
+  }
+  static thread_local std::vector<int> count;
+  count.assign((size_t)range + 1, 0);
+  for (int i = 0; i < stack_size; ++i) count[(size_t)(params7[7 * (size_t)i + 6] - lo) + 1]++;
+  for (long long d = 0; d < range; ++d) count[(size_t)d + 1] += count[(size_t)d];
+  for (int i = 0; i < stack_size; ++i) {
+    const int* p = params7 + 7 * (size_t)i;
+    const int pos = count[(size_t)(p[6] - lo)]++;
+    out3[3 * (size_t)pos] = p[3];
+    out3[3 * (size_t)pos + 1] = p[4];
+    out3[3 * (size_t)pos + 2] = p[5];
+  }
+  return true;
+}
+
 void stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize) {
   std::vector<int> bin_arr((size_t)3 * binsize * nbins);
   std::vector<int> bin_top((size_t)nbins, 0);
@@ -104,11 +158,12 @@ void stack_binning(const int* params7, int* out3, int stack_size, int nbins, int
   }
 }
 
-void accdrv_order_stack(const Config& cfg, const StackDescr& d, const int* params7, int* out3, int stack_size) {
+void accdrv_order_stack(const Config& cfg, const StackDescr& d, const int* params7, int* out3, int stack_size, bool ids_monotone) {
   const int64_t flop_per_entry = 2LL * d.max_m * d.max_n * d.max_k;
   if (cfg.stack_sort) {
-    if (flop_per_entry > cfg.min_flop_sort)
-      stack_sort(params7, out3, stack_size);
+    if (flop_per_entry > cfg.min_flop_sort) {
+      if (!(ids_monotone && stack_sort_by_block_id(params7, out3, stack_size, d.id_lo, d.id_hi))) stack_sort(params7, out3, stack_size);
+    }
     else
       stack_binning(params7, out3, stack_size, cfg.binning_nbins, cfg.binning_binsize);
   }
@@ -211,7 +266,10 @@ void LocalMultiply::reset() {
   c_col_.clear();
   c_blk_p_.clear();
   for (auto& t : rows_) {
-    if (t.count > 0) std::fill(t.ids.begin(), t.ids.end(), 0);
+    if (t.count > 0) {
+      std::fill(t.ids.begin(), t.ids.end(), 0);
+      std::fill(t.dense.begin(), t.dense.end(), 0);
+    }
     t.count = 0;
   }
   datasize_ = 0;
@@ -236,6 +294,28 @@ void LocalMultiply::preset_c(const int* rows, const int* cols, const int* blk_p,
 // new block => offset = datasize + 1, appended to the work index (src/mm/dbcsr_mm_csr.F:309-323).
 int LocalMultiply::c_lookup_or_insert(int row, int col, int nze, bool& created, bool insert) {
   RowTable& t = rows_[(size_t)row];
+  if ((int)n_sizes_.size() <= kDenseRowLimit) {
+    // few block columns: one direct table per touched row (row-local and cache resident during a CSR leaf, like the hash table
+    // it replaces; the reference's hash only affects speed, src/utils/dbcsr_hash_table.f90)
+    if (t.dense.empty()) t.dense.assign(n_sizes_.size() + 1, 0);
+    int& slot = t.dense[(size_t)col];
+    if (slot != 0) {
+      created = false;
+      return slot;
+    }
+    if (!insert) {
+      created = false;
+      return 0;
+    }
+    created = true;
+    c_row_.push_back(row);
+    c_col_.push_back(col);
+    c_blk_p_.push_back(datasize_ + 1);
+    datasize_ += nze;
+    slot = (int)c_blk_p_.size();
+    ++t.count;
+    return slot;
+  }
   if (t.mask == 0) {
     t.cols.assign(16, 0);
     t.ids.assign(16, 0);
@@ -358,6 +438,14 @@ void LocalMultiply::csr_multiply_low(int mi, int mf, int ki, int kf, int ai, int
         p[4] = b_first;
         p[5] = offset;
         p[6] = c_blk_id;
+        StackDescr& sd = descr_[ws];
+        if (fill_[ws] == 0) {
+          sd.id_lo = sd.id_hi = c_blk_id;
+        }
+        else {
+          sd.id_lo = std::min(sd.id_lo, c_blk_id);
+          sd.id_hi = std::max(sd.id_hi, c_blk_id);
+        }
         fill_[ws]++;
         flop_ += 2LL * c_nze * k_size;
         if (fill_[ws] >= cfg_.mm_stack_size) flush_stacks(false);

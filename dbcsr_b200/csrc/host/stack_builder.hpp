@@ -32,6 +32,8 @@ struct Idx3 {
 struct StackDescr {
   int m = 0, n = 0, k = 0, max_m = 0, max_n = 0, max_k = 0;
   int defined_mnk = 0;
+  // smallest / largest C block id among the entries currently in the stack (maintained by LocalMultiply; 0 = unknown)
+  int id_lo = 0, id_hi = 0;
 };
 
 // rec_sort_index (src/mm/dbcsr_mm_common.F:227-309): quadtree-like ordering of a block list, in place.
@@ -41,7 +43,10 @@ void rec_sort_index(int mi, int mf, int ni, int nf, Idx3* a, int nele, std::vect
 void stack_sort(const int* params7, int* out3, int stack_size);
 void stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize);
 // what dbcsr_mm_accdrv_process does to a stack before upload (:481-491)
-void accdrv_order_stack(const Config& cfg, const StackDescr& d, const int* params7, int* out3, int stack_size);
+// ids_monotone: the caller guarantees that c_first increases strictly with the C block id (column 7) - LocalMultiply's stacks do -
+// which allows a one-pass counting sort with the same result as the stable sort by c_first
+void accdrv_order_stack(const Config& cfg, const StackDescr& d, const int* params7, int* out3, int stack_size, bool ids_monotone = false);
+bool stack_sort_by_block_id(const int* params7, int* out3, int stack_size, int id_lo = 0, int id_hi = 0);
 
 // map_most_common (src/dist/dbcsr_dist_util.F:753-812)
 void map_most_common(const std::vector<int>& array, int nmost_common, std::vector<int>& map, std::vector<int>& elements, int& max_val);
@@ -121,7 +126,9 @@ class LocalMultiply {
   struct RowTable {
     std::vector<int> cols, ids;  // ids == 0: empty slot
     int mask = 0, count = 0;
+    std::vector<int> dense;      // direct table col -> id (0 = absent) when the matrix has few enough block columns
   };
+  static constexpr int kDenseRowLimit = 16384;  // block columns up to which a touched C row gets a direct table (64 KB)
   std::vector<int> c_row_, c_col_, c_blk_p_;
   std::vector<RowTable> rows_;
   int datasize_ = 0;
