@@ -91,6 +91,110 @@ def pack_panel(panel):
     return buf
 
 
+class DistMatrix:
+    """The blocks of a global block matrix that ONE rank holds under a 2-d block distribution (DBCSR: row_dist / col_dist map
+    block rows / cols to process rows / cols, src/dist/dbcsr_dist_methods.F): global 1-based coordinates in BCSR order plus one
+    data area of column-major blocks.  Input of make_images()."""
+
+    def __init__(self, row_sizes, col_sizes, rows, cols, data):
+        from .workload import Panel
+
+        self.panel = Panel(row_sizes, col_sizes, rows, cols, data=np.ascontiguousarray(data, dtype=np.float64))
+
+    @classmethod
+    def from_global(cls, panel, row_dist, col_dist, sched, rank):
+        """The part of a replicated global panel that `rank` owns: blocks (r, c) with (row_dist[r], col_dist[c]) = its grid
+        coordinates (what dbcsr_redistribute hands to each rank)."""
+        i, j = sched.coords(rank)
+        sel = np.nonzero((np.asarray(row_dist)[panel.rows - 1] == i) & (np.asarray(col_dist)[panel.cols - 1] == j))[0]
+        nze = panel.row_sizes[panel.rows[sel] - 1].astype(np.int64) * panel.col_sizes[panel.cols[sel] - 1]
+        idx = np.concatenate([np.arange(o, o + z) for o, z in zip(panel.offsets[sel], nze)]) if sel.size else np.zeros(0, dtype=np.int64)
+        return cls(panel.row_sizes, panel.col_sizes, panel.rows[sel], panel.cols[sel], panel.data[idx])
+
+
+def make_images(dm, kind, sched, rank, world, rsp, csp, ksp, device="cpu"):
+    """make_images (src/mm/dbcsr_mm_cannon.F:292-740) for the Cannon driver: every rank sends each of its blocks to the HOME rank
+    of the panel the block belongs to - A(I_i, K_s) lives at sched.home_a(i, s), B(K_s, J_j) at sched.home_b(s, j), i.e. the
+    redistribution includes Cannon's initial alignment - in one all-to-all of packed messages (global coordinates, block data).
+    Returns {slice s: Panel} of this rank's home panels with PANEL-LOCAL coordinates in BCSR order (rows ascending, columns
+    ascending): exactly what CannonMultiply builds from a replicated workload with Panel.sub()."""
+    import torch
+    import torch.distributed as dist
+
+    from .workload import Panel
+
+    p = dm.panel
+    rsp_, csp_, ksp_ = np.asarray(rsp), np.asarray(csp), np.asarray(ksp)
+    if kind == "a":
+        pi = np.searchsorted(rsp_, p.rows - 1, side="right") - 1  # panel row of every block
+        ps = np.searchsorted(ksp_, p.cols - 1, side="right") - 1  # k-slice
+        dest = np.array([sched.home_a(int(i), int(s_)) for i, s_ in zip(pi, ps)], dtype=np.int64)
+    else:
+        ps = np.searchsorted(ksp_, p.rows - 1, side="right") - 1
+        pj = np.searchsorted(csp_, p.cols - 1, side="right") - 1
+        dest = np.array([sched.home_b(int(s_), int(j)) for s_, j in zip(ps, pj)], dtype=np.int64)
+    nze = p.row_sizes[p.rows - 1].astype(np.int64) * p.col_sizes[p.cols - 1]
+    # one message per destination: int64 header [nblk, nelem], int32 (row, col) pairs, float64 data
+    msgs = []
+    for d in range(world):
+        sel = np.nonzero(dest == d)[0]
+        coords = np.stack([p.rows[sel], p.cols[sel]], axis=1).astype(np.int32).reshape(-1)
+        idx = np.concatenate([np.arange(o, o + z) for o, z in zip(p.offsets[sel], nze[sel])]) if sel.size else np.zeros(0, dtype=np.int64)
+        data = p.data[idx]
+        head = np.array([sel.size, data.size], dtype=np.int64)
+        pad = np.zeros((-coords.nbytes) % 8, dtype=np.uint8)
+        msgs.append(np.concatenate([head.view(np.uint8), coords.view(np.uint8), pad, data.view(np.uint8)]))
+    if world > 1:
+        # message sizes by all_gather (every backend has it), payloads by grouped send/recv (gloo has no list all_to_all)
+        sizes_out = torch.tensor([m.size for m in msgs], dtype=torch.int64, device=device)
+        all_sizes = [torch.empty(world, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes_out)
+        sizes_in_l = [int(all_sizes[src][rank]) for src in range(world)]
+        send = [torch.from_numpy(m.copy()).to(device) for m in msgs]
+        recv = [torch.empty(max(n, 1), dtype=torch.uint8, device=device) for n in sizes_in_l]
+        ops = []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            ops.append(dist.P2POp(dist.irecv, recv[peer][:sizes_in_l[peer]], peer))
+            ops.append(dist.P2POp(dist.isend, send[peer], peer))
+        for wk in (dist.batch_isend_irecv(ops) if ops else []):
+            wk.wait()
+        recv[rank] = send[rank]
+        recv = [r[:n].cpu().numpy() for r, n in zip(recv, sizes_in_l)]
+    else:
+        recv = msgs
+    # unpack, group by slice, BCSR order with local coordinates
+    rows, cols, blocks = [], [], []
+    for m in recv:
+        nblk, nelem = (int(x) for x in m[:16].view(np.int64))
+        coords = m[16:16 + 8 * nblk].view(np.int32).reshape(-1, 2)
+        off = 16 + 8 * nblk + ((-8 * nblk) % 8)
+        data = m[off:off + 8 * nelem].view(np.float64)
+        o = 0
+        for (r, c) in coords:
+            z = int(p.row_sizes[r - 1]) * int(p.col_sizes[c - 1])
+            rows.append(int(r))
+            cols.append(int(c))
+            blocks.append(data[o:o + z])
+            o += z
+    rows, cols = np.array(rows, dtype=np.int64), np.array(cols, dtype=np.int64)
+    i, j = sched.coords(rank)
+    out = {}
+    slices = sched.home_slices_a(rank) if kind == "a" else sched.home_slices_b(rank)
+    for s_ in slices:
+        if kind == "a":
+            r_lo, r_hi, c_lo, c_hi = rsp[i], rsp[i + 1], ksp[s_], ksp[s_ + 1]
+        else:
+            r_lo, r_hi, c_lo, c_hi = ksp[s_], ksp[s_ + 1], csp[j], csp[j + 1]
+        sel = np.nonzero((rows > r_lo) & (rows <= r_hi) & (cols > c_lo) & (cols <= c_hi))[0]
+        sel = sel[np.lexsort((cols[sel], rows[sel]))]
+        pan = Panel(p.row_sizes[r_lo:r_hi], p.col_sizes[c_lo:c_hi], rows[sel] - r_lo, cols[sel] - c_lo)
+        pan.data = np.concatenate([blocks[k] for k in sel]) if sel.size else np.zeros(0)
+        out[s_] = pan
+    return out
+
+
 class CannonMultiply:
     """One rank of the distributed multiply.  `device` = torch device of this rank ('cuda:N' with NCCL, 'cpu' with gloo for tests).
     acc = dbcsr_b200.lib.Acc (None on CPU: stacks are only recorded, nothing is launched)."""
@@ -121,11 +225,18 @@ class CannonMultiply:
         self.engine = host.Engine(self.m_sizes, self.n_sizes, bs, nthreads=nthreads, mode=mode, cfg=self.cfg)
         # ---- home panels (initial distribution; excluded from timing like the reference's make_images)
         self.home = {}
-        A, B = w["A"], w["B"]
-        for s in sc.home_slices_a(rank):
-            self.home[("a", s)] = A.sub(self.rsp[self.i], self.rsp[self.i + 1], self.ksp[s], self.ksp[s + 1])
-        for s in sc.home_slices_b(rank):
-            self.home[("b", s)] = B.sub(self.ksp[s], self.ksp[s + 1], self.csp[self.j], self.csp[self.j + 1])
+        if "A_dist" in w:
+            # distributed input: this rank only holds its blocks of A and B (DistMatrix); the images are made by an all-to-all
+            for s, pan in make_images(w["A_dist"], "a", sc, rank, world, self.rsp, self.csp, self.ksp, self.device).items():
+                self.home[("a", s)] = pan
+            for s, pan in make_images(w["B_dist"], "b", sc, rank, world, self.rsp, self.csp, self.ksp, self.device).items():
+                self.home[("b", s)] = pan
+        else:
+            A, B = w["A"], w["B"]
+            for s in sc.home_slices_a(rank):
+                self.home[("a", s)] = A.sub(self.rsp[self.i], self.rsp[self.i + 1], self.ksp[s], self.ksp[s + 1])
+            for s in sc.home_slices_b(rank):
+                self.home[("b", s)] = B.sub(self.ksp[s], self.ksp[s + 1], self.csp[self.j], self.csp[self.j + 1])
         self.home_buf, self.home_meta = {}, {}
         for key, p in self.home.items():
             t_ = torch.from_numpy(pack_panel(p)).to(self.device)

@@ -131,3 +131,69 @@ def test_distributed_multiply_gloo(world, sizes):
         den += float((ref ** 2).sum())
     assert (num / den) ** 0.5 <= 1e-12
     assert flop == sum(2 * int(bs[r - 1]) * int(bs[c - 1]) * int(bs[B.cols[B.rows == c] - 1].sum()) for r, c in zip(A.rows, A.cols))
+
+
+def _images_worker(rank, world, port, nblk, sizes, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(321)
+    bs = workload.block_sizes(nblk, sizes, rng)
+    A = workload.random_panel(bs, bs, 0.3, rng)
+    B = workload.random_panel(bs, bs, 0.3, rng)
+    sc = cannon.Schedule(world)
+    # a 2-d block distribution unrelated to the Cannon layout (DBCSR: random / round-robin row_dist, col_dist)
+    row_dist = rng.integers(0, sc.pr, nblk)
+    col_dist = rng.integers(0, sc.pc, nblk)
+    w_rep = dict(name="t", nblk=nblk, sizes=sizes, occupation=0.3, m_sizes=bs, n_sizes=bs, k_sizes=bs, A=A, B=B, seed=321)
+    w_dist = dict(w_rep)
+    w_dist["A_dist"] = cannon.DistMatrix.from_global(A, row_dist, col_dist, sc, rank)
+    w_dist["B_dist"] = cannon.DistMatrix.from_global(B, row_dist, col_dist, sc, rank)
+    from dbcsr_b200 import host
+
+    cfg = host.default_cfg(mm_stack_size=200, n_stacks=max(3, len(sizes)))
+    cm_rep = cannon.CannonMultiply(w_rep, rank, world, "cpu", acc=None, nthreads=1, cfg=cfg)
+    cm_dist = cannon.CannonMultiply(w_dist, rank, world, "cpu", acc=None, nthreads=1, cfg=cfg)
+    same = sorted(cm_rep.home) == sorted(cm_dist.home)
+    for key in cm_rep.home:
+        a, b = cm_rep.home[key], cm_dist.home.get(key)
+        same = same and b is not None and np.array_equal(a.rows, b.rows) and np.array_equal(a.cols, b.cols) and np.array_equal(a.data, b.data) \
+            and np.array_equal(a.row_sizes, b.row_sizes) and np.array_equal(a.col_sizes, b.col_sizes)
+    owned = (w_dist["A_dist"].panel.nblks, w_dist["B_dist"].panel.nblks)
+    st_rep, st_dist = cm_rep.run(), cm_dist.run()
+    same_stacks = len(st_rep) == len(st_dist) and all(
+        len(x) == len(y) and all(np.array_equal(p["host"], r["host"]) for p, r in zip(x, y)) for x, y in zip(st_rep, st_dist))
+    q.put((rank, bool(same), bool(same_stacks), owned, cm_dist.engine.flop()))
+    dist.barrier()
+    cm_rep.close()
+    cm_dist.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,sizes", [(2, [23]), (8, [5, 13, 23])])
+def test_make_images_from_distributed_input_gloo(world, sizes):
+    """make_images: ranks that only hold their own blocks of A and B (2-d block distribution) exchange them in one all-to-all and
+    end up with exactly the home panels (Cannon's initial alignment, panel-local BCSR order) that slicing a replicated matrix
+    gives, hence identical stacks in the multiply."""
+    import torch.multiprocessing as mp
+
+    nblk = 24
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_images_worker, args=(r, world, port, nblk, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(321)
+    bs = workload.block_sizes(nblk, sizes, rng)
+    A = workload.random_panel(bs, bs, 0.3, rng)
+    B = workload.random_panel(bs, bs, 0.3, rng)
+    assert sum(r[3][0] for r in results) == A.nblks and sum(r[3][1] for r in results) == B.nblks  # every block owned once
+    for rank, same, same_stacks, owned, flop in results:
+        assert same and same_stacks, rank
+    assert sum(r[4] for r in results) > 0
