@@ -197,3 +197,104 @@ def test_make_images_from_distributed_input_gloo(world, sizes):
     for rank, same, same_stacks, owned, flop in results:
         assert same and same_stacks, rank
     assert sum(r[4] for r in results) > 0
+
+
+def test_replay_and_pipelined_run_control_flow_with_mocked_cuda():
+    """The GPU-only driver paths of the Cannon bench (replay_step with one receive buffer per tick and all pulls posted up front;
+    _run_prefetch_all = pipelined multi-tick engine) dry-run on CPU for all 8 ranks of the 2x4 grid: CUDA streams / events are
+    mocked, peer access is emulated by handing every rank the other ranks' home buffers, libsmm_acc_process is a counter.
+    Checks: no Python error, every tick launches its recorded stacks, and after a step the buffer of every (tick, kind) holds
+    exactly the home panel of the slice that tick multiplies."""
+    import contextlib
+    import types
+    import unittest.mock as um
+
+    import torch
+
+    from dbcsr_b200 import host
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    class FakeStream:
+        def __init__(self, priority=0):
+            pass
+
+        def wait_event(self, e):
+            assert isinstance(e, FakeEvent)
+
+        def synchronize(self):
+            pass
+
+    fake_cuda = types.SimpleNamespace(Event=FakeEvent, Stream=FakeStream, stream=lambda s: contextlib.nullcontext(),
+                                      current_stream=lambda: FakeStream(), synchronize=lambda: None)
+
+    class FakeTorch:
+        def __getattr__(self, name):
+            return fake_cuda if name == "cuda" else getattr(torch, name)
+
+    launched = []
+
+    class FakeAcc:
+        def process(self, host7, dev, S, a, b, c, m, n, k, dm, s1, s2):
+            launched.append(S)
+            return 0
+
+    world = 8
+    sc = cannon.Schedule(world)
+    w = workload.make_config("cfg2", nblk=48)
+    cms = []
+    with um.patch("torch.distributed.all_reduce", lambda t, op=None: None):
+        for r in range(world):
+            cms.append(cannon.CannonMultiply(w, r, world, "cpu", acc=None, nthreads=1))
+    meta = sum(torch.from_numpy(cm.meta) for cm in cms).numpy()  # what the all_reduce of the panel sizes would have produced
+    max_bytes = int((meta[..., 1] * 8 + meta[..., 0] * 12).max())
+    orig_empty = torch.empty
+    for r, cm in enumerate(cms):
+        cm.meta = meta
+        cm.peer_buf = {(q,) + key: t for q, other in enumerate(cms) if q != r for key, t in other.home_buf.items()}
+        cm.prefetch_all, cm.nbuf = True, sc.V
+        cm.recv = {kind: [torch.empty(max(max_bytes, 16), dtype=torch.uint8) for _ in range(cm.nbuf)] for kind in "ab"}
+        cm.torch = FakeTorch()
+        assert cm.tick_order()[0] == 0  # Cannon's initial alignment: the first tick needs no pull on any rank
+        ra, rb, _ = sc.transfers(r, 0)
+        assert ra is None and rb is None
+        per_tick = cm.run()  # record mode: tick-by-tick loop with (emulated) peer copies
+        assert len(per_tick) == sc.V
+        cm.replay = [[(0, st["dev"].shape[0], st["max_m"], st["max_n"], st["max_k"], st["defined_mnk"]) for st in tick] for tick in per_tick]
+        cm.replay_stacks = torch.zeros(8, dtype=torch.int32)
+        cm.replay_cs = [torch.zeros(4), torch.zeros(4)]
+        cm.zero_stream, cm.ev_zero, cm.ev_free = FakeStream(), [FakeEvent(), FakeEvent()], [FakeEvent(), FakeEvent()]
+        cm.step_no, cm.cs, cm.cs_torch, cm.comm_stream = 0, 0, FakeStream(), FakeStream()
+        cm.acc = FakeAcc()
+        for kind in "ab":  # poison the receive buffers: the replay has to refill them
+            for b in cm.recv[kind]:
+                b.fill_(255)
+        n0 = len(launched)
+        for _ in range(3):
+            cm.replay_step()
+        assert len(launched) - n0 == 3 * sum(len(x) for x in cm.replay)
+        for t in range(sc.V):
+            for kind in "ab":
+                buf, nblk, nze = cm.panel_of_tick(t, kind)
+                s = sc.slice_at(r, t)
+                src = cm.panel_meta(kind, s, cm.i, cm.j)[0]
+                n = nze * 8 + nblk * 12
+                assert torch.equal(buf[:n], cms[src].home_buf[(kind, s)][:n]), (r, t, kind)
+    # pipelined engine path on two ranks (the engine records instead of launching)
+    for cm in cms[:2]:
+        cm.engine.reset()
+        cm.mode = host.RECORD
+        with um.patch("torch.empty", lambda *a, **k: orig_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"})):
+            per_tick = cm._run_prefetch_all()
+        assert len(per_tick) == sc.V and cm.flop > 0
+    for cm in cms:
+        cm.acc = None
+        cm.close()
