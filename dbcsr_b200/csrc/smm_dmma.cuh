@@ -353,6 +353,8 @@ constexpr int TRACE_ENTRIES = 30;
 // FLUSH: 0 = per-element RED (flush_acc), 1 = bulk reduction through the TMA (flush_acc_bulk) from a scratch buffer per warp,
 //        2 = bulk reduction from the warp's (single) operand stage, which is free between two entries: no extra shared memory,
 //            but the copies of the next entry are issued only after the bulk engine has read the stage
+//        4 = one scratch image per CTA, taken under a shared-memory lock: the copies of the next entry are issued before the
+//            flush as in the RED kernel and the price is one image instead of one per warp (experiment variant, not yet measured)
 //        3 = like 2 with the image confined to the A half of the stage, so that the B copy of the next entry is issued BEFORE
 //            the flush and only the A copy waits for the bulk engine (experiment variant, not yet measured)
 template <int M, int N, int K, int NST, int WPC, int FLUSH>
@@ -361,7 +363,9 @@ struct BaseGeom {
   static constexpr int BAR_BYTES = round_up_c(WPC * NST * 8, 128);
   static constexpr int SCRATCH = FLUSH == 1 ? scratch_bytes(M, N) : 0;
   static constexpr int PER_WARP = NST * SH::STAGE + SCRATCH;
-  static constexpr int SMEM = BAR_BYTES + WPC * PER_WARP;
+  // FLUSH 4: ONE scratch image per CTA (behind the warps' stages) + a lock word in front of it
+  static constexpr int CTA_SCRATCH = FLUSH == 4 ? 128 + scratch_bytes(M, N) : 0;
+  static constexpr int SMEM = BAR_BYTES + WPC * PER_WARP + CTA_SCRATCH;
 };
 
 template <int M, int N, int K, int NST, int WPC, int HINT = 0, bool TRACE = false, int FLUSH = 0, int ABL = 0>
@@ -385,6 +389,10 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
   // (stacks only accumulate into C with RED, so consecutive drains are independent); the matching wait sits at the very end so
   // that a kernel never COMPLETES before its predecessor has (later memcpys / events keep plain stream-order semantics).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if constexpr (FLUSH == 4) {  // the only CTA-wide barrier of this kernel: the scratch lock starts open (before any warp leaves)
+    if (threadIdx.x == 0) *reinterpret_cast<int*>(smem_raw + G::BAR_BYTES + (size_t)WPC * G::PER_WARP) = 0;
+    __syncthreads();
+  }
   if (n0 >= n1) {  // warps never synchronise with each other
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
@@ -501,6 +509,23 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
       flush_acc_bulk<M, N, K>(c_data, c_first, acc, g, t, lane, scratch);
+    }
+    else if constexpr (FLUSH == 4) {
+      // CTA-wide scratch image under a spin lock (the holder never waits for another warp, so this cannot deadlock)
+      unsigned char* cta_scratch = smem_raw + G::BAR_BYTES + (size_t)WPC * G::PER_WARP;
+      int* lock = reinterpret_cast<int*>(cta_scratch);
+      if (lane == 0) {
+        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
+        __threadfence_block();
+      }
+      __syncwarp();
+      flush_acc_bulk<M, N, K>(c_data, c_first, acc, g, t, lane, cta_scratch + 128);
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the image has been read: the next holder may overwrite it
+        __threadfence_block();
+        atomicExch(lock, 0);
+      }
+      __syncwarp();
     }
     else if constexpr (FLUSH == 2 || FLUSH == 3) {
       flush_acc_bulk<M, N, K>(c_data, c_first, acc, g, t, lane, wbase);

@@ -238,6 +238,8 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
         SMM_TUNE_CASE(120, 8, 0) SMM_TUNE_CASE(122, 8, 2) SMM_TUNE_CASE(130, 12, 0) SMM_TUNE_CASE(132, 12, 2)
         SMM_TUNE_CASE(140, 16, 0) SMM_TUNE_CASE(142, 16, 2)
 #  undef SMM_TUNE_CASE
+      case 75: return launch_base<M, N, K, 1, 4, 0, false, 4>(SMM_ARGS);
+      case 76: return launch_base<M, N, K, 1, 8, 0, false, 4>(SMM_ARGS);
       case 40: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH>(SMM_ARGS);
       case 41: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOLDS>(SMM_ARGS);
       case 42: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOTMA>(SMM_ARGS);
