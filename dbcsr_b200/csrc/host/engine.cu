@@ -70,6 +70,26 @@ struct ThreadState {
   size_t c_final_capacity = 0;
   int rc = 0;
   double build_seconds = 0.0;
+  // statistics of dbcsr_mm_sched (src/mm/dbcsr_mm_sched.F:266-382,392-461): per (m,n,k) entries / stacks handed to the
+  // accelerator and how many of those stacks ran on an untuned kernel; inhomogeneous stacks are booked under (0,0,0)
+  struct MnkStat {
+    int m = 0, n = 0, k = 0;
+    long long entries_acc = 0, nstacks_acc = 0, nstacks_acc_untuned = 0, flop = 0;
+  };
+  std::vector<MnkStat> stats;
+  void stats_add(int m, int n, int k, long long entries, long long flop, bool untuned) {
+    for (auto& x : stats)
+      if (x.m == m && x.n == n && x.k == k) {
+        x.entries_acc += entries;
+        x.nstacks_acc += 1;
+        x.nstacks_acc_untuned += untuned ? 1 : 0;
+        x.flop += flop;
+        return;
+      }
+    MnkStat x;
+    x.m = m, x.n = n, x.k = k, x.entries_acc = entries, x.nstacks_acc = 1, x.nstacks_acc_untuned = untuned ? 1 : 0, x.flop = flop;
+    stats.push_back(x);
+  }
 };
 
 }  // namespace
@@ -293,8 +313,19 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
       if (e->mode & DBCSR_B200_LAUNCH) cudaSetDevice(e->device);  // the active device is per host thread
       const auto t0 = std::chrono::steady_clock::now();
       int next_buf = 0;
+      auto book = [&](const StackDescr& d, const int* params7, int size, bool untuned) {
+        long long flop = 0;
+        if (d.defined_mnk) {
+          flop = 2LL * d.m * d.n * d.k * size;
+        }
+        else {
+          for (int i = 0; i < size; ++i) flop += 2LL * params7[7 * (size_t)i] * params7[7 * (size_t)i + 1] * params7[7 * (size_t)i + 2];
+        }
+        ts.stats_add(d.defined_mnk ? d.m : 0, d.defined_mnk ? d.n : 0, d.defined_mnk ? d.k : 0, size, flop, untuned);
+      };
       auto dispatch = [&](int stack_number, const StackDescr& d, const int* params7, int size) {
         if (ts.rc != 0) return;
+        if (!(e->mode & DBCSR_B200_LAUNCH)) book(d, params7, size, false);
         if (e->mode & DBCSR_B200_RECORD) {
           RecordedStack r;
           r.d = d;
@@ -329,6 +360,7 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
           ts.rc = rc;  // the reference would now run this stack on the CPU; this engine has no CPU path and reports the code
           return;
         }
+        book(d, params7, size, rc == 10);
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
       int slice_no = 0;
@@ -432,6 +464,52 @@ int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const in
   for (int t = 0; t < nthreads; ++t)  // the staging vectors die here
     if (e->th[(size_t)t].stream != nullptr && c_dbcsr_acc_stream_sync(e->th[(size_t)t].stream) != 0) return -1;
   return 0;
+}
+
+int dbcsr_b200_engine_stats(const dbcsr_b200_engine_t* e, long long* table, int max_rows, long long* totals) {
+  // the table DBCSR prints at finalize (dbcsr_mm_sched_print_statistics): merged over the threads like
+  // stats_collect_from_threads (src/mm/dbcsr_mm_sched.F:463-505); accumulates over all multiplies of the engine
+  if (e == nullptr) return -1;
+  std::vector<ThreadState::MnkStat> all;
+  for (const auto& ts : e->th)
+    for (const auto& x : ts.stats) {
+      bool found = false;
+      for (auto& y : all)
+        if (y.m == x.m && y.n == x.n && y.k == x.k) {
+          y.entries_acc += x.entries_acc;
+          y.nstacks_acc += x.nstacks_acc;
+          y.nstacks_acc_untuned += x.nstacks_acc_untuned;
+          y.flop += x.flop;
+          found = true;
+          break;
+        }
+      if (!found) all.push_back(x);
+    }
+  std::sort(all.begin(), all.end(), [](const ThreadState::MnkStat& a, const ThreadState::MnkStat& b) { return a.flop > b.flop; });
+  long long tot_flop = 0, tot_entries = 0, tot_stacks = 0;
+  for (const auto& x : all) {
+    tot_flop += x.flop;
+    tot_entries += x.entries_acc;
+    tot_stacks += x.nstacks_acc;
+  }
+  if (totals != nullptr) {
+    totals[0] = tot_flop;
+    totals[1] = tot_entries;
+    totals[2] = tot_stacks;
+  }
+  const int n = (int)all.size();
+  if (table != nullptr)
+    for (int i = 0; i < n && i < max_rows; ++i) {
+      long long* r = table + 7 * (size_t)i;
+      r[0] = all[(size_t)i].m;
+      r[1] = all[(size_t)i].n;
+      r[2] = all[(size_t)i].k;
+      r[3] = all[(size_t)i].entries_acc;
+      r[4] = all[(size_t)i].nstacks_acc;
+      r[5] = all[(size_t)i].nstacks_acc_untuned;
+      r[6] = all[(size_t)i].flop;
+    }
+  return n;
 }
 
 int dbcsr_b200_engine_set_c_symmetry(dbcsr_b200_engine_t* e, int on, const int* global_rows, const int* global_cols) {

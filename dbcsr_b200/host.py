@@ -42,6 +42,7 @@ def _L():
         L.dbcsr_b200_engine_set_chunk_events.argtypes = [_vp, _vp, _i]
         L.dbcsr_b200_engine_preset_c.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
         L.dbcsr_b200_engine_set_c_symmetry.argtypes = [_vp, _i, _vp, _vp]
+        L.dbcsr_b200_engine_stats.argtypes = [_vp, _vp, _i, _vp]
         L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
         L.dbcsr_b200_engine_finalize_c.argtypes = [_vp, ctypes.c_double]
@@ -213,6 +214,16 @@ class Engine:
         rc = self.L.dbcsr_b200_engine_filter_c(self.h, float(filter_eps))
         if rc != 0:
             raise acclib.AccError("dbcsr_b200_engine_filter_c returned %d" % rc)
+
+    def stats(self):
+        """Scheduler statistics (DBCSR's STATISTICS table): list of dicts per (m,n,k), ordered by flop, and the totals."""
+        n = self.L.dbcsr_b200_engine_stats(self.h, None, 0, None)
+        table = np.zeros((max(n, 1), 7), dtype=np.int64)
+        totals = np.zeros(3, dtype=np.int64)
+        n = self.L.dbcsr_b200_engine_stats(self.h, table.ctypes.data, table.shape[0], totals.ctypes.data)
+        rows = [dict(m=int(r[0]), n=int(r[1]), k=int(r[2]), entries=int(r[3]), stacks=int(r[4]), stacks_untuned=int(r[5]), flop=int(r[6]))
+                for r in table[:n]]
+        return rows, dict(flop=int(totals[0]), entries=int(totals[1]), stacks=int(totals[2]))
 
     def finalize_c(self, filter_eps=None):
         """dbcsr_finalize on the device: optional final filter, every thread's blocks in BCSR order, data compacted."""

@@ -141,6 +141,12 @@ long long dbcsr_b200_engine_flop(const dbcsr_b200_engine_t* e);
 /* seconds the host threads spent building+ordering stacks / waiting for free stack buffers in the last multiply (max over threads) */
 double dbcsr_b200_engine_build_seconds(const dbcsr_b200_engine_t* e);
 
+/* Statistics of the scheduler (dbcsr_mm_sched, src/mm/dbcsr_mm_sched.F:266-382,392-505; the table DBCSR prints at finalize),
+ * accumulated over every multiply of the engine and merged over its threads.  table: up to max_rows rows of 7 values
+ * (m, n, k, stack entries processed on the accelerator, stacks, stacks that ran on an untuned kernel, flop), ordered by flop;
+ * inhomogeneous stacks are booked under (0,0,0).  totals[3] = flop, entries, stacks.  Returns the number of distinct (m,n,k). */
+int dbcsr_b200_engine_stats(const dbcsr_b200_engine_t* e, long long* table, int max_rows, long long* totals);
+
 /* recorded stacks (RECORD mode), in dispatch order per thread then concatenated thread by thread */
 int dbcsr_b200_engine_nstacks(const dbcsr_b200_engine_t* e);
 /* info[10] = m, n, k, max_m, max_n, max_k, defined_mnk, stack_size, thread, stack_number */

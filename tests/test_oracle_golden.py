@@ -162,4 +162,13 @@ def test_h2o_statistics_from_reference_docs():
     assert len(stacks) * 50 == 1600
     assert abs(matmuls / len(stacks) - 17652.1) < 0.05
     assert all(s["m"] == 23 and s["n"] == 23 and s["k"] == 23 and s["defined_mnk"] for s in stacks)
+    # the same numbers through the engine's own STATISTICS table (dbcsr_mm_sched's counters, merged over the 32 threads), after
+    # the 50 multiplications of the perf run: one (m,n,k) row "flops 23 x 23 x 23" and the totals of the documentation
+    for _ in range(49):
+        eng.reset()
+        eng.multiply(np.array(A.index_list(), dtype=np.int32), None, np.array(B.index_list(), dtype=np.int32), None)
+    rows, totals = eng.stats()
+    assert len(rows) == 1 and (rows[0]["m"], rows[0]["n"], rows[0]["k"]) == (23, 23, 23)
+    assert rows[0]["flop"] == 687272462200 and rows[0]["entries"] == 28243300 and rows[0]["stacks"] == 1600
+    assert totals == dict(flop=687272462200, entries=28243300, stacks=1600) and rows[0]["stacks_untuned"] == 0
     eng.close()
