@@ -137,8 +137,10 @@ void stack_binning(const int* params7, int* out3, int stack_size, int nbins, int
   size_t top = 0;
   for (int i = 0; i < stack_size; ++i) {
     const int* val = params7 + 7 * (size_t)i + 3;
-    const int64_t c = val[2];
-    const int bin_id = (int)((c * (c + 3)) % nbins);
+    // src/mm/dbcsr_mm_accdrv.F:405-406: INT(val(3)*(val(3)+3), KIND=int_8) multiplies in 32-bit INTEGER before widening, so
+    // the product wraps (two's complement) for c_first > 46339; MODULO floors => bin id in [0, nbins)
+    const int32_t prod = (int32_t)((uint32_t)val[2] * (uint32_t)(val[2] + 3));
+    const int bin_id = (int)((((int64_t)prod % nbins) + nbins) % nbins);
     if (bin_top[bin_id] >= binsize) {
       std::memcpy(out3 + 3 * top, &bin_arr[(size_t)3 * binsize * bin_id], sizeof(int) * 3 * (size_t)bin_top[bin_id]);
       top += bin_top[bin_id];

@@ -278,7 +278,11 @@ class LocalMultiplyOracle:
         out = []
         for p in params:
             val = p[3:6]
-            bin_id = (val[2] * (val[2] + 3)) % nbins
+            # the reference multiplies in default (32-bit) INTEGER before widening: INT(val(3)*(val(3)+3), KIND=int_8) -- the
+            # product wraps for c_first > 46339 (gfortran: two's complement); MODULO then floors, so the bin id stays in [0, nbins)
+            c = int(val[2])
+            prod = ((c * (c + 3)) + 2 ** 31) % 2 ** 32 - 2 ** 31
+            bin_id = prod % nbins
             if len(bins[bin_id]) >= binsize:
                 out.extend(bins[bin_id])
                 bins[bin_id] = []

@@ -133,3 +133,39 @@ def run_case(case, backend, rng, symmetries=SYMMETRIES, transposes=("N", "T"), f
                                         filter_eps=filter_eps, backend=backend)
                 eps_norm = check_multiply(matrix_c, dense_a, dense_b, dense_c, transa, transb, alpha, beta, lim, retain)
                 yield "%s (%s,%s | %s,%s,%s)" % (name, transa, transb, a_symm, b_symm, c_symm), eps_norm, flop
+
+
+# ---------------------------------------------------------------------------------------------------- golden .perf cases
+def golden_cases():
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "perf_golden.json")))["cases"]
+
+
+def to_dbcsr(bm, name):
+    """oracle BlockMatrix (BCSR-ordered block list, contiguous data) -> DbcsrMatrix sharing the data."""
+    m = D.DbcsrMatrix(name, bm.row_blk_size, bm.col_blk_size)
+    m.row_p = np.concatenate([[0], np.cumsum(np.bincount(bm.rows - 1, minlength=len(bm.row_blk_size)))])
+    m.col_i = bm.cols.astype(np.int32)
+    m.blk_p = (bm.offsets + 1).astype(np.int32)
+    m.data = np.array(bm.data, dtype=np.float64, copy=True)
+    return m
+
+
+def run_golden_case(case, backend):
+    """The reference's perf driver for one tests/inputs/*.perf file (tests/dbcsr_performance_multiply.F:271,373-411,623-677):
+    matrices C, A, B from the dlarnv generator with counters 12341314/15/16, C := alpha op(A) op(B) + beta C through dbcsr_multiply,
+    then dbcsr_checksum (plain and position-weighted).  Returns (checksum, checksum_pos)."""
+    sizes_m = orc.random_block_sizes(case["M"], case["bs_m"])
+    sizes_n = orc.random_block_sizes(case["N"], case["bs_n"])
+    sizes_k = orc.random_block_sizes(case["K"], case["bs_k"])
+    ta = case["transa"] == "T"
+    C = orc.random_matrix(sizes_m, sizes_n, case["sparsity"][2], 12341314)
+    A = orc.random_matrix(sizes_k, sizes_m, case["sparsity"][0], 12341315) if ta else orc.random_matrix(sizes_m, sizes_k, case["sparsity"][0], 12341315)
+    B = orc.random_matrix(sizes_k, sizes_n, case["sparsity"][1], 12341316)
+    mc = to_dbcsr(C, "C")
+    D.dbcsr_multiply(case["transa"], case["transb"], case["alpha"][0], to_dbcsr(A, "A"), to_dbcsr(B, "B"), case["beta"][0], mc, backend=backend)
+    out = orc.BlockMatrix(mc.row_blk_size, mc.col_blk_size, mc.block_rows(), mc.col_i, data=mc.data)
+    assert np.array_equal(out.offsets + 1, mc.blk_p)  # finalized: compact data area in index order
+    return out.checksum(), out.checksum(pos=True)

@@ -12,7 +12,7 @@ from dbcsr_b200 import dbcsr as D
 from oracle import index_oracle as io
 from oracle import oracle as orc
 
-from dbcsr_multiply_cases import SYMMETRIES, UNITTEST1_CASES, check_multiply, random_matrix, run_case
+from dbcsr_multiply_cases import SYMMETRIES, UNITTEST1_CASES, check_multiply, golden_cases, random_matrix, run_case, run_golden_case
 
 
 class OracleBackend:
@@ -144,3 +144,15 @@ def test_finalize_index_cpp_matches_python_finalize():
         assert np.array_equal(gathered, m.data)
     with pytest.raises(Exception):
         host.finalize_index([1, 1], [2, 2], [4, 4])
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=[c["name"] for c in golden_cases()])
+def test_perf_golden_checksums_through_dbcsr_multiply(case):
+    """The operator mirror against the reference's STORED results: the nine golden checksum pairs of tests/inputs/*.perf
+    (tests/golden/perf_golden.json) are reproduced when the multiply goes through dbcsr_multiply (transposes, beta = 1 keeps the
+    existing C blocks, finalize) with the index oracle building the stacks -- i.e. operator logic + traversal + stack semantics
+    are pinned end to end to numbers the reference itself produced (rel. 1e-11, tests/dbcsr_performance_multiply.F:656-677)."""
+    cs, cs_pos = run_golden_case(case, OracleBackend())
+    thr = max(case["threshold"], 1e-11)
+    assert abs(cs / case["checksum"] - 1.0) <= thr, (cs, case["checksum"])
+    assert abs(cs_pos / case["checksum_pos"] - 1.0) <= thr, (cs_pos, case["checksum_pos"])

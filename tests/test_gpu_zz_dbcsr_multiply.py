@@ -10,7 +10,7 @@ import pytest
 
 from dbcsr_b200 import dbcsr as D
 
-from dbcsr_multiply_cases import UNITTEST1_CASES, random_matrix, run_case
+from dbcsr_multiply_cases import UNITTEST1_CASES, golden_cases, random_matrix, run_case, run_golden_case
 
 pytestmark = pytest.mark.gpu
 
@@ -100,3 +100,14 @@ def test_device_finalize_gives_bcsr_order_and_same_blocks(backend):
         assert 0 < len(want) < ref.nblks
     finally:
         dm.close()
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=[c["name"] for c in golden_cases()])
+def test_perf_golden_checksums_on_device(case, backend):
+    """The device path against the reference's STORED results: the nine golden checksum pairs of tests/inputs/*.perf reproduced
+    with the multiply running on the GPU (dbcsr_multiply -> host engine -> libsmm_acc_process: 5x5x5 DMMA kernel, run-time-shape
+    and generic kernels for the other block sizes), rel. 1e-11 like the reference's own check."""
+    cs, cs_pos = run_golden_case(case, backend)
+    thr = max(case["threshold"], 1e-11)
+    assert abs(cs / case["checksum"] - 1.0) <= thr, (cs, case["checksum"])
+    assert abs(cs_pos / case["checksum_pos"] - 1.0) <= thr, (cs_pos, case["checksum_pos"])

@@ -45,6 +45,11 @@ def test_stack_sort_and_binning_match_oracle():
     o = io.LocalMultiplyOracle([5], [5], [5])
     assert np.array_equal(host.stack_sort(p), np.array(o._stack_sort([tuple(r) for r in p.tolist()]), dtype=np.int32))
     assert np.array_equal(host.stack_binning(p), np.array(o._stack_binning([tuple(r) for r in p.tolist()]), dtype=np.int32))
+    # offsets beyond 46339: the reference's 32-bit product val(3)*(val(3)+3) wraps before it is widened (accdrv.F:405-406)
+    p[:, 5] = rng.integers(0, 400000, S) * 25 + 1
+    assert np.array_equal(host.stack_binning(p), np.array(o._stack_binning([tuple(r) for r in p.tolist()]), dtype=np.int32))
+    c = 50000
+    assert ((c * (c + 3)) + 2 ** 31) % 2 ** 32 - 2 ** 31 < 0  # the wrapped product is negative here; MODULO keeps the bin id >= 0
 
 
 CASES = [
