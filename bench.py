@@ -330,6 +330,7 @@ def run_single(args):
         roofline["alt_bounds"] = {"frac_of_fp64_tensor_peak": roofline["kernel_only_gflops"] / 37050.0,
                                   "frac_of_padded_fp64_tensor_ceiling": roofline["kernel_only_gflops"] / (37050.0 * pad),
                                   "mean_run_length": n_entries / max(1, sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in stacks)),
+                                  "dram_traffic_frac_of_hbm_peak": (traffic / (roofline["avg_launch_us"] * 1e-6) * 1e-9 / peak) if traffic else None,
                                   "traffic_note": "dram bytes per launch from the ncu --set full capture of the RED-flush kernel (profiles/ncu_summary.json)"}
     if bf16:
         try:
