@@ -238,6 +238,13 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
         SMM_TUNE_CASE(120, 8, 0) SMM_TUNE_CASE(122, 8, 2) SMM_TUNE_CASE(130, 12, 0) SMM_TUNE_CASE(132, 12, 2)
         SMM_TUNE_CASE(140, 16, 0) SMM_TUNE_CASE(142, 16, 2)
 #  undef SMM_TUNE_CASE
+      // deeper per-warp rings for the small shapes (shared memory is not the limit there): 150 + 2 * (NST in {2,4}) + (WPC == 8)
+#  define SMM_RING_CASE(ID, NST_, WPC_)                                                                        \
+  case ID:                                                                                                    \
+    if constexpr (BaseGeom<M, N, K, NST_, WPC_, 0>::SMEM <= 113 * 1024) return launch_base<M, N, K, NST_, WPC_, 0, false, 0>(SMM_ARGS); \
+    break;
+        SMM_RING_CASE(154, 2, 4) SMM_RING_CASE(155, 2, 8) SMM_RING_CASE(158, 4, 4) SMM_RING_CASE(159, 4, 8)
+#  undef SMM_RING_CASE
       case 75: return launch_base<M, N, K, 1, 4, 0, false, 4>(SMM_ARGS);
       case 76: return launch_base<M, N, K, 1, 8, 0, false, 4>(SMM_ARGS);
       case 40: return launch_base<M, N, K, NST, WPC, 0, false, 0, ABL_NOFLUSH>(SMM_ARGS);

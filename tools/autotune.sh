@@ -13,6 +13,10 @@ for b in ${SHAPES:-23 32 26 13 5}; do
   for v in 100 102 110 112 120 122 130 132 140 142; do
     specs="$specs $v:0:0 $v:2:0 $v:2:12"
   done
+  if [ "$b" -le 13 ]; then  # small blocks: deeper per-warp rings (2 / 4 stages) and small chunks
+    for v in 154 155 158 159; do specs="$specs $v:0:0 $v:0:6"; done
+    specs="$specs 110:0:6 120:0:6"
+  fi
   timeout 120 ./tools/kbench $L gpurun_out 1000 0.1 3 $b $specs > gpurun_out/kbench_$b.log 2>&1
   grep -c "parity exact" gpurun_out/kbench_$b.log
 done

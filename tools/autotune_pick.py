@@ -13,6 +13,8 @@ for line in open(sys.argv[1]):
     var, bal, chunk = int(var), int(bal), int(chunk)
     if 100 <= var < 150:
         desc = "warps/CTA %2d  flush %s" % (WPC[(var - 100) // 10], "bulk(stage)" if var % 10 == 2 else "RED")
+    elif var in (154, 155, 158, 159):
+        desc = "warps/CTA %2d  %d stages  flush RED" % (8 if var & 1 else 4, 2 if var < 158 else 4)
     else:
         desc = "variant %d" % var
     rows.setdefault(int(bsz), []).append((float(tf), desc, "aligned" if bal & 2 else "", "chunk %d" % chunk if chunk else "one wave", parity, int(rc)))
