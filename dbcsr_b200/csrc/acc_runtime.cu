@@ -6,8 +6,11 @@
 //     set DBCSR_B200_ABORT_ON_ERROR=1 to get the reference's fail-stop behaviour;
 //   * streams get NVTX-free names only (no profiling dependency), priorities are clamped to the device range.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
+#include <pthread.h>
 
 #include <atomic>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -267,6 +270,32 @@ int c_dbcsr_acc_dev_mem_info(size_t* mem_free, size_t* mem_total) {
   if (mem_free != nullptr) *mem_free = f;
   if (mem_total != nullptr) *mem_total = t;
   return 0;
+}
+
+// ---- optional profiling hooks (src/acc/cuda/dbcsr_cuda_profiling.F:31-56 binds them when DBCSR is built with __CUDA_PROFILING):
+// NVTX3 is header-only and resolves the tool's injection library at run time, so there is no link dependency and the calls are
+// no-ops without a profiler attached.  The colour is a stable function of the message, the payload carries its length.
+int cuda_nvtx_range_push_cu(const char* message) {
+  static const uint32_t palette[8] = {0xFF4E79A7, 0xFFF28E2B, 0xFFE15759, 0xFF76B7B2, 0xFF59A14F, 0xFFEDC948, 0xFFB07AA1, 0xFF9C755F};
+  if (message == nullptr) message = "";
+  uint32_t h = 2166136261u;
+  size_t len = 0;
+  for (const char* c = message; *c != 0; ++c, ++len) h = (h ^ (uint32_t)(unsigned char)*c) * 16777619u;
+  nvtxEventAttributes_t a;
+  memset(&a, 0, sizeof(a));
+  a.version = NVTX_VERSION;
+  a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+  a.colorType = NVTX_COLOR_ARGB;
+  a.color = palette[h & 7u];
+  a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+  a.message.ascii = message;
+  a.payloadType = NVTX_PAYLOAD_TYPE_UNSIGNED_INT64;
+  a.payload.ullValue = (uint64_t)len;
+  return nvtxRangePushEx(&a);
+}
+int cuda_nvtx_range_pop_cu(void) { return nvtxRangePop(); }
+void cuda_nvtx_name_osthread_cu(char* name) {
+  if (name != nullptr) nvtxNameOsThreadA((uint32_t)(uintptr_t)pthread_self(), name);
 }
 
 }  // extern "C"

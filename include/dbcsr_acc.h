@@ -67,6 +67,13 @@ int c_dbcsr_acc_dev_mem_info(size_t* mem_free, size_t* mem_total);
 void c_dbcsr_timeset(const char** routineN, const int* routineN_len, int* handle);
 void c_dbcsr_timestop(const int* handle);
 
+/* -- optional profiling hooks, bound by DBCSR when it is built with __CUDA_PROFILING (src/acc/cuda/dbcsr_cuda_profiling.F:31-56,
+ * reference implementation src/acc/cuda/dbcsr_cuda_nvtx_cu.cpp): NVTX ranges around DBCSR's timed routines and a name for the
+ * calling OS thread.  push/pop return the nesting level; all three are no-ops when no profiler is attached. */
+int cuda_nvtx_range_push_cu(const char* message);
+int cuda_nvtx_range_pop_cu(void);
+void cuda_nvtx_name_osthread_cu(char* name);
+
 #if defined(__cplusplus)
 }
 #endif
