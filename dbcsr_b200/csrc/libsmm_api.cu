@@ -17,6 +17,7 @@
 
 #include "../../include/dbcsr_acc_libsmm.h"
 #include "smm_bf16.cuh"
+#include "smm_dmma_big.cuh"
 #include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
 #include "smm_launch.h"
@@ -34,6 +35,7 @@ const bool g_tune_env_read = [] {
   if (const char* e = getenv("DBCSR_B200_CHUNK")) smm::g_tune.chunk.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_ALIGN")) smm::g_tune.align.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_VARIANT")) smm::g_tune.variant.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_BIGDMMA")) smm::g_tune.bigdmma.store(atoi(e));
   return true;
 }();
 
@@ -151,6 +153,43 @@ int launch_rt_t(const int* dev_stack, int stack_size, const double* a, const dou
   return (err == cudaSuccess) ? 0 : -31;
 }
 
+// cooperative DMMA kernel (smm_dmma_big.cuh) for blocks with a dimension in 33..80; opt-in until verified on the device
+bool big_eligible(int m, int n, int k) {
+  return smm::g_tune.bigdmma.load(std::memory_order_relaxed) != 0 && m <= 80 && n <= smm::BIG_MAX_N && k <= 80 && m > 0 && n > 0 && k > 0 &&
+         smm::big_smem_bytes(m, n, k) <= 110 * 1024;
+}
+
+int launch_big(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
+               uint64_t b_end, cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  const int smem = smm::big_smem_bytes(m, n, k);
+  static std::atomic<int> smem_set{0};
+  if (smem_set.load(std::memory_order_acquire) < smem) {
+    if (cudaFuncSetAttribute(smm::smm_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
+    smem_set.store(smem, std::memory_order_release);
+  }
+  int cps = (220 * 1024) / (smem + 1024);
+  if (cps > 8) cps = 8;
+  if (cps < 1) return -30;
+  const int max_grid = num_sms() * cps;
+  int grid = (stack_size + 1) / 2;  // at least two entries per CTA
+  if (grid > max_grid) grid = max_grid;
+  const int chunk = (stack_size + grid - 1) / grid;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(smm::BIG_WARPS * 32);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const unsigned long long al = a_end, bl = b_end;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_dmma_big_kernel, dev_stack, stack_size, a, b, c, al, bl, chunk, m, n, k);
+  return (err == cudaSuccess) ? 0 : -31;
+}
+
 bool rt_eligible(int m, int n, int k) {
   return m <= 32 && n <= 32 && 128 + smm::RT_WPC * (smm::rt_abuf(m, k) + smm::rt_abuf(n, k)) <= 220 * 1024;
 }
@@ -260,8 +299,9 @@ int process_inhomogeneous(const int* host7, int stack_size, const double* a, con
       rc = fn(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, a_end, b_end, stream);
     }
     else {
-      rc = rt_eligible(m, n, k) ? launch_rt(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
-                                : launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
+      rc = rt_eligible(m, n, k)    ? launch_rt(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
+           : big_eligible(m, n, k) ? launch_big(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
+                                   : launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
       if (rc == 0) rc_all = 10;
     }
     if (rc < 0) {
@@ -329,7 +369,7 @@ int libsmm_acc_gpu_warp_size(void) { return 32; }
 long long libsmm_acc_b200_launch_count(void) { return g_launches.load(); }
 const char* libsmm_acc_b200_version(void) { return "dbcsr_acc_b200 r1 (sm_100a, DMMA.8x8x4 + TMA bulk staging)"; }
 
-// Run-time knobs of the FP64 stack kernels (smm_tune.h).  Names: "balance", "align", "chunk", "variant", "trace_first", "trace_count",
+// Run-time knobs of the FP64 stack kernels (smm_tune.h).  Names: "balance", "align", "chunk", "bigdmma", "variant", "trace_first", "trace_count",
 // "seq" (launch sequence counter).  Returns 0, or -1 for an unknown name.  libsmm_acc_b200_set_trace installs a device buffer of
 // trace_count * 4096 * 128 64-bit words (NULL switches tracing off); only TRACE kernel variants of experiment builds write to it.
 int libsmm_acc_b200_set_tunable(const char* name, long long value) {
@@ -338,6 +378,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "chunk") == 0) smm::g_tune.chunk.store((int)value);
   else if (strcmp(name, "align") == 0) smm::g_tune.align.store((int)value);
   else if (strcmp(name, "variant") == 0) smm::g_tune.variant.store((int)value);
+  else if (strcmp(name, "bigdmma") == 0) smm::g_tune.bigdmma.store((int)value);
   else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
   else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
   else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
@@ -350,6 +391,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "chunk") == 0) return smm::g_tune.chunk.load();
   if (strcmp(name, "align") == 0) return smm::g_tune.align.load();
   if (strcmp(name, "variant") == 0) return smm::g_tune.variant.load();
+  if (strcmp(name, "bigdmma") == 0) return smm::g_tune.bigdmma.load();
   if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
   if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
   if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
@@ -459,7 +501,9 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
   }
   const int rc = rt_eligible(m_max, n_max, k_max)
                    ? launch_rt(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, allocation_end(a), allocation_end(b), stream)
-                   : launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, 1, stream);
+                   : big_eligible(m_max, n_max, k_max)
+                       ? launch_big(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, allocation_end(a), allocation_end(b), stream)
+                       : launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, 1, stream);
   if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return rc == 0 ? 10 : rc;  // 10 = "ran with an untuned kernel" (reference: libsmm_acc.cpp:319)
 }

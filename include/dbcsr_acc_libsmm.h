@@ -81,7 +81,7 @@ int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype)
 /* Number of kernel launches this library has enqueued since load (all threads). */
 long long libsmm_acc_b200_launch_count(void);
 /* Run-time knobs of the FP64 stack kernels (dbcsr_b200/csrc/smm_tune.h; environment defaults DBCSR_B200_BALANCE / _ALIGN / _CHUNK /
- * _VARIANT): name = "balance" | "align" | "chunk" | "variant" | "trace_first" | "trace_count" | "seq"; get also answers "experiment"
+ * _VARIANT): name = "balance" | "align" | "chunk" | "bigdmma" | "variant" | "trace_first" | "trace_count" | "seq"; get also answers "experiment"
  * (1 = library built with the kernel-variant table).  Return 0 / the value, -1 for an unknown name.
  * set_trace: device buffer of trace_count * 4096 * 128 64-bit words written by TRACE kernel variants (NULL = off). */
 int libsmm_acc_b200_set_tunable(const char* name, long long value);
