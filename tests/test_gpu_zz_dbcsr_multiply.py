@@ -3,6 +3,7 @@ driver tests/dbcsr_test_multiply.F) through the dbcsr_multiply mirror with the D
 host engine, drained by libsmm_acc_process (tuned DMMA kernels for 5/13/23 blocks, run-time-shape / generic kernels and
 inhomogeneous stacks for the 1..4-sized blocks of the reference's cases).  Criterion of dbcsr_check_multiply:
 ||C_dbcsr - C_dense||_oo / ((||A||_oo + ||B||_oo + ||C_in||_oo) * n * eps) <= 10."""
+import os
 import zlib
 
 import numpy as np
@@ -113,7 +114,9 @@ def test_perf_golden_checksums_on_device(case, backend):
     assert abs(cs_pos / case["checksum_pos"] - 1.0) <= thr, (cs_pos, case["checksum_pos"])
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in cooperative DMMA kernel for 33..80 blocks: written without GPU access, first device run")
+@pytest.mark.skipif(os.environ.get("DBCSR_B200_TEST_UNVERIFIED", "0") != "1",
+                    reason="opt-in cooperative DMMA kernel for 33..80 blocks, written without GPU access: run its first device test "
+                           "deliberately (DBCSR_B200_TEST_UNVERIFIED=1, under `timeout`), not as part of the regular suite")
 @pytest.mark.parametrize("mnk", [(33, 33, 33), (45, 67, 78), (80, 80, 80), (64, 40, 72), (40, 17, 7), (9, 80, 33)])
 def test_cooperative_dmma_kernel_for_blocks_33_to_80(backend, mnk):
     """smm_dmma_big.cuh behind libsmm_acc_b200_set_tunable("bigdmma", 1): same contract as the generic kernel it will replace
