@@ -102,10 +102,11 @@ int launch_base(const int* dev_stack, int stack_size, const double* a, const dou
   int max_chunk = g_tune.chunk.load(std::memory_order_relaxed);
   if (max_chunk < 0) {
     // per-shape policy: CHUNK entries per warp when that leaves part of the resident wave free for the next launch (programmatic
-    // dependent launch) and still gives every SM at least one CTA; otherwise one wave
+    // dependent launch) and still gives every SM at least four CTAs (measured on 30000-entry stacks: 625 CTAs = 4.2 per SM);
+    // smaller stacks keep the one-wave split, which spreads them over as many warps as possible
     max_chunk = 0;
     if (Policy<M, N, K>::CHUNK > 0 && (long long)Policy<M, N, K>::CHUNK * max_grid * WPC > stack_size &&
-        (long long)Policy<M, N, K>::CHUNK * g_num_sms * WPC <= stack_size)
+        4LL * Policy<M, N, K>::CHUNK * g_num_sms * WPC <= stack_size)
       max_chunk = Policy<M, N, K>::CHUNK;
   }
   if (max_chunk > 0)
