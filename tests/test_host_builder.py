@@ -436,3 +436,44 @@ def test_symmetric_product_skipping_matches_index_oracle(use_maps):
     assert eng.flop() == full.flop()
     for e in (eng, full, eng4):
         e.close()
+
+
+def test_fuzz_engine_equals_index_oracle_incl_presets_symmetry_and_second_tick():
+    """Random shapes (incl. 1-sized dims and blocks), occupations, stack sizes, multrec limits, with existing C blocks,
+    retain_sparsity, symmetric products, and a second Cannon tick on the same C: the C++ builder (direct row tables, counting /
+    radix ordering by block id) and the Python restatement produce identical stacks, device orders, C indices and flop counts."""
+    rng = np.random.default_rng(2024)
+    for it in range(25):
+        nrow, ncol, nk = (int(x) for x in rng.integers(1, 60, 3))
+        sizes = [int(x) for x in rng.choice([1, 2, 4, 5, 7, 13, 23, 26, 32, 40], size=int(rng.integers(1, 5)), replace=False)]
+        m_sizes, n_sizes, k_sizes = rng.choice(sizes, nrow), rng.choice(sizes, ncol), rng.choice(sizes, nk)
+        oa, ob = rng.uniform(0.05, 0.9, 2)
+        A = orc.BlockMatrix(m_sizes, k_sizes, *(x + 1 for x in np.nonzero(rng.random((nrow, nk)) < oa)))
+        B = orc.BlockMatrix(k_sizes, n_sizes, *(x + 1 for x in np.nonzero(rng.random((nk, ncol)) < ob)))
+        ssz, nst, lim = int(rng.choice([16, 50, 300, 30000])), int(rng.choice([3, 5])), int(rng.choice([4, 32, 512]))
+        sym = bool(rng.random() < 0.3) and nrow == ncol
+        keep = bool(rng.random() < 0.3)
+        preset = bool(rng.random() < 0.5) or keep
+        ora = io.LocalMultiplyOracle(m_sizes, n_sizes, k_sizes, mm_stack_size=ssz, n_stacks=nst, multrec_limit=lim)
+        eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=1, mode=host.RECORD,
+                          cfg=host.default_cfg(mm_stack_size=ssz, n_stacks=nst, multrec_limit=lim))
+        if preset:
+            pr, pc = (x + 1 for x in np.nonzero(rng.random((nrow, ncol)) < 0.3))
+            ora.preset_c(pr, pc, keep_sparsity=keep)
+            eng.preset_c(pr, pc, None, keep_sparsity=keep)
+        if sym:
+            ora.set_c_symmetry(True)
+            eng.set_c_symmetry(True)
+        a_l = np.array(A.index_list(), dtype=np.int32).reshape(-1, 3)
+        b_l = np.array(B.index_list(), dtype=np.int32).reshape(-1, 3)
+        for tick in range(2):
+            exp = ora.multiply(A.index_list(), B.index_list())
+            eng.multiply(a_l, None, b_l, None)
+            got = eng.stacks()
+            assert len(got) == len(exp), (it, tick)
+            for g, x in zip(got, exp):
+                assert np.array_equal(g["host"], x["host"]) and np.array_equal(g["dev"], x["dev"]), (it, tick)
+        rows, cols, blk_p, ds = eng.c_index(0)
+        assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p and ds == ora.datasize
+        assert eng.flop() == ora.flop
+        eng.close()
