@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace dbcsr_b200 {
 
@@ -37,6 +38,40 @@ void rec_sort_index(int mi, int mf, int ni, int nf, Idx3* a, int nele, std::vect
     if (nlow > 1) rec_sort_index(mi, mf, ni, ni + half - 1, a, nlow, tmp);
     if (nele - nlow > 1) rec_sort_index(mi, mf, ni + half, nf, a + nlow, nele - nlow, tmp);
   }
+}
+
+// The two halves produced by one split are independent: the top `depth` levels of the recursion run them concurrently (the
+// right panel of a multiply is sorted as one list of ~1e5 blocks on the critical path of every multiply; the order is the same).
+void rec_sort_index_mt(int mi, int mf, int ni, int nf, Idx3* a, int nele, int depth) {
+  if (nele <= 1) return;
+  if (depth <= 0 || nele < 8192) {
+    std::vector<Idx3> tmp;
+    rec_sort_index(mi, mf, ni, nf, a, nele, tmp);
+    return;
+  }
+  const int M = mf - mi + 1, N = nf - ni + 1;
+  const bool by_row = M > N;
+  const int half = by_row ? M / 2 : N / 2;
+  const int half_m = (by_row ? mi : ni) + half - 1;
+  int nlow = 0;
+  {
+    std::vector<Idx3> tmp((size_t)nele);
+    int p_low = 0, p_high = nele - 1;
+    for (int el = 0; el < nele; ++el) {
+      const int key = by_row ? a[el].row : a[el].col;
+      if (key <= half_m)
+        tmp[(size_t)p_low++] = a[el];
+      else
+        tmp[(size_t)p_high--] = a[el];
+    }
+    std::memcpy(a, tmp.data(), sizeof(Idx3) * (size_t)nele);
+    nlow = p_low;
+  }
+  const int lo_mf = by_row ? mi + half - 1 : mf, lo_nf = by_row ? nf : ni + half - 1;
+  const int hi_mi = by_row ? mi + half : mi, hi_ni = by_row ? ni : ni + half;
+  std::thread low([=]() { rec_sort_index_mt(mi, lo_mf, ni, lo_nf, a, nlow, depth - 1); });
+  rec_sort_index_mt(hi_mi, mf, hi_ni, nf, a + nlow, nele - nlow, depth - 1);
+  low.join();
 }
 
 void LocalMultiply::sort_panel(std::vector<Idx3>& list, int nrows, int ncols) {

@@ -38,6 +38,8 @@ struct StackDescr {
 
 // rec_sort_index (src/mm/dbcsr_mm_common.F:227-309): quadtree-like ordering of a block list, in place.
 void rec_sort_index(int mi, int mf, int ni, int nf, Idx3* a, int nele, std::vector<Idx3>& tmp);
+// same result; the top `depth` levels of the recursion sort their two halves concurrently (2^depth threads at most)
+void rec_sort_index_mt(int mi, int mf, int ni, int nf, Idx3* a, int nele, int depth);
 
 // stack_sort / stack_binning (src/mm/dbcsr_mm_accdrv.F:364-423): 7-wide host stack -> 3-wide device stack.
 void stack_sort(const int* params7, int* out3, int stack_size);

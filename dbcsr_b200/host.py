@@ -27,6 +27,7 @@ def _L():
         ip = ctypes.POINTER(_i)
         L.dbcsr_b200_cfg_default.argtypes = [ctypes.POINTER(Cfg)]
         L.dbcsr_b200_rec_sort_index.argtypes = [_i, _i, _i, _vp]
+        L.dbcsr_b200_rec_sort_index_mt.argtypes = [_i, _i, _i, _vp, _i]
         L.dbcsr_b200_stack_sort.argtypes = [_vp, _vp, _i]
         L.dbcsr_b200_stack_binning.argtypes = [_vp, _vp, _i, _i, _i]
         L.dbcsr_b200_engine_create.argtypes = [ctypes.POINTER(Cfg), _vp, _i, _vp, _i, _vp, _i, _i, _i, ctypes.c_size_t]
@@ -88,9 +89,12 @@ def default_cfg(**kw):
     return c
 
 
-def rec_sort_index(nrows, ncols, list3):
+def rec_sort_index(nrows, ncols, list3, depth=0):
     a = np.ascontiguousarray(list3, dtype=np.int32).reshape(-1, 3).copy()
-    _L().dbcsr_b200_rec_sort_index(nrows, ncols, a.shape[0], a.ctypes.data)
+    if depth > 0:
+        _L().dbcsr_b200_rec_sort_index_mt(nrows, ncols, a.shape[0], a.ctypes.data, depth)
+    else:
+        _L().dbcsr_b200_rec_sort_index(nrows, ncols, a.shape[0], a.ctypes.data)
     return a
 
 

@@ -35,6 +35,8 @@ void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg);
 
 /* rec_sort_index (src/mm/dbcsr_mm_common.F:227-309), in place on nblks (row,col,blk_p) triples */
 void dbcsr_b200_rec_sort_index(int nrows, int ncols, int nblks, int* list3);
+/* same order; the top `depth` levels of the recursion sort their halves concurrently (what the engine uses for the right panel) */
+void dbcsr_b200_rec_sort_index_mt(int nrows, int ncols, int nblks, int* list3, int depth);
 /* stack_sort / stack_binning (src/mm/dbcsr_mm_accdrv.F:364-423): params7 -> out3 */
 void dbcsr_b200_stack_sort(const int* params7, int* out3, int stack_size);
 void dbcsr_b200_stack_binning(const int* params7, int* out3, int stack_size, int nbins, int binsize);
