@@ -28,11 +28,16 @@ struct Policy {
   static constexpr int FLUSH = 0, CHUNK = 0;
   static constexpr bool ALIGN = false;
 };
-template <>
-struct Policy<23, 23, 23> {
-  static constexpr int FLUSH = 2, CHUNK = 12;
-  static constexpr bool ALIGN = true;
-};
+// the tuned records: generated from the autotune database dbcsr_b200/parameters/parameters_B200.json (tools/gen_policy.py),
+// like the reference generates parameters.h from parameters_<GPU>.json
+#define SMM_POLICY(M_, N_, K_, FLUSH_, CHUNK_, ALIGN_) \
+  template <>                                           \
+  struct Policy<M_, N_, K_> {                           \
+    static constexpr int FLUSH = FLUSH_, CHUNK = CHUNK_; \
+    static constexpr bool ALIGN = ALIGN_;               \
+  };
+#include "smm_policy.inc"
+#undef SMM_POLICY
 
 namespace {
 

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -100,3 +101,19 @@ def test_tunables_round_trip():
     if "DBCSR_B200_CHUNK" not in os.environ and "DBCSR_B200_ALIGN" not in os.environ:
         assert defaults["chunk"] == -1 and defaults["align"] == -1
     assert L.libsmm_acc_b200_get_tunable(b"experiment") in (0, 1)
+
+
+def test_autotune_database_and_generated_policy_are_in_sync():
+    """dbcsr_b200/parameters/parameters_B200.json (one record per tuned (m,n,k), the B200 counterpart of the reference's
+    parameters_<GPU>.json) and the generated smm_policy.inc the launch table includes."""
+    import json
+
+    db = json.load(open(os.path.join(ROOT, "dbcsr_b200", "parameters", "parameters_B200.json")))
+    sizes = [5, 13, 23, 26, 32]
+    assert sorted((r["m"], r["n"], r["k"]) for r in db) == sorted((m, n, k) for m in sizes for n in sizes for k in sizes)
+    for r in db:
+        assert r["algorithm"] == "dmma" and r["flush"] in (0, 2) and r["chunk"] >= 0 and r["source"].split(":")[0] in ("autotuned", "default")
+        assert (r["perf"] > 0) == r["source"].startswith("autotuned")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_policy.py"), "--print"], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "dbcsr_b200", "csrc", "smm_policy.inc")).read()
+    assert "SMM_POLICY(23, 23, 23, 2, 12, true)" in out
