@@ -275,6 +275,28 @@ def run_single(args):
         one_step()
     acc.stream_sync(s)
 
+    # self-check at full size, outside every timed region: one drain into a zeroed buffer must satisfy the size-independent
+    # property sum(C) = colsum(A) . rowsum(B) (FP64 path; tests/test_gpu_multiply.py checks the same property)
+    selfcheck = None
+    if not bf16 and not args.no_selfcheck:
+        try:
+            from dbcsr_b200.cannon import _axis_sums
+
+            acc.stream_wait_event(s, ev_zero[step_no[0] % 2])
+            acc.stream_sync(zs)
+            acc.memset_zero(d_cs[0], s)
+            drain(d_cs[0])
+            got = float(acc.to_host(d_cs[0], (max(c_datasize, 1),), np.float64, s)[:c_datasize].sum())
+            exp = float(np.dot(_axis_sums(A, 0, A.row_sizes.size, 0), _axis_sums(B, 0, B.col_sizes.size, 1)))
+            selfcheck = {"property": "sum(C) == colsum(A) . rowsum(B)", "rel_err": abs(got - exp) / max(abs(exp), 1e-300)}
+            # leave the double-buffering state as one_step expects it: buffer of the next step zeroed
+            acc.memset_zero(d_cs[step_no[0] % 2], zs)
+            acc.event_record(ev_zero[step_no[0] % 2], zs)
+            acc.stream_sync(zs)
+            acc.stream_sync(s)
+        except Exception as ex:
+            selfcheck = {"error": repr(ex)[:200]}
+
     sampler = ClockSampler(0)
     sampler.start()
     time.sleep(0.3)
@@ -401,7 +423,8 @@ def run_single(args):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if bf16 else "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
            "config": workload_config(w, {"products": n_entries, "flop": flop, "stacks": len(stacks), "c_blocks": int(c_nblks),
                                          "timed": "CUDA events on the launching stream; step = %d libsmm_acc_process calls into a zeroed C buffer + the memset of the next step's (pooled, double-buffered) C buffer on a side stream, joined before the step ends" % len(stacks)}),
-           "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu}
+           "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+           "selfcheck": selfcheck}
     print(json.dumps(out))
     for d in (d_a, d_b, d_st):
         d.free()
@@ -424,6 +447,7 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the full-size sum(C) check before the timed region")
     ap.add_argument("--ref-entries", type=int, default=4_000_000, help="stack entries in the bounded CPU sample")
     args = ap.parse_args()
     if args.warmup < 3:
