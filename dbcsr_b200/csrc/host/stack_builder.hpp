@@ -130,7 +130,7 @@ class LocalMultiply {
     int mask = 0, count = 0;
     std::vector<int> dense;      // direct table col -> id (0 = absent) when the matrix has few enough block columns
   };
-  static constexpr int kDenseRowLimit = 16384;  // block columns up to which a touched C row gets a direct table (64 KB)
+  static constexpr int kDenseRowLimit = 4096;  // block columns up to which a touched C row gets a direct table (16 KB per row, 64 MB at most)
   std::vector<int> c_row_, c_col_, c_blk_p_;
   std::vector<RowTable> rows_;
   int datasize_ = 0;
