@@ -61,6 +61,7 @@ CASES = [
     (128, 128, 128, 0.1, 0.1, [23], 4000, 3, 512),
     (10, 10, 10, 1.0, 1.0, [1, 3, 4], 50, 3, 8),
     (33, 1, 17, 0.6, 0.9, [5, 8, 9], 64, 3, 16),
+    (30, 5000, 40, 0.3, 0.004, [5, 13], 300, 3, 64),  # more than 4096 block columns: per-row hash tables instead of direct tables
 ]
 
 
