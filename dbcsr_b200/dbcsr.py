@@ -276,6 +276,34 @@ def dbcsr_finalize(row_blk_size, col_blk_size, parts, matrix_type=dbcsr_type_no_
     return out
 
 
+def dbcsr_checksum(matrix, pos=False):
+    """dbcsr_checksum (src/dist/dbcsr_dist_util.F:432-547, pd_blk_cs :549-575) of a finalized real_8 matrix: the sum of the squared
+    elements, or - position dependent - the sum of x(r,c) * log|r * c| over the full (1-based) element coordinates.  Summed block by
+    block and row by row like the reference (the order only matters at the 1e-16 level)."""
+    ro, co = matrix.row_blk_offset, matrix.col_blk_offset
+    rows = matrix.block_rows()
+    total, row_sum, cur_row = 0.0, 0.0, -1
+    for i in range(matrix.nblks):
+        r, c = int(rows[i]), int(matrix.col_i[i])
+        if r != cur_row:
+            total += row_sum
+            row_sum, cur_row = 0.0, r
+        b = matrix.block(i)
+        if pos:
+            rr = np.arange(int(ro[r - 1]), int(ro[r]), dtype=np.float64)[:, None]
+            cc = np.arange(int(co[c - 1]), int(co[c]), dtype=np.float64)[None, :]
+            row_sum += float((b * np.log(np.abs(rr * cc))).sum())
+        else:
+            row_sum += float((b * b).sum())
+    return total + row_sum
+
+
+def dbcsr_scale(matrix, alpha_scalar, limits=None):
+    """dbcsr_scale (ops/dbcsr_operations.F): in place; limits = (first_row, last_row, first_col, last_col) in full indices, 0 = open."""
+    f_row, l_row, f_col, l_col = limits if limits is not None else (0, 0, 0, 0)
+    _scale_within_limits(matrix, float(alpha_scalar), f_row, l_row, f_col, l_col)
+
+
 # ------------------------------------------------------------------------------------------------ backends
 class DeviceBackend:
     """The product path: panels go to the device, the host engine builds the stacks, libsmm_acc_process drains them

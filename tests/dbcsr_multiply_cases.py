@@ -168,4 +168,7 @@ def run_golden_case(case, backend):
     D.dbcsr_multiply(case["transa"], case["transb"], case["alpha"][0], to_dbcsr(A, "A"), to_dbcsr(B, "B"), case["beta"][0], mc, backend=backend)
     out = orc.BlockMatrix(mc.row_blk_size, mc.col_blk_size, mc.block_rows(), mc.col_i, data=mc.data)
     assert np.array_equal(out.offsets + 1, mc.blk_p)  # finalized: compact data area in index order
-    return out.checksum(), out.checksum(pos=True)
+    cs, cs_pos = out.checksum(), out.checksum(pos=True)
+    # the product-side dbcsr_checksum agrees with the oracle's restatement
+    assert abs(D.dbcsr_checksum(mc) / cs - 1.0) <= 1e-13 and abs(D.dbcsr_checksum(mc, pos=True) / cs_pos - 1.0) <= 1e-12
+    return cs, cs_pos
