@@ -1,7 +1,7 @@
 """Shared driver of the dbcsr_multiply tests (CPU: oracle backend, GPU: device backend), modelled on the reference's
 tests/dbcsr_test_multiply.F: dbcsr_test_multiplies (:66-346: symmetry table, transposes, B = +-A for products with symmetry),
 test_multiply (:348-521) and dbcsr_check_multiply (:523-788: dense GEMM on the limited sub-matrices, criterion
-||C_dbcsr - C_dense||_oo / ((||A||_oo + ||B||_oo + ||C_in||_oo) * n * eps) <= 10); cases from tests/dbcsr_unittest1.F:95-330."""
+||C_dbcsr - C_dense||_oo / ((||A||_oo + ||B||_oo + ||C_in||_oo) * n * eps) <= 10); cases from tests/dbcsr_unittest1.F:95-330, dbcsr_unittest2.F:80-107, dbcsr_unittest3.F:79-120."""
 import numpy as np
 
 from dbcsr_b200 import dbcsr as D
@@ -33,6 +33,21 @@ UNITTEST1_CASES = [
     ("multiply_LIMITS_ROW_1", (50, 50, 50), (0.0, 0.0, 0.0), False, 1.0, 0.0, [1, 2], [1, 2], [1, 2], (1, 20, 1, 50, 1, 50)),
     ("multiply_LIMITS_ROW_2", (50, 50, 50), (0.0, 0.0, 0.0), False, 1.0, 0.0, [1, 2], [1, 2], [1, 2], (9, 18, 1, 50, 1, 50)),
     ("multiply_LIMITS_ROW_3", (50, 50, 50), (0.5, 0.5, 0.5), True, 1.0, 0.0, [1, 2], [1, 2], [1, 2], (9, 18, 1, 50, 1, 50)),
+    # tests/dbcsr_unittest2.F:80-107 (large blocks, rectangular matrices) and tests/dbcsr_unittest3.F:79-120 (the GPU-targeted block mixes)
+    ("large_blocks_1", (500, 500, 500), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 100], [1, 100], [1, 100], (1, 500, 1, 500, 1, 500)),
+    ("large_blocks_2", (500, 50, 50), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 100], [1, 10], [1, 10], (1, 500, 1, 50, 1, 50)),
+    ("rectangular_matrix_M", (500, 50, 50), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 5], [1, 5], [1, 5], (1, 500, 1, 50, 1, 50)),
+    ("rectangular_matrix_K", (50, 50, 500), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 5], [1, 5], [1, 5], (1, 50, 1, 50, 1, 500)),
+    ("blocks_1_3_4", (496, 48, 48), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 1, 1, 3, 1, 4], [1, 1, 1, 3, 1, 4], [1, 1, 1, 3, 1, 4], (1, 496, 1, 48, 1, 48)),
+    ("blocks_4_5_7", (496, 48, 48), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 4, 1, 5, 1, 7], [1, 4, 1, 5, 1, 7], [1, 4, 1, 5, 1, 7], (1, 496, 1, 48, 1, 48)),
+    ("blocks_5_8_9", (506, 44, 44), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 5, 1, 8, 1, 9], [1, 5, 1, 8, 1, 9], [1, 5, 1, 8, 1, 9], (1, 506, 1, 44, 1, 44)),
+    ("blocks_4_13_25", (504, 42, 42), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 4, 1, 13, 1, 25], [1, 4, 1, 13, 1, 25], [1, 4, 1, 13, 1, 25],
+     (1, 504, 1, 42, 1, 42)),
+    ("blocks_14_29_32", (525, 75, 75), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 14, 1, 29, 1, 32], [1, 14, 1, 29, 1, 32], [1, 14, 1, 29, 1, 32],
+     (1, 525, 1, 75, 1, 75)),
+    ("blocks_H2O", (552, 46, 46), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 23], [1, 23], [1, 23], (1, 552, 1, 46, 1, 46)),
+    ("blocks_45_67_78", (570, 190, 190), (0.5, 0.5, 0.5), False, 1.0, 0.0, [1, 45, 1, 67, 1, 78], [1, 45, 1, 67, 1, 78], [1, 45, 1, 67, 1, 78],
+     (1, 570, 1, 190, 1, 190)),
     # full-range multiplies on the hot path's block sizes (tests/dbcsr_unittest3.F:76-118 mixes), also exercising symmetric products
     ("multiply_SQUARE_23", (115, 115, 115), (0.4, 0.4, 0.6), False, 1.0, 0.0, [1, 23], [1, 23], [1, 23], (1, 115, 1, 115, 1, 115)),
     ("multiply_MIX_5_13_23", (87, 87, 87), (0.5, 0.5, 0.5), False, 2.0, 1.0, [1, 5, 1, 13, 1, 23], [1, 5, 1, 13, 1, 23], [1, 5, 1, 13, 1, 23],
