@@ -5,7 +5,9 @@
  * C-sorted) exactly as bench.py does, operands resident on the device.
  *
  *   kbench <library.so> <out_dir> <nblk> <occ> <steps> <bsz> <spec> [<spec> ...]
- *   spec = variant:balance:chunk[:t]   (balance: bit 0 = balanced chunks, bit 1 = run-aligned chunk boundaries; t = record a kernel timeline of launches 100..102 of one step into out_dir)
+ *   spec = variant:balance:chunk[:t]   (balance: bit 0 = balanced chunks, bit 1 = run-aligned chunk boundaries, negative = the
+ *                                       library's per-shape policy; chunk: entries per warp, 0 = one wave, negative = policy; 0:-1:-1 is
+ *                                       what ships; t = record a kernel timeline of launches 100..102 of one step into out_dir)
  *
  * Per spec: (1) parity -- C is zeroed, every stack is drained once, the per-block sums of squares (libsmm_acc_b200_block_norms_f64)
  * are compared EXACTLY with those of the first spec (operands are small integers, so every summation order gives the same
@@ -233,8 +235,14 @@ int main(int argc, char** argv) {
       continue;
     }
     set_tun("variant", variant);
-    set_tun("balance", balance & 1);
-    set_tun("align", (balance >> 1) & 1);
+    if (balance < 0) {  /* negative: the library's per-shape policy decides about run alignment (and chunk < 0: about the chunk size) */
+      set_tun("balance", 0);
+      set_tun("align", -1);
+    }
+    else {
+      set_tun("balance", balance & 1);
+      set_tun("align", (balance >> 1) & 1);
+    }
     set_tun("chunk", chunk);
     set_trace(NULL);
     /* parity run */
