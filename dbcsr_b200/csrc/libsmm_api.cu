@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -25,7 +26,43 @@
 
 namespace smm {
 Tunables g_tune;
+
+// ---- chain registry (see smm_launch.h).  A handful of streams at most: linear search under a mutex, skipped when empty.
+namespace {
+struct ChainEntry {
+  cudaStream_t stream;
+  bool primed;  // the last launch of this library on the stream was an independent FP64 stack drain
+};
+std::mutex g_chain_mu;
+std::vector<ChainEntry> g_chain;
+std::atomic<int> g_chain_n{0};
+// DBCSR_B200_PDL_CHAIN=1: every stream is a chain (the caller guarantees that nothing but stack drains, stack uploads and event
+// waits is ever enqueued between two libsmm_acc_process calls of a stream)
+const bool g_chain_all = [] {
+  const char* e = getenv("DBCSR_B200_PDL_CHAIN");
+  return e != nullptr && atoi(e) != 0;
+}();
+}  // namespace
+
+bool stream_chain_mode(cudaStream_t stream) {
+  if (g_chain_all) return true;
+  if (g_chain_n.load(std::memory_order_acquire) == 0) return false;
+  std::lock_guard<std::mutex> lock(g_chain_mu);
+  for (auto& c : g_chain)
+    if (c.stream == stream) {
+      const bool was = c.primed;
+      c.primed = true;
+      return was;
+    }
+  return false;
 }
+void stream_chain_break(cudaStream_t stream) {
+  if (g_chain_n.load(std::memory_order_acquire) == 0) return;
+  std::lock_guard<std::mutex> lock(g_chain_mu);
+  for (auto& c : g_chain)
+    if (c.stream == stream) c.primed = false;
+}
+}  // namespace smm
 
 namespace {
 
@@ -52,6 +89,22 @@ int num_sms() {
       n = 148;
   }
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest value set per device (DBCSR picks
+// the device per rank and c_dbcsr_acc_set_active_device may switch it)
+struct SmemAttrCache {
+  std::atomic<int> set[64];
+};
+template <typename Kern>
+int ensure_smem(Kern kern, int smem, SmemAttrCache& cache) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -30;
+  if (cache.set[dev].load(std::memory_order_acquire) < smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
+    cache.set[dev].store(smem, std::memory_order_release);
+  }
+  return 0;
 }
 
 // End address of the device allocation that contains `p` (0 = unknown).  The DMMA kernel stages 16-byte-aligned windows and may
@@ -91,11 +144,8 @@ int launch_bf16(const int* dev_stack, int stack_size, const void* a_tiles, const
   if (stack_size <= 0) return 0;
   const smm::Bf16Geom g = smm::bf16_geom(m, n, k);
   const size_t smem = smm::bf16_smem_bytes(g);
-  static std::atomic<size_t> smem_set{0};
-  if (smem_set.load(std::memory_order_acquire) < smem) {
-    if (cudaFuncSetAttribute(smm::smm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -30;
-    smem_set.store(smem, std::memory_order_release);
-  }
+  static SmemAttrCache smem_set;
+  if (ensure_smem(smm::smm_bf16_kernel, (int)smem, smem_set) != 0) return -30;
   int per_sm = (int)((220 * 1024) / smem);
   if (per_sm > 512 / smm::BF_TMEM_COLS) per_sm = 512 / smm::BF_TMEM_COLS;  // TMEM: 512 columns per SM
   if (per_sm < 1) return -30;
@@ -125,14 +175,12 @@ template <int TM, int TN>
 int launch_rt_t(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
                 uint64_t b_end, cudaStream_t stream) {
   const int smem = 128 + smm::RT_WPC * (smm::rt_abuf(m, k) + smm::rt_abuf(n, k));
-  static std::atomic<int> smem_set{0};
-  if (smem_set.load(std::memory_order_acquire) < smem) {
-    if (cudaFuncSetAttribute(smm::smm_dmma_rt_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
-    smem_set.store(smem, std::memory_order_release);
-  }
+  static SmemAttrCache smem_set;
+  if (ensure_smem(smm::smm_dmma_rt_kernel<TM, TN>, smem, smem_set) != 0) return -30;
   int cps = (220 * 1024) / smem;
   if (cps > 12) cps = 12;
   if (cps < 1) return -30;
+  if (stack_size <= 0) return 0;  // stack_size 0 = prepare only
   const int max_grid = num_sms() * cps;
   int grid = (stack_size + smm::RT_WPC * 4 - 1) / (smm::RT_WPC * 4);
   if (grid > max_grid) grid = max_grid;
@@ -161,16 +209,13 @@ bool big_eligible(int m, int n, int k) {
 
 int launch_big(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
                uint64_t b_end, cudaStream_t stream) {
-  if (stack_size <= 0) return 0;
   const int smem = smm::big_smem_bytes(m, n, k);
-  static std::atomic<int> smem_set{0};
-  if (smem_set.load(std::memory_order_acquire) < smem) {
-    if (cudaFuncSetAttribute(smm::smm_dmma_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
-    smem_set.store(smem, std::memory_order_release);
-  }
+  static SmemAttrCache smem_set;
+  if (ensure_smem(smm::smm_dmma_big_kernel, smem, smem_set) != 0) return -30;
   int cps = (220 * 1024) / (smem + 1024);
   if (cps > 8) cps = 8;
   if (cps < 1) return -30;
+  if (stack_size <= 0) return 0;  // stack_size 0 = prepare only
   const int max_grid = num_sms() * cps;
   int grid = (stack_size + 1) / 2;  // at least two entries per CTA
   if (grid > max_grid) grid = max_grid;
@@ -196,7 +241,6 @@ bool rt_eligible(int m, int n, int k) {
 
 int launch_rt(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, uint64_t a_end,
               uint64_t b_end, cudaStream_t stream) {
-  if (stack_size <= 0) return 0;
   const int tm = (m + 7) / 8, tn = (n + 7) / 8;
 #define SMM_RT_CASE(TM_, TN_) \
   if (tm == TM_ && tn == TN_) return launch_rt_t<TM_, TN_>(dev_stack, stack_size, a, b, c, m, n, k, a_end, b_end, stream);
@@ -222,8 +266,10 @@ int launch_generic(const int* dev_stack, int stack_size, const double* a, const 
 
 // ---- inhomogeneous stacks (def_mnk = 0) -------------------------------------------------------------------------------------
 // The reference rejects them (-1, libsmm_acc.cpp:327) and DBCSR drains them on the CPU.  Here the 7-wide HOST stack is binned by
-// (m,n,k), every bin ordered by c_first (stable), uploaded through a small per-thread ring of pinned/device scratch buffers and
+// (m,n,k), every bin ordered by c_first (stable), uploaded through a small ring of pinned/device scratch buffers per stream and
 // drained by the kernel of its shape, all on stack_stream.  The host stack is consumed before the call returns.
+// All-or-nothing: every bin's kernel is resolved and prepared (shared-memory attribute, occupancy) BEFORE anything is enqueued,
+// so a negative return code ("redo this stack on the CPU", src/mm/dbcsr_acc_operations.F:134-135) always means C is untouched.
 struct InhomoScratch {
   int* host = nullptr;
   int* dev = nullptr;
@@ -231,34 +277,51 @@ struct InhomoScratch {
   cudaEvent_t done = nullptr;
 };
 struct InhomoRing {
+  cudaStream_t stream = nullptr;
   InhomoScratch buf[4];
   int next = 0;
-  ~InhomoRing() {
-    for (auto& b : buf) {
-      if (b.done != nullptr) cudaEventDestroy(b.done);
+};
+// Rings live as long as the library (host threads of the engine are short-lived; freeing pinned/device memory at thread exit
+// would synchronise the device under in-flight work): one per stream, created on first use, released by libsmm_acc_finalize.
+std::mutex g_inhomo_mu;
+std::vector<InhomoRing*> g_inhomo_rings;
+
+InhomoRing* inhomo_ring(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_inhomo_mu);
+  for (InhomoRing* r : g_inhomo_rings)
+    if (r->stream == stream) return r;
+  InhomoRing* r = new InhomoRing();
+  r->stream = stream;
+  g_inhomo_rings.push_back(r);
+  return r;
+}
+void inhomo_release_all() {
+  std::lock_guard<std::mutex> lock(g_inhomo_mu);
+  for (InhomoRing* r : g_inhomo_rings) {
+    for (auto& b : r->buf) {
+      if (b.done != nullptr) {
+        cudaEventSynchronize(b.done);
+        cudaEventDestroy(b.done);
+      }
       if (b.host != nullptr) cudaFreeHost(b.host);
       if (b.dev != nullptr) cudaFree(b.dev);
     }
+    delete r;
   }
+  g_inhomo_rings.clear();
+}
+
+enum BinKind { BIN_EMPTY, BIN_TUNED, BIN_RT, BIN_BIG, BIN_GENERIC_BT, BIN_GENERIC_NT };
+struct Bin {
+  int lo, hi, m, n, k;
+  BinKind kind;
+  smm::launch_fn fn;
 };
 
 int process_inhomogeneous(const int* host7, int stack_size, const double* a, const double* b, double* c, int max_kernel_dim,
                           cudaStream_t stream) {
   if (host7 == nullptr) return -1;
   if (stack_size <= 0) return 0;
-  static thread_local InhomoRing ring;
-  InhomoScratch& sc = ring.buf[ring.next];
-  ring.next = (ring.next + 1) % 4;
-  if (sc.done == nullptr && cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming) != cudaSuccess) return -30;
-  if (cudaEventSynchronize(sc.done) != cudaSuccess) return -30;  // previous user of this scratch has finished
-  const size_t need = 3 * (size_t)stack_size;
-  if (sc.cap < need) {
-    if (sc.host != nullptr) cudaFreeHost(sc.host);
-    if (sc.dev != nullptr) cudaFree(sc.dev);
-    sc.cap = std::max(need, (size_t)3 * 30000);
-    if (cudaHostAlloc(reinterpret_cast<void**>(&sc.host), sc.cap * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return -30;
-    if (cudaMalloc(reinterpret_cast<void**>(&sc.dev), sc.cap * sizeof(int)) != cudaSuccess) return -30;
-  }
   // order: by shape, then by c_first, stable
   std::vector<int> order((size_t)stack_size);
   std::iota(order.begin(), order.end(), 0);
@@ -271,48 +334,105 @@ int process_inhomogeneous(const int* host7, int stack_size, const double* a, con
     if (sx != sy) return sx < sy;
     return host7[7 * (size_t)x + 5] < host7[7 * (size_t)y + 5];
   });
+  // ---- phase 1: resolve and prepare every bin; nothing is enqueued yet, any failure leaves C untouched
+  const uint64_t a_end = allocation_end(a), b_end = allocation_end(b);
+  std::vector<Bin> bins;
+  for (int lo = 0; lo < stack_size;) {
+    int hi = lo;
+    const uint64_t sh = shape(order[(size_t)lo]);
+    while (hi < stack_size && shape(order[(size_t)hi]) == sh) ++hi;
+    const int* p = host7 + 7 * (size_t)order[(size_t)lo];
+    Bin bin = {lo, hi, p[0], p[1], p[2], BIN_EMPTY, nullptr};
+    const int m = bin.m, n = bin.n, k = bin.k;
+    int rc = 0;
+    if (m <= 0 || n <= 0 || k <= 0) {
+      bin.kind = BIN_EMPTY;  // empty blocks: nothing to do
+    }
+    else if (m > max_kernel_dim || n > max_kernel_dim || k > max_kernel_dim) {
+      bin.kind = (n <= max_kernel_dim && k <= max_kernel_dim) ? BIN_GENERIC_BT : BIN_GENERIC_NT;
+    }
+    else if ((bin.fn = lookup(m, n, k)) != nullptr) {
+      bin.kind = BIN_TUNED;
+      rc = bin.fn(nullptr, 0, a, b, c, a_end, b_end, stream);  // stack_size 0 = prepare only
+    }
+    else if (rt_eligible(m, n, k)) {
+      bin.kind = BIN_RT;
+      rc = launch_rt(nullptr, 0, a, b, c, m, n, k, a_end, b_end, stream);
+    }
+    else if (big_eligible(m, n, k)) {
+      bin.kind = BIN_BIG;
+      rc = launch_big(nullptr, 0, a, b, c, m, n, k, a_end, b_end, stream);
+    }
+    else {
+      bin.kind = BIN_GENERIC_BT;
+    }
+    if (rc < 0) return rc;
+    bins.push_back(bin);
+    lo = hi;
+  }
+  InhomoRing* ring = inhomo_ring(stream);  // calls on one stream come from one host thread at a time (DBCSR: one stream per thread)
+  InhomoScratch& sc = ring->buf[ring->next];
+  ring->next = (ring->next + 1) % 4;
+  if (sc.done == nullptr && cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming) != cudaSuccess) return -30;
+  if (cudaEventSynchronize(sc.done) != cudaSuccess) return -30;  // previous user of this scratch has finished
+  const size_t need = 3 * (size_t)stack_size;
+  if (sc.cap < need) {
+    if (sc.host != nullptr) cudaFreeHost(sc.host);
+    if (sc.dev != nullptr) cudaFree(sc.dev);
+    sc.host = nullptr;
+    sc.dev = nullptr;
+    sc.cap = 0;
+    const size_t cap = std::max(need, (size_t)3 * 30000);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&sc.host), cap * sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+      sc.host = nullptr;
+      (void)cudaGetLastError();
+      return -30;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&sc.dev), cap * sizeof(int)) != cudaSuccess) {
+      cudaFreeHost(sc.host);
+      sc.host = nullptr;
+      sc.dev = nullptr;
+      (void)cudaGetLastError();
+      return -30;
+    }
+    sc.cap = cap;  // only now: both buffers exist
+  }
   for (int i = 0; i < stack_size; ++i) {
     const int* p = host7 + 7 * (size_t)order[(size_t)i];
     sc.host[3 * (size_t)i] = p[3];
     sc.host[3 * (size_t)i + 1] = p[4];
     sc.host[3 * (size_t)i + 2] = p[5];
   }
-  if (cudaMemcpyAsync(sc.dev, sc.host, need * sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -31;
-  const uint64_t a_end = allocation_end(a), b_end = allocation_end(b);
+  if (cudaMemcpyAsync(sc.dev, sc.host, need * sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return -31;  // nothing enqueued
+  // ---- phase 2: launch.  Every kernel was prepared above, so a failure here is a device/driver fault, not an unsupported
+  // request: like the reference (ACC_API_CALL: print and exit, src/acc/cuda/acc_cuda.h:29-36) it is fatal -- a negative code
+  // would make DBCSR redo the WHOLE stack on the CPU on top of the bins already enqueued.
+  smm::stream_chain_break(stream);  // the bins read a stack uploaded by this very call
   int rc_all = 0;
-  int lo = 0;
-  while (lo < stack_size) {
-    int hi = lo;
-    const uint64_t sh = shape(order[(size_t)lo]);
-    while (hi < stack_size && shape(order[(size_t)hi]) == sh) ++hi;
-    const int* p = host7 + 7 * (size_t)order[(size_t)lo];
-    const int m = p[0], n = p[1], k = p[2];
-    int rc;
-    if (m <= 0 || n <= 0 || k <= 0) {
-      rc = 0;  // empty blocks: nothing to do
-    }
-    else if (m > max_kernel_dim || n > max_kernel_dim || k > max_kernel_dim) {
-      rc = launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, (n <= max_kernel_dim && k <= max_kernel_dim) ? 1 : 0, stream);
-      if (rc == 0) rc_all = 10;
-    }
-    else if (const smm::launch_fn fn = lookup(m, n, k)) {
-      rc = fn(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, a_end, b_end, stream);
-    }
-    else {
-      rc = rt_eligible(m, n, k)    ? launch_rt(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
-           : big_eligible(m, n, k) ? launch_big(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, a_end, b_end, stream)
-                                   : launch_generic(sc.dev + 3 * (size_t)lo, hi - lo, a, b, c, m, n, k, 1, stream);
-      if (rc == 0) rc_all = 10;
+  for (const Bin& bin : bins) {
+    const int* st = sc.dev + 3 * (size_t)bin.lo;
+    const int cnt = bin.hi - bin.lo;
+    int rc = 0;
+    switch (bin.kind) {
+      case BIN_EMPTY: continue;
+      case BIN_TUNED: rc = bin.fn(st, cnt, a, b, c, a_end, b_end, stream); break;
+      case BIN_RT: rc = launch_rt(st, cnt, a, b, c, bin.m, bin.n, bin.k, a_end, b_end, stream); break;
+      case BIN_BIG: rc = launch_big(st, cnt, a, b, c, bin.m, bin.n, bin.k, a_end, b_end, stream); break;
+      case BIN_GENERIC_BT: rc = launch_generic(st, cnt, a, b, c, bin.m, bin.n, bin.k, 1, stream); break;
+      case BIN_GENERIC_NT: rc = launch_generic(st, cnt, a, b, c, bin.m, bin.n, bin.k, 0, stream); break;
     }
     if (rc < 0) {
-      // kernels of earlier bins are already enqueued: report a hard error instead of a "redo on the CPU" code
-      cudaEventRecord(sc.done, stream);
-      return -32;
+      fprintf(stderr, "dbcsr_acc_b200: kernel launch failed (%d: %s) for the %dx%dx%d bin of an inhomogeneous stack after earlier bins were enqueued\n",
+              rc, cudaGetErrorString(cudaGetLastError()), bin.m, bin.n, bin.k);
+      abort();
     }
+    if (bin.kind != BIN_TUNED) rc_all = 10;
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    lo = hi;
   }
-  if (cudaEventRecord(sc.done, stream) != cudaSuccess) return -31;
+  if (cudaEventRecord(sc.done, stream) != cudaSuccess) {
+    fprintf(stderr, "dbcsr_acc_b200: cudaEventRecord failed behind an inhomogeneous stack\n");
+    abort();
+  }
   return rc_all;
 }
 
@@ -335,13 +455,10 @@ int launch_transpose_typed(const int* dev_trs_stack, int nblks, void* data, int 
   const size_t blk_bytes = (size_t)m * n * sizeof(T);
   int wpc = (int)((96 * 1024) / blk_bytes);
   if (wpc > 8) wpc = 8;
-  if (wpc < 1) return -3;
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    if (cudaFuncSetAttribute(smm::transpose_typed_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
-      return -30;
-    attr_set.store(true, std::memory_order_release);
-  }
+  if (wpc < 1) wpc = 1;  // 80 x 80 complex_8 = 100 KB: one warp per CTA, still within the 227 KB of an SM
+  if (blk_bytes * (size_t)wpc > 200 * 1024) return -3;  // cannot happen for m,n <= 80
+  static SmemAttrCache attr_set;
+  if (ensure_smem(smm::transpose_typed_kernel<T>, (int)(blk_bytes * wpc), attr_set) != 0) return -30;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
   if (grid > max_grid) grid = max_grid;
@@ -363,7 +480,10 @@ bool all_types_enabled() {
 extern "C" {
 
 int libsmm_acc_init(void) { return 0; }      // kernels are compiled ahead of time; nothing to set up per thread
-int libsmm_acc_finalize(void) { return 0; }
+int libsmm_acc_finalize(void) {
+  inhomo_release_all();
+  return 0;
+}
 c_dbcsr_acc_bool_t libsmm_acc_is_thread_safe(void) { return 1; }
 int libsmm_acc_gpu_warp_size(void) { return 32; }
 long long libsmm_acc_b200_launch_count(void) { return g_launches.load(); }
@@ -404,6 +524,33 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   }
   return -1;
 }
+// Declares (on != 0) or withdraws (on == 0) that `stream` carries a CHAIN of independent stack drains: between two
+// libsmm_acc_process calls on it the caller enqueues nothing that produces A, B, C or stack data except through operations that
+// are full stream dependencies anyway (memcpys, event waits).  The FP64 stack kernels then skip the grid-dependency wait in
+// front of their first read, so consecutive drains overlap tail and ramp-up (programmatic dependent launch).  The first drain
+// after the declaration -- and after any other kernel this library launches on the stream -- still waits.  Default: off.
+int libsmm_acc_b200_stream_chain(void* stream, int on) {
+  if (stream == nullptr) return -2;
+  const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
+  std::lock_guard<std::mutex> lock(smm::g_chain_mu);
+  for (size_t i = 0; i < smm::g_chain.size(); ++i)
+    if (smm::g_chain[i].stream == st) {
+      if (on == 0) {
+        smm::g_chain.erase(smm::g_chain.begin() + (long)i);
+        smm::g_chain_n.store((int)smm::g_chain.size(), std::memory_order_release);
+      }
+      else {
+        smm::g_chain[i].primed = false;
+      }
+      return 0;
+    }
+  if (on != 0) {
+    smm::g_chain.push_back({st, false});
+    smm::g_chain_n.store((int)smm::g_chain.size(), std::memory_order_release);
+  }
+  return 0;
+}
+
 void libsmm_acc_b200_set_trace(void* dev_words) { smm::g_tune.trace.store(static_cast<unsigned long long*>(dev_words)); }
 
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
@@ -412,6 +559,7 @@ int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kd
                               void* stream) {
   if (nblks <= 0) return 0;
   if (stream == nullptr || rows <= 0 || kdim <= 0 || rows > 32 || kdim > 32) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream));
   const int wpc = 8;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
@@ -452,6 +600,7 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
   if (datatype == dbcsr_type_bf16_ext) {
     // extension: A/B are BF16 tile panels made by libsmm_acc_b200_pack_bf16, C is FP32; tensor-core (tcgen05) kernel
     if (m_max > 32 || n_max > 32 || k_max > 32) return -10;
+    smm::stream_chain_break(*static_cast<cudaStream_t*>(stack_stream));
     const int rc = launch_bf16(dev_param_stack, stack_size, dev_a_data, dev_b_data, dev_c_data, m_max, n_max, k_max,
                                *static_cast<cudaStream_t*>(stack_stream));
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -462,6 +611,7 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
     // generic kernel.  B blocks of these types are transposed by libsmm_acc_transpose below under the same rule as real_8.
     if (!all_types_enabled() || def_mnk != 1) return -10;
     cudaStream_t st = *static_cast<cudaStream_t*>(stack_stream);
+    smm::stream_chain_break(st);
     const int bt = (n_max <= max_kernel_dim && k_max <= max_kernel_dim) ? 1 : 0;
     int rc = -10;
     if (datatype == dbcsr_type_real_4)
@@ -481,13 +631,15 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
   double* c = static_cast<double*>(dev_c_data);
 
   if (m_max > max_kernel_dim || n_max > max_kernel_dim || k_max > max_kernel_dim) {
-    // Large blocks.  The reference loops cublasDgemm over the HOST stack on c_stream and synchronises (libsmm_acc.cpp:256-278);
-    // here one generic launch drains the device stack asynchronously on c_stream (which already waits for the stack upload,
-    // src/mm/dbcsr_mm_accdrv.F:516).  B is transposed only if both n and k fit max_kernel_dim (libsmm_acc.cpp:267-270).
-    if (c_stream == nullptr) return -2;
+    // Large blocks.  The reference loops cublasDgemm over the HOST stack on c_stream and synchronises (libsmm_acc.cpp:256-278).
+    // Here one launch drains the DEVICE stack asynchronously on stack_stream -- the stream the stack upload was enqueued on and
+    // the one DBCSR records the stack buffer's `calculated` event on (src/mm/dbcsr_mm_accdrv.F:512-534), so the buffer and the
+    // panels cannot be recycled under the kernel whatever c_stream is; C is accumulated with atomics, so no ordering against
+    // c_stream is needed.  B is transposed only if both n and k fit max_kernel_dim (libsmm_acc.cpp:267-270).
+    const cudaStream_t big_stream = *static_cast<cudaStream_t*>(stack_stream);
+    smm::stream_chain_break(big_stream);
     const int b_transposed = (n_max <= max_kernel_dim && k_max <= max_kernel_dim) ? 1 : 0;
-    const int rc = launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, b_transposed,
-                                  *static_cast<cudaStream_t*>(c_stream));
+    const int rc = launch_generic(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, b_transposed, big_stream);
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc == 0 ? 10 : rc;
   }
@@ -499,6 +651,7 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
+  smm::stream_chain_break(stream);
   const int rc = rt_eligible(m_max, n_max, k_max)
                    ? launch_rt(dev_param_stack, stack_size, a, b, c, m_max, n_max, k_max, allocation_end(a), allocation_end(b), stream)
                    : big_eligible(m_max, n_max, k_max)
@@ -512,6 +665,7 @@ int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, v
                          int n, int max_kernel_dim, void* stream) {
   if (m > max_kernel_dim || n > max_kernel_dim) return 0;    // reference: libsmm_acc.cpp:485
   if (stack_size <= 0 || m <= 0 || n <= 0) return 0;
+  if (stream != nullptr) smm::stream_chain_break(*static_cast<cudaStream_t*>(stream));
   if (datatype != dbcsr_type_real_8) {
     // reference: "transpose not needed" (libsmm_acc.cpp:484) because it never multiplies these types on the device; this
     // library does (typed generic kernel), so their right-panel blocks are transposed exactly like real_8 ones
@@ -533,11 +687,8 @@ int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, v
   if (wpc > 8) wpc = 8;
   if (wpc < 1) return -3;  // cannot happen for m,n <= 80 (51 KB)
   const size_t smem = blk_bytes * wpc;
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    if (cudaFuncSetAttribute(smm::transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return -30;
-    attr_set.store(true, std::memory_order_release);
-  }
+  static SmemAttrCache attr_set;
+  if (ensure_smem(smm::transpose_kernel, (int)smem, attr_set) != 0) return -30;
   int grid = (stack_size + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
   if (grid > max_grid) grid = max_grid;
@@ -551,6 +702,7 @@ int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, v
 int c_calculate_norms(const double* mat, int nblks, const int* offsets, const int* nelems, float* norms, void* stream_ptr) {
   if (nblks <= 0) return 0;
   if (stream_ptr == nullptr) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream_ptr));
   const int wpc = 8;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
@@ -564,6 +716,7 @@ int c_calculate_norms(const double* mat, int nblks, const int* offsets, const in
 int libsmm_acc_b200_block_norms_f64(const double* mat, int nblks, const int* offsets, const int* nelems, double* norms, void* stream_ptr) {
   if (nblks <= 0) return 0;
   if (stream_ptr == nullptr) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream_ptr));
   const int wpc = 8;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
@@ -578,6 +731,7 @@ int libsmm_acc_b200_gather_blocks(const double* src, double* dst, int nblks, con
                                   const int* nelems, void* stream_ptr) {
   if (nblks <= 0) return 0;
   if (stream_ptr == nullptr) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream_ptr));
   const int wpc = 8;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;

@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
   unsigned char* slots_b = slots_a + (size_t)BF_SLOTS * g.slot_a;
   const size_t ring_bytes = (size_t)BF_SLOTS * (g.slot_a + g.slot_b) + (size_t)g.kg_slot * 2048 + 2048;
 
-  // Programmatic dependent launch, same protocol as the FP64 kernel (see smm_dmma.cuh)
+  // Programmatic dependent launch: become resident early, but wait for the predecessor (pack_bf16, memset, another drain) to be
+  // complete and visible before anything is read -- and before TMEM is allocated, so that a waiting dependent CTA can never hold
+  // TMEM columns a predecessor CTA still needs.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // The k padding group of every slot must read as zero (tiles carry kg groups, a slot kg_slot): zero just those bytes and the
   // slack behind the ring once; everything else is either overwritten by the TMA or only feeds discarded rows/columns.
   {
@@ -251,7 +254,6 @@ __global__ void __launch_bounds__(BF_THREADS) smm_bf16_kernel(const int* __restr
     }
   }
   __syncthreads();
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // never complete before the predecessor kernel has
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BF_TMEM_COLS) : "memory");
   }

@@ -19,8 +19,12 @@
 //     RED.ADD.F64 per element, or -- FLUSH 2, shipped for 23^3 -- an image of the run in the warp's free operand stage that ONE
 //     cp.reduce.async.bulk.add.f64 (TMA, UBLKRED) adds into C.  Runs are short on real stacks (1.7 entries on the 23^3/10 %
 //     workload), so the flush is on the critical resource list: per-element REDs leave an SM at ~1 element per cycle;
-//   * launches use programmatic dependent launch (griddepcontrol.launch_dependents at entry, .wait at exit): consecutive
-//     stack drains of a stream overlap their ramp-up/tail, completion order is still stream order.
+//   * launches use programmatic dependent launch: griddepcontrol.launch_dependents at entry lets the next kernel of the stream
+//     become resident early.  By default the kernel then executes griddepcontrol.wait BEFORE its first global read (the
+//     predecessor may be a producer of A/B/C/stack: memset, transpose, pack -- only the launch latency and the prologue
+//     overlap).  When the caller has declared the stream a chain of independent stack drains (FLAG_PDL_CHAIN, set through
+//     libsmm_acc_b200_stream_chain), the wait moves to the very end: consecutive drains overlap their ramp-up/tail and
+//     completion order is still stream order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -341,6 +345,7 @@ __device__ __forceinline__ void warp_chunk(int gw, int chunk, int extra, int sta
 
 // Kernel flags
 constexpr int FLAG_ALIGN_RUNS = 1;  // move chunk boundaries to the next change of c_first (at most 30 entries ahead)
+constexpr int FLAG_PDL_CHAIN = 2;   // the predecessor in the stream is an independent stack drain: no grid dependency before the reads
 
 // Trace record of one warp (TRACE kernels; lane 0 writes): see tools/trace_analyze.py
 //   [0] smid | n_entries << 32   [1] globaltimer at start   [2] clock at start   [3] first entry
@@ -385,10 +390,13 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
   const int gw = blockIdx.x * WPC + warp;
   int n0, n1;  // nominal chunk
   warp_chunk(gw, chunk, extra, stack_size, n0, n1);
-  // Programmatic dependent launch: let the next stack kernel of this stream start filling SMs as soon as our CTAs retire
-  // (stacks only accumulate into C with RED, so consecutive drains are independent); the matching wait sits at the very end so
-  // that a kernel never COMPLETES before its predecessor has (later memcpys / events keep plain stream-order semantics).
+  // Programmatic dependent launch: let the next stack kernel of this stream start filling SMs as soon as our CTAs retire.
+  // Unless the caller declared the stream a chain of independent drains (stacks only accumulate into C with RED), everything
+  // the predecessor wrote must be complete and visible before the first global read below.  In chain mode the matching wait
+  // sits at the very end so that a kernel never COMPLETES before its predecessor has (later memcpys / events keep plain
+  // stream-order semantics).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if ((flags & FLAG_PDL_CHAIN) == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   if constexpr (FLUSH == 4) {  // the only CTA-wide barrier of this kernel: the scratch lock starts open (before any warp leaves)
     if (threadIdx.x == 0) *reinterpret_cast<int*>(smem_raw + G::BAR_BYTES + (size_t)WPC * G::PER_WARP) = 0;
     __syncthreads();

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) smm_dmma_big_kernel(const int*
   const int e0 = min(blockIdx.x * chunk, stack_size);
   const int e1 = min(e0 + chunk, stack_size);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor may have produced A, B, C or the stack: complete + visible first
   if (e0 >= e1) {  // whole CTA
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;

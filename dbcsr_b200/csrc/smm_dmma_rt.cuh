@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(RT_WPC * 32) smm_dmma_rt_kernel(const int* __r
   const int e0 = gw * chunk;
   const int e1 = min(e0 + chunk, stack_size);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor may have produced A, B, C or the stack: complete + visible first
   if (e0 >= e1) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__((NC + 1) * 32) smm_dmma_ws_kernel(const int* _
   const int cta_len = cta_e1 - cta_e0;  // <= WS_ENT_CAP by construction of the grid
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the predecessor may have produced A, B, C or the stack: complete + visible first
   if (cta_len <= 0) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     return;

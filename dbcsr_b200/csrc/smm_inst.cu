@@ -6,8 +6,11 @@
 #include <cstdlib>
 
 #include "smm_dmma.cuh"
-#include "smm_dmma_ws.cuh"
+#if defined(SMM_EXPERIMENT)
+#  include "smm_dmma_ws.cuh"  // warp-specialised variant: a measured-slower experiment, never part of the shipped library
+#endif
 #include "smm_launch.h"
+#include "smm_tiny.cuh"
 #include "smm_tune.h"
 
 #ifndef SMM_M
@@ -25,23 +28,25 @@ namespace smm {
 // wave); ALIGN: chunk boundaries moved to changes of c_first.  The run-time knobs (smm_tune.h) override CHUNK / ALIGN when >= 0.
 template <int M, int N, int K>
 struct Policy {
+  static constexpr int ALGO = 0;  // 0 = warp-autonomous DMMA + TMA kernel (smm_dmma.cuh), 1 = lane-per-element kernel (smm_tiny.cuh)
+  static constexpr int WPC = 0;   // warps per CTA, 0 = the kernel's default (pick_wpc / 8 for the tiny kernel)
   static constexpr int FLUSH = 0, CHUNK = 0;
   static constexpr bool ALIGN = false;
 };
 // the tuned records: generated from the autotune database dbcsr_b200/parameters/parameters_B200.json (tools/gen_policy.py),
 // like the reference generates parameters.h from parameters_<GPU>.json
-#define SMM_POLICY(M_, N_, K_, FLUSH_, CHUNK_, ALIGN_) \
-  template <>                                           \
-  struct Policy<M_, N_, K_> {                           \
-    static constexpr int FLUSH = FLUSH_, CHUNK = CHUNK_; \
-    static constexpr bool ALIGN = ALIGN_;               \
+#define SMM_POLICY(M_, N_, K_, ALGO_, WPC_, FLUSH_, CHUNK_, ALIGN_) \
+  template <>                                                        \
+  struct Policy<M_, N_, K_> {                                        \
+    static constexpr int ALGO = ALGO_, WPC = WPC_;                   \
+    static constexpr int FLUSH = FLUSH_, CHUNK = CHUNK_;             \
+    static constexpr bool ALIGN = ALIGN_;                            \
   };
 #include "smm_policy.inc"
 #undef SMM_POLICY
 
 namespace {
 
-int g_num_sms = 0;
 // DBCSR_B200_PDL=0 disables programmatic dependent launch (A/B experiments); default on
 const bool g_use_pdl = [] {
   const char* e = getenv("DBCSR_B200_PDL");
@@ -58,18 +63,29 @@ unsigned long long* trace_slot() {
   return t + (size_t)(seq - first) * TRACE_WARPS * TRACE_REC;
 }
 
+// cudaFuncSetAttribute and the occupancy are PER DEVICE (DBCSR picks the device per rank, c_dbcsr_acc_set_active_device may switch
+// it): caches are arrays indexed by the active device, 0 = not yet set up on that device.
+constexpr int kMaxDevices = 64;
+struct DevCache {
+  std::atomic<int> ctas_per_sm[kMaxDevices];
+  std::atomic<int> num_sms[kMaxDevices];
+};
+
 template <typename Kern>
-int occupancy(Kern kern, int threads, int smem, std::atomic<int>& cache) {
-  int cps = cache.load(std::memory_order_acquire);
+int occupancy(Kern kern, int threads, int smem, DevCache& cache, int& num_sms) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -30;
+  int cps = cache.ctas_per_sm[dev].load(std::memory_order_acquire);
   if (cps == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -30;
-    int dev = 0, nb = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return -30;
-    if (g_num_sms == 0) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    int nb = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return -30;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) return -30;
+    cache.num_sms[dev].store(sms, std::memory_order_relaxed);
     cps = nb;
-    cache.store(cps, std::memory_order_release);
+    cache.ctas_per_sm[dev].store(cps, std::memory_order_release);
   }
+  num_sms = cache.num_sms[dev].load(std::memory_order_relaxed);
   return cps;
 }
 
@@ -97,10 +113,11 @@ int launch_base(const int* dev_stack, int stack_size, const double* a, const dou
   constexpr int SMEM = G::SMEM;
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
   auto kern = smm_dmma_kernel<M, N, K, NST, WPC, HINT, TRACE, FLUSH, ABL>;
-  static std::atomic<int> ctas_per_sm{0};
-  const int cps = occupancy(kern, WPC * 32, SMEM, ctas_per_sm);
+  static DevCache cache;  // zero-initialised
+  int g_num_sms = 0;
+  const int cps = occupancy(kern, WPC * 32, SMEM, cache, g_num_sms);
   if (cps < 0) return cps;
-  if (stack_size <= 0) return 0;
+  if (stack_size <= 0) return 0;  // stack_size 0 = "prepare": the attribute is set, nothing is launched
   const int max_grid = g_num_sms * cps;
   // at least 4 entries per warp so that the pipeline prologue and the C flush are amortised
   int grid = (stack_size + WPC * 4 - 1) / (WPC * 4);
@@ -125,12 +142,14 @@ int launch_base(const int* dev_stack, int stack_size, const double* a, const dou
     extra = stack_size % warps;
   }
   const int align = g_tune.align.load(std::memory_order_relaxed);
-  const int flags = (align < 0 ? Policy<M, N, K>::ALIGN : align != 0) ? FLAG_ALIGN_RUNS : 0;
+  const int flags = ((align < 0 ? Policy<M, N, K>::ALIGN : align != 0) ? FLAG_ALIGN_RUNS : 0) |
+                    ((g_use_pdl && stream_chain_mode(stream)) ? FLAG_PDL_CHAIN : 0);
   unsigned long long* trace = TRACE ? trace_slot() : nullptr;
   const unsigned long long al = a_limit, bl = b_limit;
   return launch_pdl(kern, grid, WPC * 32, SMEM, stream, dev_stack, stack_size, a, b, c, al, bl, chunk, extra, flags, trace);
 }
 
+#if defined(SMM_EXPERIMENT)
 // warp-specialised kernel (smm_dmma_ws.cuh): NC consumer warps with D stages each + one producer warp per CTA
 template <int M, int N, int K, int NC, int D, int HINT, bool TRACE, int FLUSH = 0, bool STAG = false>
 int launch_ws(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
@@ -138,8 +157,9 @@ int launch_ws(const int* dev_stack, int stack_size, const double* a, const doubl
   using G = WsGeom<M, N, K, NC, D>;
   static_assert(G::SMEM <= 227 * 1024, "shared memory budget exceeded");
   auto kern = smm_dmma_ws_kernel<M, N, K, NC, D, HINT, TRACE, FLUSH, STAG>;
-  static std::atomic<int> ctas_per_sm{0};
-  const int cps = occupancy(kern, G::THREADS, G::SMEM, ctas_per_sm);
+  static DevCache cache;
+  int g_num_sms = 0;
+  const int cps = occupancy(kern, G::THREADS, G::SMEM, cache, g_num_sms);
   if (cps < 0) return cps;
   if (stack_size <= 0) return 0;
   const int max_grid = g_num_sms * cps;
@@ -159,6 +179,27 @@ int launch_ws(const int* dev_stack, int stack_size, const double* a, const doubl
   return launch_pdl(kern, grid, G::THREADS, G::SMEM, stream, dev_stack, stack_size, a, b, c, al, bl, base, extra, trace);
 }
 
+#endif
+
+// lane-per-element kernel for tiny blocks (smm_tiny.cuh): no shared memory, WPC warps per CTA, one resident wave
+template <int M, int N, int K, int WPC>
+int launch_tiny(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, cudaStream_t stream) {
+  auto kern = smm_tiny_kernel<M, N, K, WPC>;
+  static DevCache cache;
+  int num_sms = 0;
+  const int cps = occupancy(kern, WPC * 32, 0, cache, num_sms);
+  if (cps < 0) return cps;
+  if (stack_size <= 0) return 0;
+  const int max_warps = num_sms * cps * WPC;
+  int chunk = g_tune.chunk.load(std::memory_order_relaxed);
+  if (chunk <= 0) chunk = (stack_size + max_warps - 1) / max_warps;
+  if (chunk < 8) chunk = 8;  // amortise the per-warp prologue and the flush of the last run
+  const int warps = (stack_size + chunk - 1) / chunk;
+  const int grid = (warps + WPC - 1) / WPC;
+  const int flags = (g_use_pdl && stream_chain_mode(stream)) ? FLAG_PDL_CHAIN : 0;
+  return launch_pdl(kern, grid, WPC * 32, 0, stream, dev_stack, stack_size, a, b, c, chunk, flags);
+}
+
 template <int M, int N, int K>
 int launch(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, uint64_t a_limit, uint64_t b_limit,
            cudaStream_t stream) {
@@ -168,7 +209,35 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
   constexpr int WPC = (SMM_FORCE_WPC * SMM_FORCE_NST * SH::STAGE <= 220 * 1024) ? SMM_FORCE_WPC : pick_wpc(SH::STAGE);
 #else
   constexpr int NST = pick_nst(SH::STAGE);
-  constexpr int WPC = pick_wpc(SH::STAGE);
+  constexpr int WPC = (Policy<M, N, K>::WPC > 0 && Policy<M, N, K>::WPC * NST * SH::STAGE <= 220 * 1024) ? Policy<M, N, K>::WPC : pick_wpc(SH::STAGE);
+#endif
+#if defined(SMM_EXPERIMENT)
+  // autotune grid carried by EVERY triplet (tools/autotune.sh): 100 + 10 * (index of warps per CTA in {2,4,8}) + FLUSH (0 or 2);
+  // 200 / 201 = lane-per-element kernel with 8 / 4 warps per CTA (m*n <= 96 only)
+  if constexpr (!(N == M && K == M)) {
+#  define SMM_ARGS dev_stack, stack_size, a, b, c, a_limit, b_limit, stream
+#  define SMM_TUNE_CASE(ID, WPC_, FLUSH_)                                                                      \
+  case ID:                                                                                                    \
+    if constexpr (BaseGeom<M, N, K, 1, WPC_, FLUSH_>::SMEM <= 227 * 1024 &&                                    \
+                  (FLUSH_ != 2 || Shape<M, N, K>::STAGE >= scratch_bytes(M, N)))                               \
+      return launch_base<M, N, K, 1, WPC_, 0, false, FLUSH_>(SMM_ARGS);                                        \
+    break;
+    switch (g_tune.variant.load(std::memory_order_relaxed)) {
+      case 9: return launch_base<M, N, K, NST, WPC, 0, false, 0>(SMM_ARGS);
+        SMM_TUNE_CASE(100, 2, 0) SMM_TUNE_CASE(102, 2, 2) SMM_TUNE_CASE(110, 4, 0) SMM_TUNE_CASE(112, 4, 2)
+        SMM_TUNE_CASE(120, 8, 0) SMM_TUNE_CASE(122, 8, 2)
+      default: break;
+    }
+#  undef SMM_TUNE_CASE
+#  undef SMM_ARGS
+  }
+  if constexpr (M * N <= TINY_MAX_MN) {
+    switch (g_tune.variant.load(std::memory_order_relaxed)) {
+      case 200: return launch_tiny<M, N, K, 8>(dev_stack, stack_size, a, b, c, stream);
+      case 201: return launch_tiny<M, N, K, 4>(dev_stack, stack_size, a, b, c, stream);
+      default: break;
+    }
+  }
 #endif
 #if defined(SMM_EXPERIMENT)
   // kernel variants for tools/kbench (one experiment library, run-time switch); only the cubic shape carries them
@@ -294,7 +363,9 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
 #  undef SMM_ARGS
   }
 #endif
-  if constexpr (Policy<M, N, K>::FLUSH == 2 && NST == 1)
+  if constexpr (Policy<M, N, K>::ALGO == 1 && M * N <= TINY_MAX_MN)
+    return launch_tiny<M, N, K, (Policy<M, N, K>::WPC > 0 ? Policy<M, N, K>::WPC : 8)>(dev_stack, stack_size, a, b, c, stream);
+  else if constexpr (Policy<M, N, K>::FLUSH == 2 && NST == 1 && SH::STAGE >= scratch_bytes(M, N))
     return launch_base<M, N, K, NST, WPC, 0, false, 2>(dev_stack, stack_size, a, b, c, a_limit, b_limit, stream);
   else
     return launch_base<M, N, K, NST, WPC, 0, false, 0>(dev_stack, stack_size, a, b, c, a_limit, b_limit, stream);

@@ -30,7 +30,7 @@ SMM_SYMBOLS = [
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
     "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
-    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace",
+    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
@@ -91,6 +91,7 @@ def load():
     L.libsmm_acc_b200_get_tunable.restype = ctypes.c_longlong
     L.libsmm_acc_b200_set_trace.argtypes = [_vp]
     L.libsmm_acc_b200_set_trace.restype = None
+    L.libsmm_acc_b200_stream_chain.argtypes = [_vp, _i]
     L.c_dbcsr_acc_clear_errors.restype = None
     _lib = L
     return L
@@ -242,6 +243,11 @@ class Acc:
 
     def bf16_tile_bytes(self, rows, kdim):
         return int(self.L.libsmm_acc_b200_bf16_tile_bytes(rows, kdim))
+
+    def stream_chain(self, stream, on=True):
+        """Declare `stream` a chain of independent stack drains (programmatic dependent launch without the grid-dependency wait in
+        front of the reads, include/dbcsr_acc_libsmm.h); on=False withdraws the declaration."""
+        _ck(self.L.libsmm_acc_b200_stream_chain(stream, 1 if on else 0), "stream_chain")
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())

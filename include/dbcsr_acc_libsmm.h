@@ -87,6 +87,12 @@ long long libsmm_acc_b200_launch_count(void);
 int libsmm_acc_b200_set_tunable(const char* name, long long value);
 long long libsmm_acc_b200_get_tunable(const char* name);
 void libsmm_acc_b200_set_trace(void* dev_words);
+/* Programmatic-dependent-launch chain mode.  on != 0: the caller declares that `stream` (an acc stream handle) carries a chain of
+ * independent stack drains -- between two libsmm_acc_process calls nothing that produces A, B, C or stack data is enqueued on it
+ * except through full stream dependencies (memcpys, event waits).  The FP64 stack kernels then do not wait for their predecessor
+ * grid before reading, so consecutive drains overlap tail and ramp-up; completion order stays stream order.  Default (and after
+ * on == 0): every kernel waits for its predecessor before its first global read.  Returns 0, -2 for a NULL stream. */
+int libsmm_acc_b200_stream_chain(void* stream, int on);
 /* Library identification string (static storage). */
 const char* libsmm_acc_b200_version(void);
 

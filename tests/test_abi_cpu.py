@@ -112,8 +112,11 @@ def test_autotune_database_and_generated_policy_are_in_sync():
     sizes = [5, 13, 23, 26, 32]
     assert sorted((r["m"], r["n"], r["k"]) for r in db) == sorted((m, n, k) for m in sizes for n in sizes for k in sizes)
     for r in db:
-        assert r["algorithm"] == "dmma" and r["flush"] in (0, 2) and r["chunk"] >= 0 and r["source"].split(":")[0] in ("autotuned", "default")
+        assert r["algorithm"] in ("dmma", "tiny") and r["flush"] in (0, 2) and r["chunk"] >= 0 and r["source"].split(":")[0] in ("autotuned", "default")
+        assert r["algorithm"] == "dmma" or r["m"] * r["n"] <= 96
+        assert r.get("warps_per_cta", 0) in (0, 2, 4, 8, 12, 16)
         assert (r["perf"] > 0) == r["source"].startswith("autotuned")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_policy.py"), "--print"], capture_output=True, text=True, check=True).stdout
     assert out == open(os.path.join(ROOT, "dbcsr_b200", "csrc", "smm_policy.inc")).read()
-    assert "SMM_POLICY(23, 23, 23, 2, 12, true)" in out
+    rec = [r for r in db if (r["m"], r["n"], r["k"]) == (23, 23, 23)][0]
+    assert "SMM_POLICY(23, 23, 23, 0, %d, 2, %d, %s)" % (rec["warps_per_cta"], rec["chunk"], "true" if rec["align_runs"] else "false") in out

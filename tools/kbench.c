@@ -4,7 +4,7 @@
  * Bernoulli(occ) block presence (own LCG, seeded), stacks built by the library's host engine (multrec order, MM_STACK_SIZE 30000,
  * C-sorted) exactly as bench.py does, operands resident on the device.
  *
- *   kbench <library.so> <out_dir> <nblk> <occ> <steps> <bsz> <spec> [<spec> ...]
+ *   kbench <library.so> <out_dir> <nblk> <occ> <steps> <bsz | m,n,k> <spec> [<spec> ...]
  *   spec = variant:balance:chunk[:t]   (balance: bit 0 = balanced chunks, bit 1 = run-aligned chunk boundaries, negative = the
  *                                       library's per-shape policy; chunk: entries per warp, 0 = one wave, negative = policy; 0:-1:-1 is
  *                                       what ships; t = record a kernel timeline of launches 100..102 of one step into out_dir)
@@ -12,6 +12,9 @@
  * Per spec: (1) parity -- C is zeroed, every stack is drained once, the per-block sums of squares (libsmm_acc_b200_block_norms_f64)
  * are compared EXACTLY with those of the first spec (operands are small integers, so every summation order gives the same
  * doubles); (2) timing -- `steps` repetitions of the whole drain (334 launches), wall clock around stream synchronisation.
+ * KBENCH_ACC_LIB=<other.so>: take the acc/libsmm ABI functions (init, streams, memory, libsmm_acc_process) from that library instead,
+ * e.g. baseline/_ref/libdbcsr_acc_ref.so = the reference's own CUDA backend built for this GPU (baseline/Makefile): the same
+ * stacks, the same parity check (block norms by the main library's kernel) and the same timing loop give the same-box GPU baseline.
  * This is a development tool: bench.py is the bench contract.
  */
 #define _GNU_SOURCE
@@ -48,6 +51,16 @@ typedef long long (*fn_eng_flop)(const dbcsr_b200_engine_t*);
 typedef void (*fn_eng_destroy)(dbcsr_b200_engine_t*);
 
 static void* lib;
+static void* acc_lib; /* library providing the acc/libsmm ABI (== lib unless KBENCH_ACC_LIB is set) */
+static void* sym_from(void* l, const char* name) {
+  void* p = dlsym(l, name);
+  if (p == NULL) {
+    fprintf(stderr, "kbench: missing symbol %s\n", name);
+    exit(2);
+  }
+  return p;
+}
+static int noop_set_tun(const char* n, long long v) { (void)n; (void)v; return 0; }
 static void* sym(const char* name) {
   void* p = dlsym(lib, name);
   if (p == NULL) {
@@ -81,7 +94,7 @@ static inline double lcg_uniform(void) {  /* xorshift64* */
   } while (0)
 
 /* BCSR-ordered list index (row, col, blk_p) of a random nblk x nblk pattern; returns the number of blocks */
-static int make_pattern(int nblk, double occ, int bsz, int** list3_out) {
+static int make_pattern(int nblk, double occ, int blk_elems, int** list3_out) {
   int cap = (int)(nblk * (double)nblk * occ * 1.2) + 1024, n = 0;
   int* l = (int*)malloc(sizeof(int) * 3 * (size_t)cap);
   for (int r = 1; r <= nblk; ++r)
@@ -89,7 +102,7 @@ static int make_pattern(int nblk, double occ, int bsz, int** list3_out) {
       if (lcg_uniform() < occ && n < cap) {
         l[3 * n] = r;
         l[3 * n + 1] = c;
-        l[3 * n + 2] = 1 + n * bsz * bsz;
+        l[3 * n + 2] = 1 + n * blk_elems;
         ++n;
       }
   *list3_out = l;
@@ -105,26 +118,38 @@ int main(int argc, char** argv) {
   const int nblk = atoi(argv[3]);
   const double occ = atof(argv[4]);
   const int steps = atoi(argv[5]);
-  const int bsz = atoi(argv[6]);
+  int bm = 0, bn = 0, bk = 0;
+  if (sscanf(argv[6], "%d,%d,%d", &bm, &bn, &bk) != 3) bm = bn = bk = atoi(argv[6]);
+  const int bsz = bm; /* label of the result line for cubic shapes */
   const int first_spec = 7;
   const double t_start = now();
-  lib = dlopen(argv[1], RTLD_NOW | RTLD_GLOBAL);
+  lib = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   if (lib == NULL) {
     fprintf(stderr, "kbench: dlopen %s: %s\n", argv[1], dlerror());
     return 2;
   }
-  fn_i_v acc_init = (fn_i_v)sym("c_dbcsr_acc_init");
-  fn_set_dev set_dev = (fn_set_dev)sym("c_dbcsr_acc_set_active_device");
-  fn_stream_create stream_create = (fn_stream_create)sym("c_dbcsr_acc_stream_create");
-  fn_stream_sync stream_sync = (fn_stream_sync)sym("c_dbcsr_acc_stream_sync");
-  fn_dev_alloc dev_alloc = (fn_dev_alloc)sym("c_dbcsr_acc_dev_mem_allocate");
-  fn_dev_free dev_free = (fn_dev_free)sym("c_dbcsr_acc_dev_mem_deallocate");
-  fn_memcpy h2d = (fn_memcpy)sym("c_dbcsr_acc_memcpy_h2d");
-  fn_memcpy d2h = (fn_memcpy)sym("c_dbcsr_acc_memcpy_d2h");
-  fn_memset memset_zero = (fn_memset)sym("c_dbcsr_acc_memset_zero");
-  fn_process process = (fn_process)sym("libsmm_acc_process");
+  acc_lib = lib;
+  const char* other = getenv("KBENCH_ACC_LIB");
+  if (other != NULL && other[0] != 0) {
+    acc_lib = dlopen(other, RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND); /* its internal calls must bind to its own definitions */
+    if (acc_lib == NULL) {
+      fprintf(stderr, "kbench: dlopen %s: %s\n", other, dlerror());
+      return 2;
+    }
+    printf("kbench: acc/libsmm ABI from %s\n", other);
+  }
+  fn_i_v acc_init = (fn_i_v)sym_from(acc_lib, "c_dbcsr_acc_init");
+  fn_set_dev set_dev = (fn_set_dev)sym_from(acc_lib, "c_dbcsr_acc_set_active_device");
+  fn_stream_create stream_create = (fn_stream_create)sym_from(acc_lib, "c_dbcsr_acc_stream_create");
+  fn_stream_sync stream_sync = (fn_stream_sync)sym_from(acc_lib, "c_dbcsr_acc_stream_sync");
+  fn_dev_alloc dev_alloc = (fn_dev_alloc)sym_from(acc_lib, "c_dbcsr_acc_dev_mem_allocate");
+  fn_dev_free dev_free = (fn_dev_free)sym_from(acc_lib, "c_dbcsr_acc_dev_mem_deallocate");
+  fn_memcpy h2d = (fn_memcpy)sym_from(acc_lib, "c_dbcsr_acc_memcpy_h2d");
+  fn_memcpy d2h = (fn_memcpy)sym_from(acc_lib, "c_dbcsr_acc_memcpy_d2h");
+  fn_memset memset_zero = (fn_memset)sym_from(acc_lib, "c_dbcsr_acc_memset_zero");
+  fn_process process = (fn_process)sym_from(acc_lib, "libsmm_acc_process");
   fn_norms block_norms = (fn_norms)sym("libsmm_acc_b200_block_norms_f64");
-  fn_set_tun set_tun = (fn_set_tun)sym("libsmm_acc_b200_set_tunable");
+  fn_set_tun set_tun = acc_lib == lib ? (fn_set_tun)sym("libsmm_acc_b200_set_tunable") : noop_set_tun;
   fn_get_tun get_tun = (fn_get_tun)sym("libsmm_acc_b200_get_tunable");
   fn_set_trace set_trace = (fn_set_trace)sym("libsmm_acc_b200_set_trace");
   fn_cfg_default cfg_default = (fn_cfg_default)sym("dbcsr_b200_cfg_default");
@@ -141,13 +166,15 @@ int main(int argc, char** argv) {
 
   /* ---- workload: patterns, stacks (host only) */
   int *a_list, *b_list;
-  const int na = make_pattern(nblk, occ, bsz, &a_list), nb = make_pattern(nblk, occ, bsz, &b_list);
+  const int na = make_pattern(nblk, occ, bm * bk, &a_list), nb = make_pattern(nblk, occ, bk * bn, &b_list);
   int* sizes = (int*)malloc(sizeof(int) * (size_t)nblk);
-  for (int i = 0; i < nblk; ++i) sizes[i] = bsz;
+  int* sizes_n = (int*)malloc(sizeof(int) * (size_t)nblk);
+  int* sizes_k = (int*)malloc(sizeof(int) * (size_t)nblk);
+  for (int i = 0; i < nblk; ++i) sizes[i] = bm, sizes_n[i] = bn, sizes_k[i] = bk;
   dbcsr_b200_cfg_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg_default(&cfg);
-  dbcsr_b200_engine_t* eng = eng_create(&cfg, sizes, nblk, sizes, nblk, sizes, nblk, 1, DBCSR_B200_RECORD, 0);
+  dbcsr_b200_engine_t* eng = eng_create(&cfg, sizes, nblk, sizes_n, nblk, sizes_k, nblk, 1, DBCSR_B200_RECORD, 0);
   if (eng == NULL) {
     fprintf(stderr, "kbench: engine_create failed\n");
     return 3;
@@ -163,7 +190,7 @@ int main(int argc, char** argv) {
   for (int i = 0; i < nstacks; ++i) {
     int info[10];
     eng_stack_info(eng, i, info);
-    if (info[0] != bsz || info[1] != bsz || info[2] != bsz || info[6] != 1) {
+    if (info[0] != bm || info[1] != bn || info[2] != bk || info[6] != 1) {
       fprintf(stderr, "kbench: unexpected stack shape\n");
       return 3;
     }
@@ -180,7 +207,7 @@ int main(int argc, char** argv) {
   const int* blk_p = eng_c_blk_p(eng, 0);
   for (int i = 0; i < c_nblks; ++i) {
     c_off[i] = blk_p[i] - 1;
-    c_len[i] = bsz * bsz;
+    c_len[i] = bm * bn;
   }
   const double t_built = now();
   printf("kbench: nblk %d occ %.3f  A %d B %d blocks  products %zu  stacks %d  C %d blocks  flop %lld  (host setup %.2f s)\n", nblk, occ,
@@ -192,7 +219,7 @@ int main(int argc, char** argv) {
   CHECK(acc_init());
   void* stream = NULL;
   CHECK(stream_create(&stream, "kbench", 0));
-  const size_t a_elems = (size_t)na * bsz * bsz, b_elems = (size_t)nb * bsz * bsz;
+  const size_t a_elems = (size_t)na * bm * bk, b_elems = (size_t)nb * bk * bn;
   const size_t ab_max = a_elems > b_elems ? a_elems : b_elems;
   double* h = (double*)malloc(sizeof(double) * ab_max);
   for (size_t i = 0; i < ab_max; ++i) h[i] = A_VAL(i);
@@ -249,7 +276,7 @@ int main(int argc, char** argv) {
     CHECK(memset_zero(d_c, 0, c_elems * 8, stream));
     int rc_bad = 0;
     for (int i = 0; i < nstacks; ++i) {
-      const int rc = process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bsz, bsz, bsz, 80, 1, stream, stream);
+      const int rc = process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bm, bn, bk, 80, 1, stream, stream);
       if (rc != 0) rc_bad = rc;
     }
     CHECK(block_norms((const double*)d_c, c_nblks, (const int*)d_off, (const int*)d_len, (double*)d_norm, stream));
@@ -264,19 +291,19 @@ int main(int argc, char** argv) {
       const int probe[4] = {0, 1, c_nblks / 2, c_nblks - 1};
       for (int q = 0; q < 4; ++q) {
         const int cf = c_off[probe[q]] + 1;
-        double* blk = (double*)calloc((size_t)bsz * bsz, sizeof(double));
+        double* blk = (double*)calloc((size_t)bm * bn, sizeof(double));
         for (size_t e = 0; e < total_entries; ++e)
           if (all_stacks[3 * e + 2] == cf) {
             const size_t a0 = (size_t)all_stacks[3 * e] - 1, b0 = (size_t)all_stacks[3 * e + 1] - 1;
-            for (int j = 0; j < bsz; ++j)
-              for (int i = 0; i < bsz; ++i) {
+            for (int j = 0; j < bn; ++j)
+              for (int i = 0; i < bm; ++i) {
                 double acc = 0.0;
-                for (int k = 0; k < bsz; ++k) acc += A_VAL(a0 + i + (size_t)k * bsz) * B_VAL(b0 + j + (size_t)k * bsz);
-                blk[i + j * bsz] += acc;
+                for (int k = 0; k < bk; ++k) acc += A_VAL(a0 + i + (size_t)k * bm) * B_VAL(b0 + j + (size_t)k * bn);
+                blk[i + j * bm] += acc;
               }
           }
         double n2 = 0.0;
-        for (int i = 0; i < bsz * bsz; ++i) n2 += blk[i] * blk[i];
+        for (int i = 0; i < bm * bn; ++i) n2 += blk[i] * blk[i];
         free(blk);
         printf("kbench: host check of C block %d: %s (host %.17g, device %.17g)\n", probe[q], n2 == norms[probe[q]] ? "exact" : "MISMATCH", n2,
                norms[probe[q]]);
@@ -290,7 +317,7 @@ int main(int argc, char** argv) {
       CHECK(stream_sync(stream));
       const double t0 = now();
       for (int i = 0; i < nstacks; ++i)
-        process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bsz, bsz, bsz, 80, 1, stream, stream);
+        process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bm, bn, bk, 80, 1, stream, stream);
       CHECK(stream_sync(stream));
       const double dt = now() - t0;
       if (it > 0) {  /* first repetition = warm-up */
@@ -301,9 +328,9 @@ int main(int argc, char** argv) {
     const double mean = sum / steps;
     char line[512];
     snprintf(line, sizeof(line),
-             "bsz %2d spec %-10s variant %2d balance %d chunk %2d  rc %d  parity %s (mismatching blocks %lld, sum %.6e)  mean %.3f ms  best %.3f ms  "
+             "bsz %2d mnk %d,%d,%d spec %-10s variant %2d balance %d chunk %2d  rc %d  parity %s (mismatching blocks %lld, sum %.6e)  mean %.3f ms  best %.3f ms  "
              "%.2f TFLOP/s (best %.2f)  %.2f us/launch",
-             bsz, argv[s], variant, balance, chunk, rc_bad, (s == first_spec) ? "reference" : (mismatches == 0 ? "exact" : "MISMATCH"), mismatches, total,
+             bsz, bm, bn, bk, argv[s], variant, balance, chunk, rc_bad, (s == first_spec) ? "reference" : (mismatches == 0 ? "exact" : "MISMATCH"), mismatches, total,
              mean * 1e3, best * 1e3, flop / mean * 1e-12, flop / best * 1e-12, mean * 1e6 / nstacks);
     printf("%s\n", line);
     fflush(stdout);
@@ -320,7 +347,7 @@ int main(int argc, char** argv) {
       set_tun("trace_count", 3);
       set_trace(d_trace);
       for (int i = 0; i < nstacks; ++i)
-        process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bsz, bsz, bsz, 80, 1, stream, stream);
+        process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bm, bn, bk, 80, 1, stream, stream);
       CHECK(stream_sync(stream));
       set_trace(NULL);
       CHECK(d2h(d_trace, h_trace, trace_words * 8, stream));
