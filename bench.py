@@ -115,8 +115,13 @@ def cpu_reference_sample(w, target_entries, cores=None, n_stacks=3):
     from dbcsr_b200 import host
     from oracle import oracle as orc
 
-    ncores = os.cpu_count() or 1
-    cores = min(cores or ncores, orc.lib().orc_max_threads(), 64)
+    # all the host cores this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 and the oracle sets
+    # its team size explicitly (omp parallel num_threads(cores))
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    cores = max(1, min(cores or ncores, 64))
     A, B, bs = w["A"], w["B"], w["m_sizes"]
     t0 = time.perf_counter()
     eng = host.Engine(bs, bs, bs, nthreads=cores, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=1000, n_stacks=n_stacks))
@@ -153,7 +158,7 @@ def cpu_reference_sample(w, target_entries, cores=None, n_stacks=3):
     info = {"value": flop / dt * 1e-9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
             "sample": "%d of %d stack entries (first stacks of each of %d threads), %s, stack build %.2fs not included"
                       % (params.shape[0], total_entries, cores, "OpenBLAS dgemm (scipy)" if dg else "naive triple loop", t_build),
-            "host_cpus": ncores}
+            "host_cpus": ncores, "cpu_model": cpu_model()}
     return info
 
 
@@ -193,241 +198,465 @@ def workload_config(w, extra=None):
     return c
 
 
+# ------------------------------------------------------------------------------------------------ checker (outside timed regions)
+def probe_c_blocks(A, B, coords, got_blocks, n_probe=1000, seed=7):
+    """Element-wise check of randomly probed C blocks against the oracle's block product (orc_block_gemm: plain loops, the
+    arithmetic of the reference's CPU driver).  coords = [(global_row, global_col)], got_blocks(i) -> the device result of block i
+    as a flat column-major array.  Returns (number probed, worst relative Frobenius error of a block).  Checker only."""
+    from oracle import oracle as orc
+
+    L = orc.lib()
+    n = len(coords)
+    if n == 0:
+        return 0, 0.0
+    rng = np.random.default_rng(seed)
+    pick = rng.choice(n, size=min(n_probe, n), replace=False)
+    a_row_start = np.searchsorted(A.rows, np.arange(1, A.row_sizes.size + 2))      # BCSR: rows ascending
+    b_order = np.argsort(B.cols, kind="stable")                                     # B blocks grouped by column, rows ascending
+    b_col_start = np.searchsorted(B.cols[b_order], np.arange(1, B.col_sizes.size + 2))
+    worst = 0.0
+    for i in pick:
+        r, c = coords[int(i)]
+        m, nn = int(A.row_sizes[r - 1]), int(B.col_sizes[c - 1])
+        exp = np.zeros(m * nn)
+        ia = np.arange(a_row_start[r - 1], a_row_start[r])
+        ib = b_order[b_col_start[c - 1]:b_col_start[c]]
+        common, xa, xb = np.intersect1d(A.cols[ia], B.rows[ib], return_indices=True)
+        for kk, qa, qb in zip(common, ia[xa], ib[xb]):
+            k = int(A.col_sizes[kk - 1])
+            L.orc_block_gemm(m, nn, k, A.data[A.offsets[qa]:A.offsets[qa] + m * k], 0, B.data[B.offsets[qb]:B.offsets[qb] + k * nn], exp)
+        got = np.asarray(got_blocks(int(i)), dtype=np.float64).reshape(-1)
+        den = float(np.linalg.norm(exp))
+        worst = max(worst, float(np.linalg.norm(got - exp)) / max(den, 1e-300))
+    return int(pick.size), worst
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def gpu_baseline_reference_kernels(bsz=23, nblk=1000, occ=0.1, timeout=240):
+    """Same-box GPU baseline: the reference's OWN CUDA backend (libsmm_acc, NVRTC-JIT kernels, H100 parameter set, built for
+    compute_100 by baseline/Makefile into baseline/_ref) draining the same kind of stacks through the same ABI, driven by
+    tools/kbench (KBENCH_ACC_LIB).  Kernel-only, like `roofline.kernel_only_gflops`."""
+    ref = os.path.join(ROOT, "baseline", "_ref", "libdbcsr_acc_ref.so")
+    kb = os.path.join(ROOT, "tools", "kbench")
+    ours = os.path.join(ROOT, "dbcsr_b200", "lib", "libdbcsr_acc_b200.so")
+    if not (os.path.exists(ref) and os.path.exists(kb)):
+        return {"unavailable": "baseline/_ref/libdbcsr_acc_ref.so or tools/kbench not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    env = dict(os.environ, KBENCH_ACC_LIB=ref)
+    try:
+        out = subprocess.run([kb, ours, os.path.join(ROOT, "gpurun_out"), str(nblk), str(occ), "3", str(bsz), "0:0:0"], env=env, capture_output=True,
+                             text=True, timeout=timeout)
+    except Exception as ex:
+        return {"unavailable": repr(ex)[:200]}
+    import re
+
+    m = re.search(r"parity (\S+).*?mean ([\d.]+) ms.*?([\d.]+) TFLOP/s", out.stdout)
+    host_ok = out.stdout.count(": exact")
+    if out.returncode != 0 or not m:
+        return {"unavailable": "kbench rc %d: %s" % (out.returncode, (out.stderr or out.stdout)[-300:])}
+    return {"value": float(m.group(3)) * 1e3, "unit": "GFLOP/s", "ms_per_multiply": float(m.group(2)), "kind": "reference libsmm_acc kernels (NVRTC, parameters_H100.json) on this GPU, kernel-only",
+            "workload": "%dx%d block grid, %d^3 blocks, %.0f%% occupation, 30000-entry C-sorted stacks (tools/kbench)" % (nblk, nblk, bsz, 100 * occ),
+            "host_checked_blocks_exact": host_ok}
+
+
 # ------------------------------------------------------------------------------------------------ our arm, one GPU
-def run_single(args):
-    import torch
+class Fp64Run:
+    """One FP64 config on one GPU: stacks pre-built (one host thread = the reference's traversal order) and resident, panels
+    resident, drained through libsmm_acc_process."""
 
-    from dbcsr_b200 import host, workload
-    from dbcsr_b200 import lib as acclib
-    from dbcsr_b200.multiply import DeviceMultiply
+    def __init__(self, acc, cfg_name, nblk, s):
+        from dbcsr_b200 import host, workload
 
-    acc = acclib.Acc(0)
-    w = workload.make_config(args.config, nblk=args.nblk)
-    A, B, bs = w["A"], w["B"], w["m_sizes"]
-    n_st = 3 if len(w["sizes"]) <= 3 else len(w["sizes"])
-    cfg = host.default_cfg(n_stacks=n_st)
+        self.acc, self.s = acc, s
+        self.w = w = workload.make_config(cfg_name, nblk=nblk)
+        A, B, bs = w["A"], w["B"], w["m_sizes"]
+        self.n_st = 3 if len(w["sizes"]) <= 3 else len(w["sizes"])
+        eng = host.Engine(bs, bs, bs, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(n_stacks=self.n_st))
+        eng.multiply(A.list3(), None, B.list3(), None)
+        self.stacks = eng.stacks()
+        self.flop = eng.flop()
+        self.c_rows, self.c_cols, self.c_blk_p, self.c_datasize = eng.c_index(0)
+        self.c_rows, self.c_cols, self.c_blk_p = self.c_rows.copy(), self.c_cols.copy(), self.c_blk_p.copy()
+        eng.close()
+        self.n_entries = sum(st["dev"].shape[0] for st in self.stacks)
+        self.d_a = acc.to_device(A.data, s)
+        self.d_b = acc.to_device(B.data, s)
+        host.transpose_panel(acc, B.list3(), bs, bs, self.d_b.ptr, s)
+        all_dev = np.concatenate([st["dev"].reshape(-1) for st in self.stacks]).astype(np.int32)
+        self.d_st = acc.to_device(all_dev, s)
+        self.offs = np.concatenate([[0], np.cumsum([st["dev"].size for st in self.stacks])]).astype(np.int64)
+        self.alg_bytes = algorithmic_bytes(self.stacks)
+        self.runs = sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in self.stacks if st["dev"].shape[0])
+        # Two pooled C buffers: while the stacks of step k accumulate into buffer k%2, the buffer of step k+1 is zeroed on a side
+        # stream (DBCSR zeroes its pooled device C buffer asynchronously at accdrv_init, src/mm/dbcsr_mm_accdrv.F:209-216).  Every
+        # step still contains exactly one full memset and waits for it before it ends.
+        nbytes = 8 * max(self.c_datasize, 1)
+        self.d_cs = [acc.dev_alloc(nbytes), acc.dev_alloc(nbytes)]
+        self.zs = acc.stream_create("bench zero", 0)
+        self.ev_zero = [acc.event_create(), acc.event_create()]
+        self.ev_free = [acc.event_create(), acc.event_create()]
+        acc.memset_zero(self.d_cs[0], self.zs)
+        acc.event_record(self.ev_zero[0], self.zs)
+        acc.event_record(self.ev_free[1], s)
+        self.step_no = 0
 
-    # ---- build the stacks once on the host (one thread => the reference's traversal order), keep device-order copies
-    eng = host.Engine(bs, bs, bs, nthreads=1, mode=host.RECORD, cfg=cfg)
-    eng.multiply(A.list3(), None, B.list3(), None)
-    stacks = eng.stacks()
-    flop = eng.flop()
-    c_datasize = eng.c_index(0)[3]
-    c_nblks = eng.c_index(0)[0].size
-    eng.close()
-    n_entries = sum(s["dev"].shape[0] for s in stacks)
-
-    s = acc.stream_create("bench", 0)
-    raw_stream = acclib.ctypes.c_void_p.from_address(s).value
-    tstream = torch.cuda.ExternalStream(raw_stream)
-    d_a = acc.to_device(A.data, s)
-    d_b = acc.to_device(B.data, s)
-    host.transpose_panel(acc, B.list3(), bs, bs, d_b.ptr, s)
-    all_dev = np.concatenate([st["dev"].reshape(-1) for st in stacks]).astype(np.int32)
-    d_st = acc.to_device(all_dev, s)
-    offs = np.concatenate([[0], np.cumsum([st["dev"].size for st in stacks])]).astype(np.int64)
-    bf16 = args.config == "cfg4"
-    dtype_id = acclib.DBCSR_TYPE_BF16_EXT if bf16 else acclib.DBCSR_TYPE_REAL_8
-    if bf16:  # pack both panels once into BF16 operand tiles (A: m x k col-major, B: transposed n x k col-major)
-        mm_ = int(w["sizes"][0])
-        ta_bytes = acc.bf16_tile_bytes(mm_, mm_)
-        p_a, p_b = acc.dev_alloc(A.nblks * ta_bytes), acc.dev_alloc(B.nblks * ta_bytes)
-        acc.pack_bf16(d_a.ptr, A.nblks, mm_, mm_, 1, mm_, p_a.ptr, s)
-        acc.pack_bf16(d_b.ptr, B.nblks, mm_, mm_, 1, mm_, p_b.ptr, s)
-        acc.stream_sync(s)
-        d_a.free()
-        d_b.free()
-        d_a, d_b = p_a, p_b
-    d_c = acc.dev_alloc((4 if bf16 else 8) * max(c_datasize, 1))
-    alg_bytes = algorithmic_bytes(stacks)
-
-    def drain(d_c):
-        for i, st in enumerate(stacks):
-            rc = acc.process(None, d_st.ptr + 4 * int(offs[i]), st["dev"].shape[0], d_a.ptr, d_b.ptr, d_c.ptr, st["max_m"], st["max_n"],
-                             st["max_k"], st["defined_mnk"], s, s, datatype=dtype_id)
+    def drain(self, d_c):
+        acc, s = self.acc, self.s
+        for i, st in enumerate(self.stacks):
+            rc = acc.process(None, self.d_st.ptr + 4 * int(self.offs[i]), st["dev"].shape[0], self.d_a.ptr, self.d_b.ptr, d_c.ptr, st["max_m"],
+                             st["max_n"], st["max_k"], st["defined_mnk"], s, s)
             if rc < 0:
                 raise RuntimeError("libsmm_acc_process returned %d for stack %d" % (rc, i))
 
-    # Two pooled C buffers: while the stacks of step k accumulate into buffer k%2, the buffer of step k+1 is zeroed on a side
-    # stream (DBCSR zeroes its pooled device C buffer asynchronously at accdrv_init, src/mm/dbcsr_mm_accdrv.F:209-216).  Every
-    # step still contains exactly one full memset and waits for it before it ends, so step time = max(drain, memset) + epsilon.
-    d_cs = [d_c, acc.dev_alloc((4 if bf16 else 8) * max(c_datasize, 1))]
-    zs = acc.stream_create("bench zero", 0)
-    ev_zero = [acc.event_create(), acc.event_create()]
-    ev_free = [acc.event_create(), acc.event_create()]
-    acc.memset_zero(d_cs[0], zs)
-    acc.event_record(ev_zero[0], zs)
-    acc.event_record(ev_free[1], s)
-    step_no = [0]
+    def one_step(self):
+        acc, s, zs = self.acc, self.s, self.zs
+        k = self.step_no % 2
+        self.step_no += 1
+        acc.stream_wait_event(zs, self.ev_free[1 - k])     # the other buffer's last reader (step k-1) has finished
+        acc.memset_zero(self.d_cs[1 - k], zs)
+        acc.event_record(self.ev_zero[1 - k], zs)
+        acc.stream_wait_event(s, self.ev_zero[k])          # zeroed during the previous step
+        self.drain(self.d_cs[k])
+        acc.event_record(self.ev_free[k], s)
+        acc.stream_wait_event(s, self.ev_zero[1 - k])      # the step owns the memset it issued
 
-    def one_step():
-        k = step_no[0] % 2
-        step_no[0] += 1
-        acc.stream_wait_event(zs, ev_free[1 - k])     # the other buffer's last reader (step k-1) has finished
-        acc.memset_zero(d_cs[1 - k], zs)
-        acc.event_record(ev_zero[1 - k], zs)
-        acc.stream_wait_event(s, ev_zero[k])          # zeroed during the previous step
-        drain(d_cs[k])
-        acc.event_record(ev_free[k], s)
-        acc.stream_wait_event(s, ev_zero[1 - k])      # the step owns the memset it issued
+    def selfcheck(self, n_probe):
+        """Full size, outside every timed region: one drain into a zeroed buffer; (1) sum(C) = colsum(A) . rowsum(B),
+        (2) n_probe random C blocks element-wise against the oracle's block product."""
+        from dbcsr_b200.cannon import _axis_sums
 
-    for _ in range(args.warmup):
-        one_step()
-    acc.stream_sync(s)
+        acc, s, w = self.acc, self.s, self.w
+        A, B = w["A"], w["B"]
+        acc.stream_wait_event(s, self.ev_zero[self.step_no % 2])
+        acc.stream_sync(self.zs)
+        acc.memset_zero(self.d_cs[0], s)
+        self.drain(self.d_cs[0])
+        c = acc.to_host(self.d_cs[0], (max(self.c_datasize, 1),), np.float64, s)
+        got = float(c[:self.c_datasize].sum())
+        exp = float(np.dot(_axis_sums(A, 0, A.row_sizes.size, 0), _axis_sums(B, 0, B.col_sizes.size, 1)))
+        out = {"property": "sum(C) == colsum(A) . rowsum(B)", "rel_err": abs(got - exp) / max(abs(exp), 1e-300)}
+        bs = w["m_sizes"]
+        coords = list(zip(self.c_rows.tolist(), self.c_cols.tolist()))
 
-    # self-check at full size, outside every timed region: one drain into a zeroed buffer must satisfy the size-independent
-    # property sum(C) = colsum(A) . rowsum(B) (FP64 path; tests/test_gpu_multiply.py checks the same property)
-    selfcheck = None
-    if not bf16 and not args.no_selfcheck:
-        try:
-            from dbcsr_b200.cannon import _axis_sums
+        def got_block(i):
+            o = int(self.c_blk_p[i]) - 1
+            return c[o:o + int(bs[self.c_rows[i] - 1]) * int(bs[self.c_cols[i] - 1])]
 
-            acc.stream_wait_event(s, ev_zero[step_no[0] % 2])
-            acc.stream_sync(zs)
-            acc.memset_zero(d_cs[0], s)
-            drain(d_cs[0])
-            got = float(acc.to_host(d_cs[0], (max(c_datasize, 1),), np.float64, s)[:c_datasize].sum())
-            exp = float(np.dot(_axis_sums(A, 0, A.row_sizes.size, 0), _axis_sums(B, 0, B.col_sizes.size, 1)))
-            selfcheck = {"property": "sum(C) == colsum(A) . rowsum(B)", "rel_err": abs(got - exp) / max(abs(exp), 1e-300)}
-            # leave the double-buffering state as one_step expects it: buffer of the next step zeroed
-            acc.memset_zero(d_cs[step_no[0] % 2], zs)
-            acc.event_record(ev_zero[step_no[0] % 2], zs)
-            acc.stream_sync(zs)
-            acc.stream_sync(s)
-        except Exception as ex:
-            selfcheck = {"error": repr(ex)[:200]}
+        npr, worst = probe_c_blocks(A, B, coords, got_block, n_probe=n_probe)
+        out.update({"probed_blocks": npr, "probe_max_rel_err": worst, "probe": "random C blocks, element-wise vs oracle orc_block_gemm (tolerance 1e-10)",
+                    "ok": bool(out["rel_err"] <= 1e-9 and worst <= 1e-10)})
+        # leave the double-buffering state as one_step expects it: buffer of the next step zeroed
+        acc.memset_zero(self.d_cs[self.step_no % 2], self.zs)
+        acc.event_record(self.ev_zero[self.step_no % 2], self.zs)
+        acc.stream_sync(self.zs)
+        acc.stream_sync(s)
+        return out
 
-    sampler = ClockSampler(0)
-    sampler.start()
-    time.sleep(0.3)
-    launches0 = acc.launch_count()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    def free_c(self):
+        for d in self.d_cs:
+            d.free()
+        self.d_cs = []
+
+    def close(self):
+        self.free_c()
+        for d in (self.d_a, self.d_b, self.d_st):
+            d.free()
+        self.acc.stream_destroy(self.zs)
+
+
+def timed_steps(torch, tstream, acc, s, fn, steps):
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
     torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
+    t0 = time.perf_counter()
     with torch.cuda.stream(tstream):
-        for k in range(args.steps):
+        for k in range(steps):
             ev[k][0].record(tstream)
-            one_step()
+            fn()
             ev[k][1].record(tstream)
     acc.stream_sync(s)
     torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
+    return [ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)], time.perf_counter() - t0
+
+
+def measure_fp64_peaks(torch, acc, s):
+    """Denominators measured in this run on this GPU: the DMMA.8x8x4 register-operand loop of the library (what the stack kernel's
+    pipe can do) and cuBLAS DGEMM 8192^3 through torch.matmul (what NVIDIA's own FP64 GEMM reaches)."""
+    dmma = acc.fp64_peak_gflops(s)
+    dgemm = None
+    try:
+        n = 8192
+        x = torch.rand((n, n), dtype=torch.float64, device="cuda")
+        y = torch.rand((n, n), dtype=torch.float64, device="cuda")
+        best = 1e30
+        for i in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(x, y)
+            e1.record()
+            e1.synchronize()
+            if i:
+                best = min(best, e0.elapsed_time(e1))
+        dgemm = 2.0 * n ** 3 / (best * 1e-3) * 1e-9
+        del x, y
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        print("bench: cuBLAS DGEMM peak probe failed: %r" % (ex,), file=sys.stderr)
+    return dmma, dgemm
+
+
+def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peaks, ncu_key):
+    """Warm-up, self-check, timed steps (value) and kernel-only drains (roofline) of one FP64 config."""
+    for _ in range(warmup):
+        run.one_step()
+    acc.stream_sync(s)
+    check = run.selfcheck(n_probe) if n_probe else None
+    launches0 = acc.launch_count()
+    step_ms, t_wall = timed_steps(torch, tstream, acc, s, run.one_step, steps)
     launches = acc.launch_count() - launches0
-    clocks = sampler.stop()
-    # kernel-only time of one drain (no memset in flight), for the roofline of the dominant kernel
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(3)]
-    with torch.cuda.stream(tstream):
-        for k in range(3):
-            kev[k][0].record(tstream)
-            drain(d_cs[0])
-            kev[k][1].record(tstream)
-    torch.cuda.synchronize()
-    kern_ms = [kev[k][0].elapsed_time(kev[k][1]) for k in range(3)]
-    step_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]
+    kern_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 3)
     ms_per_step = float(np.mean(step_ms))
-    value = flop / (ms_per_step * 1e-3) * 1e-9
-    peak, peak_src = measured_peaks()
-    achieved = alg_bytes / (float(np.mean(kern_ms)) * 1e-3) * 1e-9
+    k_ms = float(np.mean(kern_ms))
+    value = run.flop / (ms_per_step * 1e-3) * 1e-9
+    kernel_only = run.flop / (k_ms * 1e-3) * 1e-9
+    hbm_peak, hbm_src = measured_peaks()
+    dmma_peak, dgemm_peak = peaks
+    nst = max(len(run.stacks), 1)
     traffic = None
     ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(ncu_json):
         try:
-            traffic = json.load(open(ncu_json)).get(args.config, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(ncu_json)).get(ncu_key, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    if bf16:
-        tile = acc.bf16_tile_bytes(int(w["sizes"][0]), int(w["sizes"][0]))
-        runs = sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in stacks)
-        alg_bytes = n_entries * (2 * tile + 12) + runs * 2 * 4 * int(w["sizes"][0]) ** 2
-        achieved = alg_bytes / (float(np.mean(kern_ms)) * 1e-3) * 1e-9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "smm_dmma_kernel<%s> (x%d launches/step)" % (",".join(str(x) for x in (stacks[0]["m"], stacks[0]["n"], stacks[0]["k"])), len(stacks)),
-                "algorithmic_bytes_per_launch": alg_bytes / max(len(stacks), 1), "avg_launch_us": float(np.mean(kern_ms)) * 1e3 / max(len(stacks), 1),
-                "kernel_only_gflops": flop / (float(np.mean(kern_ms)) * 1e-3) * 1e-9, "fp64_tensor_peak_gflops_measured": 37050.0}
-    if not bf16:
-        # the streaming-HBM model is not what binds this kernel (operands are re-used out of L2: frac > 1); the FP64 tensor pipe
-        # (DMMA.8x8x4, measured 37.05 TFLOP/s, profiles/microbench_r01.txt) and its padded ceiling (tiles of 8x8x4) are quoted beside it
-        m0, n0, k0 = stacks[0]["m"], stacks[0]["n"], stacks[0]["k"]
-        pad = (m0 * n0 * k0) / float(((m0 + 7) // 8 * 8) * ((n0 + 7) // 8 * 8) * ((k0 + 3) // 4 * 4))
-        roofline["alt_bounds"] = {"frac_of_fp64_tensor_peak": roofline["kernel_only_gflops"] / 37050.0,
-                                  "frac_of_padded_fp64_tensor_ceiling": roofline["kernel_only_gflops"] / (37050.0 * pad),
-                                  "mean_run_length": n_entries / max(1, sum(1 + int(np.count_nonzero(st["dev"][1:, 2] != st["dev"][:-1, 2])) for st in stacks)),
-                                  "dram_traffic_frac_of_hbm_peak": (traffic / (roofline["avg_launch_us"] * 1e-6) * 1e-9 / peak) if traffic else None,
-                                  "traffic_note": "dram bytes per launch from the ncu --set full capture of the RED-flush kernel (profiles/ncu_summary.json)"}
-    if bf16:
-        try:
-            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) * 1e3
-        except Exception:
-            tpeak = 1590e3
-        useful = roofline["kernel_only_gflops"]
-        issued = useful * (128.0 * 32 * 32) / (23.0 ** 3)  # per entry two tcgen05.mma of M=128,N=32,K=16
-        roofline.update({"kernel": "smm_bf16_kernel (tcgen05.mma M128 N32 K16, x%d launches/step)" % len(stacks),
-                         "tensor": {"peak_gflops": tpeak, "useful_frac": useful / tpeak, "issued_frac": issued / tpeak,
-                                    "note": "useful = 2*23^3 per product; issued = padded MMA flops (M128 x N32 x K32 per product)"}})
+    st0 = max(run.stacks, key=lambda st: st["dev"].shape[0] * st["m"] * st["n"] * st["k"])
+    m0, n0, k0 = st0["m"], st0["n"], st0["k"]
+    pad = (m0 * n0 * k0) / float(((m0 + 7) // 8 * 8) * ((n0 + 7) // 8 * 8) * ((k0 + 3) // 4 * 4))
+    launch_us = k_ms * 1e3 / nst
+    alg_gbs = run.alg_bytes / (k_ms * 1e-3) * 1e-9
+    roofline = {
+        "bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4 = mma.sync.m8n8k4.f64; tcgen05 has no f64 kind)",
+        "achieved": kernel_only * 1e-3, "peak": dmma_peak * 1e-3, "unit": "TFLOP/s", "frac": kernel_only / dmma_peak if dmma_peak > 0 else None,
+        "traffic": traffic,
+        "peak_source": "measured in this run: register-operand DMMA loop of the library (libsmm_acc_b200_fp64_peak_gflops); cuBLAS DGEMM 8192^3 beside it",
+        "cublas_dgemm_8192_gflops": dgemm_peak,
+        "kernel": "smm_dmma_kernel<%d,%d,%d> (dominant of %d launches/step)" % (m0, n0, k0, nst),
+        "algorithmic_flop_per_launch": run.flop / nst, "avg_launch_us": launch_us, "kernel_only_gflops": kernel_only,
+        "frac_on_timed_value": value / dmma_peak if dmma_peak > 0 else None,
+        "alt_bounds": {
+            "padded_tensor_ceiling": {"note": "tiles of 8x8x4: %dx%dx%d is %.0f%% useful" % (m0, n0, k0, 100 * pad), "frac": kernel_only / (dmma_peak * pad) if dmma_peak > 0 else None},
+            "hbm_streaming_model": {"note": "SURVEY 8(d) bytes: A+B block and 12 B per entry, C read+write per run of equal c_first; frac > 1 means operands are re-used out of L2",
+                                    "achieved": alg_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": alg_gbs / hbm_peak, "peak_source": hbm_src,
+                                    "algorithmic_bytes_per_launch": run.alg_bytes / nst, "mean_run_length": run.n_entries / max(1, run.runs)},
+            "hbm_real_traffic": ({"note": "dram__bytes_read+write per launch of the shipped kernel (ncu --set full, profiles/ncu_summary.json)",
+                                  "achieved": traffic / (launch_us * 1e-6) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": traffic / (launch_us * 1e-6) * 1e-9 / hbm_peak} if traffic else None)}}
+    return {"value": value, "ms_per_step": ms_per_step, "kernel_only_gflops": kernel_only, "launches": int(launches), "wall_s": t_wall, "roofline": roofline,
+            "selfcheck": check, "products": run.n_entries, "flop": run.flop, "stacks": len(run.stacks), "c_blocks": int(run.c_rows.size)}
+
+
+def bf16_config_report(torch, acc, s, tstream, nblk, steps, warmup, n_probe=200):
+    """BASELINE config 4 (23x23 blocks, 50 % occupation, BF16 operands / FP32 C) through the tiled tcgen05 SpGEMM
+    (libsmm_acc_b200_bf16_spgemm): one launch per multiply, C tiles accumulate in TMEM and are written once."""
+    from dbcsr_b200 import workload
+    from dbcsr_b200.bf16 import Bf16SpGemm
+
+    w = workload.make_config("cfg4", nblk=nblk)
+    A, B = w["A"], w["B"]
+    mm = Bf16SpGemm(acc, A, B, s)
+    m, n = mm.m, mm.n
+    for _ in range(warmup):
+        mm.run()
+    acc.stream_sync(s)
+    # parity (outside the timed region): probed C blocks against the FP64 oracle on the UNROUNDED inputs, tolerance 1e-3
+    check = None
+    if n_probe:
+        c = mm.result()
+        coords = [(r + 1, cc + 1) for r in range(mm.nrb) for cc in range(mm.ncb)]
+        npr, worst = probe_c_blocks(A, B, coords, lambda i: c[i // mm.ncb, i % mm.ncb].reshape(-1), n_probe=n_probe)
+        check = {"probed_blocks": npr, "probe_max_rel_err": worst, "probe": "random C blocks vs FP64 oracle orc_block_gemm on unrounded inputs (tolerance 1e-3)",
+                 "ok": bool(worst <= 1e-3)}
+        del c
+    launches0 = acc.launch_count()
+    step_ms, _ = timed_steps(torch, tstream, acc, s, mm.run, steps)
+    launches = acc.launch_count() - launches0
+    ms = float(np.mean(step_ms))
+    value = mm.flop / (ms * 1e-3) * 1e-9
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        tpeak, tsrc = float(pk["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: cuBLAS bf16 8192^3 back to back)"
+    except Exception:
+        tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md)"
+    hbm_peak, _ = measured_peaks()
+    tile_bytes = acc.bf16_rk_tile_bytes(m)
+    compulsory = (A.nblks + B.nblks) * tile_bytes + 4 * mm.c_elems  # every operand tile read once, C written once
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("cfg4_tiled", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "pipe": "tcgen05.mma kind::f16 (BF16 operands, FP32 accumulators in TMEM)", "achieved": value * 1e-3, "peak": tpeak,
+                "unit": "TFLOP/s", "frac": value * 1e-3 / tpeak, "traffic": traffic, "peak_source": tsrc,
+                "kernel": "smm_bf16_tiled_kernel (1 launch/step; M=128 x N=32 x K=16 MMAs, 2 per existing B block, tile and k block)",
+                "useful_flop_per_launch": mm.flop, "issued_flop_per_launch": mm.issued_flop, "issued_frac": mm.issued_flop / (ms * 1e-3) * 1e-12 / tpeak,
+                "useful_over_issued": mm.flop / max(mm.issued_flop, 1),
+                "alt_bounds": {"hbm_compulsory": {"note": "operand tiles once + C once", "bytes": compulsory, "achieved": compulsory / (ms * 1e-3) * 1e-9,
+                                                  "peak": hbm_peak, "unit": "GB/s", "frac": compulsory / (ms * 1e-3) * 1e-9 / hbm_peak}}}
+    out = {"metric": METRIC_NAMES["cfg4"], "value": value, "unit": "GFLOP/s", "ms_per_step": ms, "dtype": "bf16", "kernel_only_gflops": value,
+           "config": workload_config(w, {"products": mm.products, "flop": mm.flop, "timed": "CUDA events around one libsmm_acc_b200_bf16_spgemm launch per step (C is overwritten, no memset)"}),
+           "gpu_launches": int(launches), "roofline": roofline, "selfcheck": check}
+    mm.close()
+    return out
+
+
+def run_single_bf16(args):
+    import torch
+
+    from dbcsr_b200 import lib as acclib
+
+    acc = acclib.Acc(0)
+    s = acc.stream_create("bench", 0)
+    tstream = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(s).value)
+    sampler = ClockSampler(0)
+    sampler.start()
+    rep = bf16_config_report(torch, acc, s, tstream, args.nblk, args.steps, args.warmup, 0 if args.no_selfcheck else 200)
+    clocks = sampler.stop()
+    rep.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))", "clocks": clocks, "e2e": None, "cpu_baseline": None})
+    print(json.dumps(rep))
+    acc.stream_destroy(s)
+
+
+def run_single(args):
+    import torch
+
+    from dbcsr_b200 import host
+    from dbcsr_b200 import lib as acclib
+    from dbcsr_b200.multiply import DeviceMultiply
+
+    if args.config == "cfg4":
+        return run_single_bf16(args)
+    acc = acclib.Acc(0)
+    s = acc.stream_create("bench", 0)
+    # the bench stream carries nothing but stack drains between event waits: declare it a chain (programmatic dependent launch
+    # without the grid-dependency wait in front of the reads, include/dbcsr_acc_libsmm.h)
+    if not args.no_chain:
+        acc.stream_chain(s, True)
+    tstream = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(s).value)
+    peaks = measure_fp64_peaks(torch, acc, s)
+    run = Fp64Run(acc, args.config, args.nblk, s)
+    w = run.w
+    A, B, bs = w["A"], w["B"], w["m_sizes"]
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    rep = fp64_config_report(torch, tstream, acc, s, run, args.steps, args.warmup, 0 if args.no_selfcheck else args.probe_blocks, peaks, args.config)
+    clocks = sampler.stop()
 
     # ---- end to end through the host engine, host buffers pinned
     e2e = None
-    if not args.no_e2e and not bf16:
-      try:
-          nthreads = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2))
-          for d in d_cs:
-              d.free()
-          pa = acc.host_alloc((A.data.size,), np.float64)
-          pb = acc.host_alloc((B.data.size,), np.float64)
-          pa.array[:] = A.data
-          pb.array[:] = B.data
-          cfg_e2e = host.default_cfg(n_stacks=n_st, row_chunks=args.row_chunks)
-          dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e)
-          a_l, b_l = A.list3(), B.list3()
-          pcs = None
-          times = []
-          for it in range(max(1, args.e2e_warmup) + args.e2e_steps):
-              acc.device_synchronize()
-              t0 = time.perf_counter()
-              dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if args.pipelined_upload else None)
-              t_up = time.perf_counter()
-              dm.multiply(a_l, b_l)
-              t_mul = time.perf_counter()
-              if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
-                  dm.engine.sync()
-                  pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
-                  prod = dm.download_c([p.array for p in pcs])
-                  dm.set_result_buffers([p.array for p in pcs])
-              else:
-                  prod = dm.download_c()
-              dt = time.perf_counter() - t0
-              if it >= max(1, args.e2e_warmup):
-                  times.append(dt)
-                  phases = {"enqueue_upload_ms": (t_up - t0) * 1e3, "host_build_and_enqueue_ms": (t_mul - t_up) * 1e3,
-                            "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
-          stack_bytes = 12 * n_entries
-          e2e = {"value": flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
-                 "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads, "row_chunks_per_thread": args.row_chunks, "pipelined_upload": bool(args.pipelined_upload),
-                 "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases, "timing": "wall clock around the public call, device synchronised on both sides"}
-          dm.close()
-          for p in [pa, pb] + pcs:
-              p.free()
+    if not args.no_e2e:
+        try:
+            nthreads = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2))
+            run.free_c()
+            pa = acc.host_alloc((A.data.size,), np.float64)
+            pb = acc.host_alloc((B.data.size,), np.float64)
+            pa.array[:] = A.data
+            pb.array[:] = B.data
+            cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=args.row_chunks)
+            dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e)
+            a_l, b_l = A.list3(), B.list3()
+            pcs = None
+            times = []
+            for it in range(max(1, args.e2e_warmup) + args.e2e_steps):
+                acc.device_synchronize()
+                t0 = time.perf_counter()
+                dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if args.pipelined_upload else None)
+                t_up = time.perf_counter()
+                dm.multiply(a_l, b_l)
+                t_mul = time.perf_counter()
+                if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
+                    dm.engine.sync()
+                    pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
+                    prod = dm.download_c([p.array for p in pcs])
+                    dm.set_result_buffers([p.array for p in pcs])
+                else:
+                    prod = dm.download_c()
+                dt = time.perf_counter() - t0
+                if it >= max(1, args.e2e_warmup):
+                    times.append(dt)
+                    phases = {"enqueue_upload_ms": (t_up - t0) * 1e3, "host_build_and_enqueue_ms": (t_mul - t_up) * 1e3,
+                              "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
+            stack_bytes = 12 * run.n_entries
+            e2e = {"value": run.flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
+                   "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads,
+                   "row_chunks_per_thread": args.row_chunks, "pipelined_upload": bool(args.pipelined_upload),
+                   "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases,
+                   "timing": "wall clock around the public call, device synchronised on both sides"}
+            dm.close()
+            for p_ in [pa, pb] + pcs:
+                p_.free()
+        except Exception as ex:  # the headline line must still be printed (e.g. not enough pinned memory on this host) -- but loudly
+            import traceback
 
-      except Exception as ex:  # the headline line must still be printed (e.g. not enough pinned memory on this host)
-        e2e = {"value": None, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
+            traceback.print_exc(file=sys.stderr)
+            print("bench: the end-to-end leg FAILED: %r" % (ex,), file=sys.stderr)
+            e2e = {"value": None, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
 
     cpu = None
-    if not args.no_cpu and not bf16:
+    if not args.no_cpu:
         try:
-            cpu = cpu_reference_sample(w, args.ref_entries, n_stacks=n_st)
+            cpu = cpu_reference_sample(w, args.ref_entries, n_stacks=run.n_st)
         except Exception as ex:
             cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(ex)[:200]}
+    run.close()
+
+    # ---- the other single-GPU configs of BASELINE.json at their full size (driver-visible; not bench lines of their own)
+    extra = {}
+    if args.config == "cfg2" and not args.no_extra and (args.nblk is None or args.extra_nblk is not None):
+        try:
+            r3 = Fp64Run(acc, "cfg3", args.extra_nblk, s)
+            rep3 = fp64_config_report(torch, tstream, acc, s, r3, max(3, args.steps // 2), 3, 0 if args.no_selfcheck else args.probe_blocks, peaks, "cfg3")
+            extra["cfg3"] = {"metric": METRIC_NAMES["cfg3"], "value": rep3["value"], "unit": "GFLOP/s", "ms_per_step": rep3["ms_per_step"], "dtype": "f64",
+                             "kernel_only_gflops": rep3["kernel_only_gflops"], "config": workload_config(r3.w, {"products": rep3["products"], "flop": rep3["flop"],
+                                                                                                           "stacks": rep3["stacks"]}),
+                             "gpu_launches": rep3["launches"], "roofline": rep3["roofline"], "selfcheck": rep3["selfcheck"]}
+            r3.close()
+        except Exception as ex:
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            extra["cfg3"] = {"error": repr(ex)[:300]}
+        try:
+            extra["cfg4"] = bf16_config_report(torch, acc, s, tstream, args.extra_nblk, max(3, args.steps // 2), 3, 0 if args.no_selfcheck else 200)
+        except Exception as ex:
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            extra["cfg4"] = {"error": repr(ex)[:300]}
+
+    gpu_base = None
+    if not args.no_gpu_baseline and args.config == "cfg2":
+        acc.device_synchronize()
+        gpu_base = gpu_baseline_reference_kernels(nblk=args.nblk or 1000)
 
     out = {"metric": METRIC_NAMES[args.config],
-           "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if bf16 else "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
-           "config": workload_config(w, {"products": n_entries, "flop": flop, "stacks": len(stacks), "c_blocks": int(c_nblks),
-                                         "timed": "CUDA events on the launching stream; step = %d libsmm_acc_process calls into a zeroed C buffer + the memset of the next step's (pooled, double-buffered) C buffer on a side stream, joined before the step ends" % len(stacks)}),
-           "clocks": clocks, "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-           "selfcheck": selfcheck}
+           "value": rep["value"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rep["ms_per_step"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
+           "config": workload_config(w, {"products": rep["products"], "flop": rep["flop"], "stacks": rep["stacks"], "c_blocks": rep["c_blocks"],
+                                         "timed": "CUDA events on the launching stream; step = %d libsmm_acc_process calls into a zeroed C buffer + the memset of the next step's (pooled, double-buffered) C buffer on a side stream, joined before the step ends" % rep["stacks"],
+                                         "pdl_chain": not args.no_chain}),
+           "clocks": clocks, "gpu_launches": rep["launches"], "wall_s_timed_region": rep["wall_s"], "roofline": rep["roofline"], "e2e": e2e, "cpu_baseline": cpu,
+           "gpu_baseline": gpu_base, "selfcheck": rep["selfcheck"], "extra_configs": extra or None}
     print(json.dumps(out))
-    for d in (d_a, d_b, d_st):
-        d.free()
     acc.stream_destroy(s)
 
 
@@ -447,7 +676,12 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-selfcheck", action="store_true", help="skip the full-size sum(C) check before the timed region")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the full-size sum(C) / probed-block check before the timed region")
+    ap.add_argument("--probe-blocks", type=int, default=1000, help="random C blocks checked element-wise against the oracle in the self-check")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (cfg3, cfg4 at full size)")
+    ap.add_argument("--extra-nblk", type=int, default=None, help="block-grid size of the extra_configs legs (default: the full 1000)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels-on-this-GPU leg")
+    ap.add_argument("--no-chain", action="store_true", help="do not declare the bench stream a chain of independent drains (every kernel waits for its predecessor)")
     ap.add_argument("--ref-entries", type=int, default=4_000_000, help="stack entries in the bounded CPU sample")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -451,7 +451,9 @@ class CannonMultiply:
         rec.engine = host.Engine(self.m_sizes, self.n_sizes, self.w["m_sizes"], nthreads=1, mode=host.RECORD, cfg=self.cfg)
         per_tick = rec.run()
         self.flop = rec.engine.flop()
-        self.replay_datasize = rec.engine.c_index(0)[3]
+        ci = rec.engine.c_index(0)
+        self.replay_datasize = ci[3]
+        self.replay_c_index = (ci[0].copy(), ci[1].copy(), ci[2].copy())  # local (row, col, blk_p) of this rank's C blocks
         rec.engine.close()
         flat = [st["dev"].reshape(-1) for tick in per_tick for st in tick]
         all_dev = np.concatenate(flat).astype(np.int32) if flat else np.zeros(3, dtype=np.int32)
@@ -472,6 +474,10 @@ class CannonMultiply:
         self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
         self.step_no = 0
         self.cs = acc.stream_create("cannon compute", 0)
+        # between the event waits of two ticks the compute stream carries nothing but stack drains: programmatic dependent launch
+        # without the grid-dependency wait in front of the reads (include/dbcsr_acc_libsmm.h, libsmm_acc_b200_stream_chain)
+        if os.environ.get("DBCSR_B200_CHAIN", "1") != "0":
+            acc.stream_chain(self.cs, True)
         from . import lib as acclib
 
         self.cs_torch = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(self.cs).value)
@@ -622,7 +628,7 @@ def bench_main(args):
 
     from . import host, workload
     from . import lib as acclib
-    from bench import ClockSampler, measured_peaks, workload_config
+    from bench import ClockSampler, measured_peaks, probe_c_blocks, workload_config
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -668,14 +674,34 @@ def bench_main(args):
 
     # self-check of the replayed multiply (every rank, before anything is timed): sum(C_local) against the host expectation.
     # If the prefetch-everything exchange order fails it, fall back to the double-buffered order and check again.
+    n_probe = 0 if getattr(args, "no_selfcheck", False) else max(1, getattr(args, "probe_blocks", 1000) // world)
+    probe_info = {"probed_blocks": 0, "probe_max_rel_err": 0.0}
+
     def selfcheck():
+        """Replayed multiply of this rank against the host: sum(C_local) (a misplaced panel shows up here) and n_probe randomly
+        chosen C blocks of this rank element-wise against the oracle's block product of the GLOBAL matrices (a misplaced or
+        permuted block shows up here); max over ranks."""
         cm.replay_step()
         torch.cuda.synchronize()
         got = float(cm.replay_c.sum().item())
         exp = expected_local_c_sum(cm)
-        err = torch.tensor([abs(got - exp) / max(abs(exp), 1e-300)], dtype=torch.float64, device="cuda")
+        worst, npr = 0.0, 0
+        if n_probe:
+            rows, cols, blk_p = cm.replay_c_index
+            r0, c0 = cm.rsp[cm.i], cm.csp[cm.j]
+            coords = [(int(r) + r0, int(c) + c0) for r, c in zip(rows, cols)]
+
+            def got_block(i):
+                nz = int(cm.m_sizes[rows[i] - 1]) * int(cm.n_sizes[cols[i] - 1])
+                return cm.replay_c[int(blk_p[i]) - 1:int(blk_p[i]) - 1 + nz].cpu().numpy()
+
+            npr, worst = probe_c_blocks(w["A"], w["B"], coords, got_block, n_probe=n_probe, seed=100 + rank)
+        err = torch.tensor([abs(got - exp) / max(abs(exp), 1e-300), worst], dtype=torch.float64, device="cuda")
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
-        return float(err.item())
+        cnt = torch.tensor([float(npr)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        probe_info.update({"probed_blocks": int(cnt.item()), "probe_max_rel_err": float(err[1].item())})
+        return max(float(err[0].item()), float(err[1].item()) * 10.0)  # 1e-10 on blocks, 1e-9 on the sum
 
     selfcheck_err = selfcheck()
     selfcheck_mode = "prefetch_all" if cm.prefetch_all else "double_buffered"
@@ -723,10 +749,27 @@ def bench_main(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: stacks built by the host threads every step and streamed to the device (engine path), C stays on the device
+    c_pinned = []
+
     def one_multiply():
+        """One whole multiply through the engine incl. the download of this rank's C shard into pinned host buffers."""
         cm.engine.reset()
         cm.last_build_s = 0.0
         cm.run()
+        for th in range(cm.engine.nthreads):
+            ds = cm.engine.c_index(th)[3]
+            while len(c_pinned) <= th:
+                c_pinned.append(None)
+            if ds and (c_pinned[th] is None or c_pinned[th].array.size < ds):
+                if c_pinned[th] is not None:
+                    c_pinned[th].free()
+                c_pinned[th] = acc.host_alloc((int(ds * 1.05) + 1024,), np.float64)
+            if ds:
+                cm.engine.c_to_host_async(th, c_pinned[th].array)
+        cm.engine.sync()
+
+    def c_shard_bytes():
+        return sum(8 * cm.engine.c_index(th)[3] for th in range(cm.engine.nthreads))
 
     def engine_c_sum():
         tot = 0.0
@@ -758,7 +801,9 @@ def bench_main(args):
         for _ in range(max(1, args.e2e_warmup)):
             one_multiply()
         e2e_times = timed(one_multiply, args.e2e_steps, False)
-    t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times)), float(cm.n_replay_launches)],
+    d2h_local = float(c_shard_bytes()) if not args.no_e2e else 0.0
+    t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times)), float(cm.n_replay_launches),
+                      d2h_local],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -774,20 +819,21 @@ def bench_main(args):
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
                "config": workload_config(w, {"grid": "%dx%d" % (sc.pr, sc.pc), "k_slices": sc.V, "host_threads_per_rank": nthreads,
-                                             "flop": flop, "parallelism": "cannon %dx%d over NCCL send/recv" % (sc.pr, sc.pc),
-                                             "timed": "whole multiply per step: C memset, %d ticks of (NCCL panel exchange || stack kernels on pre-built device stacks); max over ranks of CUDA-event time; initial distribution excluded" % sc.V}),
+                                             "flop": flop, "parallelism": "cannon %dx%d, one rank per GPU; panels moved by %s" % (sc.pr, sc.pc, "copy-engine peer pull over NVLink (CUDA IPC), NCCL for set-up collectives" if cm.peer_buf is not None else "NCCL grouped send/recv"),
+                                             "timed": "whole multiply per step: C memset, %d ticks of (panel exchange || stack kernels on pre-built device stacks); max over ranks of CUDA-event time; initial distribution excluded" % sc.V}),
                "clocks": clocks, "gpu_launches": int(float(tsum[2])) if not use_graph else int(args.steps * float(tsum[5])),
                "gpu_launches_note": "kernels of this library per timed region, summed over ranks (graph replays counted from the captured launch list)",
                "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
                             "note": "per-kernel roofline is reported by the N=1 run; this line is the distributed multiply"},
                "e2e": ({"value": flop / (float(tmax[4]) * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": float(tmax[4]),
-                        "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": 0,
+                        "h2d_bytes_per_step": int(12 * flop / (2 * 23 ** 3)), "d2h_bytes_per_step": int(float(tsum[6])),
                         "selfcheck": e2e_check,
-                        "note": "panels device-resident at their home ranks, stacks built by the host threads and uploaded every step, C stays on the device"}
+                        "note": "panels device-resident at their home ranks (the initial distribution is outside the multiply, like the reference's make_images); every step the host threads build and upload the stacks and every rank downloads its C shard into pinned host memory"}
                        if not args.no_e2e else None),
                "cpu_baseline": None, "host_build_seconds_max": float(tmax[3]), "cuda_graph": use_graph, "exchange": "cuda-ipc peer pull (copy engines over NVLink)" if cm.peer_buf is not None else "nccl send/recv",
-               "selfcheck": {"property": "sum(C_local) == colsum(A(I,:)) . rowsum(B(:,J)), max relative error over ranks", "rel_err": selfcheck_err,
-                             "exchange_order": selfcheck_mode},
+               "selfcheck": {"property": "sum(C_local) == colsum(A(I,:)) . rowsum(B(:,J)) and randomly probed C blocks element-wise vs oracle orc_block_gemm; max over ranks",
+                             "rel_err": selfcheck_err, "probed_blocks": probe_info["probed_blocks"], "probe_max_rel_err": probe_info["probe_max_rel_err"],
+                             "ok": bool(selfcheck_err <= 1e-9), "exchange_order": selfcheck_mode},
                "graph_capture_error": getattr(cm, "capture_error", None), "wall_ms_per_step_incl_barriers": t_host * 1e3}
         print(json.dumps(out), flush=True)
     dist.barrier()

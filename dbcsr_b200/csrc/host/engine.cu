@@ -56,7 +56,11 @@ struct ThreadState {
   void* stream = nullptr;
   std::vector<StackBuffer> bufs;
   void* c_dev = nullptr;
-  size_t c_capacity = 0;
+  size_t c_capacity = 0;   // elements of the device C buffer
+  size_t c_requested = 0;  // capacity asked for at creation (0 = estimate)
+  size_t c_used_high = 0;  // largest datasize since the buffer was last zeroed: what reset has to clear
+  // statistics of the host-driver route (stacks the accelerator refused): entries, stacks, flop
+  long long cpu_entries = 0, cpu_stacks = 0, cpu_flop = 0;
   std::vector<RecordedStack> recorded;
   int a_first = 1, a_last = 0;
   std::vector<std::pair<int, int>> slices;  // (a_first, a_last) of every row chunk this thread owns, in row order
@@ -108,6 +112,11 @@ struct dbcsr_b200_engine {
   std::vector<int> blk_tmp;
   // optional: events[c] = "the A rows of chunk c are on the device" (pipelined panel upload); consumed by the next multiply
   std::vector<void*> chunk_events;
+  // host driver of the scheduler (dbcsr_mm_sched_process: a stack the accelerator refuses is processed by the CPU driver,
+  // src/mm/dbcsr_mm_sched.F:340-363).  Supplied by the caller; this library contains no CPU compute path.
+  dbcsr_b200_host_driver_fn host_driver = nullptr;
+  void* host_driver_ctx = nullptr;
+  size_t nnz_hint = 0;  // elements of the panels of the current multiply (initial size estimate of the C buffers)
 };
 
 extern "C" {
@@ -166,7 +175,7 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
         if (c_dbcsr_acc_dev_mem_allocate(&b.dev, bytes) != 0) goto fail;
         if (c_dbcsr_acc_event_create(&b.calculated) != 0) goto fail;
       }
-      ts.c_capacity = c_capacity;
+      ts.c_requested = c_capacity;
     }
   }
   return e;
@@ -191,33 +200,71 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e) {
   delete e;
 }
 
-// device C buffers (dbcsr_mm_accdrv_init: sized like the work area, zeroed asynchronously); created at first use
-static int ensure_c_buffers(dbcsr_b200_engine_t* e) {
-  if (!(e->mode & DBCSR_B200_LAUNCH)) return 0;
+// device C buffers (dbcsr_mm_accdrv_init, src/mm/dbcsr_mm_accdrv.F:170-219: sized like the work area, zeroed asynchronously);
+// created at first use.  Initial size: the requested capacity, else the dense upper bound of the thread's block rows when all
+// threads' bounds together fit into a quarter of the free device memory (then the buffer never grows), else an estimate from
+// the panels' element counts; grow_c_buffer enlarges it on demand like dbcsr_data_ensure_size (src/mm/dbcsr_mm_accdrv.F:471-473).
+constexpr size_t kMaxOffsets = 0x7fffffffull;  // offsets are int32 (hard part 8)
+
+static size_t dense_bound(const dbcsr_b200_engine_t* e, int t) {
   const int nthreads = (int)e->th.size();
   size_t sum_n = 0;
   for (int v : e->n_sizes) sum_n += (size_t)v;
+  const int rcn = std::max(1, e->cfg.row_chunks);
+  const int nchunks = nthreads * rcn;
+  size_t sum_m = 0;
+  for (int c = t; c < nchunks; c += nthreads) {  // ALL block rows this thread owns (later Cannon ticks may touch rows that have
+                                                 // no A block in the first panel)
+    const int row_lo = (int)(((long long)e->nrows * c) / nchunks), row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
+    for (int r = row_lo; r < row_hi; ++r) sum_m += (size_t)e->m_sizes[(size_t)r];
+  }
+  return sum_m * sum_n;
+}
+
+static int ensure_c_buffers(dbcsr_b200_engine_t* e) {
+  if (!(e->mode & DBCSR_B200_LAUNCH)) return 0;
+  const int nthreads = (int)e->th.size();
+  size_t dense_total = 0;
+  for (int t = 0; t < nthreads; ++t) dense_total += std::min(dense_bound(e, t), kMaxOffsets);
+  size_t free_b = 0, total_b = 0;
+  const bool dense_fits = c_dbcsr_acc_dev_mem_info(&free_b, &total_b) == 0 && dense_total * sizeof(double) <= free_b / 4;
   for (int t = 0; t < nthreads; ++t) {
     ThreadState& ts = e->th[t];
     if (ts.c_dev != nullptr) continue;
-    size_t cap = ts.c_capacity;
-    if (cap == 0) {  // dense upper bound over ALL block rows this thread owns (later Cannon ticks may touch rows that have
-                     // no A block in the first panel)
-      const int rcn = std::max(1, e->cfg.row_chunks);
-      const int nchunks = nthreads * rcn;
-      size_t sum_m = 0;
-      for (int c = t; c < nchunks; c += nthreads) {
-        const int row_lo = (int)(((long long)e->nrows * c) / nchunks), row_hi = (int)(((long long)e->nrows * (c + 1)) / nchunks);
-        for (int r = row_lo; r < row_hi; ++r) sum_m += (size_t)e->m_sizes[(size_t)r];
-      }
-      cap = sum_m * sum_n;
+    size_t cap = ts.c_requested;
+    if (cap == 0) {
+      const size_t dense = dense_bound(e, t);
+      // sparse products: start from twice the operands' share of this thread and grow on demand
+      cap = dense_fits ? dense : std::min(dense, std::max<size_t>(2 * e->nnz_hint / (size_t)nthreads, (size_t)1 << 20));
     }
     if (cap == 0) cap = 1;
-    if (cap > 0x7fffffffull) cap = 0x7fffffffull;  // offsets are int32 (hard part 8)
-    ts.c_capacity = cap;
+    if (cap > kMaxOffsets) cap = kMaxOffsets;
     if (c_dbcsr_acc_dev_mem_allocate(&ts.c_dev, cap * sizeof(double)) != 0) return -40;
+    ts.c_capacity = cap;
+    ts.c_used_high = 0;
     if (c_dbcsr_acc_memset_zero(ts.c_dev, 0, cap * sizeof(double), ts.stream) != 0) return -41;
   }
+  return 0;
+}
+
+// dbcsr_data_ensure_size(c_buffer, datasize, factor) of the accelerator driver: a larger buffer, the old contents copied device
+// to device behind everything enqueued on the thread's stream, the new tail zeroed; the old buffer is released after the stream
+// has drained (stack kernels and downloads that still use it are all on this stream).
+static int grow_c_buffer(ThreadState& ts, size_t need) {
+  if (need > kMaxOffsets) return -42;
+  size_t cap = std::max(need + need / 2, ts.c_capacity * 2);
+  if (cap > kMaxOffsets) cap = kMaxOffsets;
+  void* bigger = nullptr;
+  if (c_dbcsr_acc_dev_mem_allocate(&bigger, cap * sizeof(double)) != 0) {
+    cap = need;  // second try: exactly what is needed
+    if (c_dbcsr_acc_dev_mem_allocate(&bigger, cap * sizeof(double)) != 0) return -40;
+  }
+  if (c_dbcsr_acc_memcpy_d2d(ts.c_dev, bigger, ts.c_capacity * sizeof(double), ts.stream) != 0) return -41;
+  if (c_dbcsr_acc_memset_zero(bigger, ts.c_capacity * sizeof(double), (cap - ts.c_capacity) * sizeof(double), ts.stream) != 0) return -41;
+  if (c_dbcsr_acc_stream_sync(ts.stream) != 0) return -41;
+  if (c_dbcsr_acc_dev_mem_deallocate(ts.c_dev) != 0) return -41;
+  ts.c_dev = bigger;
+  ts.c_capacity = cap;
   return 0;
 }
 
@@ -237,6 +284,14 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
   const int nthreads = (int)e->th.size();
   const bool filter = a_norms != nullptr && b_norms != nullptr && !e->row_eps.empty();
   for (auto& ts : e->th) ts.filtered = false;
+  {
+    size_t nnz = 0;
+    for (int i = 0; i < na; ++i)
+      nnz += (size_t)e->m_sizes[(size_t)a_list3[3 * (size_t)i] - 1] * (size_t)e->th[0].mm->k_size(a_list3[3 * (size_t)i + 1]);
+    for (int i = 0; i < nb; ++i)
+      nnz += (size_t)e->th[0].mm->k_size(b_list3[3 * (size_t)i]) * (size_t)e->n_sizes[(size_t)b_list3[3 * (size_t)i + 1] - 1];
+    e->nnz_hint = nnz;
+  }
   // --- left panel: split the BCSR-ordered list over the threads by block rows (DBCSR: thr_c slices of coo_l, each slice
   //     rec-sorted on its own with the full panel extents, src/mm/dbcsr_mm_cannon.F:2910-2967)
   e->a_sorted.resize((size_t)na);
@@ -343,10 +398,14 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
           ts.recorded.push_back(std::move(r));
         }
         if (!(e->mode & DBCSR_B200_LAUNCH)) return;
-        if ((size_t)ts.mm->datasize() > ts.c_capacity) {
-          ts.rc = -42;  // device C buffer too small (the reference would grow it, src/mm/dbcsr_mm_accdrv.F:471-473)
-          return;
+        if ((size_t)ts.mm->datasize() > ts.c_capacity) {  // new C blocks beyond the buffer: grow it (src/mm/dbcsr_mm_accdrv.F:471-473)
+          const int grc = grow_c_buffer(ts, (size_t)ts.mm->datasize());
+          if (grc != 0) {
+            ts.rc = grc;
+            return;
+          }
         }
+        ts.c_used_high = std::max(ts.c_used_high, (size_t)ts.mm->datasize());
         // pick a stack buffer whose previous kernel has finished (round robin + event wait instead of the reference's busy poll)
         StackBuffer& b = ts.bufs[(size_t)next_buf];
         next_buf = (next_buf + 1) % (int)ts.bufs.size();
@@ -362,7 +421,24 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
         const int rc = libsmm_acc_process(params7, static_cast<const int*>(b.dev), size, dbcsr_type_real_8, a_dev, b_dev, ts.c_dev,
                                           d.max_m, d.max_n, d.max_k, kMaxKernelDim, d.defined_mnk, ts.stream, ts.stream);
         if (rc < 0) {
-          ts.rc = rc;  // the reference would now run this stack on the CPU; this engine has no CPU path and reports the code
+          // The accelerator refused the stack and left C untouched.  dbcsr_mm_sched_process now hands the stack to the host driver
+          // (src/mm/dbcsr_mm_sched.F:340-363), whose contributions live in the HOST work matrix and are added to the downloaded
+          // device buffer at finalize (src/mm/dbcsr_mm_accdrv.F:340-362).  This library has no CPU compute path: the route exists
+          // only when the caller installed a host driver (dbcsr_b200_engine_set_host_driver); otherwise the multiply fails loudly.
+          if (e->host_driver == nullptr) {
+            ts.rc = rc;
+            return;
+          }
+          const int hrc = e->host_driver(e->host_driver_ctx, t, d.m, d.n, d.k, d.defined_mnk, params7, size, ts.mm->datasize());
+          if (hrc != 0) {
+            ts.rc = hrc < 0 ? hrc : -50;
+            return;
+          }
+          long long flop = 0;
+          for (int i = 0; i < size; ++i) flop += 2LL * params7[7 * (size_t)i] * params7[7 * (size_t)i + 1] * params7[7 * (size_t)i + 2];
+          ts.cpu_entries += size;
+          ts.cpu_stacks += 1;
+          ts.cpu_flop += flop;
           return;
         }
         book(d, params7, size, rc == 10);
@@ -462,7 +538,11 @@ int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const in
     ts.mm->set_keep_sparsity(keep_sparsity != 0);
     ts.has_preset = true;
     if ((e->mode & DBCSR_B200_LAUNCH) && !data[(size_t)t].empty()) {
-      if ((size_t)ds[(size_t)t] > ts.c_capacity) return -42;
+      if ((size_t)ds[(size_t)t] > ts.c_capacity) {
+        const int grc = grow_c_buffer(ts, (size_t)ds[(size_t)t]);
+        if (grc != 0) return grc;
+      }
+      ts.c_used_high = std::max(ts.c_used_high, (size_t)ds[(size_t)t]);
       if (c_dbcsr_acc_memcpy_h2d(data[(size_t)t].data(), ts.c_dev, data[(size_t)t].size() * sizeof(double), ts.stream) != 0) return -44;
     }
   }
@@ -515,6 +595,24 @@ int dbcsr_b200_engine_stats(const dbcsr_b200_engine_t* e, long long* table, int 
       r[6] = all[(size_t)i].flop;
     }
   return n;
+}
+
+int dbcsr_b200_engine_set_host_driver(dbcsr_b200_engine_t* e, dbcsr_b200_host_driver_fn fn, void* ctx) {
+  if (e == nullptr) return -1;
+  e->host_driver = fn;
+  e->host_driver_ctx = ctx;
+  return 0;
+}
+
+int dbcsr_b200_engine_stats_cpu(const dbcsr_b200_engine_t* e, long long* totals) {
+  if (e == nullptr || totals == nullptr) return -1;
+  totals[0] = totals[1] = totals[2] = 0;
+  for (const auto& ts : e->th) {
+    totals[0] += ts.cpu_flop;
+    totals[1] += ts.cpu_entries;
+    totals[2] += ts.cpu_stacks;
+  }
+  return 0;
 }
 
 int dbcsr_b200_engine_set_c_symmetry(dbcsr_b200_engine_t* e, int on, const int* global_rows, const int* global_cols) {
@@ -755,12 +853,15 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
   // src/data/dbcsr_mem_methods.F:41-251): forget the product index, clear recorded stacks, zero the C buffer asynchronously
   if (e == nullptr) return -1;
   for (auto& ts : e->th) {
-    ts.mm->reset();
-    ts.mm->set_k_sizes(e->k_sizes);
     ts.recorded.clear();
     ts.has_preset = false;
     ts.filtered = false;
-    if (ts.c_dev != nullptr && c_dbcsr_acc_memset_zero(ts.c_dev, 0, ts.c_capacity * sizeof(double), ts.stream) != 0) return -41;
+    // only what the last multiply touched needs clearing (everything behind it is still zero)
+    const size_t used = std::min(std::max(ts.c_used_high, (size_t)ts.mm->datasize()), ts.c_capacity);
+    ts.mm->reset();
+    ts.mm->set_k_sizes(e->k_sizes);
+    if (ts.c_dev != nullptr && used > 0 && c_dbcsr_acc_memset_zero(ts.c_dev, 0, used * sizeof(double), ts.stream) != 0) return -41;
+    ts.c_used_high = 0;
   }
   return 0;
 }

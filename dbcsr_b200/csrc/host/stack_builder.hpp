@@ -90,6 +90,7 @@ class LocalMultiply {
   // Cannon ticks bring panels with different k-slices: block sizes of the contraction index of the CURRENT panels
   // (DBCSR passes k_sizes per dbcsr_mm_multrec_multiply call, src/mm/dbcsr_mm_multrec.F:263-296; the stack map stays as built).
   void set_k_sizes(const std::vector<int>& k_sizes) { k_sizes_ = k_sizes; }
+  int k_size(int kblk_1based) const { return (kblk_1based >= 1 && kblk_1based <= (int)k_sizes_.size()) ? k_sizes_[(size_t)kblk_1based - 1] : 0; }
 
   // per-C-row threshold row_max_epss (src/mm/dbcsr_mm_cannon.F:1100-1107); empty = no filtering
   void set_row_eps(const std::vector<float>& eps) { row_eps_ = eps; }

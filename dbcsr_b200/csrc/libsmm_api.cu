@@ -18,6 +18,7 @@
 
 #include "../../include/dbcsr_acc_libsmm.h"
 #include "smm_bf16.cuh"
+#include "smm_bf16_tiled.cuh"
 #include "smm_dmma_big.cuh"
 #include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
@@ -73,6 +74,7 @@ const bool g_tune_env_read = [] {
   if (const char* e = getenv("DBCSR_B200_ALIGN")) smm::g_tune.align.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_VARIANT")) smm::g_tune.variant.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BIGDMMA")) smm::g_tune.bigdmma.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_INHOMOGENEOUS")) smm::g_tune.inhomogeneous.store(atoi(e));
   return true;
 }();
 
@@ -475,6 +477,23 @@ bool all_types_enabled() {
   return v;
 }
 
+// Register-only DMMA.8x8x4 loop: the FP64 tensor-pipe peak of THIS device, measured in place so that roofline fractions have a
+// live denominator (bench.py).  9 independent accumulator pairs per warp like the 23^3 kernel's 3 x 3 tiles.
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double x, double y) {
+  double c0[9], c1[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c0[i] = c1[i] = (double)(threadIdx.x + i);
+  const double a = x + threadIdx.x * 1e-9, b = y;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) smm::dmma884(c0[i], c1[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s += c0[i] + c1[i];
+  if (s == 1.2345e300) out[0] = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -499,6 +518,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "align") == 0) smm::g_tune.align.store((int)value);
   else if (strcmp(name, "variant") == 0) smm::g_tune.variant.store((int)value);
   else if (strcmp(name, "bigdmma") == 0) smm::g_tune.bigdmma.store((int)value);
+  else if (strcmp(name, "inhomogeneous") == 0) smm::g_tune.inhomogeneous.store((int)value);
   else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
   else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
   else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
@@ -512,6 +532,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "align") == 0) return smm::g_tune.align.load();
   if (strcmp(name, "variant") == 0) return smm::g_tune.variant.load();
   if (strcmp(name, "bigdmma") == 0) return smm::g_tune.bigdmma.load();
+  if (strcmp(name, "inhomogeneous") == 0) return smm::g_tune.inhomogeneous.load();
   if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
   if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
   if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
@@ -553,6 +574,84 @@ int libsmm_acc_b200_stream_chain(void* stream, int on) {
 
 void libsmm_acc_b200_set_trace(void* dev_words) { smm::g_tune.trace.store(static_cast<unsigned long long*>(dev_words)); }
 
+// Measured FP64 tensor-pipe (DMMA.8x8x4) throughput of the active device in GFLOP/s: 16 warps per SM, register operands, best of
+// three timed launches on `stream` (synchronises it).  Returns <= 0 on failure.  Introspection only: not on any product path.
+double libsmm_acc_b200_fp64_peak_gflops(void* stream) {
+  if (stream == nullptr) return -2.0;
+  const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
+  const int sms = num_sms(), warps = 16, iters = 4096;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -30.0;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 1.0, 1e-9);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      best = -31.0;
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 8 * 8 * 4 * 9.0 * iters * (double)warps * sms;
+    if (rep > 0 && ms > 0.f) best = std::max(best, flop / (ms * 1e-3) * 1e-9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+
+// ---- tiled BF16 SpGEMM (smm_bf16_tiled.cuh): driven by the block index instead of parameter stacks -----------------------------
+int libsmm_acc_b200_bf16_rk_tile_bytes(int rows) { return ((rows + 7) / 8) * 512; }
+
+int libsmm_acc_b200_pack_bf16_rk(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
+                                 void* stream) {
+  if (nblks <= 0) return 0;
+  if (stream == nullptr || rows <= 0 || kdim <= 0 || rows > 32 || kdim > 32) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream));
+  const int wpc = 8;
+  int grid = (nblks + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::pack_bf16_rk_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream)>>>(dev_src, nblks, rows, kdim, row_stride, k_stride,
+                                                                                    static_cast<unsigned char*>(dev_dst));
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const void* b_tiles, const int* dev_b_map, float* dev_c,
+                                const int* dev_c_off, int nrb, int ncb, int nkb, int m, int n, int k, void* stream) {
+  if (stream == nullptr || nrb < 0 || ncb < 0 || nkb < 0) return -2;
+  if (m <= 0 || n <= 0 || k <= 0 || m > 32 || n > 32 || k > 32) return -10;
+  if (nrb == 0 || ncb == 0) return 0;
+  const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
+  smm::stream_chain_break(st);
+  const smm::BtGeom g = smm::bt_geom(m, n);
+  const int smem = (int)smm::bt_smem_bytes(g);
+  static SmemAttrCache smem_set;
+  if (ensure_smem(smm::smm_bf16_tiled_kernel, smem, smem_set) != 0) return -30;
+  const int bpt = g.bpt < 5 ? g.bpt : 5;
+  const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + smm::BT_NB - 1) / smm::BT_NB;
+  int grid = n_rg * n_cg;
+  if (grid > num_sms()) grid = num_sms();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(smm::BT_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_bf16_tiled_kernel, static_cast<const unsigned char*>(a_tiles), dev_a_map,
+                                             static_cast<const unsigned char*>(b_tiles), dev_b_map, dev_c, dev_c_off, nrb, ncb, nkb, m, n);
+  if (err != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
 
 int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
@@ -588,10 +687,7 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
   if (def_mnk != 1) {
     // inhomogeneous stack: the reference returns -1 here (libsmm_acc.cpp:327) and DBCSR falls back to the CPU; this library
     // bins the host stack by shape and drains every bin on the GPU (DBCSR_B200_INHOMOGENEOUS=0 restores the reference behaviour)
-    static const bool enabled = [] {
-      const char* e = getenv("DBCSR_B200_INHOMOGENEOUS");
-      return e == nullptr || atoi(e) != 0;
-    }();
+    const bool enabled = smm::g_tune.inhomogeneous.load(std::memory_order_relaxed) != 0;
     if (!enabled || datatype != dbcsr_type_real_8) return -1;
     return process_inhomogeneous(host_param_stack, stack_size, static_cast<const double*>(dev_a_data),
                                  static_cast<const double*>(dev_b_data), static_cast<double*>(dev_c_data), max_kernel_dim,

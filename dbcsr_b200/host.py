@@ -44,6 +44,8 @@ def _L():
         L.dbcsr_b200_engine_preset_c.argtypes = [_vp, _vp, _vp, _i, _vp, _i]
         L.dbcsr_b200_engine_set_c_symmetry.argtypes = [_vp, _i, _vp, _vp]
         L.dbcsr_b200_engine_stats.argtypes = [_vp, _vp, _i, _vp]
+        L.dbcsr_b200_engine_set_host_driver.argtypes = [_vp, _vp, _vp]
+        L.dbcsr_b200_engine_stats_cpu.argtypes = [_vp, _vp]
         L.dbcsr_b200_filter_index.argtypes = [ctypes.c_double, _vp, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_longlong)]
         L.dbcsr_b200_engine_filter_c.argtypes = [_vp, ctypes.c_double]
         L.dbcsr_b200_engine_finalize_c.argtypes = [_vp, ctypes.c_double]
@@ -228,6 +230,35 @@ class Engine:
         rows = [dict(m=int(r[0]), n=int(r[1]), k=int(r[2]), entries=int(r[3]), stacks=int(r[4]), stacks_untuned=int(r[5]), flop=int(r[6]))
                 for r in table[:n]]
         return rows, dict(flop=int(totals[0]), entries=int(totals[1]), stacks=int(totals[2]))
+
+    def set_host_driver(self, fn):
+        """Install the scheduler's host-driver route (include/dbcsr_b200_host.h): fn(thread, m, n, k, defined_mnk, params7, c_datasize)
+        with params7 an (S, 7) int32 array; it must apply the stack to the caller's host work area of `thread` and return 0.
+        None removes it (a stack the accelerator refuses then fails the multiply).  The library itself never computes on the CPU."""
+        if fn is None:
+            self._host_driver_cb = None
+            self.L.dbcsr_b200_engine_set_host_driver(self.h, None, None)
+            return
+        proto = ctypes.CFUNCTYPE(_i, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _i, _i)
+
+        def trampoline(ctx, thread, m, n, k, defined, params, size, datasize):
+            try:
+                p7 = np.ctypeslib.as_array(params, shape=(size, 7)).copy()
+                return int(fn(thread, m, n, k, defined, p7, datasize) or 0)
+            except Exception:  # an exception must not unwind through C
+                import traceback
+
+                traceback.print_exc()
+                return -51
+
+        self._host_driver_cb = proto(trampoline)  # keep alive
+        self.L.dbcsr_b200_engine_set_host_driver(self.h, ctypes.cast(self._host_driver_cb, _vp), None)
+
+    def stats_cpu(self):
+        """Totals of the stacks that took the host-driver route: dict(flop, entries, stacks)."""
+        t = np.zeros(3, dtype=np.int64)
+        self.L.dbcsr_b200_engine_stats_cpu(self.h, t.ctypes.data)
+        return dict(flop=int(t[0]), entries=int(t[1]), stacks=int(t[2]))
 
     def finalize_c(self, filter_eps=None):
         """dbcsr_finalize on the device: optional final filter, every thread's blocks in BCSR order, data compacted."""

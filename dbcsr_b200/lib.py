@@ -30,7 +30,8 @@ SMM_SYMBOLS = [
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
     "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
-    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain",
+    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops",
+    "libsmm_acc_b200_bf16_rk_tile_bytes", "libsmm_acc_b200_pack_bf16_rk", "libsmm_acc_b200_bf16_spgemm",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
@@ -92,6 +93,11 @@ def load():
     L.libsmm_acc_b200_set_trace.argtypes = [_vp]
     L.libsmm_acc_b200_set_trace.restype = None
     L.libsmm_acc_b200_stream_chain.argtypes = [_vp, _i]
+    L.libsmm_acc_b200_bf16_rk_tile_bytes.argtypes = [_i]
+    L.libsmm_acc_b200_pack_bf16_rk.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp]
+    L.libsmm_acc_b200_bf16_spgemm.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+    L.libsmm_acc_b200_fp64_peak_gflops.argtypes = [_vp]
+    L.libsmm_acc_b200_fp64_peak_gflops.restype = ctypes.c_double
     L.c_dbcsr_acc_clear_errors.restype = None
     _lib = L
     return L
@@ -248,6 +254,20 @@ class Acc:
         """Declare `stream` a chain of independent stack drains (programmatic dependent launch without the grid-dependency wait in
         front of the reads, include/dbcsr_acc_libsmm.h); on=False withdraws the declaration."""
         _ck(self.L.libsmm_acc_b200_stream_chain(stream, 1 if on else 0), "stream_chain")
+
+    def bf16_rk_tile_bytes(self, rows):
+        return int(self.L.libsmm_acc_b200_bf16_rk_tile_bytes(rows))
+
+    def pack_bf16_rk(self, src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream):
+        _ck(self.L.libsmm_acc_b200_pack_bf16_rk(src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream), "pack_bf16_rk")
+
+    def bf16_spgemm(self, a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream):
+        _ck(self.L.libsmm_acc_b200_bf16_spgemm(a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream),
+            "bf16_spgemm")
+
+    def fp64_peak_gflops(self, stream):
+        """Measured DMMA.8x8x4 throughput of this device (register operands), GFLOP/s."""
+        return float(self.L.libsmm_acc_b200_fp64_peak_gflops(stream))
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())

@@ -76,6 +76,19 @@ int libsmm_acc_gpu_warp_size(void);
 int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
   void* stream);
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim);
+/* Tiled BF16 SpGEMM (dbcsr_b200/csrc/smm_bf16_tiled.cuh; BASELINE config 4): for dense-ish products the multiply is driven by the
+ * block index instead of parameter stacks.  pack_bf16_rk converts nblks FP64 blocks (addressing as in pack_bf16) into BF16 "rk"
+ * operand tiles of libsmm_acc_b200_bf16_rk_tile_bytes(rows) bytes (K padded to 32).  bf16_spgemm computes, for every block row rb <
+ * nrb and block column cb < ncb with dev_c_off[rb*ncb + cb] >= 0, the FP32 block C(rb,cb) = sum over kb < nkb of A(rb,kb) * B(kb,cb)
+ * (m x n column-major at element offset dev_c_off[..]; blocks with no contribution are written as zeros; C is OVERWRITTEN, it need not be
+ * zeroed), where dev_a_map[kb*nrb + rb] / dev_b_map[kb*ncb + cb] is the index of the packed tile of A(rb,kb) (rows = m, kdim = k) /
+ * of B(kb,cb) TRANSPOSED (rows = n, kdim = k) in a_tiles / b_tiles, or -1 for an absent block.  All block rows have m, all block columns
+ * n, all k blocks k elements; m, n, k <= 32 (else -10, nothing enqueued).  Asynchronous on `stream`. */
+int libsmm_acc_b200_bf16_rk_tile_bytes(int rows);
+int libsmm_acc_b200_pack_bf16_rk(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
+  void* stream);
+int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const void* b_tiles, const int* dev_b_map, float* dev_c,
+  const int* dev_c_off, int nrb, int ncb, int nkb, int m, int n, int k, void* stream);
 /* Which kernel would libsmm_acc_process use for (m,n,k)?  0 = none, 1 = specialised DMMA kernel, 2 = generic kernel, 3 = BF16 tcgen05. */
 int libsmm_acc_b200_kernel_kind(int m, int n, int k, libsmm_acc_data_t datatype);
 /* Number of kernel launches this library has enqueued since load (all threads). */
@@ -93,6 +106,9 @@ void libsmm_acc_b200_set_trace(void* dev_words);
  * grid before reading, so consecutive drains overlap tail and ramp-up; completion order stays stream order.  Default (and after
  * on == 0): every kernel waits for its predecessor before its first global read.  Returns 0, -2 for a NULL stream. */
 int libsmm_acc_b200_stream_chain(void* stream, int on);
+/* Measured FP64 tensor-pipe (DMMA.8x8x4, register operands) throughput of the active device in GFLOP/s; synchronises `stream`.
+ * Introspection for roofline reports (bench.py); <= 0 on failure. */
+double libsmm_acc_b200_fp64_peak_gflops(void* stream);
 /* Library identification string (static storage). */
 const char* libsmm_acc_b200_version(void);
 

@@ -49,7 +49,8 @@ typedef struct dbcsr_b200_engine dbcsr_b200_engine_t;
 #define DBCSR_B200_RECORD 2 /* keep every dispatched stack (host 7-wide + device-order 3-wide) for inspection / replay */
 
 /* m_sizes/n_sizes/k_sizes: block sizes of the local C rows, C cols and the contraction index.
- * c_capacity: elements of device C buffer per engine (0 = dense upper bound).  Returns NULL on failure. */
+ * c_capacity: initial elements of every thread's device C buffer (0 = dense upper bound of the thread's block rows when that fits
+ * comfortably into device memory, else an estimate from the panels); the buffer grows on demand.  Returns NULL on failure. */
 dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const int* m_sizes, int nrows, const int* n_sizes,
   int ncols, const int* k_sizes, int nk, int nthreads, int mode, size_t c_capacity);
 void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e);
@@ -148,6 +149,19 @@ double dbcsr_b200_engine_build_seconds(const dbcsr_b200_engine_t* e);
  * (m, n, k, stack entries processed on the accelerator, stacks, stacks that ran on an untuned kernel, flop), ordered by flop;
  * inhomogeneous stacks are booked under (0,0,0).  totals[3] = flop, entries, stacks.  Returns the number of distinct (m,n,k). */
 int dbcsr_b200_engine_stats(const dbcsr_b200_engine_t* e, long long* table, int max_rows, long long* totals);
+
+/* Host-driver route of the scheduler (dbcsr_mm_sched_process, src/mm/dbcsr_mm_sched.F:340-363): when libsmm_acc_process
+ * refuses a stack (negative return code, C untouched: inhomogeneous stack with DBCSR_B200_INHOMOGENEOUS=0, unsupported type, ...)
+ * DBCSR drains it with its CPU driver into the HOST work matrix and adds the downloaded device buffer to it at finalize
+ * (src/mm/dbcsr_mm_accdrv.F:340-362).  This library has no CPU compute path; the route exists when the caller installs a driver:
+ * fn(ctx, thread, m, n, k, defined_mnk, params7, stack_size, c_datasize) must apply the stack (7 ints per entry, 1-based offsets,
+ * B blocks as they are on the device) to the caller's host work area of `thread` (at least c_datasize elements) and return 0.
+ * Without a driver a refused stack fails the multiply with the accelerator's code.  stats_cpu: totals[3] = flop, entries, stacks
+ * that took this route. */
+typedef int (*dbcsr_b200_host_driver_fn)(void* ctx, int thread, int m, int n, int k, int defined_mnk, const int* params7, int stack_size,
+  int c_datasize);
+int dbcsr_b200_engine_set_host_driver(dbcsr_b200_engine_t* e, dbcsr_b200_host_driver_fn fn, void* ctx);
+int dbcsr_b200_engine_stats_cpu(const dbcsr_b200_engine_t* e, long long* totals);
 
 /* recorded stacks (RECORD mode), in dispatch order per thread then concatenated thread by thread */
 int dbcsr_b200_engine_nstacks(const dbcsr_b200_engine_t* e);

@@ -81,6 +81,12 @@ class FakeAcc:
     def event_create(self):
         return object()
 
+    def fp64_peak_gflops(self, s):
+        return 37000.0
+
+    def bf16_rk_tile_bytes(self, rows):
+        return (rows + 7) // 8 * 512
+
     def __getattr__(self, name):  # stream_sync, memset_zero, event_record, stream_wait_event, stream_destroy, ...
         return lambda *a, **k: None
 
@@ -97,7 +103,8 @@ def _common_patches():
 
 def test_run_single_dry_run():
     args = types.SimpleNamespace(config="cfg2", nblk=40, warmup=3, steps=2, no_e2e=True, no_cpu=True, no_selfcheck=False, threads=0,
-                                 row_chunks=4, pipelined_upload=False, e2e_steps=1, e2e_warmup=1, ref_entries=1000, gpus=1, impl="ours")
+                                 row_chunks=4, pipelined_upload=False, e2e_steps=1, e2e_warmup=1, ref_entries=1000, gpus=1, impl="ours",
+                                 no_chain=False, probe_blocks=50, no_extra=False, extra_nblk=24, no_gpu_baseline=True)
     out = io.StringIO()
     with contextlib.ExitStack() as st:
         for p in _common_patches() + [um.patch.object(host, "transpose_panel", lambda *a, **k: None)]:
@@ -109,8 +116,14 @@ def test_run_single_dry_run():
                 "data", "config", "clocks", "gpu_launches", "roofline", "e2e", "cpu_baseline", "selfcheck"):
         assert key in d, key
     assert d["gpu_launches"] > 0 and d["selfcheck"]["rel_err"] == 1.0  # the fake device returns zeros: the check really compares
+    assert d["selfcheck"]["probed_blocks"] == 50 and d["selfcheck"]["probe_max_rel_err"] == 1.0 and d["selfcheck"]["ok"] is False
     r = d["roofline"]
-    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic", "alt_bounds")) <= set(r) and r["alt_bounds"]["mean_run_length"] >= 1.0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic", "alt_bounds")) <= set(r) and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert r["alt_bounds"]["hbm_streaming_model"]["mean_run_length"] >= 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    x = d["extra_configs"]
+    assert x["cfg3"]["value"] > 0 and x["cfg3"]["selfcheck"]["probed_blocks"] > 0 and "mixed" in x["cfg3"]["metric"]
+    assert x["cfg4"]["value"] > 0 and x["cfg4"]["dtype"] == "bf16" and x["cfg4"]["roofline"]["useful_over_issued"] > 0
+    assert x["cfg4"]["selfcheck"]["probe_max_rel_err"] == 1.0
 
 
 def test_cannon_bench_main_dry_run():
@@ -130,7 +143,8 @@ def test_cannon_bench_main_dry_run():
     def fake_exit(code):
         raise SystemExit(code)
 
-    args = types.SimpleNamespace(config="cfg2", nblk=40, warmup=3, steps=2, no_e2e=True, no_cpu=True, threads=0, e2e_steps=1, e2e_warmup=1, gpus=1)
+    args = types.SimpleNamespace(config="cfg2", nblk=40, warmup=3, steps=2, no_e2e=True, no_cpu=True, threads=0, e2e_steps=1, e2e_warmup=1, gpus=1,
+                                 no_selfcheck=False, probe_blocks=40)
     out = io.StringIO()
     env = dict(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
     with contextlib.ExitStack() as st:
@@ -148,4 +162,6 @@ def test_cannon_bench_main_dry_run():
     d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][-1])
     for key in ("metric", "value", "n_gpus", "ms_per_step", "scaling", "config", "gpu_launches", "roofline", "e2e", "selfcheck", "exchange"):
         assert key in d, key
-    assert d["selfcheck"]["rel_err"] == 1.0 and d["scaling"] == "strong"
+    # zeros from the fake device: sum error 1.0, every probed block off by 1.0 (weighted x10 in the combined figure)
+    assert d["selfcheck"]["rel_err"] == 10.0 and d["selfcheck"]["probe_max_rel_err"] == 1.0 and d["selfcheck"]["probed_blocks"] > 0
+    assert d["selfcheck"]["ok"] is False and d["scaling"] == "strong" and "peer pull" in d["config"]["parallelism"] or "NCCL" in d["config"]["parallelism"]

@@ -334,3 +334,74 @@ def test_pipelined_left_panel_upload(acc, nthreads, row_chunks):
     cfg = host.default_cfg(mm_stack_size=500, row_chunks=row_chunks)
     prod, flop = multiply(acc, A, B, ms, ns, ks, nthreads=nthreads, cfg=cfg, pipelined=True)
     check_against_oracle(A, B, prod, ms, ns)
+
+
+def test_scheduler_host_driver_route(acc):
+    """dbcsr_mm_sched_process: a stack the accelerator refuses (here: the inhomogeneous default stack with the reference's
+    behaviour switched on, libsmm_acc_process returns -1 and leaves C untouched) goes to the HOST driver, whose contributions live
+    in the host work matrix and are added to the downloaded device buffer at finalize (src/mm/dbcsr_mm_sched.F:340-363,
+    src/mm/dbcsr_mm_accdrv.F:340-362).  The library has no CPU path: the driver is the caller's (here: the oracle's
+    blas_process_mm_stack_d restatement on the host copies of the panels, B untransposed).  Without a driver the multiply fails."""
+    from dbcsr_b200 import lib as acclib
+    from dbcsr_b200.multiply import ProductC
+
+    sizes = [5, 13, 23, 26, 32]
+    rng = np.random.default_rng(77)
+    nr, nc, nk = 40, 36, 44
+    ms, ns, ks = (workload.block_sizes(n, sizes, rng) for n in (nr, nc, nk))
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    nthreads = 2
+    saved = acc.get_tunable("inhomogeneous")
+    acc.set_tunable("inhomogeneous", 0)
+    try:
+        dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=400, n_stacks=3))
+        dm.upload_panels(A.data, B.data, B.list3())
+        with pytest.raises(acclib.AccError):  # no host driver installed: the refusal is reported, nothing is computed on the CPU
+            dm.multiply(A.list3(), B.list3())
+        dm.engine.sync()
+        host_c = [np.zeros(0) for _ in range(nthreads)]
+        calls = []
+
+        def driver(thread, m, n, k, defined_mnk, params7, c_datasize):
+            if host_c[thread].size < c_datasize:
+                host_c[thread] = np.concatenate([host_c[thread], np.zeros(c_datasize - host_c[thread].size)])
+            orc.host_stack(params7, A.data, B.data, host_c[thread])  # in place
+            calls.append((thread, defined_mnk, params7.shape[0]))
+            return 0
+
+        dm.engine.set_host_driver(driver)
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        dev = dm.download_c()
+        cpu = dm.engine.stats_cpu()
+        assert calls and all(d == 0 for _, d, _ in calls) and cpu["stacks"] == len(calls) and cpu["entries"] == sum(c[2] for c in calls)
+        rows_acc, tot_acc = dm.engine.stats()
+        assert tot_acc["entries"] > 0  # the homogeneous stacks still ran on the accelerator
+        prod = ProductC(ms, ns)
+        for t, (rows, cols, blk_p, data) in enumerate(dev.parts):
+            d = np.array(data, dtype=np.float64, copy=True)
+            d[:min(d.size, host_c[t].size)] += host_c[t][:d.size]   # block_add of the two work areas
+            prod.add(rows, cols, blk_p, d)
+        dm.close()
+    finally:
+        acc.set_tunable("inhomogeneous", saved)
+    check_against_oracle(A, B, prod, ms, ns)
+
+
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_device_c_buffer_grows_on_demand(acc, nthreads):
+    """A device C buffer that starts far too small (c_capacity = 1000 elements) is enlarged while the stacks stream
+    (dbcsr_data_ensure_size in the accelerator driver, src/mm/dbcsr_mm_accdrv.F:471-473): old contents kept, new tail zeroed;
+    also across repeated multiplies on the pooled (now larger) buffer."""
+    rng = np.random.default_rng(5)
+    ms = ns = ks = workload.block_sizes(50, [13, 23], rng)
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=200), c_capacity=1000)
+    for _ in range(2):
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        check_against_oracle(A, B, dm.download_c(), ms, ns)
+    assert all(dm.engine.c_capacity(t) >= dm.engine.c_index(t)[3] for t in range(nthreads))
+    dm.close()

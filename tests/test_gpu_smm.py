@@ -381,3 +381,102 @@ def test_launch_knobs_keep_results(acc, mnk):
     finally:
         for name, v in saved.items():
             acc.set_tunable(name, v)
+
+
+@pytest.mark.parametrize("chain", [False, True])
+def test_producer_kernels_in_front_of_process_on_one_stream(acc, chain):
+    """Every stack kernel is launched with programmatic stream serialization.  Whatever precedes it on the SAME stream -- a memset
+    of C, the in-place transpose of the right panel, an earlier drain -- must be complete and visible before the kernel reads:
+    no host synchronisation anywhere in the loop, 40 rounds of memset -> transpose -> process -> process -> transpose back, on
+    integer-valued data (exact).  chain=True declares the stream a chain of independent drains (libsmm_acc_b200_stream_chain):
+    the library itself falls back to the waiting mode behind its own transpose kernels."""
+    m = n = k = 23
+    rng = np.random.default_rng(31)
+    n_a = n_b = 400
+    n_c, S = 1500, 20000
+    a = rng.integers(0, 4, n_a * m * k).astype(np.float64)
+    b = rng.integers(0, 4, n_b * k * n).astype(np.float64)   # untransposed k x n blocks
+    stack = np.zeros((S, 3), dtype=np.int32)
+    stack[:, 0] = rng.integers(0, n_a, S) * m * k + 1
+    stack[:, 1] = rng.integers(0, n_b, S) * k * n + 1
+    stack[:, 2] = np.sort(rng.integers(0, n_c, S)) * m * n + 1
+    host7 = np.zeros((S, 7), dtype=np.int32)
+    host7[:, 0], host7[:, 1], host7[:, 2] = m, n, k
+    host7[:, 3:6] = stack
+    c_ref = 2.0 * orc.host_stack(host7, a, b, np.zeros(n_c * m * n))  # two drains per round
+    d_a, d_b, d_s = acc.to_device(a, acc.s), acc.to_device(b, acc.s), acc.to_device(stack, acc.s)
+    d_t = acc.to_device((np.arange(n_b, dtype=np.int32) * k * n), acc.s)
+    d_c = acc.dev_alloc(n_c * m * n * 8)
+    out = acc.host_alloc((n_c * m * n,), np.float64)
+    acc.stream_chain(acc.s, chain)
+    try:
+        for rnd in range(40):
+            acc.memset_zero(d_c, acc.s)
+            acc.transpose(d_t.ptr, 0, n_b, d_b.ptr, k, n, acc.s)           # B -> Bt in place
+            for _ in range(2):
+                assert acc.process(None, d_s.ptr, S, d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s) == 0
+            acc.transpose(d_t.ptr, 0, n_b, d_b.ptr, n, k, acc.s)           # back to k x n for the next round
+            if rnd % 8 == 7:
+                acc.d2h(d_c, out.array, acc.s)
+                acc.stream_sync(acc.s)
+                assert np.array_equal(out.array, c_ref), (rnd, float(np.abs(out.array - c_ref).max()))
+    finally:
+        acc.stream_chain(acc.s, False)
+    for d in (d_a, d_b, d_s, d_t, d_c):
+        d.free()
+    out.free()
+
+
+def test_chain_mode_many_drains_exact(acc):
+    """Chain mode proper: 60 drains of different stacks back to back into one C buffer, nothing else on the stream."""
+    m = n = k = 23
+    rng = np.random.default_rng(32)
+    n_a = n_b = 500
+    n_c, S, reps = 4000, 30000, 60
+    a = rng.integers(0, 3, n_a * m * k).astype(np.float64)
+    bt = rng.integers(0, 3, n_b * k * n).astype(np.float64)
+    stacks = []
+    c_ref = np.zeros(n_c * m * n)
+    for r in range(3):
+        st = np.zeros((S, 3), dtype=np.int32)
+        st[:, 0] = rng.integers(0, n_a, S) * m * k + 1
+        st[:, 1] = rng.integers(0, n_b, S) * k * n + 1
+        st[:, 2] = np.sort(rng.integers(0, n_c, S)) * m * n + 1
+        stacks.append(st)
+        c_ref += (reps // 3) * orc.stack_calc(st, np.zeros(n_c * m * n), a, bt, m, n, k)
+    d_a, d_b = acc.to_device(a, acc.s), acc.to_device(bt, acc.s)
+    d_s = [acc.to_device(st, acc.s) for st in stacks]
+    d_c = acc.dev_alloc(n_c * m * n * 8)
+    acc.memset_zero(d_c, acc.s)
+    acc.stream_chain(acc.s, True)
+    try:
+        for r in range(reps):
+            assert acc.process(None, d_s[r % 3].ptr, S, d_a.ptr, d_b.ptr, d_c.ptr, m, n, k, True, acc.s, acc.s) == 0
+        c = acc.to_host(d_c, (n_c * m * n,), np.float64, acc.s)
+    finally:
+        acc.stream_chain(acc.s, False)
+    assert np.array_equal(c, c_ref), float(np.abs(c - c_ref).max())
+    for d in [d_a, d_b, d_c] + d_s:
+        d.free()
+
+
+@pytest.mark.parametrize("mnk", [(5, 5, 5), (5, 5, 32), (5, 13, 23), (13, 5, 26), (5, 13, 5), (13, 5, 13)])
+def test_tiny_block_shapes_long_and_short_runs(acc, mnk):
+    """Shapes with m*n <= 96 (candidates of the lane-per-element kernel, smm_tiny.cuh; which kernel runs is the autotune
+    database's choice): exact on integer data for sorted stacks with long runs, short runs, unsorted stacks and tiny stacks."""
+    m, n, k = mnk
+    rng = np.random.default_rng(33)
+    n_a = n_b = 700
+    a = rng.integers(0, 4, n_a * m * k).astype(np.float64)
+    bt = rng.integers(0, 4, n_b * k * n).astype(np.float64)
+    for S, n_c, shuffle in [(1, 1, False), (33, 2, False), (5000, 4000, False), (30000, 9, False), (30000, 30000, False), (7000, 500, True)]:
+        stack = np.zeros((S, 3), dtype=np.int32)
+        stack[:, 0] = rng.integers(0, n_a, S) * m * k + 1
+        stack[:, 1] = rng.integers(0, n_b, S) * k * n + 1
+        stack[:, 2] = np.sort(rng.integers(0, n_c, S)) * m * n + 1
+        if shuffle:
+            stack = stack[rng.permutation(S)]
+        rc, c = run_process(acc, stack, a, bt, n_c * m * n, m, n, k, pad_elems=1 if S == 5000 else 0)
+        assert rc == 0
+        c_ref = orc.stack_calc(stack, np.zeros(n_c * m * n), a, bt, m, n, k)
+        assert np.array_equal(c, c_ref), (mnk, S, n_c, shuffle, float(np.abs(c - c_ref).max()))
