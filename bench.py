@@ -328,6 +328,22 @@ class Fp64Run:
         acc.event_record(self.ev_free[k], s)
         acc.stream_wait_event(s, self.ev_zero[1 - k])      # the step owns the memset it issued
 
+    def one_step_serial(self):
+        """Same work as one_step with the memset IN LINE: zero the C buffer, then drain into it, all on the bench stream.  The
+        overlapped variant hides the memset behind the drain but makes both fight for HBM; which one is faster is measured."""
+        self.acc.memset_zero(self.d_cs[0], self.s)
+        self.drain(self.d_cs[0])
+
+    def restore_overlap_state(self):
+        """Leave the double-buffering state as one_step expects it: the buffer of the next step zeroed, nothing in flight."""
+        acc = self.acc
+        acc.stream_sync(self.s)
+        acc.memset_zero(self.d_cs[self.step_no % 2], self.zs)
+        acc.event_record(self.ev_zero[self.step_no % 2], self.zs)
+        acc.event_record(self.ev_free[1 - self.step_no % 2], self.s)
+        acc.stream_sync(self.zs)
+        acc.stream_sync(self.s)
+
     def selfcheck(self, n_probe):
         """Full size, outside every timed region: one drain into a zeroed buffer; (1) sum(C) = colsum(A) . rowsum(B),
         (2) n_probe random C blocks element-wise against the oracle's block product."""
@@ -353,11 +369,7 @@ class Fp64Run:
         npr, worst = probe_c_blocks(A, B, coords, got_block, n_probe=n_probe)
         out.update({"probed_blocks": npr, "probe_max_rel_err": worst, "probe": "random C blocks, element-wise vs oracle orc_block_gemm (tolerance 1e-10)",
                     "ok": bool(out["rel_err"] <= 1e-9 and worst <= 1e-10)})
-        # leave the double-buffering state as one_step expects it: buffer of the next step zeroed
-        acc.memset_zero(self.d_cs[self.step_no % 2], self.zs)
-        acc.event_record(self.ev_zero[self.step_no % 2], self.zs)
-        acc.stream_sync(self.zs)
-        acc.stream_sync(s)
+        self.restore_overlap_state()
         return out
 
     def free_c(self):
@@ -418,8 +430,16 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
         run.one_step()
     acc.stream_sync(s)
     check = run.selfcheck(n_probe) if n_probe else None
+    # how the per-step memset of C is scheduled is the caller's choice (DBCSR zeroes its pooled buffer asynchronously): measure both
+    # the overlapped and the in-line variant on three steps each and time the faster one
+    trial_overlap, _ = timed_steps(torch, tstream, acc, s, run.one_step, 3)
+    acc.stream_sync(s)
+    trial_serial, _ = timed_steps(torch, tstream, acc, s, run.one_step_serial, 3)
+    zero_mode = "in line on the bench stream" if float(np.mean(trial_serial)) < float(np.mean(trial_overlap)) else "overlapped on a side stream"
+    step_fn = run.one_step_serial if zero_mode.startswith("in line") else run.one_step
+    run.restore_overlap_state()
     launches0 = acc.launch_count()
-    step_ms, t_wall = timed_steps(torch, tstream, acc, s, run.one_step, steps)
+    step_ms, t_wall = timed_steps(torch, tstream, acc, s, step_fn, steps)
     launches = acc.launch_count() - launches0
     kern_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 3)
     ms_per_step = float(np.mean(step_ms))
@@ -459,6 +479,7 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
                                   "achieved": traffic / (launch_us * 1e-6) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": traffic / (launch_us * 1e-6) * 1e-9 / hbm_peak} if traffic else None)}}
     return {"value": value, "ms_per_step": ms_per_step, "kernel_only_gflops": kernel_only, "launches": int(launches), "wall_s": t_wall, "roofline": roofline,
+            "zero_mode": zero_mode, "zero_mode_trial_ms": {"overlapped": float(np.mean(trial_overlap)), "in_line": float(np.mean(trial_serial))},
             "selfcheck": check, "products": run.n_entries, "flop": run.flop, "stacks": len(run.stacks), "c_blocks": int(run.c_rows.size)}
 
 
@@ -628,7 +649,7 @@ def run_single(args):
             extra["cfg3"] = {"metric": METRIC_NAMES["cfg3"], "value": rep3["value"], "unit": "GFLOP/s", "ms_per_step": rep3["ms_per_step"], "dtype": "f64",
                              "kernel_only_gflops": rep3["kernel_only_gflops"], "config": workload_config(r3.w, {"products": rep3["products"], "flop": rep3["flop"],
                                                                                                            "stacks": rep3["stacks"]}),
-                             "gpu_launches": rep3["launches"], "roofline": rep3["roofline"], "selfcheck": rep3["selfcheck"]}
+                             "gpu_launches": rep3["launches"], "roofline": rep3["roofline"], "selfcheck": rep3["selfcheck"], "zero_mode": rep3["zero_mode"]}
             r3.close()
         except Exception as ex:
             import traceback
@@ -652,7 +673,7 @@ def run_single(args):
            "value": rep["value"], "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rep["ms_per_step"],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
            "config": workload_config(w, {"products": rep["products"], "flop": rep["flop"], "stacks": rep["stacks"], "c_blocks": rep["c_blocks"],
-                                         "timed": "CUDA events on the launching stream; step = %d libsmm_acc_process calls into a zeroed C buffer + the memset of the next step's (pooled, double-buffered) C buffer on a side stream, joined before the step ends" % rep["stacks"],
+                                         "timed": "CUDA events on the launching stream; step = one memset of the whole C buffer + %d libsmm_acc_process calls into it; memset %s (trial: %s)" % (rep["stacks"], rep["zero_mode"], json.dumps(rep["zero_mode_trial_ms"])),
                                          "pdl_chain": not args.no_chain}),
            "clocks": clocks, "gpu_launches": rep["launches"], "wall_s_timed_region": rep["wall_s"], "roofline": rep["roofline"], "e2e": e2e, "cpu_baseline": cpu,
            "gpu_baseline": gpu_base, "selfcheck": rep["selfcheck"], "extra_configs": extra or None}

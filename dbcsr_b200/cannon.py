@@ -483,6 +483,30 @@ class CannonMultiply:
         self.cs_torch = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(self.cs).value)
         self.comm_stream = torch.cuda.Stream(priority=-1)
         self.n_replay_launches = sum(len(x) for x in self.replay)
+        # The whole step as ONE C call (dbcsr_b200_replay_step: peer pulls + stack launches + events, no Python between them) when
+        # every panel is pulled from read-only home buffers into its own receive buffer; otherwise the Python loop below.
+        self.creplay = None
+        # (the per-tick device timeline, DBCSR_B200_CANNON_TRACE, needs the Python loop's timing events: both paths keep their own
+        # double-buffering state, so one run uses one of them)
+        if os.environ.get("DBCSR_B200_REPLAY", "c") == "c" and not os.environ.get("DBCSR_B200_CANNON_TRACE") and \
+                (self.prefetch_all or self.world == 1):
+            order = self.tick_order()
+            R = host.Replay(len(order))
+            base = self.replay_stacks.data_ptr()
+            for it, t in enumerate(order):
+                (abuf, _, _), (bbuf, _, _) = self.panel_of_tick(t, "a"), self.panel_of_tick(t, "b")
+                R.set_panels(it, abuf.data_ptr(), bbuf.data_ptr())
+                ra, rb, _ = self.sched.transfers(self.rank, t)
+                s = self.sched.slice_at(self.rank, t)
+                for kind, src in (("a", ra), ("b", rb)):
+                    if src is not None:
+                        _, nblk, nze = self.panel_meta(kind, s, self.i, self.j)
+                        R.add_pull(it, self.recv[kind][t % self.nbuf].data_ptr(), self.peer_buf[(src, kind, s)].data_ptr(), nze * 8 + nblk * 12)
+                for off, S, mm, nn, kk, dm in self.replay[t]:
+                    R.add_stack(it, base + 4 * off, S, mm, nn, kk, dm)
+            R.set_c(self.replay_cs[0].data_ptr(), self.replay_cs[1].data_ptr(), 8 * max(self.replay_datasize, 1),
+                    zero_overlap=os.environ.get("DBCSR_B200_ZERO_OVERLAP", "1") != "0")
+            self.creplay = R
 
     def replay_step(self, fork_from_compute=False):
         """One whole multiply, enqueued without any host synchronisation: C memset, then per tick the NCCL exchange of the next
@@ -490,6 +514,12 @@ class CannonMultiply:
         torch, acc = self.torch, self.acc
         V = self.sched.V
         cs = self.cs_torch
+        if getattr(self, "creplay", None) is not None and not fork_from_compute:
+            self.creplay.step(self.cs)
+            cur = self.creplay.current_c()
+            self.replay_c = self.replay_cs[0] if cur == self.replay_cs[0].data_ptr() else self.replay_cs[1]
+            self.step_no += 1
+            return
         if fork_from_compute:  # graph capture: the comm stream has to branch off the capturing stream
             ev0 = torch.cuda.Event()
             ev0.record(cs)
@@ -590,6 +620,9 @@ class CannonMultiply:
             return False
 
     def close(self):
+        if getattr(self, "creplay", None) is not None:
+            self.creplay.close()
+            self.creplay = None
         self.engine.close()
 
 

@@ -203,7 +203,7 @@ int launch_rt_t(const int* dev_stack, int stack_size, const double* a, const dou
   return (err == cudaSuccess) ? 0 : -31;
 }
 
-// cooperative DMMA kernel (smm_dmma_big.cuh) for blocks with a dimension in 33..80; opt-in until verified on the device
+// cooperative DMMA kernel (smm_dmma_big.cuh) for blocks with a dimension in 33..80 (default; "bigdmma" = 0 falls back to the generic kernel)
 bool big_eligible(int m, int n, int k) {
   return smm::g_tune.bigdmma.load(std::memory_order_relaxed) != 0 && m <= 80 && n <= smm::BIG_MAX_N && k <= 80 && m > 0 && n > 0 && k > 0 &&
          smm::big_smem_bytes(m, n, k) <= 110 * 1024;
@@ -519,6 +519,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "variant") == 0) smm::g_tune.variant.store((int)value);
   else if (strcmp(name, "bigdmma") == 0) smm::g_tune.bigdmma.store((int)value);
   else if (strcmp(name, "inhomogeneous") == 0) smm::g_tune.inhomogeneous.store((int)value);
+  else if (strcmp(name, "bf16_merge") == 0) smm::g_tune.bf16_merge.store((int)value);
   else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
   else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
   else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
@@ -533,6 +534,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "variant") == 0) return smm::g_tune.variant.load();
   if (strcmp(name, "bigdmma") == 0) return smm::g_tune.bigdmma.load();
   if (strcmp(name, "inhomogeneous") == 0) return smm::g_tune.inhomogeneous.load();
+  if (strcmp(name, "bf16_merge") == 0) return smm::g_tune.bf16_merge.load();
   if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
   if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
   if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
@@ -629,9 +631,11 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   smm::stream_chain_break(st);
   const smm::BtGeom g = smm::bt_geom(m, n);
   const int smem = (int)smm::bt_smem_bytes(g);
+  // "bf16_merge" tunable (default 1): adjacent existing B blocks are multiplied by one wide MMA
+  const int flags = smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0;
   static SmemAttrCache smem_set;
   if (ensure_smem(smm::smm_bf16_tiled_kernel, smem, smem_set) != 0) return -30;
-  const int bpt = g.bpt < 5 ? g.bpt : 5;
+  const int bpt = g.bpt;
   const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + smm::BT_NB - 1) / smm::BT_NB;
   int grid = n_rg * n_cg;
   if (grid > num_sms()) grid = num_sms();
@@ -646,7 +650,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const cudaError_t err = cudaLaunchKernelEx(&cfg, smm::smm_bf16_tiled_kernel, static_cast<const unsigned char*>(a_tiles), dev_a_map,
-                                             static_cast<const unsigned char*>(b_tiles), dev_b_map, dev_c, dev_c_off, nrb, ncb, nkb, m, n);
+                                             static_cast<const unsigned char*>(b_tiles), dev_b_map, dev_c, dev_c_off, nrb, ncb, nkb, m, n, flags);
   if (err != cudaSuccess) return -31;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

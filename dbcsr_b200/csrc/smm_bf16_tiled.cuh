@@ -10,9 +10,11 @@
 //     plain coalesced stores -- no atomics, no memset of C, no read of C;
 //   * per k block: the A blocks of the BPT rows that exist are staged by one TMA bulk copy each (1.5 KB, operand layout, see
 //     below) into their row slot of the 128 x 32 A operand (absent slots are zero-filled once and stay zero until reused), the B
-//     blocks that exist among the 16 columns into their column slot; ONE thread then issues two tcgen05.mma (M=128, N=32, K=16)
-//     per existing B block with the accumulator of that block column: absent B blocks cost nothing, absent A blocks cost padding
-//     rows (the MMA is an outer product: it cannot skip rows per k);
+//     blocks that exist among the 16 columns into their column slot (2 KB pitch = 32 operand rows); ONE elected thread then issues
+//     two tcgen05.mma (M=128, K=16) per RUN of adjacent existing B blocks, N = 32 x run length, into the accumulators of those
+//     block columns: absent B blocks cost nothing, absent A blocks cost padding rows (the MMA is an outer product: it cannot
+//     skip rows per k).  Merging runs halves the MMA count (4.3 instead of 8 per k step at 50 % occupation) and with it the
+//     re-reads of the A operand from shared memory, which bound small-N MMAs;
 //   * the A operand of a k block is shared by up to 16 MMAs pairs, a B block by 5 block rows: 15.8 KB of L2 traffic per k block
 //     and tile instead of 8 x 5 x 2.2 KB = 90 KB for the same products through the stack kernel;
 //   * warp-specialised, persistent (one CTA per SM, static round-robin over tiles ordered so that the ~148 concurrently running
@@ -32,11 +34,13 @@
 
 namespace smm {
 
-constexpr int BT_STAGES = 6;
+constexpr int BT_STAGES = 5;
 constexpr int BT_NB = 16;            // block columns per tile (TMEM: 16 x 32 columns)
 constexpr int BT_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
 constexpr int BT_A_BYTES = 16 * 512; // A operand of one k block: 16 row groups x 4 k groups x 128 B
 constexpr int BT_KC = 8;             // presence-map entries prefetched per lane
+constexpr int BT_B_SLOT = 2048;      // B slot pitch: 32 operand rows (4 row groups), so that adjacent slots form one N = 32 r operand
+constexpr int BT_FLAG_MERGE_RUNS = 1;
 
 struct BtGeom {
   int rg_a, rg_b;      // row groups per A / B block
@@ -49,10 +53,11 @@ __host__ __device__ inline BtGeom bt_geom(int m, int n) {
   g.rg_a = (m + 7) / 8;
   g.rg_b = (n + 7) / 8;
   g.bpt = 16 / g.rg_a;
+  if (g.bpt > 5) g.bpt = 5;  // the producer warp has five A lanes; small blocks (m <= 16) leave MMA rows unused
   g.tile_a = g.rg_a * 512;
   g.tile_b = g.rg_b * 512;
-  // B slots at a pitch of tile_b; the N = 32 MMA of the last slot reads (4 - rg_b) row groups past it -> 2 KB of slack
-  g.stage = BT_A_BYTES + BT_NB * g.tile_b + 2048;
+  // B slots at a pitch of 32 rows: the row groups a block does not fill stay zero (never written after the initial clear)
+  g.stage = BT_A_BYTES + BT_NB * BT_B_SLOT;
   return g;
 }
 __host__ __device__ inline size_t bt_smem_bytes(const BtGeom& g) { return 1024 + (size_t)BT_STAGES * g.stage; }
@@ -80,6 +85,19 @@ __global__ void pack_bf16_rk_kernel(const double* __restrict__ src, int nblks, i
   }
 }
 
+// one lane of a converged warp (elect.sync): the predicate is warp-uniform knowledge for the compiler, unlike `lane == 0`
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "elect.sync _|p, 0xffffffff;\n"
+    "selp.u32 %0, 1, 0, p;\n"
+    "}\n"
+    : "=r"(pred));
+  return pred;
+}
+
 // tile t -> (row group, column group): panels of BT_PANEL row groups, inside a panel column groups outer, row groups inner, so
 // that gridDim.x consecutive tiles cover about 12 x 12 tiles
 constexpr int BT_PANEL = 12;
@@ -97,7 +115,7 @@ __host__ __device__ inline int bt_num_tiles(int n_rg, int n_cg) { return n_rg * 
 __global__ void __launch_bounds__(BT_THREADS, 1)
   smm_bf16_tiled_kernel(const unsigned char* __restrict__ a_tiles, const int* __restrict__ a_map, const unsigned char* __restrict__ b_tiles,
                         const int* __restrict__ b_map, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb,
-                        int m, int n) {
+                        int m, int n, int flags) {
   extern __shared__ __align__(1024) unsigned char bt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BtGeom g = bt_geom(m, n);
@@ -140,8 +158,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 
   if (warp == 0) {
     // ===================================== TMA producer (whole warp) =====================================
-    // lane l < bpt owns A slot l, lane 5 + c owns B slot c (bpt <= 5 since rg_a >= 3 ... for rg_a < 3 only 5 rows are used)
-    const int bpt = min(g.bpt, 5);
+    // lane l < bpt owns A slot l (bpt <= 5), lane 5 + c owns B slot c
+    const int bpt = g.bpt;
     const bool is_a = lane < bpt, is_b = lane >= 5 && lane < 5 + BT_NB;
     uint32_t zero_state = 0;  // bit (5 * stage + slot): A slot is known to hold zeros (everything is zero at start)
     for (int s = 0; s < BT_STAGES; ++s) zero_state |= 0x1fu << (5 * s);
@@ -156,7 +174,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       const int mstride = is_a ? nrb : ncb;
       const unsigned char* __restrict__ tiles = is_a ? a_tiles : b_tiles;
       const uint32_t tbytes = is_a ? (uint32_t)g.tile_a : (uint32_t)g.tile_b;
-      const uint32_t slot_off = is_a ? (uint32_t)lane * (uint32_t)g.tile_a : (uint32_t)BT_A_BYTES + (uint32_t)(lane - 5) * (uint32_t)g.tile_b;
+      const uint32_t slot_off = is_a ? (uint32_t)lane * (uint32_t)g.tile_a : (uint32_t)BT_A_BYTES + (uint32_t)(lane - 5) * (uint32_t)BT_B_SLOT;
       int cur[BT_KC], nxt[BT_KC];
 #pragma unroll
       for (int j = 0; j < BT_KC; ++j) cur[j] = (valid && j < nkb) ? __ldg(mp + (size_t)j * mstride) : -1;
@@ -205,40 +223,71 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     }
   }
   else if (warp == 1) {
-    // ===================================== MMA issuer (one thread) =====================================
-    if (lane == 0) {
-      // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10),[10,13), K-major A and B,
-      // N >> 3 at [17,23), M >> 4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t b_pitch16 = (uint32_t)g.tile_b >> 4;
-      uint32_t it = 0, tile_no = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
-        mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained the previous tile's accumulators
+    // ===================================== MMA issuer =====================================
+    // The whole warp walks the loop (barrier waits and masks are warp-uniform); ONE elected lane issues the MMAs and commits, so
+    // that descriptors live in uniform registers and no per-lane serialisation is generated around tcgen05.mma.
+    // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10),[10,13), K-major A and B,
+    // N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const bool merge = (flags & BT_FLAG_MERGE_RUNS) != 0;
+    uint32_t it = 0, tile_no = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
+      mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained the previous tile's accumulators
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t inited = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = (int)(it % BT_STAGES);
+        mbar_wait(&full[s], (it / BT_STAGES) & 1u);
+        const uint32_t bm = meta[s];
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t inited = 0;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = (int)(it % BT_STAGES);
-          mbar_wait(&full[s], (it / BT_STAGES) & 1u);
-          const uint32_t bm = meta[s];
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
           const uint32_t sa = smem_u32(stages + (size_t)s * g.stage);
           const uint64_t adesc0 = umma_desc(sa, 128u, 512u), adesc1 = umma_desc(sa + 256u, 128u, 512u);
           const uint64_t bdesc0 = umma_desc(sa + (uint32_t)BT_A_BYTES, 128u, 512u);
-#pragma unroll
-          for (int c = 0; c < BT_NB; ++c) {
-            if ((bm >> c) & 1u) {
-              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)c * b_pitch16);  // start-address field is in 16-byte units
-              umma_bf16(tmem_base + 32u * (uint32_t)c, adesc0, bd, idesc, (inited >> c) & 1u);
-              umma_bf16(tmem_base + 32u * (uint32_t)c, adesc1, bd + 16u, idesc, 1u);  // k = 16..31: +256 B
+          uint32_t todo = bm;
+          if (merge && (inited & bm) == bm) {
+            // steady state: every touched accumulator is initialised -> runs of adjacent existing blocks, always accumulating
+            while (todo != 0) {
+              const int c0 = __ffs(todo) - 1;
+              const int r = min(__ffs(~(todo >> c0)) - 1, 8);                                       // N <= 256
+              const uint32_t idesc = idesc_base | ((uint32_t)(4 * r) << 17);                        // N = 32 r
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)c0 * (uint32_t)(BT_B_SLOT >> 4));  // start address in 16-byte units
+              const uint32_t d = tmem_base + 32u * (uint32_t)c0;
+              umma_bf16(d, adesc0, bd, idesc, 1u);
+              umma_bf16(d, adesc1, bd + 16u, idesc, 1u);  // k = 16..31: +256 B
+              todo &= ~(((1u << r) - 1u) << c0);
             }
           }
-          inited |= bm;
+          else {
+            while (todo != 0) {
+              const int c0 = __ffs(todo) - 1;
+              int r = 1;
+              if (merge) {
+                // adjacent existing blocks whose accumulators are in the same state (all initialised or all fresh), at most 8
+                r = __ffs(~(todo >> c0)) - 1;
+                const uint32_t st = inited >> c0;
+                const int same = (st & 1u) ? (__ffs(~st) - 1) : (st == 0 ? 32 : __ffs(st) - 1);
+                r = min(min(r, same), 8);
+              }
+              const uint32_t idesc = idesc_base | ((uint32_t)(4 * r) << 17);
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)c0 * (uint32_t)(BT_B_SLOT >> 4));
+              const uint32_t d = tmem_base + 32u * (uint32_t)c0;
+              umma_bf16(d, adesc0, bd, idesc, (inited >> c0) & 1u);
+              umma_bf16(d, adesc1, bd + 16u, idesc, 1u);
+              todo &= ~(((1u << r) - 1u) << c0);
+            }
+          }
           umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
         }
+        inited |= bm;
+        __syncwarp();
+      }
+      if (elect_one()) {
         *tile_inited = inited;
         __threadfence_block();  // the epilogue reads tile_inited after the (asynchronous) commit-arrive on tmem_full
         umma_commit(tmem_full);
       }
+      __syncwarp();
     }
   }
   else {
@@ -251,8 +300,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
       int rg, cg;
       bt_tile_coords(t, n_rg, n_cg, rg, cg);
-      const int rb = rg * min(g.bpt, 5) + blk;
-      const bool row_ok = blk < min(g.bpt, 5) && r_in < m && rb < nrb;
+      const int rb = rg * g.bpt + blk;
+      const bool row_ok = blk < g.bpt && r_in < m && rb < nrb;
       mbar_wait(tmem_full, tile_no & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t inited = *tile_inited;

@@ -6,8 +6,9 @@
 // tiles (warp (wr, wc) owns tile rows wr, wr+4, wr+8 and tile columns wc, wc+2, ..., wc+8: up to 3 x 5 tiles = 30 accumulator
 // registers per lane, enough for 96 x 80), every k-step each warp loads <= 3 A and <= 5 B fragments from shared memory and issues
 // <= 15 DMMA.8x8x4, and a run of equal c_first stays in registers until it is flushed with RED.ADD.F64.
-// OPT-IN (libsmm_acc_b200_set_tunable("bigdmma", 1) / DBCSR_B200_BIGDMMA=1) until it has been verified and tuned on a B200:
-// the default path for these shapes is the scalar generic kernel (smm_generic.cuh).  Replaces the reference's medium/large
+// Default for these shapes since its first device run (round 2: exact on integer data for all six test shapes incl. runs,
+// unsorted stacks and odd alignment); libsmm_acc_b200_set_tunable("bigdmma", 0) / DBCSR_B200_BIGDMMA=0 selects the scalar generic
+// kernel (smm_generic.cuh) instead.  Replaces the reference's medium/large
 // kernels for this size range (src/acc/libsmm_acc/kernels/smm_acc_dnt_{medium,largeDB1,largeDB2}.h).
 #pragma once
 #include "smm_dmma_rt.cuh"

@@ -5,7 +5,7 @@
 //   DBCSR_B200_ALIGN=0|1    move chunk boundaries to changes of c_first, so that a run is flushed once (default: per-shape policy)
 //   DBCSR_B200_CHUNK=n      n > 0: at most n entries per warp; the grid may then exceed one resident wave; 0 = one wave
 //                           (default: per-shape policy)
-//   DBCSR_B200_BIGDMMA=0|1  cooperative DMMA kernel for 33..80 blocks instead of the scalar generic kernel (default 0: not yet verified)
+//   DBCSR_B200_BIGDMMA=0|1  cooperative DMMA kernel for 33..80 blocks instead of the scalar generic kernel (default 1; verified on B200 in round 2)
 //   DBCSR_B200_INHOMOGENEOUS=0|1  0 = reject inhomogeneous stacks with -1 like the reference (DBCSR then uses its CPU driver); default 1
 //   DBCSR_B200_VARIANT=v    kernel variant id (see smm_inst.cu; only experiment builds carry more than the default)
 // The trace window (kernel-timeline instrumentation, tools/kbench.c + tools/trace_analyze.py) is set through the setter only.
@@ -19,8 +19,9 @@ constexpr int TRACE_REC = 128;     // 64-bit words per warp record
 
 struct Tunables {
   std::atomic<int> variant{0};
-  std::atomic<int> bigdmma{0};  // 1: blocks with a dimension in 33..80 use the cooperative DMMA kernel (smm_dmma_big.cuh) - unverified, opt-in
+  std::atomic<int> bigdmma{1};  // 1 (default): blocks with a dimension in 33..80 use the cooperative DMMA kernel (smm_dmma_big.cuh); 0: scalar generic kernel
   std::atomic<int> inhomogeneous{1};  // 1: def_mnk = 0 stacks are binned by shape and drained on the GPU; 0: -1 like the reference
+  std::atomic<int> bf16_merge{1};     // tiled BF16 SpGEMM: 1 = one wide MMA per run of adjacent existing B blocks, 0 = one per block
   std::atomic<int> balance{0};
   std::atomic<int> chunk{-1};  // -1 = per-shape policy (smm_inst.cu), 0 = one resident wave, n > 0 = n entries per warp
   std::atomic<int> align{-1};  // -1 = per-shape policy, 0 / 1 = off / on

@@ -79,6 +79,17 @@ def _L():
             fn.argtypes = [_vp, _i]
             fn.restype = ip
         L.dbcsr_b200_transpose_panel.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dbcsr_b200_replay_create.argtypes = [_i]
+        L.dbcsr_b200_replay_create.restype = _vp
+        L.dbcsr_b200_replay_destroy.argtypes = [_vp]
+        L.dbcsr_b200_replay_destroy.restype = None
+        L.dbcsr_b200_replay_set_panels.argtypes = [_vp, _i, _vp, _vp]
+        L.dbcsr_b200_replay_add_pull.argtypes = [_vp, _i, _vp, _vp, ctypes.c_size_t]
+        L.dbcsr_b200_replay_add_stack.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i]
+        L.dbcsr_b200_replay_set_c.argtypes = [_vp, _vp, _vp, ctypes.c_size_t, _i]
+        L.dbcsr_b200_replay_current_c.argtypes = [_vp]
+        L.dbcsr_b200_replay_current_c.restype = _vp
+        L.dbcsr_b200_replay_step.argtypes = [_vp, _vp]
         _bound = True
     return L
 
@@ -341,6 +352,44 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class Replay:
+    """One rank's whole Cannon multiply on pre-built device stacks, enqueued by ONE C call per step (include/dbcsr_b200_host.h,
+    dbcsr_b200_replay_*): peer pulls on a side stream, stack kernels on the compute stream, C zeroed once per multiply."""
+
+    def __init__(self, nticks):
+        self.L = _L()
+        self.h = self.L.dbcsr_b200_replay_create(nticks)
+        if not self.h:
+            raise acclib.AccError("dbcsr_b200_replay_create failed")
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise acclib.AccError("dbcsr_b200_replay_%s returned %d" % (what, rc))
+
+    def set_panels(self, tick, a_ptr, b_ptr):
+        self._ck(self.L.dbcsr_b200_replay_set_panels(self.h, tick, a_ptr, b_ptr), "set_panels")
+
+    def add_pull(self, tick, dst_ptr, src_ptr, nbytes):
+        self._ck(self.L.dbcsr_b200_replay_add_pull(self.h, tick, dst_ptr, src_ptr, nbytes), "add_pull")
+
+    def add_stack(self, tick, dev_stack_ptr, size, m, n, k, defined_mnk):
+        self._ck(self.L.dbcsr_b200_replay_add_stack(self.h, tick, dev_stack_ptr, size, m, n, k, 1 if defined_mnk else 0), "add_stack")
+
+    def set_c(self, c0_ptr, c1_ptr, nbytes, zero_overlap=True):
+        self._ck(self.L.dbcsr_b200_replay_set_c(self.h, c0_ptr, c1_ptr, nbytes, 1 if zero_overlap else 0), "set_c")
+
+    def step(self, compute_stream):
+        self._ck(self.L.dbcsr_b200_replay_step(self.h, compute_stream), "step")
+
+    def current_c(self):
+        return self.L.dbcsr_b200_replay_current_c(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.dbcsr_b200_replay_destroy(self.h)
+            self.h = None
 
 
 def transpose_panel(acc, b_list3, k_sizes, n_sizes, b_dev_ptr, stream):

@@ -170,6 +170,24 @@ void dbcsr_b200_engine_stack_info(const dbcsr_b200_engine_t* e, int i, int* info
 const int* dbcsr_b200_engine_stack_host(const dbcsr_b200_engine_t* e, int i); /* 7 ints per entry */
 const int* dbcsr_b200_engine_stack_dev(const dbcsr_b200_engine_t* e, int i);  /* 3 ints per entry, accdrv order */
 
+/* ---- replay of one rank's whole Cannon multiply on PRE-BUILT device stacks (the multi-GPU "stack-kernel only" measurement, cf.
+ * src/acc/acc_bench.c:338-345; schedule from dbcsr_b200/cannon.py, src/mm/dbcsr_mm_cannon.F:839-1771).  Ticks are numbered in the
+ * order the rank takes them.  Per tick: device-to-device copies that fetch the tick's panels from their home ranks (peer memory
+ * mapped by the caller; copy engines, issued on an internal side stream and ordered by events), the panels' device pointers,
+ * and the tick's stacks (device-order int32 triples resident in HBM).  set_c: one or two pooled C buffers of `bytes` bytes;
+ * zero_overlap != 0 with two buffers zeroes the next step's buffer on a side stream while this step's stacks run, else the
+ * buffer is zeroed in line.  replay_step enqueues a whole multiply on `compute_stream` (an acc stream handle) without any host
+ * synchronisation and returns 0 or the negative code of the failing call; replay_current_c = the buffer the last step wrote. */
+typedef struct dbcsr_b200_replay dbcsr_b200_replay_t;
+dbcsr_b200_replay_t* dbcsr_b200_replay_create(int nticks);
+void dbcsr_b200_replay_destroy(dbcsr_b200_replay_t* r);
+int dbcsr_b200_replay_set_panels(dbcsr_b200_replay_t* r, int tick, const void* a_dev, const void* b_dev);
+int dbcsr_b200_replay_add_pull(dbcsr_b200_replay_t* r, int tick, void* dst, const void* src, size_t bytes);
+int dbcsr_b200_replay_add_stack(dbcsr_b200_replay_t* r, int tick, const int* dev_stack, int size, int m, int n, int k, int defined_mnk);
+int dbcsr_b200_replay_set_c(dbcsr_b200_replay_t* r, void* c0, void* c1, size_t bytes, int zero_overlap);
+void* dbcsr_b200_replay_current_c(const dbcsr_b200_replay_t* r);
+int dbcsr_b200_replay_step(dbcsr_b200_replay_t* r, void* compute_stream);
+
 /* acc_transpose_blocks (src/mm/dbcsr_mm_common.F:346-496): in-place transpose of every block of the right panel on the device,
  * one libsmm_acc_transpose call per distinct (k,n) size pair.  b_list3 = (row=k index, col, blk_p). Synchronous w.r.t. `stream`
  * ordering only (no host sync).  scratch_dev must hold nb ints. */

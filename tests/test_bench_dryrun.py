@@ -146,7 +146,7 @@ def test_cannon_bench_main_dry_run():
     args = types.SimpleNamespace(config="cfg2", nblk=40, warmup=3, steps=2, no_e2e=True, no_cpu=True, threads=0, e2e_steps=1, e2e_warmup=1, gpus=1,
                                  no_selfcheck=False, probe_blocks=40)
     out = io.StringIO()
-    env = dict(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    env = dict(RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", DBCSR_B200_REPLAY="py")  # the C replay creates CUDA streams; the Python loop is mocked
     with contextlib.ExitStack() as st:
         for p in _common_patches() + [um.patch.object(torch, "tensor", tensor_cpu), um.patch.object(cannon, "CannonMultiply", CpuCannon),
                                       um.patch.object(dist, "init_process_group", lambda *a, **k: None),

@@ -114,13 +114,12 @@ def test_perf_golden_checksums_on_device(case, backend):
     assert abs(cs_pos / case["checksum_pos"] - 1.0) <= thr, (cs_pos, case["checksum_pos"])
 
 
-@pytest.mark.skipif(os.environ.get("DBCSR_B200_TEST_UNVERIFIED", "0") != "1",
-                    reason="opt-in cooperative DMMA kernel for 33..80 blocks, written without GPU access: run its first device test "
-                           "deliberately (DBCSR_B200_TEST_UNVERIFIED=1, under `timeout`), not as part of the regular suite")
+@pytest.mark.parametrize("bigdmma", [1, 0])
 @pytest.mark.parametrize("mnk", [(33, 33, 33), (45, 67, 78), (80, 80, 80), (64, 40, 72), (40, 17, 7), (9, 80, 33)])
-def test_cooperative_dmma_kernel_for_blocks_33_to_80(backend, mnk):
-    """smm_dmma_big.cuh behind libsmm_acc_b200_set_tunable("bigdmma", 1): same contract as the generic kernel it will replace
-    (return code 10, results within 1e-10 of the oracle; exact on integer inputs), incl. runs, unsorted stacks and odd alignment."""
+def test_cooperative_dmma_kernel_for_blocks_33_to_80(backend, mnk, bigdmma):
+    """smm_dmma_big.cuh (the default for blocks with a dimension in 33..80) and the scalar generic kernel it replaced
+    ("bigdmma" = 0): same contract (return code 10 = untuned, exact on integer inputs), incl. runs, unsorted stacks and odd
+    alignment."""
     from oracle import oracle as orc
     from test_gpu_smm import run_process
 
@@ -132,7 +131,8 @@ def test_cooperative_dmma_kernel_for_blocks_33_to_80(backend, mnk):
     n_a = n_b = 60
     a = rng.integers(0, 4, n_a * m * k).astype(np.float64)
     b = rng.integers(0, 4, n_b * k * n).astype(np.float64)
-    acc.set_tunable("bigdmma", 1)
+    saved = acc.get_tunable("bigdmma")
+    acc.set_tunable("bigdmma", bigdmma)
     try:
         for S, n_c, shuffle, pad in [(1, 1, False, 0), (37, 5, False, 1), (500, 40, False, 0), (300, 7, True, 1)]:
             stack = np.zeros((S, 3), dtype=np.int32)
@@ -146,4 +146,4 @@ def test_cooperative_dmma_kernel_for_blocks_33_to_80(backend, mnk):
             assert rc == 10
             assert np.array_equal(c, c_ref), (mnk, S, float(np.abs(c - c_ref).max()))
     finally:
-        acc.set_tunable("bigdmma", 0)
+        acc.set_tunable("bigdmma", saved)

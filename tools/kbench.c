@@ -219,6 +219,16 @@ int main(int argc, char** argv) {
   CHECK(acc_init());
   void* stream = NULL;
   CHECK(stream_create(&stream, "kbench", 0));
+  /* the sweep stream carries nothing but stack drains between synchronisations: declare it a chain (programmatic dependent launch
+   * without the grid-dependency wait in front of the reads); KBENCH_NO_CHAIN=1 measures the waiting mode instead */
+  {
+    typedef int (*fn_chain)(void*, int);
+    fn_chain chain = acc_lib == lib ? (fn_chain)dlsym(lib, "libsmm_acc_b200_stream_chain") : NULL;
+    const char* nc = getenv("KBENCH_NO_CHAIN");
+    const int on = chain != NULL && !(nc != NULL && nc[0] == '1');
+    if (on) CHECK(chain(stream, 1));
+    printf("kbench: chain mode %s\n", on ? "on" : "off");
+  }
   const size_t a_elems = (size_t)na * bm * bk, b_elems = (size_t)nb * bk * bn;
   const size_t ab_max = a_elems > b_elems ? a_elems : b_elems;
   double* h = (double*)malloc(sizeof(double) * ab_max);
