@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -78,7 +78,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smmax, reasons = [], [], set()
+        sm, smmax, power, reasons = [], [], [], set()
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
@@ -86,13 +86,15 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 smmax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(smmax) if smmax else None,
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_min_mhz_under_load": float(min(load)) if load else None,
+                "sm_max_mhz": max(smmax) if smmax else None, "power_w_max": max(power) if power else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -402,6 +404,7 @@ def measure_fp64_peaks(torch, acc, s):
     """Denominators measured in this run on this GPU: the DMMA.8x8x4 register-operand loop of the library (what the stack kernel's
     pipe can do) and cuBLAS DGEMM 8192^3 through torch.matmul (what NVIDIA's own FP64 GEMM reaches)."""
     dmma = acc.fp64_peak_gflops(s)
+    dmma_sustained = acc.fp64_peak_sustained_gflops(s, 0.4)
     dgemm = None
     try:
         n = 8192
@@ -421,7 +424,7 @@ def measure_fp64_peaks(torch, acc, s):
         torch.cuda.empty_cache()
     except Exception as ex:
         print("bench: cuBLAS DGEMM peak probe failed: %r" % (ex,), file=sys.stderr)
-    return dmma, dgemm
+    return {"dmma_burst": dmma, "dmma_sustained": dmma_sustained, "dgemm": dgemm}
 
 
 def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peaks, ncu_key):
@@ -432,9 +435,15 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
     check = run.selfcheck(n_probe) if n_probe else None
     # how the per-step memset of C is scheduled is the caller's choice (DBCSR zeroes its pooled buffer asynchronously): measure both
     # the overlapped and the in-line variant on three steps each and time the faster one
-    trial_overlap, _ = timed_steps(torch, tstream, acc, s, run.one_step, 3)
-    acc.stream_sync(s)
-    trial_serial, _ = timed_steps(torch, tstream, acc, s, run.one_step_serial, 3)
+    # (interleaved A B A B after the warm-up, so that both see the same clocks: the board's power limit pulls the SM clock down within
+    # ~50 ms of sustained load)
+    trial_overlap, trial_serial = [], []
+    for _ in range(2):
+        t_, _ = timed_steps(torch, tstream, acc, s, run.one_step, 3)
+        trial_overlap += t_
+        run.restore_overlap_state()
+        t_, _ = timed_steps(torch, tstream, acc, s, run.one_step_serial, 3)
+        trial_serial += t_
     zero_mode = "in line on the bench stream" if float(np.mean(trial_serial)) < float(np.mean(trial_overlap)) else "overlapped on a side stream"
     step_fn = run.one_step_serial if zero_mode.startswith("in line") else run.one_step
     run.restore_overlap_state()
@@ -442,12 +451,16 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
     step_ms, t_wall = timed_steps(torch, tstream, acc, s, step_fn, steps)
     launches = acc.launch_count() - launches0
     kern_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 3)
+    # the same drain as a burst: one drain after the device has idled for half a second (clocks back at maximum)
+    time.sleep(0.5)
+    burst_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 1)
     ms_per_step = float(np.mean(step_ms))
     k_ms = float(np.mean(kern_ms))
     value = run.flop / (ms_per_step * 1e-3) * 1e-9
     kernel_only = run.flop / (k_ms * 1e-3) * 1e-9
     hbm_peak, hbm_src = measured_peaks()
-    dmma_peak, dgemm_peak = peaks
+    dmma_peak, dmma_burst, dgemm_peak = peaks["dmma_sustained"], peaks["dmma_burst"], peaks["dgemm"]
+    kernel_burst = run.flop / (float(burst_ms[0]) * 1e-3) * 1e-9
     nst = max(len(run.stacks), 1)
     traffic = None
     ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -465,7 +478,9 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
         "bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4 = mma.sync.m8n8k4.f64; tcgen05 has no f64 kind)",
         "achieved": kernel_only * 1e-3, "peak": dmma_peak * 1e-3, "unit": "TFLOP/s", "frac": kernel_only / dmma_peak if dmma_peak > 0 else None,
         "traffic": traffic,
-        "peak_source": "measured in this run: register-operand DMMA loop of the library (libsmm_acc_b200_fp64_peak_gflops); cuBLAS DGEMM 8192^3 beside it",
+        "peak_source": "measured in this run: register-operand DMMA loop of the library run back to back for 0.4 s (libsmm_acc_b200_fp64_peak_sustained_gflops) -- the kernel is timed inside long steps, under the board's power limit; burst figures and cuBLAS DGEMM 8192^3 beside it",
+        "burst": {"note": "one drain / one peak-probe launch after the device idled (SM clock at maximum)", "kernel_only_gflops": kernel_burst,
+                  "peak_gflops": dmma_burst, "frac": kernel_burst / dmma_burst if dmma_burst > 0 else None},
         "cublas_dgemm_8192_gflops": dgemm_peak,
         "kernel": "smm_dmma_kernel<%d,%d,%d> (dominant of %d launches/step)" % (m0, n0, k0, nst),
         "algorithmic_flop_per_launch": run.flop / nst, "avg_launch_us": launch_us, "kernel_only_gflops": kernel_only,

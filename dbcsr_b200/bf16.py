@@ -26,20 +26,28 @@ class Bf16SpGemm:
         m, n, k = self.m, self.n, self.k
         # ---- FP64 panels -> BF16 operand tiles (one per block, block order = tile order); B is packed straight from its
         #      untransposed k x n column-major blocks: operand row = block column index, element (col, kk) at src[kk + col*k]
-        ta, tb = acc.bf16_rk_tile_bytes(m), acc.bf16_rk_tile_bytes(n)
-        self.a_tiles = acc.dev_alloc(max(A.nblks, 1) * ta)
-        self.b_tiles = acc.dev_alloc(max(B.nblks, 1) * tb)
-        self.h2d_bytes = 0
-        for panel, tiles, rows, rs, ks in ((A, self.a_tiles, m, 1, m), (B, self.b_tiles, n, k, 1)):
+        #      A tiles are stored in block-COLUMN order (slot = rank in (k block, block row) order), B tiles in block-row order at the
+        #      2 KB slot pitch: tiles of blocks that are adjacent in a k block's operand are then adjacent in memory and the kernel
+        #      fetches a run of them with one bulk copy
+        pa, pb = acc.bf16_rk_slot_bytes(m, False), acc.bf16_rk_slot_bytes(n, True)
+        self.a_tiles = acc.dev_alloc(max(A.nblks, 1) * pa)
+        self.b_tiles = acc.dev_alloc(max(B.nblks, 1) * pb)
+        a_slot = np.empty(A.nblks, dtype=np.int32)
+        a_slot[np.lexsort((A.rows, A.cols))] = np.arange(A.nblks, dtype=np.int32)
+        d_slot = acc.to_device(a_slot, stream) if A.nblks else None
+        self.h2d_bytes = a_slot.nbytes
+        for panel, tiles, rows, rs, ks, pitch, slot in ((A, self.a_tiles, m, 1, m, pa, d_slot), (B, self.b_tiles, n, k, 1, pb, None)):
             if panel.nblks:
                 d = acc.to_device(panel.data, stream)
                 self.h2d_bytes += panel.data.nbytes
-                acc.pack_bf16_rk(d.ptr, panel.nblks, rows, k, rs, ks, tiles.ptr, stream)
+                acc.pack_bf16_rk(d.ptr, panel.nblks, rows, k, rs, ks, tiles.ptr, pitch, slot.ptr if slot is not None else None, stream)
                 acc.stream_sync(stream)
                 d.free()
-        # ---- presence maps: tile index of block (rb, kb) of A / (kb, cb) of B, or -1
+        if d_slot is not None:
+            d_slot.free()
+        # ---- presence maps: slot of the tile of block (rb, kb) of A / (kb, cb) of B, or -1
         a_map = np.full((self.nkb, self.nrb), -1, dtype=np.int32)
-        a_map[A.cols - 1, A.rows - 1] = np.arange(A.nblks, dtype=np.int32)
+        a_map[A.cols - 1, A.rows - 1] = a_slot
         b_map = np.full((self.nkb, self.ncb), -1, dtype=np.int32)
         b_map[B.rows - 1, B.cols - 1] = np.arange(B.nblks, dtype=np.int32)
         c_elems = self.nrb * self.ncb * m * n
@@ -60,8 +68,9 @@ class Bf16SpGemm:
         bpt = min(16 // ((m + 7) // 8), 5)
         a_any = np.zeros((self.nkb, (self.nrb + bpt - 1) // bpt), dtype=np.int64)
         np.maximum.at(a_any, (A.cols - 1, (A.rows - 1) // bpt), 1)
-        b_cnt = np.zeros((self.nkb, (self.ncb + 15) // 16), dtype=np.int64)
-        np.add.at(b_cnt, (B.rows - 1, (B.cols - 1) // 16), 1)
+        nb = 15 if acc.get_tunable("bf16_a_tmem") else 16  # block columns per tile (smm_bf16_tiled.cuh)
+        b_cnt = np.zeros((self.nkb, (self.ncb + nb - 1) // nb), dtype=np.int64)
+        np.add.at(b_cnt, (B.rows - 1, (B.cols - 1) // nb), 1)
         self.mma_pairs = int(np.einsum("kr,kc->", a_any, b_cnt))
         self.issued_flop = self.mma_pairs * 2 * 128 * 32 * 32
 

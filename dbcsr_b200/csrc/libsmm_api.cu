@@ -75,6 +75,8 @@ const bool g_tune_env_read = [] {
   if (const char* e = getenv("DBCSR_B200_VARIANT")) smm::g_tune.variant.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BIGDMMA")) smm::g_tune.bigdmma.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_INHOMOGENEOUS")) smm::g_tune.inhomogeneous.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_BF16_MERGE")) smm::g_tune.bf16_merge.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_BF16_A_TMEM")) smm::g_tune.bf16_a_tmem.store(atoi(e));
   return true;
 }();
 
@@ -520,6 +522,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "bigdmma") == 0) smm::g_tune.bigdmma.store((int)value);
   else if (strcmp(name, "inhomogeneous") == 0) smm::g_tune.inhomogeneous.store((int)value);
   else if (strcmp(name, "bf16_merge") == 0) smm::g_tune.bf16_merge.store((int)value);
+  else if (strcmp(name, "bf16_a_tmem") == 0) smm::g_tune.bf16_a_tmem.store((int)value);
   else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
   else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
   else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
@@ -535,6 +538,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "bigdmma") == 0) return smm::g_tune.bigdmma.load();
   if (strcmp(name, "inhomogeneous") == 0) return smm::g_tune.inhomogeneous.load();
   if (strcmp(name, "bf16_merge") == 0) return smm::g_tune.bf16_merge.load();
+  if (strcmp(name, "bf16_a_tmem") == 0) return smm::g_tune.bf16_a_tmem.load();
   if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
   if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
   if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
@@ -606,17 +610,20 @@ double libsmm_acc_b200_fp64_peak_gflops(void* stream) {
 // ---- tiled BF16 SpGEMM (smm_bf16_tiled.cuh): driven by the block index instead of parameter stacks -----------------------------
 int libsmm_acc_b200_bf16_rk_tile_bytes(int rows) { return ((rows + 7) / 8) * 512; }
 
+int libsmm_acc_b200_bf16_rk_slot_bytes(int rows, int b_operand) { return b_operand ? smm::BT_B_SLOT : ((rows + 7) / 8) * 512; }
+
 int libsmm_acc_b200_pack_bf16_rk(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
-                                 void* stream) {
+                                 int dst_pitch, const int* dev_dst_slot, void* stream) {
   if (nblks <= 0) return 0;
   if (stream == nullptr || rows <= 0 || kdim <= 0 || rows > 32 || kdim > 32) return -2;
+  if (dst_pitch < ((rows + 7) / 8) * 512 || dst_pitch % 512 != 0) return -2;
   smm::stream_chain_break(*static_cast<cudaStream_t*>(stream));
   const int wpc = 8;
   int grid = (nblks + wpc - 1) / wpc;
   const int max_grid = num_sms() * 8;
   if (grid > max_grid) grid = max_grid;
   smm::pack_bf16_rk_kernel<<<grid, wpc * 32, 0, *static_cast<cudaStream_t*>(stream)>>>(dev_src, nblks, rows, kdim, row_stride, k_stride,
-                                                                                    static_cast<unsigned char*>(dev_dst));
+                                                                                    static_cast<unsigned char*>(dev_dst), dst_pitch, dev_dst_slot);
   if (cudaPeekAtLastError() != cudaSuccess) return -31;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -632,11 +639,14 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   const smm::BtGeom g = smm::bt_geom(m, n);
   const int smem = (int)smm::bt_smem_bytes(g);
   // "bf16_merge" tunable (default 1): adjacent existing B blocks are multiplied by one wide MMA
-  const int flags = smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0;
+  // "bf16_a_tmem" tunable: stage the A operand in TMEM (15 block columns per tile instead of 16)
+  const int flags = (smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0) |
+                    (smm::g_tune.bf16_a_tmem.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_A_TMEM : 0);
+  const int nb = (flags & smm::BT_FLAG_A_TMEM) ? smm::BT_NB_A_TMEM : smm::BT_NB;
   static SmemAttrCache smem_set;
   if (ensure_smem(smm::smm_bf16_tiled_kernel, smem, smem_set) != 0) return -30;
   const int bpt = g.bpt;
-  const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + smm::BT_NB - 1) / smm::BT_NB;
+  const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + nb - 1) / nb;
   int grid = n_rg * n_cg;
   if (grid > num_sms()) grid = num_sms();
   cudaLaunchConfig_t cfg = {};
@@ -654,6 +664,33 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   if (err != cudaSuccess) return -31;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// Same loop run back to back for `seconds` (power / thermal limits act within tens of milliseconds on a B200: a kernel timed
+// inside a long step has to be compared with THIS figure, a kernel timed alone with the burst figure above): throughput over the
+// second half of the interval.  Synchronises `stream`.
+double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) {
+  if (stream == nullptr || !(seconds > 0.0) || seconds > 10.0) return -2.0;
+  const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
+  const int sms = num_sms(), warps = 16, iters = 4096;
+  const double flop = 2.0 * 8 * 8 * 4 * 9.0 * iters * (double)warps * sms;  // ~1.2 ms per launch at 37 TFLOP/s
+  const int n = (int)(seconds / 1.2e-3) + 2;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -30.0;
+  for (int i = 0; i < n; ++i) {
+    if (i == n / 2) cudaEventRecord(e0, st);
+    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 1.0, 1e-9);
+  }
+  cudaEventRecord(e1, st);
+  double out = -31.0;
+  if (cudaEventSynchronize(e1) == cudaSuccess) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms > 0.f) out = flop * (n - n / 2) / (ms * 1e-3) * 1e-9;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return out;
 }
 
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }

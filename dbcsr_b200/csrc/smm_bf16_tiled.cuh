@@ -18,8 +18,12 @@
 //   * the A operand of a k block is shared by up to 16 MMAs pairs, a B block by 5 block rows: 15.8 KB of L2 traffic per k block
 //     and tile instead of 8 x 5 x 2.2 KB = 90 KB for the same products through the stack kernel;
 //   * warp-specialised, persistent (one CTA per SM, static round-robin over tiles ordered so that the ~148 concurrently running
-//     tiles form a ~12 x 12 patch of the tile grid and share their A/B panels in L2): warp 0 = TMA producer (all lanes: presence
-//     map prefetch, zero-fill, one bulk copy per lane), warp 1 lane 0 = MMA issuer, warps 2-5 = epilogue (tcgen05.ld -> st.global).
+//     tiles form a ~12 x 12 patch of the tile grid and share their A/B panels in L2): warp 0 = TMA producer of the B blocks,
+//     warp 6 = TMA producer of the A blocks (+ zero-fill of absent A slots), warp 1 = MMA issuer (one elected lane), warps 2-5 =
+//     epilogue (tcgen05.ld -> st.global).  The first version had ONE producer warp and one bulk copy per block: ncu showed that
+//     warp executing 259 instructions per k block, 1230 cycles, with the MMA warp waiting for it 40 % of its time -- so the
+//     copies of ADJACENT existing blocks are merged (tiles of adjacent blocks are adjacent in memory: A tiles are packed in
+//     block-column order, B tiles in block-row order at the 2 KB slot pitch) and the work is split over two warps.
 //
 // Operand tile format ("rk", one per block, ROWS <= 32, K padded to 32): element (row, kk) at byte
 //     (row / 8) * 512 + (kk / 8) * 128 + (row % 8) * 16 + (kk % 8) * 2
@@ -36,11 +40,13 @@ namespace smm {
 
 constexpr int BT_STAGES = 5;
 constexpr int BT_NB = 16;            // block columns per tile (TMEM: 16 x 32 columns)
-constexpr int BT_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
+constexpr int BT_THREADS = 224;      // B producer warp, MMA warp, 4 epilogue warps, A producer warp
 constexpr int BT_A_BYTES = 16 * 512; // A operand of one k block: 16 row groups x 4 k groups x 128 B
 constexpr int BT_KC = 8;             // presence-map entries prefetched per lane
 constexpr int BT_B_SLOT = 2048;      // B slot pitch: 32 operand rows (4 row groups), so that adjacent slots form one N = 32 r operand
 constexpr int BT_FLAG_MERGE_RUNS = 1;
+constexpr int BT_FLAG_A_TMEM = 2;     // stage the A operand of every k block in TMEM (tcgen05.cp) and multiply from there
+constexpr int BT_NB_A_TMEM = 15;      // block columns per tile in that mode: 15 x 32 accumulator columns + 2 x 16 columns of A
 
 struct BtGeom {
   int rg_a, rg_b;      // row groups per A / B block
@@ -63,21 +69,22 @@ __host__ __device__ inline BtGeom bt_geom(int m, int n) {
 __host__ __device__ inline size_t bt_smem_bytes(const BtGeom& g) { return 1024 + (size_t)BT_STAGES * g.stage; }
 
 // FP64 block (element (row,kk) at src[row*row_stride + kk*k_stride]) -> BF16 "rk" tile, round to nearest even; one warp per block.
+// Tile of block b goes to dst + slot * pitch, slot = dst_slot[b] (nullptr: b); pitch >= tile size, the gap is zero-filled.
 __global__ void pack_bf16_rk_kernel(const double* __restrict__ src, int nblks, int rows, int kdim, int row_stride, int k_stride,
-                                    unsigned char* __restrict__ dst) {
+                                    unsigned char* __restrict__ dst, int pitch, const int* __restrict__ dst_slot) {
   const int wpc = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rg = (rows + 7) / 8;
-  const int tile_bytes = rg * 512;
-  const int nelem = rg * 256;  // bf16 elements per tile incl. padding
+  const int nelem = pitch / 2;  // bf16 elements per slot incl. padding
   for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
     const double* __restrict__ s = src + (size_t)b * rows * kdim;
-    unsigned short* __restrict__ d = reinterpret_cast<unsigned short*>(dst + (size_t)b * tile_bytes);
+    const int slot = dst_slot != nullptr ? __ldg(dst_slot + b) : b;
+    unsigned short* __restrict__ d = reinterpret_cast<unsigned short*>(dst + (size_t)slot * pitch);
     for (int i = lane; i < nelem; i += 32) {
       const int kk8 = i & 7, r8 = (i >> 3) & 7, kgi = (i >> 6) & 3, rgi = i >> 8;
       const int row = rgi * 8 + r8, kk = kgi * 8 + kk8;
       float v = 0.f;
-      if (row < rows && kk < kdim) v = (float)s[(size_t)row * row_stride + (size_t)kk * k_stride];
+      if (rgi < rg && row < rows && kk < kdim) v = (float)s[(size_t)row * row_stride + (size_t)kk * k_stride];
       unsigned int u = __float_as_uint(v);
       u += 0x7fffu + ((u >> 16) & 1u);
       d[i] = (unsigned short)(u >> 16);
@@ -98,6 +105,23 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// tcgen05.cp: 128 lanes x 256 bit from the shared-memory matrix `desc` (same descriptor format as an MMA operand: 16 row groups
+// at SBO, two 16-byte k chunks at LBO) into TMEM columns [taddr, taddr + 8)
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
+// tcgen05.mma with the A operand in TMEM (M = 128 rows = lanes, K = 16 BF16 = 8 columns), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "setp.ne.b32 p, %4, 0;\n"
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+    "}\n" ::"r"(tmem_d),
+    "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
+
 // tile t -> (row group, column group): panels of BT_PANEL row groups, inside a panel column groups outer, row groups inner, so
 // that gridDim.x consecutive tiles cover about 12 x 12 tiles
 constexpr int BT_PANEL = 12;
@@ -116,10 +140,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   smm_bf16_tiled_kernel(const unsigned char* __restrict__ a_tiles, const int* __restrict__ a_map, const unsigned char* __restrict__ b_tiles,
                         const int* __restrict__ b_map, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb,
                         int m, int n, int flags) {
+  // Block columns per tile.  SS mode: 16 (all 512 TMEM columns are accumulators).  A-in-TMEM mode: 15, the last 32 columns hold
+  // the A operand of the current / next k block: small-N MMAs are bound by re-reading the 128-row A operand from shared memory
+  // for every instruction (ncu: 47 operand wavefronts per M=128 x N=60 MMA, 32 of them A); one tcgen05.cp per 16 k stages it in
+  // TMEM once and every MMA of the stage reads it from there.
+  const int nb = (flags & BT_FLAG_A_TMEM) ? BT_NB_A_TMEM : BT_NB;
   extern __shared__ __align__(1024) unsigned char bt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BtGeom g = bt_geom(m, n);
-  const int n_rg = (nrb + g.bpt - 1) / g.bpt, n_cg = (ncb + BT_NB - 1) / BT_NB;
+  const int n_rg = (nrb + g.bpt - 1) / g.bpt, n_cg = (ncb + nb - 1) / nb;
   const int n_tiles = bt_num_tiles(n_rg, n_cg);
 
   uint64_t* full = reinterpret_cast<uint64_t*>(bt_smem);  // [BT_STAGES]
@@ -139,7 +168,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     *reinterpret_cast<uint4*>(stages + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < BT_STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 2);  // the two producer warps
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
@@ -156,25 +185,29 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
-    // ===================================== TMA producer (whole warp) =====================================
-    // lane l < bpt owns A slot l (bpt <= 5), lane 5 + c owns B slot c
+  if (warp == 0 || warp == 6) {
+    // ===================================== TMA producers (whole warps) =====================================
+    // Both warps read the same presence-map entries (lane l < bpt: A slot l, lane 5 + c: B slot c) and derive identical masks;
+    // warp 6 copies the A blocks and keeps absent A slots zero, warp 0 copies the B blocks and publishes the stage's column mask.
+    const bool a_role = warp == 6;
     const int bpt = g.bpt;
-    const bool is_a = lane < bpt, is_b = lane >= 5 && lane < 5 + BT_NB;
+    const bool is_a = lane < bpt, is_b = lane >= 5 && lane < 5 + nb;
+    const bool mine = a_role ? is_a : is_b;
     uint32_t zero_state = 0;  // bit (5 * stage + slot): A slot is known to hold zeros (everything is zero at start)
-    for (int s = 0; s < BT_STAGES; ++s) zero_state |= 0x1fu << (5 * s);
-    uint32_t it = 0;  // stage use counter (over all tiles)
+    for (int s0 = 0; s0 < BT_STAGES; ++s0) zero_state |= 0x1fu << (5 * s0);
+    int s = 0;
+    uint32_t ph = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       int rg, cg;
       bt_tile_coords(t, n_rg, n_cg, rg, cg);
       // this lane's presence-map column: &map[0 * stride + col]; valid = inside the matrix
-      const int rb = rg * bpt + lane, cb = cg * BT_NB + (lane - 5);
+      const int rb = rg * bpt + lane, cb = cg * nb + (lane - 5);
       const bool valid = is_a ? (rb < nrb) : (is_b ? (cb < ncb) : false);
       const int* __restrict__ mp = is_a ? (a_map + rb) : (b_map + cb);
       const int mstride = is_a ? nrb : ncb;
       const unsigned char* __restrict__ tiles = is_a ? a_tiles : b_tiles;
-      const uint32_t tbytes = is_a ? (uint32_t)g.tile_a : (uint32_t)g.tile_b;
-      const uint32_t slot_off = is_a ? (uint32_t)lane * (uint32_t)g.tile_a : (uint32_t)BT_A_BYTES + (uint32_t)(lane - 5) * (uint32_t)BT_B_SLOT;
+      const uint32_t pitch = is_a ? (uint32_t)g.tile_a : (uint32_t)BT_B_SLOT;  // tile pitch in global AND shared memory
+      const uint32_t slot_off = is_a ? (uint32_t)lane * pitch : (uint32_t)BT_A_BYTES + (uint32_t)(lane - 5) * pitch;
       int cur[BT_KC], nxt[BT_KC];
 #pragma unroll
       for (int j = 0; j < BT_KC; ++j) cur[j] = (valid && j < nkb) ? __ldg(mp + (size_t)j * mstride) : -1;
@@ -184,15 +217,18 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < BT_KC; ++j) {
           if (k0 + j < nkb) {  // warp-uniform
-            const int s = (int)(it % BT_STAGES);
-            const uint32_t ph = (it / BT_STAGES) & 1u;
             const int idx = cur[j];
             const unsigned mask = __ballot_sync(0xffffffffu, idx >= 0);
             const uint32_t am = mask & 0x1fu;
             const uint32_t bm = am != 0 ? ((mask >> 5) & 0xffffu) : 0u;  // no A block in these rows: nothing to multiply
+            // a lane CONTINUES the copy of its left neighbour when both blocks exist and their tiles are adjacent in memory
+            // (never across the A | B boundary): one bulk copy per run instead of one per block
+            const int idx_left = __shfl_up_sync(0xffffffffu, idx, 1);
+            const bool cont = idx >= 0 && idx_left >= 0 && idx == idx_left + 1 && lane != 0 && lane != 5;
+            const unsigned contm = __ballot_sync(0xffffffffu, cont);
             mbar_wait(&empty[s], ph ^ 1u);
             unsigned char* stg = stages + (size_t)s * g.stage;
-            if (bm != 0) {
+            if (a_role && bm != 0) {
               // absent A slots must read as zeros: fill those that held data
               const uint32_t zs = (zero_state >> (5 * s)) & 0x1fu;
               uint32_t fill = ~am & ~zs & ((1u << bpt) - 1u);
@@ -208,13 +244,20 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
               zero_state = (zero_state & ~(0x1fu << (5 * s))) | ((~am & 0x1fu) << (5 * s));
             }
             if (lane == 0) {
-              meta[s] = bm;
-              const uint32_t bytes = bm != 0 ? (uint32_t)__popc(am) * (uint32_t)g.tile_a + (uint32_t)__popc(bm) * (uint32_t)g.tile_b : 0u;
-              mbar_expect_tx(&full[s], bytes);  // the one arrival of this phase; completes when the bytes have landed
+              if (!a_role) meta[s] = bm;
+              const uint32_t bytes = bm == 0 ? 0u : (a_role ? (uint32_t)__popc(am) * (uint32_t)g.tile_a : (uint32_t)__popc(bm) * (uint32_t)BT_B_SLOT);
+              mbar_expect_tx(&full[s], bytes);  // this warp's arrival; the phase completes when both warps' bytes have landed
             }
             __syncwarp();
-            if (bm != 0 && idx >= 0) bulk_g2s(stg + slot_off, tiles + (size_t)idx * tbytes, tbytes, &full[s]);
-            ++it;
+            if (bm != 0 && mine && idx >= 0 && !cont) {
+              const unsigned above = contm >> (lane + 1);  // lanes <= 20
+              const uint32_t len = (uint32_t)__ffs(~above);  // 1 + number of continuing lanes to the right
+              bulk_g2s(stg + slot_off, tiles + (size_t)idx * pitch, len * pitch, &full[s]);
+            }
+            if (++s == BT_STAGES) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
         }
 #pragma unroll
@@ -229,15 +272,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10),[10,13), K-major A and B,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-    const bool merge = (flags & BT_FLAG_MERGE_RUNS) != 0;
-    uint32_t it = 0, tile_no = 0;
+    const bool merge = (flags & BT_FLAG_MERGE_RUNS) != 0, a_tmem = (flags & BT_FLAG_A_TMEM) != 0;
+    uint32_t it = 0, tile_no = 0, ph = 0;
+    int s = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
       mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained the previous tile's accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t inited = 0;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = (int)(it % BT_STAGES);
-        mbar_wait(&full[s], (it / BT_STAGES) & 1u);
+        mbar_wait(&full[s], ph);
         const uint32_t bm = meta[s];
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -245,7 +288,32 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
           const uint64_t adesc0 = umma_desc(sa, 128u, 512u), adesc1 = umma_desc(sa + 256u, 128u, 512u);
           const uint64_t bdesc0 = umma_desc(sa + (uint32_t)BT_A_BYTES, 128u, 512u);
           uint32_t todo = bm;
-          if (merge && (inited & bm) == bm) {
+          if (a_tmem) {
+            // A operand: shared memory -> TMEM once per stage (2 x 128 lanes x 256 bit = k 0..15 | 16..31), double buffered; the
+            // copies and the MMAs execute in issue order, so no barrier is needed between them
+            const uint32_t ta = tmem_base + (uint32_t)(BT_NB_A_TMEM * 32) + 16u * (it & 1u);
+            if (bm != 0) {
+              utccp_128x256b(ta, adesc0);
+              utccp_128x256b(ta + 8u, adesc1);
+            }
+            while (todo != 0) {
+              const int c0 = __ffs(todo) - 1;
+              int r = 1;
+              if (merge) {
+                r = __ffs(~(todo >> c0)) - 1;
+                const uint32_t st = inited >> c0;
+                const int same = (st & 1u) ? (__ffs(~st) - 1) : (st == 0 ? 32 : __ffs(st) - 1);
+                r = min(min(r, same), 8);
+              }
+              const uint32_t idesc = idesc_base | ((uint32_t)(4 * r) << 17);
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)c0 * (uint32_t)(BT_B_SLOT >> 4));
+              const uint32_t d = tmem_base + 32u * (uint32_t)c0;
+              umma_bf16_ts(d, ta, bd, idesc, (inited >> c0) & 1u);
+              umma_bf16_ts(d, ta + 8u, bd + 16u, idesc, 1u);
+              todo &= ~(((1u << r) - 1u) << c0);
+            }
+          }
+          else if (merge && (inited & bm) == bm) {
             // steady state: every touched accumulator is initialised -> runs of adjacent existing blocks, always accumulating
             while (todo != 0) {
               const int c0 = __ffs(todo) - 1;
@@ -281,6 +349,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
         }
         inited |= bm;
         __syncwarp();
+        if (++s == BT_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       if (elect_one()) {
         *tile_inited = inited;
@@ -290,7 +362,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       __syncwarp();
     }
   }
-  else {
+  else if (warp < 6) {
     // ===================================== epilogue (4 warps = 128 TMEM lanes) =====================================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;      // row of the 128-row tile
@@ -305,8 +377,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       mbar_wait(tmem_full, tile_no & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t inited = *tile_inited;
-      for (int c = 0; c < BT_NB; ++c) {
-        const int cb = cg * BT_NB + c;
+      for (int c = 0; c < nb; ++c) {
+        const int cb = cg * nb + c;
         if (cb >= ncb) break;  // warp-uniform
         uint32_t r[32];
         asm volatile(

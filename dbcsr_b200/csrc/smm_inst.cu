@@ -121,13 +121,17 @@ int launch_base(const int* dev_stack, int stack_size, const double* a, const dou
   const int max_grid = g_num_sms * cps;
   // at least 4 entries per warp so that the pipeline prologue and the C flush are amortised
   int grid = (stack_size + WPC * 4 - 1) / (WPC * 4);
+  // chain mode (libsmm_acc_b200_stream_chain): the previous drain of the stream is still running when this one starts
+  const bool chained = g_use_pdl && stream_chain_mode(stream);
   int max_chunk = g_tune.chunk.load(std::memory_order_relaxed);
   if (max_chunk < 0) {
     // per-shape policy: CHUNK entries per warp when that leaves part of the resident wave free for the next launch (programmatic
     // dependent launch) and still gives every SM at least four CTAs (measured on 30000-entry stacks: 625 CTAs = 4.2 per SM);
-    // smaller stacks keep the one-wave split, which spreads them over as many warps as possible
+    // smaller stacks keep the one-wave split, which spreads them over as many warps as possible.  Only in chain mode: a kernel
+    // that waits for its predecessor gains nothing from free CTA slots and wants every slot filled (23^3, 30000 entries, waiting
+    // mode: 37.6 us with the one-wave split, 49.0 us with 12-entry chunks; profiles/r02_kbench_chain_vs_wait.txt)
     max_chunk = 0;
-    if (Policy<M, N, K>::CHUNK > 0 && (long long)Policy<M, N, K>::CHUNK * max_grid * WPC > stack_size &&
+    if (chained && Policy<M, N, K>::CHUNK > 0 && (long long)Policy<M, N, K>::CHUNK * max_grid * WPC > stack_size &&
         4LL * Policy<M, N, K>::CHUNK * g_num_sms * WPC <= stack_size)
       max_chunk = Policy<M, N, K>::CHUNK;
   }
@@ -142,8 +146,7 @@ int launch_base(const int* dev_stack, int stack_size, const double* a, const dou
     extra = stack_size % warps;
   }
   const int align = g_tune.align.load(std::memory_order_relaxed);
-  const int flags = ((align < 0 ? Policy<M, N, K>::ALIGN : align != 0) ? FLAG_ALIGN_RUNS : 0) |
-                    ((g_use_pdl && stream_chain_mode(stream)) ? FLAG_PDL_CHAIN : 0);
+  const int flags = ((align < 0 ? Policy<M, N, K>::ALIGN : align != 0) ? FLAG_ALIGN_RUNS : 0) | (chained ? FLAG_PDL_CHAIN : 0);
   unsigned long long* trace = TRACE ? trace_slot() : nullptr;
   const unsigned long long al = a_limit, bl = b_limit;
   return launch_pdl(kern, grid, WPC * 32, SMEM, stream, dev_stack, stack_size, a, b, c, al, bl, chunk, extra, flags, trace);
@@ -183,7 +186,7 @@ int launch_ws(const int* dev_stack, int stack_size, const double* a, const doubl
 
 // lane-per-element kernel for tiny blocks (smm_tiny.cuh): no shared memory, WPC warps per CTA, one resident wave
 template <int M, int N, int K, int WPC>
-int launch_tiny(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, cudaStream_t stream) {
+int launch_tiny(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, cudaStream_t stream, int policy_chunk = 0) {
   auto kern = smm_tiny_kernel<M, N, K, WPC>;
   static DevCache cache;
   int num_sms = 0;
@@ -192,6 +195,7 @@ int launch_tiny(const int* dev_stack, int stack_size, const double* a, const dou
   if (stack_size <= 0) return 0;
   const int max_warps = num_sms * cps * WPC;
   int chunk = g_tune.chunk.load(std::memory_order_relaxed);
+  if (chunk < 0) chunk = policy_chunk;  // per-shape policy (autotune database)
   if (chunk <= 0) chunk = (stack_size + max_warps - 1) / max_warps;
   if (chunk < 8) chunk = 8;  // amortise the per-warp prologue and the flush of the last run
   const int warps = (stack_size + chunk - 1) / chunk;
@@ -364,7 +368,7 @@ int launch(const int* dev_stack, int stack_size, const double* a, const double* 
   }
 #endif
   if constexpr (Policy<M, N, K>::ALGO == 1 && M * N <= TINY_MAX_MN)
-    return launch_tiny<M, N, K, (Policy<M, N, K>::WPC > 0 ? Policy<M, N, K>::WPC : 8)>(dev_stack, stack_size, a, b, c, stream);
+    return launch_tiny<M, N, K, (Policy<M, N, K>::WPC > 0 ? Policy<M, N, K>::WPC : 8)>(dev_stack, stack_size, a, b, c, stream, Policy<M, N, K>::CHUNK);
   else if constexpr (Policy<M, N, K>::FLUSH == 2 && NST == 1 && SH::STAGE >= scratch_bytes(M, N))
     return launch_base<M, N, K, NST, WPC, 0, false, 2>(dev_stack, stack_size, a, b, c, a_limit, b_limit, stream);
   else

@@ -30,8 +30,8 @@ SMM_SYMBOLS = [
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
     "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
-    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops",
-    "libsmm_acc_b200_bf16_rk_tile_bytes", "libsmm_acc_b200_pack_bf16_rk", "libsmm_acc_b200_bf16_spgemm",
+    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops", "libsmm_acc_b200_fp64_peak_sustained_gflops",
+    "libsmm_acc_b200_bf16_rk_tile_bytes", "libsmm_acc_b200_bf16_rk_slot_bytes", "libsmm_acc_b200_pack_bf16_rk", "libsmm_acc_b200_bf16_spgemm",
 ]
 
 DBCSR_TYPE_REAL_8 = 3
@@ -94,8 +94,11 @@ def load():
     L.libsmm_acc_b200_set_trace.restype = None
     L.libsmm_acc_b200_stream_chain.argtypes = [_vp, _i]
     L.libsmm_acc_b200_bf16_rk_tile_bytes.argtypes = [_i]
-    L.libsmm_acc_b200_pack_bf16_rk.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _vp]
+    L.libsmm_acc_b200_bf16_rk_slot_bytes.argtypes = [_i, _i]
+    L.libsmm_acc_b200_pack_bf16_rk.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]
     L.libsmm_acc_b200_bf16_spgemm.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+    L.libsmm_acc_b200_fp64_peak_sustained_gflops.argtypes = [_vp, ctypes.c_double]
+    L.libsmm_acc_b200_fp64_peak_sustained_gflops.restype = ctypes.c_double
     L.libsmm_acc_b200_fp64_peak_gflops.argtypes = [_vp]
     L.libsmm_acc_b200_fp64_peak_gflops.restype = ctypes.c_double
     L.c_dbcsr_acc_clear_errors.restype = None
@@ -258,8 +261,12 @@ class Acc:
     def bf16_rk_tile_bytes(self, rows):
         return int(self.L.libsmm_acc_b200_bf16_rk_tile_bytes(rows))
 
-    def pack_bf16_rk(self, src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream):
-        _ck(self.L.libsmm_acc_b200_pack_bf16_rk(src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, stream), "pack_bf16_rk")
+    def bf16_rk_slot_bytes(self, rows, b_operand):
+        return int(self.L.libsmm_acc_b200_bf16_rk_slot_bytes(rows, 1 if b_operand else 0))
+
+    def pack_bf16_rk(self, src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, dst_pitch, dst_slot_ptr, stream):
+        _ck(self.L.libsmm_acc_b200_pack_bf16_rk(src_ptr, nblks, rows, kdim, row_stride, k_stride, dst_ptr, dst_pitch, dst_slot_ptr, stream),
+            "pack_bf16_rk")
 
     def bf16_spgemm(self, a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream):
         _ck(self.L.libsmm_acc_b200_bf16_spgemm(a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream),
@@ -268,6 +275,10 @@ class Acc:
     def fp64_peak_gflops(self, stream):
         """Measured DMMA.8x8x4 throughput of this device (register operands), GFLOP/s."""
         return float(self.L.libsmm_acc_b200_fp64_peak_gflops(stream))
+
+    def fp64_peak_sustained_gflops(self, stream, seconds=0.4):
+        """The same loop back to back for `seconds`: throughput over the second half (sustained, under the power limit)."""
+        return float(self.L.libsmm_acc_b200_fp64_peak_sustained_gflops(stream, float(seconds)))
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())

@@ -77,16 +77,22 @@ int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kd
   void* stream);
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim);
 /* Tiled BF16 SpGEMM (dbcsr_b200/csrc/smm_bf16_tiled.cuh; BASELINE config 4): for dense-ish products the multiply is driven by the
- * block index instead of parameter stacks.  pack_bf16_rk converts nblks FP64 blocks (addressing as in pack_bf16) into BF16 "rk"
- * operand tiles of libsmm_acc_b200_bf16_rk_tile_bytes(rows) bytes (K padded to 32).  bf16_spgemm computes, for every block row rb <
- * nrb and block column cb < ncb with dev_c_off[rb*ncb + cb] >= 0, the FP32 block C(rb,cb) = sum over kb < nkb of A(rb,kb) * B(kb,cb)
- * (m x n column-major at element offset dev_c_off[..]; blocks with no contribution are written as zeros; C is OVERWRITTEN, it need not be
- * zeroed), where dev_a_map[kb*nrb + rb] / dev_b_map[kb*ncb + cb] is the index of the packed tile of A(rb,kb) (rows = m, kdim = k) /
- * of B(kb,cb) TRANSPOSED (rows = n, kdim = k) in a_tiles / b_tiles, or -1 for an absent block.  All block rows have m, all block columns
- * n, all k blocks k elements; m, n, k <= 32 (else -10, nothing enqueued).  Asynchronous on `stream`. */
+ * block index instead of parameter stacks.
+ * pack_bf16_rk converts nblks FP64 blocks (addressing as in pack_bf16) into BF16 "rk" operand tiles (K padded to 32): the tile of block b
+ *   goes to dev_dst + slot * dst_pitch with slot = dev_dst_slot[b] (NULL: b); dst_pitch = libsmm_acc_b200_bf16_rk_slot_bytes(rows,
+ *   b_operand) (A operand: the tile size ceil(rows/8)*512; B operand: 2048), the gap behind a tile is zero-filled.
+ *   Tiles of blocks that are adjacent in the operand should be adjacent in memory (the kernel then fetches them with one copy): A tiles in
+ *   block-COLUMN order (slot = rank of the block in (k block, block row) order), B tiles in block-row order (= BCSR order, NULL).
+ * bf16_spgemm computes, for every block row rb < nrb and block column cb < ncb with dev_c_off[rb*ncb + cb] >= 0, the FP32 block
+ *   C(rb,cb) = sum over kb < nkb of A(rb,kb) * B(kb,cb) (m x n column-major at element offset dev_c_off[..]; blocks with no contribution are
+ *   written as zeros; C is OVERWRITTEN, it need not be zeroed), where dev_a_map[kb*nrb + rb] / dev_b_map[kb*ncb + cb] is the SLOT of the
+ *   packed tile of A(rb,kb) (rows = m, kdim = k) / of B(kb,cb) TRANSPOSED (rows = n, kdim = k) in a_tiles / b_tiles, or -1 for an absent
+ *   block.  All block rows have m, all block columns n, all k blocks k elements; m, n, k <= 32 (else -10, nothing enqueued).
+ *   Asynchronous on `stream`. */
 int libsmm_acc_b200_bf16_rk_tile_bytes(int rows);
+int libsmm_acc_b200_bf16_rk_slot_bytes(int rows, int b_operand);
 int libsmm_acc_b200_pack_bf16_rk(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,
-  void* stream);
+  int dst_pitch, const int* dev_dst_slot, void* stream);
 int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const void* b_tiles, const int* dev_b_map, float* dev_c,
   const int* dev_c_off, int nrb, int ncb, int nkb, int m, int n, int k, void* stream);
 /* Which kernel would libsmm_acc_process use for (m,n,k)?  0 = none, 1 = specialised DMMA kernel, 2 = generic kernel, 3 = BF16 tcgen05. */
@@ -109,6 +115,9 @@ int libsmm_acc_b200_stream_chain(void* stream, int on);
 /* Measured FP64 tensor-pipe (DMMA.8x8x4, register operands) throughput of the active device in GFLOP/s; synchronises `stream`.
  * Introspection for roofline reports (bench.py); <= 0 on failure. */
 double libsmm_acc_b200_fp64_peak_gflops(void* stream);
+/* The same loop run back to back for `seconds` (0 < seconds <= 10): throughput over the second half -- the denominator for a kernel
+ * timed inside a long step (power limits act within tens of milliseconds). */
+double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds);
 /* Library identification string (static storage). */
 const char* libsmm_acc_b200_version(void);
 

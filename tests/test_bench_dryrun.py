@@ -84,8 +84,14 @@ class FakeAcc:
     def fp64_peak_gflops(self, s):
         return 37000.0
 
+    def fp64_peak_sustained_gflops(self, s, seconds=0.4):
+        return 33000.0
+
     def bf16_rk_tile_bytes(self, rows):
         return (rows + 7) // 8 * 512
+
+    def bf16_rk_slot_bytes(self, rows, b_operand):
+        return 2048 if b_operand else (rows + 7) // 8 * 512
 
     def __getattr__(self, name):  # stream_sync, memset_zero, event_record, stream_wait_event, stream_destroy, ...
         return lambda *a, **k: None

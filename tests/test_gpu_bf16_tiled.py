@@ -74,8 +74,23 @@ def run_case(acc, nrb, ncb, nkb, m, n, k, occ_a, occ_b, seed, knock_out=False):
     return err, err_r
 
 
+# kernel modes (run-time tunables, dbcsr_b200/csrc/smm_tune.h): one MMA per existing B block / per run of adjacent blocks, A operand
+# read from shared memory by every MMA / staged once per k block in TMEM (tcgen05.cp)
+MODES = [dict(bf16_merge=1, bf16_a_tmem=0), dict(bf16_merge=0, bf16_a_tmem=0), dict(bf16_merge=1, bf16_a_tmem=1), dict(bf16_merge=0, bf16_a_tmem=1)]
+
+
+@pytest.fixture(params=MODES, ids=lambda m: "merge%d_atmem%d" % (m["bf16_merge"], m["bf16_a_tmem"]))
+def mode(acc, request):
+    saved = {k: acc.get_tunable(k) for k in request.param}
+    for k, v in request.param.items():
+        acc.set_tunable(k, v)
+    yield request.param
+    for k, v in saved.items():
+        acc.set_tunable(k, v)
+
+
 @pytest.mark.parametrize("shape", [(5, 16, 4), (1, 1, 1), (7, 19, 9), (23, 40, 31), (64, 64, 64), (3, 70, 2)])
-def test_tiled_bf16_23_blocks(acc, shape):
+def test_tiled_bf16_23_blocks(acc, mode, shape):
     nrb, ncb, nkb = shape
     err, err_r = run_case(acc, nrb, ncb, nkb, 23, 23, 23, 0.5, 0.5, seed=11 + nrb)
     assert err <= 1e-3, err      # north_star tolerance for BF16
@@ -83,16 +98,19 @@ def test_tiled_bf16_23_blocks(acc, shape):
 
 
 @pytest.mark.parametrize("occ", [0.02, 0.1, 1.0])
-def test_tiled_bf16_occupations_and_empty_rows(acc, occ):
+def test_tiled_bf16_occupations_and_empty_rows(acc, mode, occ):
     err, err_r = run_case(acc, 33, 37, 29, 23, 23, 23, occ, occ, seed=3, knock_out=True)
     assert err <= 1e-3 and err_r <= 5e-6, (err, err_r)
 
 
 @pytest.mark.parametrize("mnk", [(5, 5, 5), (13, 13, 13), (26, 26, 26), (32, 32, 32), (23, 5, 32), (13, 32, 5), (8, 16, 16), (1, 1, 1), (24, 24, 24)])
-def test_tiled_bf16_block_sizes(acc, mnk):
+def test_tiled_bf16_block_sizes(acc, mode, mnk):
     m, n, k = mnk
     err, err_r = run_case(acc, 21, 35, 17, m, n, k, 0.4, 0.6, seed=5)
-    assert err <= 1e-3 and err_r <= 5e-6, (mnk, err, err_r)
+    # 1e-3 is the tolerance of the 23x23x23 configuration, where a C element averages the BF16 rounding of 23 x ~250 terms; a C
+    # element of 1x1 blocks sums ~4 products, each off by up to 2^-8 relative (two operands rounded to 8 mantissa bits)
+    tol = 1e-3 if k >= 13 else 4e-3
+    assert err <= tol and err_r <= 5e-6, (mnk, err, err_r)
 
 
 def test_tiled_bf16_rejects_large_blocks(acc):
