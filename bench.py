@@ -78,7 +78,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smmax, power, reasons = [], [], [], set()
+        sm, smmax, power, reasons, trace = [], [], [], set(), []
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
@@ -87,6 +87,7 @@ class ClockSampler:
                 sm.append(float(f[1]))
                 smmax.append(float(f[2]))
                 power.append(float(f[3]))
+                trace.append([float(f[1]), float(f[3])])
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -95,7 +96,8 @@ class ClockSampler:
         load = [s for s in sm if s > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": float(np.median(load)) if load else None, "sm_min_mhz_under_load": float(min(load)) if load else None,
                 "sm_max_mhz": max(smmax) if smmax else None, "power_w_max": max(power) if power else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "trace_every_20ms_sm_mhz_power_w": trace[::max(1, len(trace) // 60)]}
 
 
 def algorithmic_bytes(stacks):
@@ -274,10 +276,17 @@ class Fp64Run:
     """One FP64 config on one GPU: stacks pre-built (one host thread = the reference's traversal order) and resident, panels
     resident, drained through libsmm_acc_process."""
 
-    def __init__(self, acc, cfg_name, nblk, s):
+    def __init__(self, acc, cfg_name, nblk, s, nstreams=1):
         from dbcsr_b200 import host, workload
 
         self.acc, self.s = acc, s
+        # further streams for the drain (stack i runs on stream i mod nstreams): DBCSR drives one stream per OpenMP thread, so stacks
+        # of different threads overlap on the device; 1 = everything on the bench stream (the headline configuration)
+        self.side = [acc.stream_create("bench side %d" % i, 0) for i in range(1, nstreams)]
+        for st_ in self.side:
+            acc.stream_chain(st_, True)
+        self.ev_fork = acc.event_create()
+        self.ev_join = [acc.event_create() for _ in self.side]
         self.w = w = workload.make_config(cfg_name, nblk=nblk)
         A, B, bs = w["A"], w["B"], w["m_sizes"]
         self.n_st = 3 if len(w["sizes"]) <= 3 else len(w["sizes"])
@@ -309,21 +318,37 @@ class Fp64Run:
         acc.event_record(self.ev_zero[0], self.zs)
         acc.event_record(self.ev_free[1], s)
         self.step_no = 0
+        self.trickle_ctas = 8
 
     def drain(self, d_c):
         acc, s = self.acc, self.s
+        streams = [s] + self.side
+        if self.side:  # fork: the side streams start behind everything enqueued on the bench stream so far
+            acc.event_record(self.ev_fork, s)
+            for st_ in self.side:
+                acc.stream_wait_event(st_, self.ev_fork)
         for i, st in enumerate(self.stacks):
+            q = streams[i % len(streams)]
             rc = acc.process(None, self.d_st.ptr + 4 * int(self.offs[i]), st["dev"].shape[0], self.d_a.ptr, self.d_b.ptr, d_c.ptr, st["max_m"],
-                             st["max_n"], st["max_k"], st["defined_mnk"], s, s)
+                             st["max_n"], st["max_k"], st["defined_mnk"], q, q)
             if rc < 0:
                 raise RuntimeError("libsmm_acc_process returned %d for stack %d" % (rc, i))
+        for st_, ev in zip(self.side, self.ev_join):  # join
+            acc.event_record(ev, st_)
+            acc.stream_wait_event(s, ev)
 
-    def one_step(self):
+    def one_step_trickle(self):
+        self.one_step(trickle=True)
+
+    def one_step(self, trickle=False):
         acc, s, zs = self.acc, self.s, self.zs
         k = self.step_no % 2
         self.step_no += 1
         acc.stream_wait_event(zs, self.ev_free[1 - k])     # the other buffer's last reader (step k-1) has finished
-        acc.memset_zero(self.d_cs[1 - k], zs)
+        if trickle:  # the same zeros written by a handful of CTAs over the length of the drain instead of one burst
+            acc.memset_zero_trickle(self.d_cs[1 - k], zs, nctas=self.trickle_ctas)
+        else:
+            acc.memset_zero(self.d_cs[1 - k], zs)
         acc.event_record(self.ev_zero[1 - k], zs)
         acc.stream_wait_event(s, self.ev_zero[k])          # zeroed during the previous step
         self.drain(self.d_cs[k])
@@ -384,6 +409,9 @@ class Fp64Run:
         for d in (self.d_a, self.d_b, self.d_st):
             d.free()
         self.acc.stream_destroy(self.zs)
+        for st_ in self.side:
+            self.acc.stream_chain(st_, False)
+            self.acc.stream_destroy(st_)
 
 
 def timed_steps(torch, tstream, acc, s, fn, steps):
@@ -437,15 +465,17 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
     # the overlapped and the in-line variant on three steps each and time the faster one
     # (interleaved A B A B after the warm-up, so that both see the same clocks: the board's power limit pulls the SM clock down within
     # ~50 ms of sustained load)
-    trial_overlap, trial_serial = [], []
+    modes = {"overlapped on a side stream (cudaMemsetAsync)": run.one_step, "overlapped on a side stream at a bounded rate (8 CTAs)": run.one_step_trickle,
+             "in line on the bench stream": run.one_step_serial}
+    trials = {name: [] for name in modes}
     for _ in range(2):
-        t_, _ = timed_steps(torch, tstream, acc, s, run.one_step, 3)
-        trial_overlap += t_
-        run.restore_overlap_state()
-        t_, _ = timed_steps(torch, tstream, acc, s, run.one_step_serial, 3)
-        trial_serial += t_
-    zero_mode = "in line on the bench stream" if float(np.mean(trial_serial)) < float(np.mean(trial_overlap)) else "overlapped on a side stream"
-    step_fn = run.one_step_serial if zero_mode.startswith("in line") else run.one_step
+        for name, fn in modes.items():
+            t_, _ = timed_steps(torch, tstream, acc, s, fn, 3)
+            trials[name] += t_
+            run.restore_overlap_state()
+    trial_ms = {name: float(np.mean(v)) for name, v in trials.items()}
+    zero_mode = min(trial_ms, key=trial_ms.get)
+    step_fn = modes[zero_mode]
     run.restore_overlap_state()
     launches0 = acc.launch_count()
     step_ms, t_wall = timed_steps(torch, tstream, acc, s, step_fn, steps)
@@ -494,7 +524,7 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
                                   "achieved": traffic / (launch_us * 1e-6) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                                   "frac": traffic / (launch_us * 1e-6) * 1e-9 / hbm_peak} if traffic else None)}}
     return {"value": value, "ms_per_step": ms_per_step, "kernel_only_gflops": kernel_only, "launches": int(launches), "wall_s": t_wall, "roofline": roofline,
-            "zero_mode": zero_mode, "zero_mode_trial_ms": {"overlapped": float(np.mean(trial_overlap)), "in_line": float(np.mean(trial_serial))},
+            "zero_mode": zero_mode, "zero_mode_trial_ms": trial_ms,
             "selfcheck": check, "products": run.n_entries, "flop": run.flop, "stacks": len(run.stacks), "c_blocks": int(run.c_rows.size)}
 
 
@@ -659,11 +689,11 @@ def run_single(args):
     extra = {}
     if args.config == "cfg2" and not args.no_extra and (args.nblk is None or args.extra_nblk is not None):
         try:
-            r3 = Fp64Run(acc, "cfg3", args.extra_nblk, s)
+            r3 = Fp64Run(acc, "cfg3", args.extra_nblk, s, nstreams=args.cfg3_streams)
             rep3 = fp64_config_report(torch, tstream, acc, s, r3, max(3, args.steps // 2), 3, 0 if args.no_selfcheck else args.probe_blocks, peaks, "cfg3")
             extra["cfg3"] = {"metric": METRIC_NAMES["cfg3"], "value": rep3["value"], "unit": "GFLOP/s", "ms_per_step": rep3["ms_per_step"], "dtype": "f64",
                              "kernel_only_gflops": rep3["kernel_only_gflops"], "config": workload_config(r3.w, {"products": rep3["products"], "flop": rep3["flop"],
-                                                                                                           "stacks": rep3["stacks"]}),
+                                                                                                           "stacks": rep3["stacks"], "streams": args.cfg3_streams}),
                              "gpu_launches": rep3["launches"], "roofline": rep3["roofline"], "selfcheck": rep3["selfcheck"], "zero_mode": rep3["zero_mode"]}
             r3.close()
         except Exception as ex:
@@ -715,6 +745,7 @@ def main():
     ap.add_argument("--no-selfcheck", action="store_true", help="skip the full-size sum(C) / probed-block check before the timed region")
     ap.add_argument("--probe-blocks", type=int, default=1000, help="random C blocks checked element-wise against the oracle in the self-check")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs legs (cfg3, cfg4 at full size)")
+    ap.add_argument("--cfg3-streams", type=int, default=4, help="streams the 125 stacks of the cfg3 extra config are spread over (DBCSR: one per OpenMP thread)")
     ap.add_argument("--extra-nblk", type=int, default=None, help="block-grid size of the extra_configs legs (default: the full 1000)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels-on-this-GPU leg")
     ap.add_argument("--no-chain", action="store_true", help="do not declare the bench stream a chain of independent drains (every kernel waits for its predecessor)")

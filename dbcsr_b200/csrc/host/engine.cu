@@ -983,10 +983,10 @@ const int* dbcsr_b200_engine_stack_dev(const dbcsr_b200_engine_t* e, int i) {
   return r ? r->dev.data() : nullptr;
 }
 
-int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
-                               void* scratch_dev, void* stream) {
+static int transpose_panel_impl(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+                                void* scratch_dev, float* dev_norms, void* stream) {
   // group the blocks by (k,n) size pair, 0-based offsets (blk_p - 1), one transpose stack per pair
-  // (src/mm/dbcsr_mm_common.F:346-496)
+  // (src/mm/dbcsr_mm_common.F:346-496); with dev_norms the second half of the scratch carries the list position of every block
   if (nb <= 0) return 0;
   std::vector<int> order((size_t)nb);
   for (int i = 0; i < nb; ++i) order[(size_t)i] = i;
@@ -996,19 +996,41 @@ int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, c
   };
   std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key(x) < key(y); });
   for (int i = 0; i < nb; ++i) scratch_host[i] = b_list3[3 * (size_t)order[(size_t)i] + 2] - 1;
-  if (c_dbcsr_acc_memcpy_h2d(scratch_host, scratch_dev, sizeof(int) * (size_t)nb, stream) != 0) return -1;
+  const bool fused = dev_norms != nullptr;
+  if (fused)
+    for (int i = 0; i < nb; ++i) scratch_host[(size_t)nb + i] = order[(size_t)i];
+  if (c_dbcsr_acc_memcpy_h2d(scratch_host, scratch_dev, sizeof(int) * (size_t)nb * (fused ? 2 : 1), stream) != 0) return -1;
+  const int* d_offs = static_cast<const int*>(scratch_dev);
   int start = 0;
   while (start < nb) {
     int end = start;
     const long long k0 = key(order[(size_t)start]);
     while (end < nb && key(order[(size_t)end]) == k0) ++end;
     const int k = (int)(k0 >> 32), n = (int)(k0 & 0xffffffff);
-    const int rc = libsmm_acc_transpose(static_cast<const int*>(scratch_dev), start, end - start, b_dev, dbcsr_type_real_8, k, n,
-                                        kMaxKernelDim, stream);
+    int rc;
+    if (fused && k <= kMaxKernelDim && n <= kMaxKernelDim) {
+      rc = libsmm_acc_b200_transpose_norms(d_offs, d_offs + nb, start, end - start, static_cast<double*>(b_dev), k, n, kMaxKernelDim, dev_norms,
+                                           stream);
+    }
+    else {
+      rc = libsmm_acc_transpose(d_offs, start, end - start, b_dev, dbcsr_type_real_8, k, n, kMaxKernelDim, stream);
+      if (rc == 0 && fused) rc = -3;  // blocks above max_kernel_dim are not transposed: the caller computes their norms separately
+    }
     if (rc != 0) return rc;
     start = end;
   }
   return 0;
+}
+
+int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+                               void* scratch_dev, void* stream) {
+  return transpose_panel_impl(b_list3, nb, k_sizes, n_sizes, b_dev, scratch_host, scratch_dev, nullptr, stream);
+}
+
+int dbcsr_b200_transpose_panel_norms(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+                                     void* scratch_dev, float* dev_norms, void* stream) {
+  if (dev_norms == nullptr) return -2;
+  return transpose_panel_impl(b_list3, nb, k_sizes, n_sizes, b_dev, scratch_host, scratch_dev, dev_norms, stream);
 }
 
 }  // extern "C"

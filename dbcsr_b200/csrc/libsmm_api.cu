@@ -479,6 +479,15 @@ bool all_types_enabled() {
   return v;
 }
 
+// Zeroing at a bounded rate: `gridDim.x` CTAs (a handful) stream 16-byte zero stores over the range.  cudaMemsetAsync zeroes a
+// 4 GB buffer in under a millisecond -- and for that millisecond takes most of the HBM bandwidth away from stack kernels running
+// beside it; a caller that zeroes the NEXT multiply's C buffer while this multiply's stacks run (bench.py, cannon replay) wants the
+// same bytes spread over the whole multiply instead.
+__global__ void __launch_bounds__(1024) zero_trickle_kernel(uint4* __restrict__ p, size_t n16) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stcs(p + i, z);
+}
+
 // Register-only DMMA.8x8x4 loop: the FP64 tensor-pipe peak of THIS device, measured in place so that roofline fractions have a
 // live denominator (bench.py).  9 independent accumulator pairs per warp like the 23^3 kernel's 3 x 3 tiles.
 __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double x, double y) {
@@ -579,6 +588,17 @@ int libsmm_acc_b200_stream_chain(void* stream, int on) {
 }
 
 void libsmm_acc_b200_set_trace(void* dev_words) { smm::g_tune.trace.store(static_cast<unsigned long long*>(dev_words)); }
+
+// memset_zero at a bounded rate (see zero_trickle_kernel): `nctas` CTAs of 1024 threads; offset and nbytes multiples of 16.
+int libsmm_acc_b200_memset_zero_trickle(void* dev_mem, size_t offset, size_t nbytes, int nctas, void* stream) {
+  if (nbytes == 0) return 0;
+  if (dev_mem == nullptr || stream == nullptr || nctas < 1 || (offset & 15) != 0 || (nbytes & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(dev_mem) & 15) != 0)
+    return -2;
+  zero_trickle_kernel<<<nctas, 1024, 0, *static_cast<cudaStream_t*>(stream)>>>(reinterpret_cast<uint4*>(static_cast<char*>(dev_mem) + offset),
+                                                                            nbytes / 16);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -31;
+}
 
 // Measured FP64 tensor-pipe (DMMA.8x8x4) throughput of the active device in GFLOP/s: 16 warps per SM, register operands, best of
 // three timed launches on `stream` (synchronises it).  Returns <= 0 on failure.  Introspection only: not on any product path.
@@ -798,6 +818,28 @@ int libsmm_acc_process(const int* host_param_stack, const int* dev_param_stack, 
   return rc == 0 ? 10 : rc;  // 10 = "ran with an untuned kernel" (reference: libsmm_acc.cpp:319)
 }
 
+namespace {
+int launch_transpose_f64(const int* dev_trs_stack, int stack_size, double* data, int m, int n, const int* dev_trs_blk, float* dev_norms,
+                         void* stream) {
+  if (stream == nullptr) return -2;
+  const size_t blk_bytes = (size_t)m * n * sizeof(double);
+  int wpc = (int)((96 * 1024) / blk_bytes);
+  if (wpc > 8) wpc = 8;
+  if (wpc < 1) return -3;  // cannot happen for m,n <= 80 (51 KB)
+  const size_t smem = blk_bytes * wpc;
+  static SmemAttrCache attr_set;
+  if (ensure_smem(smm::transpose_kernel, (int)smem, attr_set) != 0) return -30;
+  int grid = (stack_size + wpc - 1) / wpc;
+  const int max_grid = num_sms() * 8;
+  if (grid > max_grid) grid = max_grid;
+  smm::transpose_kernel<<<grid, wpc * 32, smem, *static_cast<cudaStream_t*>(stream)>>>(dev_trs_stack, stack_size, data, m, n, dev_trs_blk,
+                                                                                        dev_norms);
+  if (cudaPeekAtLastError() != cudaSuccess) return -31;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+}  // namespace
+
 int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, void* dev_data, libsmm_acc_data_t datatype, int m,
                          int n, int max_kernel_dim, void* stream) {
   if (m > max_kernel_dim || n > max_kernel_dim) return 0;    // reference: libsmm_acc.cpp:485
@@ -818,22 +860,21 @@ int libsmm_acc_transpose(const int* dev_trs_stack, int offset, int stack_size, v
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
     return rc;
   }
-  if (stream == nullptr) return -2;
-  const size_t blk_bytes = (size_t)m * n * sizeof(double);
-  int wpc = (int)((96 * 1024) / blk_bytes);
-  if (wpc > 8) wpc = 8;
-  if (wpc < 1) return -3;  // cannot happen for m,n <= 80 (51 KB)
-  const size_t smem = blk_bytes * wpc;
-  static SmemAttrCache attr_set;
-  if (ensure_smem(smm::transpose_kernel, (int)smem, attr_set) != 0) return -30;
-  int grid = (stack_size + wpc - 1) / wpc;
-  const int max_grid = num_sms() * 8;
-  if (grid > max_grid) grid = max_grid;
-  smm::transpose_kernel<<<grid, wpc * 32, smem, *static_cast<cudaStream_t*>(stream)>>>(dev_trs_stack + offset, stack_size,
-                                                                                        static_cast<double*>(dev_data), m, n);
-  if (cudaPeekAtLastError() != cudaSuccess) return -31;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return 0;
+  return launch_transpose_f64(dev_trs_stack + offset, stack_size, static_cast<double*>(dev_data), m, n, nullptr, nullptr, stream);
+}
+
+// Transpose + block norms in ONE pass over the right panel: like libsmm_acc_transpose for real_8, and in
+// addition dev_norms[dev_trs_blk[i]] = sum of squares of block i (float, what c_calculate_norms computes), for every
+// i in [offset, offset + stack_size).  Blocks with a dimension above max_kernel_dim are not transposed by DBCSR: -3, nothing done
+// (use c_calculate_norms for those).
+int libsmm_acc_b200_transpose_norms(const int* dev_trs_stack, const int* dev_trs_blk, int offset, int stack_size, double* dev_data, int m,
+                                    int n, int max_kernel_dim, float* dev_norms, void* stream) {
+  if (m > max_kernel_dim || n > max_kernel_dim) return -3;
+  if (stack_size <= 0 || m <= 0 || n <= 0) return 0;
+  if (stream == nullptr || dev_norms == nullptr) return -2;
+  smm::stream_chain_break(*static_cast<cudaStream_t*>(stream));
+  return launch_transpose_f64(dev_trs_stack + offset, stack_size, dev_data, m, n, dev_trs_blk != nullptr ? dev_trs_blk + offset : nullptr,
+                              dev_norms, stream);
 }
 
 int c_calculate_norms(const double* mat, int nblks, const int* offsets, const int* nelems, float* norms, void* stream_ptr) {

@@ -190,7 +190,11 @@ __global__ void __launch_bounds__(GEN_WPC * 32) smm_generic_kernel(const int* __
 
 // In-place transpose of m x n col-major blocks (result n x m col-major): out[i] = in[(i % n) * m + i / n].
 // One warp per block, grid-stride; the block is parked in the warp's slice of dynamic shared memory.
-__global__ void transpose_kernel(const int* __restrict__ trs_stack, int nblks, double* __restrict__ data, int m, int n) {
+// Fused norms (norms != nullptr): while the block sits in shared memory its sum of squares is reduced and stored as float at
+// norms[trs_blk[b]] (trs_blk: position of the block in the panel's list; nullptr = b) -- what c_calculate_norms would compute in
+// a second pass over the panel (src/acc/cuda_hip/calculate_norms.cpp:48-96); the transpose does not change a block's norm.
+__global__ void transpose_kernel(const int* __restrict__ trs_stack, int nblks, double* __restrict__ data, int m, int n,
+                                 const int* __restrict__ trs_blk, float* __restrict__ norms) {
   extern __shared__ double tr_smem[];
   const int wpc = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,11 +202,21 @@ __global__ void transpose_kernel(const int* __restrict__ trs_stack, int nblks, d
   double* buf = tr_smem + (size_t)warp * mn;
   for (int b = blockIdx.x * wpc + warp; b < nblks; b += gridDim.x * wpc) {
     double* blk = data + __ldg(trs_stack + b);
-    for (int i = lane; i < mn; i += 32) buf[i] = blk[i];
+    double ss = 0.0;
+    for (int i = lane; i < mn; i += 32) {
+      const double v = blk[i];
+      buf[i] = v;
+      ss = fma(v, v, ss);
+    }
     __syncwarp();
     for (int i = lane; i < mn; i += 32) {
       const int r_out = i % n, c_out = i / n;
       blk[i] = buf[r_out * m + c_out];
+    }
+    if (norms != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) norms[trs_blk != nullptr ? __ldg(trs_blk + b) : b] = (float)ss;
     }
     __syncwarp();
   }

@@ -79,6 +79,7 @@ def _L():
             fn.argtypes = [_vp, _i]
             fn.restype = ip
         L.dbcsr_b200_transpose_panel.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        L.dbcsr_b200_transpose_panel_norms.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.dbcsr_b200_replay_create.argtypes = [_i]
         L.dbcsr_b200_replay_create.restype = _vp
         L.dbcsr_b200_replay_destroy.argtypes = [_vp]

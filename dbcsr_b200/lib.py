@@ -31,6 +31,7 @@ SMM_SYMBOLS = [
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
     "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
     "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops", "libsmm_acc_b200_fp64_peak_sustained_gflops",
+    "libsmm_acc_b200_memset_zero_trickle", "libsmm_acc_b200_transpose_norms",
     "libsmm_acc_b200_bf16_rk_tile_bytes", "libsmm_acc_b200_bf16_rk_slot_bytes", "libsmm_acc_b200_pack_bf16_rk", "libsmm_acc_b200_bf16_spgemm",
 ]
 
@@ -97,6 +98,8 @@ def load():
     L.libsmm_acc_b200_bf16_rk_slot_bytes.argtypes = [_i, _i]
     L.libsmm_acc_b200_pack_bf16_rk.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]
     L.libsmm_acc_b200_bf16_spgemm.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
+    L.libsmm_acc_b200_memset_zero_trickle.argtypes = [_vp, _sz, _sz, _i, _vp]
+    L.libsmm_acc_b200_transpose_norms.argtypes = [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]
     L.libsmm_acc_b200_fp64_peak_sustained_gflops.argtypes = [_vp, ctypes.c_double]
     L.libsmm_acc_b200_fp64_peak_sustained_gflops.restype = ctypes.c_double
     L.libsmm_acc_b200_fp64_peak_gflops.argtypes = [_vp]
@@ -271,6 +274,13 @@ class Acc:
     def bf16_spgemm(self, a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream):
         _ck(self.L.libsmm_acc_b200_bf16_spgemm(a_tiles_ptr, a_map_ptr, b_tiles_ptr, b_map_ptr, c_ptr, c_off_ptr, nrb, ncb, nkb, m, n, k, stream),
             "bf16_spgemm")
+
+    def memset_zero_trickle(self, dev, stream, nctas=8, nbytes=None):
+        """Zero `dev` with `nctas` CTAs only (bounded rate), see include/dbcsr_acc_libsmm.h."""
+        n = dev.nbytes if nbytes is None else nbytes
+        _ck(self.L.libsmm_acc_b200_memset_zero_trickle(dev.ptr, 0, n // 16 * 16, nctas, stream), "memset_zero_trickle")
+        if n % 16:
+            _ck(self.L.c_dbcsr_acc_memset_zero(dev.ptr, n // 16 * 16, n % 16, stream), "memset_zero")
 
     def fp64_peak_gflops(self, stream):
         """Measured DMMA.8x8x4 throughput of this device (register operands), GFLOP/s."""

@@ -55,14 +55,16 @@ class DeviceMultiply:
         self.copy_stream = acc.stream_create("panels", 0)
         self.d_a = acc.dev_alloc(8 * max(a_nze_max, 1))
         self.d_b = acc.dev_alloc(8 * max(b_nze_max, 1))
-        self.trs_h = acc.host_alloc((max(nb_max, 1),), np.int32)
-        self.trs_d = acc.dev_alloc(4 * max(nb_max, 1))
+        self.trs_h = acc.host_alloc((2 * max(nb_max, 1),), np.int32)   # transpose stack + (fused norms) list positions
+        self.trs_d = acc.dev_alloc(8 * max(nb_max, 1))
+        self.d_bnorm = acc.dev_alloc(4 * max(nb_max, 1))
+        self.b_norms_fused = None
         self.first = True
         self.panels_ready = acc.event_create()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def upload_panels(self, a_data, b_data, b_list3, a_list3=None):
+    def upload_panels(self, a_data, b_data, b_list3, a_list3=None, want_b_norms=False):
         """host2dev of both panels + acc_transpose_blocks of the right one, all asynchronous on the copy stream; the event
         `panels_ready` orders the stack kernels behind them (the reference synchronises the whole device here,
         src/mm/dbcsr_mm_cannon.F:1642-1646; an event lets the host build stacks while the panels are still in flight).
@@ -75,10 +77,23 @@ class DeviceMultiply:
         if not pipelined:
             acc.h2d(a_data, self.d_a, self.copy_stream)
         acc.h2d(b_data, self.d_b, self.copy_stream)
-        rc = acc.L.dbcsr_b200_transpose_panel(b.ctypes.data, b.shape[0], self.k_sizes.ctypes.data, self.n_sizes.ctypes.data, self.d_b.ptr,
-                                              self.trs_h.ptr, self.trs_d.ptr, self.copy_stream)
-        if rc != 0:
-            raise acclib.AccError("transpose_panel returned %d" % rc)
+        self.b_norms_fused = None
+        rc = -3
+        if want_b_norms and b.shape[0]:
+            # transpose and squared block norms of the right panel in ONE pass (libsmm_acc_b200_transpose_norms); -3 = the panel has
+            # blocks above max_kernel_dim, which are not transposed: separate passes as in the reference
+            rc = acc.L.dbcsr_b200_transpose_panel_norms(b.ctypes.data, b.shape[0], self.k_sizes.ctypes.data, self.n_sizes.ctypes.data, self.d_b.ptr,
+                                                        self.trs_h.ptr, self.trs_d.ptr, self.d_bnorm.ptr, self.copy_stream)
+            if rc == 0:
+                self.b_norms_fused = np.empty(b.shape[0], dtype=np.float32)
+                acc.d2h(self.d_bnorm, self.b_norms_fused, self.copy_stream)
+            elif rc != -3:
+                raise acclib.AccError("transpose_panel_norms returned %d" % rc)
+        if rc == -3:
+            rc = acc.L.dbcsr_b200_transpose_panel(b.ctypes.data, b.shape[0], self.k_sizes.ctypes.data, self.n_sizes.ctypes.data, self.d_b.ptr,
+                                                  self.trs_h.ptr, self.trs_d.ptr, self.copy_stream)
+            if rc != 0:
+                raise acclib.AccError("transpose_panel returned %d" % rc)
         acc.event_record(self.panels_ready, self.copy_stream)
         self._chunk_events_armed = None
         if pipelined:
@@ -156,7 +171,12 @@ class DeviceMultiply:
         if total_row_counts is None:
             total_row_counts = np.bincount(a[:, 0] - 1, minlength=self.m_sizes.size)
         self.a_norms = self.panel_norms(a, self.m_sizes, self.k_sizes, self.d_a)
-        self.b_norms = self.panel_norms(b_list3, self.k_sizes, self.n_sizes, self.d_b)
+        if self.b_norms_fused is not None:  # computed together with the transpose (upload_panels(want_b_norms=True))
+            acc_ = self.acc
+            acc_.stream_sync(self.copy_stream)
+            self.b_norms = self.b_norms_fused
+        else:
+            self.b_norms = self.panel_norms(b_list3, self.k_sizes, self.n_sizes, self.d_b)
         self.engine.set_filter(host.row_max_epss(filter_eps, total_row_counts))
         self.engine.multiply(a, self.d_a.ptr, b_list3, self.d_b.ptr, a_norms=self.a_norms, b_norms=self.b_norms)
 
@@ -204,7 +224,7 @@ class DeviceMultiply:
 
     def close(self):
         self.engine.close()
-        for d in (self.d_a, self.d_b, self.trs_d):
+        for d in (self.d_a, self.d_b, self.trs_d, self.d_bnorm):
             d.free()
         self.trs_h.free()
         self.acc.event_destroy(self.panels_ready)

@@ -62,6 +62,12 @@ int libsmm_acc_b200_block_norms_f64(const double* mat, int nblks, const int* off
 int libsmm_acc_b200_gather_blocks(const double* src, double* dst, int nblks, const int* src_offsets, const int* dst_offsets,
   const int* nelems, void* stream_ptr);
 
+/* Transpose + block norms in ONE pass over the right panel (the reference runs libsmm_acc_transpose and, with
+ * filter_eps, c_calculate_norms as two passes): libsmm_acc_transpose semantics for real_8, plus dev_norms[dev_trs_blk[i]] = sum of squares
+ * of block i (float) for i in [offset, offset + stack_size); dev_trs_blk NULL = i.  -3 (nothing done) if m or n > max_kernel_dim. */
+int libsmm_acc_b200_transpose_norms(const int* dev_trs_stack, const int* dev_trs_blk, int offset, int stack_size, double* dev_data, int m,
+  int n, int max_kernel_dim, float* dev_norms, void* stream);
+
 /* Declared by DBCSR (interface in src/core/dbcsr_lib.F:111-116) but never defined by the reference; exported for safety. */
 int libsmm_acc_gpu_warp_size(void);
 
@@ -112,6 +118,9 @@ void libsmm_acc_b200_set_trace(void* dev_words);
  * grid before reading, so consecutive drains overlap tail and ramp-up; completion order stays stream order.  Default (and after
  * on == 0): every kernel waits for its predecessor before its first global read.  Returns 0, -2 for a NULL stream. */
 int libsmm_acc_b200_stream_chain(void* stream, int on);
+/* c_dbcsr_acc_memset_zero at a bounded rate: `nctas` CTAs (a handful) stream the zeros, so that a caller zeroing the NEXT multiply's C
+ * buffer beside running stack kernels does not take the HBM bandwidth away from them in one burst.  offset, nbytes: multiples of 16. */
+int libsmm_acc_b200_memset_zero_trickle(void* dev_mem, size_t offset, size_t nbytes, int nctas, void* stream);
 /* Measured FP64 tensor-pipe (DMMA.8x8x4, register operands) throughput of the active device in GFLOP/s; synchronises `stream`.
  * Introspection for roofline reports (bench.py); <= 0 on failure. */
 double libsmm_acc_b200_fp64_peak_gflops(void* stream);

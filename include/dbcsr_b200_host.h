@@ -193,6 +193,12 @@ int dbcsr_b200_replay_step(dbcsr_b200_replay_t* r, void* compute_stream);
  * ordering only (no host sync).  scratch_dev must hold nb ints. */
 int dbcsr_b200_transpose_panel(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
   void* scratch_dev, void* stream);
+/* The same with the blocks' squared norms (float, list order; what acc_calculate_norms delivers for the on-the-fly filter,
+ * src/mm/dbcsr_mm_common.F:498-591) computed in the SAME pass over the panel (libsmm_acc_b200_transpose_norms): dev_norms holds nb floats,
+ * scratch_host / scratch_dev 2*nb ints.  Returns -3 when the panel has a block with a dimension above max_kernel_dim (80): those are not
+ * transposed, the panel is left as libsmm_acc_transpose leaves it and the caller falls back to c_calculate_norms. */
+int dbcsr_b200_transpose_panel_norms(const int* b_list3, int nb, const int* k_sizes, const int* n_sizes, void* b_dev, int* scratch_host,
+  void* scratch_dev, float* dev_norms, void* stream);
 
 #if defined(__cplusplus)
 }

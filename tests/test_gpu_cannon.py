@@ -1,6 +1,6 @@
 """Multi-process Cannon multiply on real GPUs, checked block by block against the oracle.
 The reference tests every distributed multiply against dense DGEMM with 2 MPI ranks (tests/CMakeLists.txt:130-137,
-tests/dbcsr_test_multiply.F:753-759); here 2 and 4 ranks = 1x2 and 2x2 Cannon grids, engine path and replay path, 23x23 and
+tests/dbcsr_test_multiply.F:753-759); here 2, 4 and 8 ranks = 1x2, 2x2 and 2x4 Cannon grids (2x4: four virtual k-slices on a non-square grid), engine path and replay path, 23x23 and
 mixed block sizes.  One rank per GPU over NCCL when the box has enough GPUs; otherwise the ranks share GPU 0 (gloo set-up
 collectives, CUDA IPC peer pull) so that the distributed path is exercised on a single-GPU box too."""
 import os
@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_cannon_blocks_match_oracle(world):
     import torch
 

@@ -177,8 +177,9 @@ def test_full_size_properties(acc, cfgname, nblk):
     assert abs(got / expected - 1.0) <= 1e-10, (got, expected)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["norms_separate", "norms_fused_with_transpose"])
 @pytest.mark.parametrize("nthreads", [1, 3])
-def test_on_the_fly_filter(acc, nthreads):
+def test_on_the_fly_filter(acc, nthreads, fused):
     """dbcsr_multiply(filter_eps=...): block norms from c_calculate_norms on the device (src/mm/dbcsr_mm_common.F:498-591),
     thresholds row_max_epss (src/mm/dbcsr_mm_cannon.F:1098-1107), products with a_norm*b_norm < row_eps skipped
     (src/mm/dbcsr_mm_csr.F:270-278).  Expected C = sum over exactly the surviving products, computed on the CPU."""
@@ -193,7 +194,9 @@ def test_on_the_fly_filter(acc, nthreads):
     eps = 0.5
     dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=host.default_cfg(mm_stack_size=400))
     try:
-        dm.upload_panels(A.data, B.data, B.list3())
+        # fused: the right panel's norms come out of the SAME pass that transposes it (libsmm_acc_b200_transpose_norms)
+        dm.upload_panels(A.data, B.data, B.list3(), want_b_norms=fused)
+        assert (dm.b_norms_fused is not None) == fused
         dm.multiply(A.list3(), B.list3(), filter_eps=eps)
         prod = dm.download_c()
         a_n, b_n = dm.a_norms, dm.b_norms

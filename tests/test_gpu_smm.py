@@ -480,3 +480,54 @@ def test_tiny_block_shapes_long_and_short_runs(acc, mnk):
         assert rc == 0
         c_ref = orc.stack_calc(stack, np.zeros(n_c * m * n), a, bt, m, n, k)
         assert np.array_equal(c, c_ref), (mnk, S, n_c, shuffle, float(np.abs(c - c_ref).max()))
+
+
+def test_transpose_norms_fused_matches_separate_passes(acc):
+    """libsmm_acc_b200_transpose_norms = libsmm_acc_transpose + c_calculate_norms in one pass: the transposed panel is identical,
+    the norms land at the list positions given by dev_trs_blk and equal the oracle's (float sum of squares); offset argument;
+    blocks above max_kernel_dim are refused with -3 and left untouched."""
+    rng = np.random.default_rng(41)
+    for m, n in [(23, 23), (5, 13), (32, 7), (80, 80), (1, 1)]:
+        nblk, skip = 53, 4
+        mat = rng.random(nblk * m * n) * 10.0 ** rng.uniform(-3, 3, nblk * m * n)
+        offs = (np.arange(nblk, dtype=np.int32) * m * n).astype(np.int32)
+        perm = rng.permutation(nblk).astype(np.int32)  # transpose-stack position -> list position
+        d_m, d_o, d_p = acc.to_device(mat, acc.s), acc.to_device(offs, acc.s), acc.to_device(perm, acc.s)
+        d_n = acc.dev_alloc(4 * nblk)
+        acc.h2d(np.full(nblk, np.float32(-1.0)), d_n, acc.s)
+        rc = acc.L.libsmm_acc_b200_transpose_norms(d_o.ptr, d_p.ptr, skip, nblk - skip, d_m.ptr, m, n, 80, d_n.ptr, acc.s)
+        assert rc == 0
+        out = acc.to_host(d_m, mat.shape, np.float64, acc.s)
+        norms = acc.to_host(d_n, (nblk,), np.float32, acc.s)
+        ref = mat.copy()
+        orc.transpose_blocks(offs[skip:], ref, m, n)
+        assert np.array_equal(out, ref), (m, n)
+        ref_n = orc.norms(mat, offs, np.full(nblk, m * n, dtype=np.int32))
+        touched = np.zeros(nblk, dtype=bool)
+        touched[perm[skip:]] = True
+        assert np.allclose(norms[perm[skip:]], ref_n[skip:], rtol=1e-5, atol=0), (m, n)
+        assert np.all(norms[~touched] == -1.0)
+        for d in (d_m, d_o, d_p, d_n):
+            d.free()
+    d_m = acc.to_device(np.ones(81 * 81), acc.s)
+    d_o = acc.to_device(np.zeros(1, dtype=np.int32), acc.s)
+    d_n = acc.dev_alloc(4)
+    assert acc.L.libsmm_acc_b200_transpose_norms(d_o.ptr, None, 0, 1, d_m.ptr, 81, 81, 80, d_n.ptr, acc.s) == -3
+    for d in (d_m, d_o, d_n):
+        d.free()
+
+
+def test_memset_zero_trickle(acc):
+    """Bounded-rate zeroing (libsmm_acc_b200_memset_zero_trickle): same result as c_dbcsr_acc_memset_zero, any CTA count, offset."""
+    n = 1 << 20
+    d = acc.dev_alloc(8 * n)
+    for nctas, off in [(1, 0), (8, 16 * 1000), (64, 0)]:
+        acc.h2d(np.full(n, 3.25), d, acc.s)
+        rc = acc.L.libsmm_acc_b200_memset_zero_trickle(d.ptr, off, 8 * n - off - 32, nctas, acc.s)
+        assert rc == 0
+        out = acc.to_host(d, (n,), np.float64, acc.s)
+        exp = np.full(n, 3.25)
+        exp[off // 8:n - 4] = 0.0
+        assert np.array_equal(out, exp), (nctas, off)
+    assert acc.L.libsmm_acc_b200_memset_zero_trickle(d.ptr, 8, 64, 4, acc.s) == -2  # misaligned offset
+    d.free()
