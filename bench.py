@@ -414,12 +414,17 @@ class Fp64Run:
             self.acc.stream_destroy(st_)
 
 
-def timed_steps(torch, tstream, acc, s, fn, steps):
+def timed_steps(torch, tstream, acc, s, fn, steps, lookahead=2):
+    """CUDA-event time of `steps` calls of fn() on the bench stream.  The host enqueues at most `lookahead` steps ahead of the device
+    (it waits for the end event of step k - lookahead before enqueuing step k): the device never idles between steps, and the launch
+    queue never holds more than a few hundred kernels."""
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.cuda.stream(tstream):
         for k in range(steps):
+            if lookahead and k >= lookahead:
+                ev[k - lookahead][1].synchronize()
             ev[k][0].record(tstream)
             fn()
             ev[k][1].record(tstream)
@@ -483,7 +488,16 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
     kern_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 3)
     # the same drain as a burst: one drain after the device has idled for half a second (clocks back at maximum)
     time.sleep(0.5)
+    t_enq0 = time.perf_counter()
     burst_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 1)
+    acc.stream_sync(s)
+    t_enq0 = time.perf_counter()
+    run.drain(run.d_cs[0])
+    host_enqueue_us = (time.perf_counter() - t_enq0) * 1e6 / max(len(run.stacks), 1)  # host time per libsmm_acc_process call (Python + ctypes + launch)
+    acc.stream_sync(s)
+    # how the drain time develops under continuous load: 12 drains back to back after another idle half second
+    time.sleep(0.5)
+    series_ms, _ = timed_steps(torch, tstream, acc, s, lambda: run.drain(run.d_cs[0]), 12)
     ms_per_step = float(np.mean(step_ms))
     k_ms = float(np.mean(kern_ms))
     value = run.flop / (ms_per_step * 1e-3) * 1e-9
@@ -514,6 +528,8 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
         "cublas_dgemm_8192_gflops": dgemm_peak,
         "kernel": "smm_dmma_kernel<%d,%d,%d> (dominant of %d launches/step)" % (m0, n0, k0, nst),
         "algorithmic_flop_per_launch": run.flop / nst, "avg_launch_us": launch_us, "kernel_only_gflops": kernel_only,
+        "host_enqueue_us_per_launch": host_enqueue_us,
+        "drain_series_after_idle_ms": [round(float(x), 3) for x in series_ms],
         "frac_on_timed_value": value / dmma_peak if dmma_peak > 0 else None,
         "alt_bounds": {
             "padded_tensor_ceiling": {"note": "tiles of 8x8x4: %dx%dx%d is %.0f%% useful" % (m0, n0, k0, 100 * pad), "frac": kernel_only / (dmma_peak * pad) if dmma_peak > 0 else None},
@@ -622,7 +638,8 @@ def run_single(args):
     A, B, bs = w["A"], w["B"], w["m_sizes"]
 
     sampler = ClockSampler(0)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     time.sleep(0.3)
     rep = fp64_config_report(torch, tstream, acc, s, run, args.steps, args.warmup, 0 if args.no_selfcheck else args.probe_blocks, peaks, args.config)
     clocks = sampler.stop()
@@ -748,6 +765,7 @@ def main():
     ap.add_argument("--cfg3-streams", type=int, default=4, help="streams the 125 stacks of the cfg3 extra config are spread over (DBCSR: one per OpenMP thread)")
     ap.add_argument("--extra-nblk", type=int, default=None, help="block-grid size of the extra_configs legs (default: the full 1000)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels-on-this-GPU leg")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll nvidia-smi during the run (diagnostic)")
     ap.add_argument("--no-chain", action="store_true", help="do not declare the bench stream a chain of independent drains (every kernel waits for its predecessor)")
     ap.add_argument("--ref-entries", type=int, default=4_000_000, help="stack entries in the bounded CPU sample")
     args = ap.parse_args()

@@ -489,15 +489,29 @@ __global__ void __launch_bounds__(1024) zero_trickle_kernel(uint4* __restrict__ 
 }
 
 // Register-only DMMA.8x8x4 loop: the FP64 tensor-pipe peak of THIS device, measured in place so that roofline fractions have a
-// live denominator (bench.py).  9 independent accumulator pairs per warp like the 23^3 kernel's 3 x 3 tiles.
-__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double x, double y) {
+// live denominator (bench.py).  9 independent accumulator pairs per warp like the 23^3 kernel's 3 x 3 tiles.  The operands carry
+// RANDOM mantissas (per-thread hash): the power a B200 draws for FP64 multiplies depends on the operand bits, and with uniform(0,1)
+// matrix data the board's power limit pulls the SM clock down after ~50 ms of sustained DMMA load -- a probe fed with constants
+// or small integers never sees that limit (it reads 37 TFLOP/s for as long as it runs) and would overstate what is attainable.
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, unsigned seed) {
   double c0[9], c1[9];
+  unsigned long long h = (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + seed;
+  auto rnd = [&]() {  // uniform in [0,1) with 52 random mantissa bits
+    h ^= h >> 12;
+    h ^= h << 25;
+    h ^= h >> 27;
+    return __longlong_as_double((long long)(((h * 2685821657736338717ull) >> 12) | 0x3FF0000000000000ull)) - 1.0;
+  };
 #pragma unroll
-  for (int i = 0; i < 9; ++i) c0[i] = c1[i] = (double)(threadIdx.x + i);
-  const double a = x + threadIdx.x * 1e-9, b = y;
+  for (int i = 0; i < 9; ++i) c0[i] = rnd(), c1[i] = rnd();
+  double a[3], b[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) a[i] = rnd(), b[i] = rnd() - 0.5;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) smm::dmma884(c0[i], c1[i], a, b);
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) smm::dmma884(c0[3 * i + j], c1[3 * i + j], a[i], b[j]);
   }
   double s = 0.0;
 #pragma unroll
@@ -611,7 +625,7 @@ double libsmm_acc_b200_fp64_peak_gflops(void* stream) {
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0, st);
-    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 1.0, 1e-9);
+    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) {
       best = -31.0;
@@ -699,7 +713,7 @@ double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) 
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -30.0;
   for (int i = 0; i < n; ++i) {
     if (i == n / 2) cudaEventRecord(e0, st);
-    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 1.0, 1e-9);
+    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
   }
   cudaEventRecord(e1, st);
   double out = -31.0;

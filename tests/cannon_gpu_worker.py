@@ -94,6 +94,10 @@ def main():
         report["cases"].append({"config": cfg_name, "path": "replay", "blocks": nb, "worst_rel_err": worst})
         dist.barrier()
         cm.close()
+    outdir = os.environ.get("CANNON_TEST_OUT")
+    if outdir:
+        with open(os.path.join(outdir, "rank%d.json" % rank), "w") as f:
+            json.dump(report, f)
     print("CANNON_WORKER_OK " + json.dumps(report), flush=True)
     dist.barrier()
     torch.cuda.synchronize()

@@ -29,17 +29,24 @@ def test_cannon_blocks_match_oracle(world):
 
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
-    env = dict(os.environ, OMP_NUM_THREADS="2")
-    env.pop("DBCSR_B200_EXCHANGE", None)
+    import tempfile
+
+    outdir = tempfile.mkdtemp(prefix="cannon_test_")
+    env = dict(os.environ, OMP_NUM_THREADS="2", CANNON_TEST_OUT=outdir)  # every rank writes its report to a file: stdout lines of
+    env.pop("DBCSR_B200_EXCHANGE", None)                                # concurrently printing ranks interleave
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "cannon_gpu_worker.py")]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    ok = re.findall(r"CANNON_WORKER_OK (\{.*\})", out.stdout)
-    assert out.returncode == 0 and len(ok) == world, "rc %d\nstdout:\n%s\nstderr:\n%s" % (out.returncode, out.stdout[-3000:], out.stderr[-3000:])
     import json
 
-    for line in ok:
-        rep = json.loads(line)
+    reports = []
+    for r in range(world):
+        f = os.path.join(outdir, "rank%d.json" % r)
+        if os.path.exists(f):
+            reports.append(json.load(open(f)))
+    assert out.returncode == 0 and len(reports) == world, "rc %d, %d reports\nstdout:\n%s\nstderr:\n%s" % (out.returncode, len(reports), out.stdout[-3000:],
+                                                                                                        out.stderr[-3000:])
+    for rep in reports:
         assert len(rep["cases"]) == 4
         for case in rep["cases"]:
             assert case["blocks"] > 0 and case["worst_rel_err"] <= 1e-10

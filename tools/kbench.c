@@ -323,6 +323,24 @@ int main(int argc, char** argv) {
       for (int i = 0; i < c_nblks; ++i) mismatches += (norms[i] != norms0[i]);
     /* timing */
     double best = 1e30, sum = 0.0;
+    const char* nosync = getenv("KBENCH_NOSYNC");
+    if (nosync != NULL && nosync[0] == '1') {
+      /* all repetitions enqueued back to back, ONE synchronisation at the end (deep launch queue, like a multi-step bench loop) */
+      for (int i = 0; i < nstacks; ++i)
+        process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bm, bn, bk, 80, 1, stream, stream);
+      CHECK(stream_sync(stream));
+      const double t0 = now();
+      for (int it = 0; it < steps; ++it)
+        for (int i = 0; i < nstacks; ++i)
+          process(NULL, (const int*)d_st + 3 * st_off[i], st_size[i], 3, d_a, d_b, d_c, bm, bn, bk, 80, 1, stream, stream);
+      const double t_enq = now() - t0;
+      CHECK(stream_sync(stream));
+      sum = now() - t0;
+      best = sum / steps;
+      printf("kbench: no-sync mode: %d drains enqueued in %.3f ms (%.2f us per launch on the host), done after %.3f ms\n", steps, t_enq * 1e3,
+             t_enq * 1e6 / ((double)steps * nstacks), sum * 1e3);
+    }
+    else
     for (int it = 0; it < steps + 1; ++it) {
       CHECK(stream_sync(stream));
       const double t0 = now();
