@@ -17,6 +17,7 @@
 #include "../../../include/dbcsr_acc_libsmm.h"
 #include "../../../include/dbcsr_b200_host.h"
 #include "stack_builder.hpp"
+#include "device_builder.hpp"
 
 using dbcsr_b200::Config;
 using dbcsr_b200::Idx3;
@@ -74,6 +75,14 @@ struct ThreadState {
   size_t c_final_capacity = 0;
   int rc = 0;
   double build_seconds = 0.0;
+  // device-side builder (DBCSR_B200_DEVICE_BUILD): own stream for the index passes, joined into `stream` by an event
+  std::unique_ptr<dbcsr_b200::IDeviceBuilder> devb;
+  cudaStream_t build_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // early D2H of finished row slices beside the stack kernels
+  cudaEvent_t build_done = nullptr, drain_done = nullptr, slice_done = nullptr;
+  bool dev_index = false;  // the product index of the current multiply lives in the device builder
+  long long dev_ticks = 0;  // ticks built by the device passes (introspection)
+  std::vector<int> h7, h3, idx_r, idx_c, idx_p;
   // statistics of dbcsr_mm_sched (src/mm/dbcsr_mm_sched.F:266-382,392-461): per (m,n,k) entries / stacks handed to the
   // accelerator and how many of those stacks ran on an untuned kernel; inhomogeneous stacks are booked under (0,0,0)
   struct MnkStat {
@@ -177,6 +186,20 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
       }
       ts.c_requested = c_capacity;
     }
+    if (mode & DBCSR_B200_DEVICE_BUILD) {
+      if (mode & DBCSR_B200_LAUNCH) {
+        if (cudaStreamCreateWithFlags(&ts.build_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ts.build_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ts.drain_done, cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ts.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ts.slice_done, cudaEventDisableTiming) != cudaSuccess)
+          goto fail;
+        ts.devb.reset(dbcsr_b200::make_device_builder(ts.build_stream));
+      }
+      else {
+        ts.devb.reset(dbcsr_b200::make_emulated_builder());
+      }
+    }
   }
   return e;
 fail:
@@ -195,6 +218,15 @@ void dbcsr_b200_engine_destroy(dbcsr_b200_engine_t* e) {
     }
     if (ts.c_dev != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_dev);
     if (ts.c_final != nullptr) c_dbcsr_acc_dev_mem_deallocate(ts.c_final);
+    ts.devb.reset();
+    if (ts.build_done != nullptr) cudaEventDestroy(ts.build_done);
+    if (ts.drain_done != nullptr) cudaEventDestroy(ts.drain_done);
+    if (ts.slice_done != nullptr) cudaEventDestroy(ts.slice_done);
+    if (ts.copy_stream != nullptr) {
+      cudaStreamSynchronize(ts.copy_stream);
+      cudaStreamDestroy(ts.copy_stream);
+    }
+    if (ts.build_stream != nullptr) cudaStreamDestroy(ts.build_stream);
     if (ts.stream != nullptr) c_dbcsr_acc_stream_destroy(ts.stream);
   }
   delete e;
@@ -277,6 +309,144 @@ static int owner_of_row(const dbcsr_b200_engine_t* e, int row) {
   while (c < nchunks - 1 && row > (int)(((long long)e->nrows * (c + 1)) / nchunks)) ++c;
   return c % nthreads;
 }
+
+}  // extern "C"
+
+// One tick of host thread t with the device-side builder (device_builder.hpp): all row slices of the thread in one pass, then
+// the stacks in the host builder's dispatch order.  Stacks the accelerator driver sorts by c_first arrive in device order; the
+// others (binning, inhomogeneous) are ordered on the host from their 7-wide entries, exactly like the host path.
+template <class BookFn>
+static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, const void* b_dev, int nb, const BookFn& book) {
+  ThreadState& ts = e->th[(size_t)t];
+  const bool launch = (e->mode & DBCSR_B200_LAUNCH) != 0;
+  const int na = (int)e->a_sorted.size();
+  if (launch && ts.drain_done != nullptr) {
+    // the previous tick's stack kernels read the stack array this build overwrites
+    if (cudaEventRecord(ts.drain_done, *static_cast<cudaStream_t*>(ts.stream)) != cudaSuccess ||
+        cudaStreamWaitEvent(ts.build_stream, ts.drain_done, 0) != cudaSuccess)
+      return -45;
+  }
+  dbcsr_b200::DevBuildResult r;
+  const int rc_b = ts.devb->build(*ts.mm, e->a_sorted.data(), na, ts.slices, e->b_sorted.data(), nb, r);
+  if (rc_b != 0) return rc_b;
+  // new part of the C index -> host work index (the engine's accessors, finalize and the downloads use it)
+  const int nnew = r.nblk_after - r.nblk_before;
+  ts.idx_r.resize((size_t)std::max(nnew, 1));
+  ts.idx_c.resize((size_t)std::max(nnew, 1));
+  ts.idx_p.resize((size_t)std::max(nnew, 1));
+  if (int rc = ts.devb->fetch_index(r.nblk_before, nnew, ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data())) return rc;
+  long long flop = 0;
+  const size_t S7 = 7 * (size_t)std::max(1, e->kcfg.mm_stack_size);
+  // stacks ordered on the host
+  for (const auto& d : r.dispatch) {
+    const StackDescr& sd = ts.mm->descr(d.ws);
+    const bool on_dev = dbcsr_b200::IDeviceBuilder::device_ordered(e->kcfg, sd);
+    if (on_dev && !(e->mode & DBCSR_B200_RECORD)) continue;
+    ts.h7.resize(std::max(ts.h7.size(), S7));
+    ts.h3.resize(std::max(ts.h3.size(), S7));
+    if (int rc = ts.devb->fetch_params7(d, ts.h7.data())) return rc;
+    if (!on_dev) {
+      dbcsr_b200::accdrv_order_stack(e->kcfg, sd, ts.h7.data(), ts.h3.data(), d.size, true);
+      if (int rc = ts.devb->store_stack3(d, ts.h3.data())) return rc;
+    }
+    if (e->mode & DBCSR_B200_RECORD) {
+      RecordedStack rec;
+      rec.d = sd;
+      rec.thread = t;
+      rec.stack_number = d.ws;
+      rec.size = d.size;
+      rec.host.assign(ts.h7.begin(), ts.h7.begin() + 7 * (size_t)d.size);
+      rec.dev.resize(3 * (size_t)d.size);
+      if (on_dev) {
+        if (int rc = ts.devb->fetch_stack3(d, rec.dev.data())) return rc;
+      }
+      else {
+        std::copy(ts.h3.begin(), ts.h3.begin() + 3 * (size_t)d.size, rec.dev.begin());
+      }
+      ts.recorded.push_back(std::move(rec));
+    }
+  }
+  for (const auto& d : r.dispatch) {
+    const StackDescr& sd = ts.mm->descr(d.ws);
+    if (sd.defined_mnk) flop += 2LL * sd.m * sd.n * sd.k * d.size;
+  }
+  // inhomogeneous stacks: flop from their entries (only these need the host copy again)
+  ts.mm->append_index(ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data(), nnew, r.datasize_after, 0);
+  if (!launch) {
+    for (const auto& d : r.dispatch) {
+      const StackDescr& sd = ts.mm->descr(d.ws);
+      if (!sd.defined_mnk) {
+        ts.h7.resize(std::max(ts.h7.size(), S7));
+        if (int rc = ts.devb->fetch_params7(d, ts.h7.data())) return rc;
+        for (int i = 0; i < d.size; ++i) flop += 2LL * ts.h7[7 * (size_t)i] * ts.h7[7 * (size_t)i + 1] * ts.h7[7 * (size_t)i + 2];
+      }
+      book(sd, ts.h7.data(), d.size, false);
+    }
+    ts.mm->append_index(nullptr, nullptr, nullptr, 0, r.datasize_after, flop);
+    return 0;
+  }
+  // ---- LAUNCH: C buffer large enough, stack kernels behind the build
+  if ((size_t)r.datasize_after > ts.c_capacity) {
+    if (ts.copy_stream != nullptr) cudaStreamSynchronize(ts.copy_stream);  // downloads of earlier slices read the old buffer
+    if (int grc = grow_c_buffer(ts, (size_t)r.datasize_after)) return grc;
+  }
+  ts.c_used_high = std::max(ts.c_used_high, (size_t)r.datasize_after);
+  cudaStream_t st = *static_cast<cudaStream_t*>(ts.stream);
+  if (cudaEventRecord(ts.build_done, ts.build_stream) != cudaSuccess || cudaStreamWaitEvent(st, ts.build_done, 0) != cudaSuccess) return -45;
+  const int nslices = (int)ts.slices.size();
+  size_t di = 0;
+  int ds_prev = r.datasize_before;
+  for (int s = 0; s < nslices; ++s) {
+    const int chunk = t + s * (int)e->th.size();
+    if (chunk < (int)e->chunk_events.size() && e->chunk_events[(size_t)chunk] != nullptr) {
+      if (c_dbcsr_acc_stream_wait_event(ts.stream, e->chunk_events[(size_t)chunk]) != 0) return -49;
+    }
+    for (; di < r.dispatch.size() && r.dispatch[di].slice == s; ++di) {
+      const auto& d = r.dispatch[di];
+      const StackDescr& sd = ts.mm->descr(d.ws);
+      const int* host7 = nullptr;
+      if (!sd.defined_mnk) {  // the library bins an inhomogeneous stack from its host entries
+        ts.h7.resize(std::max(ts.h7.size(), S7));
+        if (int rc = ts.devb->fetch_params7(d, ts.h7.data())) return rc;
+        host7 = ts.h7.data();
+        for (int i = 0; i < d.size; ++i) flop += 2LL * host7[7 * (size_t)i] * host7[7 * (size_t)i + 1] * host7[7 * (size_t)i + 2];
+      }
+      const int rc = libsmm_acc_process(host7, ts.devb->stack3(d), d.size, dbcsr_type_real_8, a_dev, b_dev, ts.c_dev, sd.max_m, sd.max_n, sd.max_k,
+                                        kMaxKernelDim, sd.defined_mnk, ts.stream, ts.stream);
+      if (rc < 0) {
+        if (e->host_driver == nullptr) return rc;
+        if (host7 == nullptr) {
+          ts.h7.resize(std::max(ts.h7.size(), S7));
+          if (int frc = ts.devb->fetch_params7(d, ts.h7.data())) return frc;
+          host7 = ts.h7.data();
+        }
+        const int hrc = e->host_driver(e->host_driver_ctx, t, sd.m, sd.n, sd.k, sd.defined_mnk, host7, d.size, r.datasize_after);
+        if (hrc != 0) return hrc < 0 ? hrc : -50;
+        long long f = 0;
+        for (int i = 0; i < d.size; ++i) f += 2LL * host7[7 * (size_t)i] * host7[7 * (size_t)i + 1] * host7[7 * (size_t)i + 2];
+        ts.cpu_entries += d.size;
+        ts.cpu_stacks += 1;
+        ts.cpu_flop += f;
+        continue;
+      }
+      book(sd, host7, d.size, rc == 10);
+    }
+    const int ds1 = r.slice_datasize[(size_t)s];
+    if (ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds_prev) {
+      // the C blocks created by this slice are final once its stacks have drained: download them on the copy stream while the
+      // stacks of the next slice run
+      if (cudaEventRecord(ts.slice_done, st) != cudaSuccess || cudaStreamWaitEvent(ts.copy_stream, ts.slice_done, 0) != cudaSuccess ||
+          cudaMemcpyAsync(ts.c_host + ds_prev, static_cast<double*>(ts.c_dev) + ds_prev, (size_t)(ds1 - ds_prev) * sizeof(double),
+                          cudaMemcpyDeviceToHost, ts.copy_stream) != cudaSuccess)
+        return -46;
+    }
+    ds_prev = ds1;
+  }
+  ts.mm->append_index(nullptr, nullptr, nullptr, 0, r.datasize_after, flop);
+  return 0;
+}
+
+extern "C" {
 
 static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int na, const void* a_dev, const float* a_norms,
                                 const int* b_list3, int nb, const void* b_dev, const float* b_norms) {
@@ -444,6 +614,21 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
         book(d, params7, size, rc == 10);
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
+      // ---- device-side builder: plain products only, and only when the index of this multiply has been on the device from its
+      //      first tick (a multiply uses one builder from reset to reset)
+      const bool dev_ok = ts.devb != nullptr && !filter && !ts.has_preset && ts.mm->plain_product() &&
+                          (ts.dev_index || ts.mm->c_row().empty());
+      if (dev_ok) {
+        ts.dev_index = true;
+        const int rc_dev = device_build_tick(e, t, a_dev, b_dev, nb, book);
+        if (rc_dev == 0) ++ts.dev_ticks;
+        if (rc_dev != -60) {  // -60: more stacks than the device passes handle => host builder below
+          if (rc_dev != 0 && ts.rc == 0) ts.rc = rc_dev;
+          ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+          return;
+        }
+        ts.dev_index = false;
+      }
       int slice_no = 0;
       for (const auto& sl : ts.slices) {
         const int chunk = t + (slice_no++) * (int)e->th.size();
@@ -860,6 +1045,9 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
     const size_t used = std::min(std::max(ts.c_used_high, (size_t)ts.mm->datasize()), ts.c_capacity);
     ts.mm->reset();
     ts.mm->set_k_sizes(e->k_sizes);
+    ts.dev_index = false;
+    if (ts.copy_stream != nullptr && cudaStreamSynchronize(ts.copy_stream) != cudaSuccess) return -41;
+    if (ts.devb != nullptr && ts.devb->reset() != 0) return -41;
     if (ts.c_dev != nullptr && used > 0 && c_dbcsr_acc_memset_zero(ts.c_dev, 0, used * sizeof(double), ts.stream) != 0) return -41;
     ts.c_used_high = 0;
   }
@@ -868,9 +1056,18 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
 
 int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e) {
   if (e == nullptr) return -1;
-  for (auto& ts : e->th)
+  for (auto& ts : e->th) {
     if (ts.stream != nullptr && c_dbcsr_acc_stream_sync(ts.stream) != 0) return -1;
+    if (ts.copy_stream != nullptr && cudaStreamSynchronize(ts.copy_stream) != cudaSuccess) return -1;
+  }
   return 0;
+}
+
+long long dbcsr_b200_engine_device_built_ticks(const dbcsr_b200_engine_t* e) {
+  long long n = 0;
+  if (e != nullptr)
+    for (const auto& ts : e->th) n += ts.dev_ticks;
+  return n;
 }
 
 int dbcsr_b200_engine_nthreads(const dbcsr_b200_engine_t* e) { return (int)e->th.size(); }

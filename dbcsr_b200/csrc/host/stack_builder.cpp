@@ -517,6 +517,10 @@ void LocalMultiply::sparse_multrec(int mi, int mf, int ni, int nf, int ki, int k
                                    const Idx3* b) {
   if (af < ai || bf < bi || mf < mi || nf < ni || kf < ki) return;
   if (af - ai + 1 <= cfg_.multrec_limit && bf - bi + 1 <= cfg_.multrec_limit) {
+    if (plan_out_ != nullptr) {
+      plan_out_->push_back(Leaf{ai, af, bi, bf});
+      return;
+    }
     csr_multiply_low(mi, mf, ki, kf, ai, af, bi, bf, a, b);
     return;
   }
@@ -555,6 +559,20 @@ void LocalMultiply::multiply(const Idx3* a_index, int a_first, int a_last, const
   flush_stacks(true);
   dispatch_ = nullptr;
   a_norms_ = b_norms_ = nullptr;
+}
+
+void LocalMultiply::plan(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, std::vector<Leaf>& out) {
+  plan_out_ = &out;
+  sparse_multrec(1, (int)m_sizes_.size(), 1, (int)n_sizes_.size(), 1, (int)k_sizes_.size(), a_first, a_last, a_index, 1, nb, b_index);
+  plan_out_ = nullptr;
+}
+
+void LocalMultiply::append_index(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize, int64_t flop_add) {
+  c_row_.insert(c_row_.end(), rows, rows + nblks);
+  c_col_.insert(c_col_.end(), cols, cols + nblks);
+  c_blk_p_.insert(c_blk_p_.end(), blk_p, blk_p + nblks);
+  datasize_ = datasize;
+  flop_ += flop_add;
 }
 
 }  // namespace dbcsr_b200

@@ -107,6 +107,26 @@ class LocalMultiply {
   int nstacks() const { return nstacks_; }
   const StackDescr& descr(int istack) const { return descr_[istack]; }  // 1-based
 
+  // ---- hooks of the device-side builder (device_builder.hpp) -------------------------------------------
+  // A leaf of sparse_multrec: the block-list ranges [ai,af] x [bi,bf] (1-based, inclusive) handed to the CSR multiply.
+  struct Leaf {
+    int ai, af, bi, bf;
+  };
+  // The recursion of multiply() without its leaves: the same cuts in the same order, the leaves appended to `out`.
+  void plan(const Idx3* a_index, int a_first, int a_last, const Idx3* b_index, int nb, std::vector<Leaf>& out);
+  // Blocks created outside csr_multiply_low (by the device builder, in first-touch order) become part of the work index; the
+  // per-row lookup tables are NOT updated: a multiply uses either the host or the device builder from reset() to reset().
+  void append_index(const int* rows, const int* cols, const int* blk_p, int nblks, int datasize, int64_t flop_add);
+  const std::vector<int>& m_sizes() const { return m_sizes_; }
+  const std::vector<int>& n_sizes() const { return n_sizes_; }
+  const std::vector<int>& k_sizes() const { return k_sizes_; }
+  const std::vector<int>& m_map() const { return m_map_; }
+  const std::vector<int>& n_map() const { return n_map_; }
+  const std::vector<int>& k_map() const { return k_map_; }
+  const std::vector<int>& stack_map() const { return stack_map_; }
+  const Config& config() const { return cfg_; }
+  bool plain_product() const { return !keep_sparsity_ && !c_sym_ && row_eps_.empty(); }
+
  private:
   void init_stack_map();
   void sparse_multrec(int mi, int mf, int ni, int nf, int ki, int kf, int ai, int af, const Idx3* a, int bi, int bf, const Idx3* b);
@@ -145,6 +165,7 @@ class LocalMultiply {
   std::vector<float> row_eps_, a_csr_norms_, b_csr_norms_;
   const float* a_norms_ = nullptr;
   const float* b_norms_ = nullptr;
+  std::vector<Leaf>* plan_out_ = nullptr;
 };
 
 }  // namespace dbcsr_b200

@@ -9,7 +9,7 @@ import numpy as np
 from . import lib as acclib
 
 _vp, _i = ctypes.c_void_p, ctypes.c_int
-LAUNCH, RECORD = 1, 2
+LAUNCH, RECORD, DEVICE_BUILD = 1, 2, 4
 
 
 class Cfg(ctypes.Structure):
@@ -290,6 +290,12 @@ class Engine:
     def sync(self):
         if self.L.dbcsr_b200_engine_sync(self.h) != 0:
             raise acclib.AccError("dbcsr_b200_engine_sync failed")
+
+    @property
+    def device_built_ticks(self):
+        self.L.dbcsr_b200_engine_device_built_ticks.restype = ctypes.c_longlong
+        self.L.dbcsr_b200_engine_device_built_ticks.argtypes = [_vp]
+        return int(self.L.dbcsr_b200_engine_device_built_ticks(self.h))
 
     @property
     def nthreads(self):

@@ -47,6 +47,13 @@ typedef struct dbcsr_b200_engine dbcsr_b200_engine_t;
 /* mode bits */
 #define DBCSR_B200_LAUNCH 1 /* enqueue every dispatched stack on the accelerator (needs a device) */
 #define DBCSR_B200_RECORD 2 /* keep every dispatched stack (host 7-wide + device-order 3-wide) for inspection / replay */
+#define DBCSR_B200_DEVICE_BUILD 4 /* build the stacks and the C index ON THE DEVICE: the host only sorts the
+                                     lists and walks the recursion of sparse_multrec down to its leaves; products, C blocks in first-touch
+                                     order, stack filling / flushing and stack_sort run as data-parallel passes, with stacks, dispatch
+                                     order and C index identical to the host builder's.  Used for plain products (no existing C blocks,
+                                     no retain_sparsity, no symmetry skipping, no on-the-fly filter, n_stacks^3 + 1 <= 254); other
+                                     multiplies of the engine use the host builder.  Without LAUNCH the same passes run in host loops
+                                     (test harness on machines without a GPU). */
 
 /* m_sizes/n_sizes/k_sizes: block sizes of the local C rows, C cols and the contraction index.
  * c_capacity: initial elements of every thread's device C buffer (0 = dense upper bound of the thread's block rows when that fits
@@ -122,6 +129,8 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e);
 int dbcsr_b200_engine_sync(dbcsr_b200_engine_t* e);
 
 /* product work matrices, one per thread (pre-finalize index in order of first touch) */
+/* (thread, tick) pairs whose stacks were built by the device passes since the engine was created (DBCSR_B200_DEVICE_BUILD) */
+long long dbcsr_b200_engine_device_built_ticks(const dbcsr_b200_engine_t* e);
 int dbcsr_b200_engine_nthreads(const dbcsr_b200_engine_t* e);
 int dbcsr_b200_engine_c_nblks(const dbcsr_b200_engine_t* e, int thread);
 int dbcsr_b200_engine_c_datasize(const dbcsr_b200_engine_t* e, int thread);
