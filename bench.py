@@ -648,44 +648,78 @@ def run_single(args):
     e2e = None
     if not args.no_e2e:
         try:
-            nthreads = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2))
             run.free_c()
             pa = acc.host_alloc((A.data.size,), np.float64)
             pb = acc.host_alloc((B.data.size,), np.float64)
             pa.array[:] = A.data
             pb.array[:] = B.data
-            cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=args.row_chunks)
-            dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e)
             a_l, b_l = A.list3(), B.list3()
-            pcs = None
-            times = []
-            for it in range(max(1, args.e2e_warmup) + args.e2e_steps):
-                acc.device_synchronize()
-                t0 = time.perf_counter()
-                dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if args.pipelined_upload else None)
-                t_up = time.perf_counter()
-                dm.multiply(a_l, b_l)
-                t_mul = time.perf_counter()
-                if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
-                    dm.engine.sync()
-                    pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
-                    prod = dm.download_c([p.array for p in pcs])
-                    dm.set_result_buffers([p.array for p in pcs])
+
+            def e2e_leg(builder):
+                """One variant of the end-to-end multiply: `host` = multi-threaded host stack builder (stacks uploaded),
+                `device` = device-side builder (index lists uploaded, stacks never leave the device)."""
+                if builder == "device":
+                    nthreads, rchunks, mode = args.dev_threads, args.dev_row_chunks, host.LAUNCH | host.DEVICE_BUILD
                 else:
-                    prod = dm.download_c()
-                dt = time.perf_counter() - t0
-                if it >= max(1, args.e2e_warmup):
-                    times.append(dt)
-                    phases = {"enqueue_upload_ms": (t_up - t0) * 1e3, "host_build_and_enqueue_ms": (t_mul - t_up) * 1e3,
-                              "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
-            stack_bytes = 12 * run.n_entries
-            e2e = {"value": run.flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
-                   "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "host_threads": nthreads,
-                   "row_chunks_per_thread": args.row_chunks, "pipelined_upload": bool(args.pipelined_upload),
-                   "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases,
-                   "timing": "wall clock around the public call, device synchronised on both sides"}
-            dm.close()
-            for p_ in [pa, pb] + pcs:
+                    nthreads, rchunks, mode = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2)), args.row_chunks, host.LAUNCH
+                cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=rchunks)
+                dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e, mode=mode)
+                pcs = None
+                times = []
+                try:
+                    for it in range(max(1, args.e2e_warmup) + args.e2e_steps):
+                        acc.device_synchronize()
+                        t0 = time.perf_counter()
+                        dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if (args.pipelined_upload and builder == "host") else None)
+                        t_up = time.perf_counter()
+                        dm.multiply(a_l, b_l)
+                        t_mul = time.perf_counter()
+                        if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
+                            dm.engine.sync()
+                            pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
+                            prod = dm.download_c([p.array for p in pcs])
+                            dm.set_result_buffers([p.array for p in pcs])
+                        else:
+                            prod = dm.download_c()
+                        dt = time.perf_counter() - t0
+                        if it >= max(1, args.e2e_warmup):
+                            times.append(dt)
+                            phases = {"enqueue_upload_ms": (t_up - t0) * 1e3, "host_build_and_enqueue_ms": (t_mul - t_up) * 1e3,
+                                      "drain_and_d2h_ms": (time.perf_counter() - t_mul) * 1e3}
+                    # the product of the last step, checked where it arrived (pinned host buffers): sum property
+                    got = sum(float(p[3].sum()) for p in prod.parts)
+                    stack_bytes = 12 * run.n_entries if builder == "host" else 12 * (A.nblks + B.nblks)
+                    leg = {"value": run.flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
+                           "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "stack_builder": builder,
+                           "host_threads": nthreads, "row_chunks_per_thread": rchunks, "pipelined_upload": bool(args.pipelined_upload and builder == "host"),
+                           "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases,
+                           "device_built_ticks": dm.engine.device_built_ticks, "sum_c": got,
+                           "timing": "wall clock around the public call, device synchronised on both sides"}
+                finally:
+                    dm.close()
+                    for p_ in pcs or []:
+                        p_.free()
+                return leg
+
+            legs = {}
+            for b_ in (["host", "device"] if args.e2e_builder == "both" else [args.e2e_builder]):
+                try:
+                    legs[b_] = e2e_leg(b_)
+                except Exception as ex:
+                    import traceback
+
+                    traceback.print_exc(file=sys.stderr)
+                    legs[b_] = {"value": None, "error": repr(ex)[:300], "stack_builder": b_}
+            ok = [v for v in legs.values() if v.get("value")]
+            if not ok:
+                raise RuntimeError("no e2e variant ran: %r" % ({k: v.get("error") for k, v in legs.items()},))
+            if len(ok) == 2 and abs(ok[0]["sum_c"] / ok[1]["sum_c"] - 1.0) > 1e-12:
+                raise RuntimeError("e2e variants disagree: sum(C) %r vs %r" % (ok[0]["sum_c"], ok[1]["sum_c"]))
+            e2e = dict(max(ok, key=lambda v: v["value"]))
+            e2e["variants"] = {k: {kk: v.get(kk) for kk in ("value", "ms_per_step", "host_threads", "row_chunks_per_thread", "host_build_seconds",
+                                                          "phases_last_step", "h2d_bytes_per_step", "error") if v.get(kk) is not None}
+                               for k, v in legs.items()}
+            for p_ in [pa, pb]:
                 p_.free()
         except Exception as ex:  # the headline line must still be printed (e.g. not enough pinned memory on this host) -- but loudly
             import traceback
@@ -755,6 +789,10 @@ def main():
     ap.add_argument("--row-chunks", type=int, default=4, help="block-row chunks per host thread in the e2e engine (earlier D2H)")
     ap.add_argument("--pipelined-upload", action="store_true",
                     help="e2e: upload the left panel in block-row chunks behind the right panel (measured neutral on cfg2: 96.2 vs 95.2 ms)")
+    ap.add_argument("--e2e-builder", default="both", choices=["host", "device", "both"],
+                    help="stack builder of the e2e leg: multi-threaded host builder, device-side builder, or both (the faster one is reported)")
+    ap.add_argument("--dev-threads", type=int, default=2, help="host threads (= independent device build pipelines) of the device-builder e2e leg")
+    ap.add_argument("--dev-row-chunks", type=int, default=4, help="block-row slices per thread of the device-builder e2e leg (early D2H)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

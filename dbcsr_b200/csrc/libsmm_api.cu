@@ -493,6 +493,10 @@ __global__ void __launch_bounds__(1024) zero_trickle_kernel(uint4* __restrict__ 
 // RANDOM mantissas (per-thread hash): the power a B200 draws for FP64 multiplies depends on the operand bits, and with uniform(0,1)
 // matrix data the board's power limit pulls the SM clock down after ~50 ms of sustained DMMA load -- a probe fed with constants
 // or small integers never sees that limit (it reads 37 TFLOP/s for as long as it runs) and would overstate what is attainable.
+// FRESH: the A/B fragments get new random mantissas every iteration (two integer ops per operand, hidden behind the 16-cycle DMMA
+// issue interval) like a kernel that loads new fragments for every DMMA; with constant operands the multiplier inputs never toggle
+// and the probe draws far less power than any real contraction.
+template <bool FRESH>
 __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, unsigned seed) {
   double c0[9], c1[9];
   unsigned long long h = (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + seed;
@@ -508,6 +512,16 @@ __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, 
 #pragma unroll
   for (int i = 0; i < 3; ++i) a[i] = rnd(), b[i] = rnd() - 0.5;
   for (int it = 0; it < iters; ++it) {
+    if (FRESH) {
+      h ^= h >> 12;
+      h ^= h << 25;
+      h ^= h >> 27;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {  // new mantissa bits, exponent and sign kept: values stay in their range
+        a[i] = __longlong_as_double(__double_as_longlong(a[i]) ^ (long long)((h >> (4 * i)) & 0x000FFFFFFFFFFFF0ull));
+        b[i] = __longlong_as_double(__double_as_longlong(b[i]) ^ (long long)((h >> (4 * i + 2)) & 0x0007FFFFFFFFFFF0ull));
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -616,7 +630,14 @@ int libsmm_acc_b200_memset_zero_trickle(void* dev_mem, size_t offset, size_t nby
 
 // Measured FP64 tensor-pipe (DMMA.8x8x4) throughput of the active device in GFLOP/s: 16 warps per SM, register operands, best of
 // three timed launches on `stream` (synchronises it).  Returns <= 0 on failure.  Introspection only: not on any product path.
-double libsmm_acc_b200_fp64_peak_gflops(void* stream) {
+static void launch_peak(int sms, int warps, int iters, bool fresh, cudaStream_t st) {
+  if (fresh)
+    fp64_peak_kernel<true><<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
+  else
+    fp64_peak_kernel<false><<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
+}
+
+static double peak_burst(void* stream, bool fresh) {
   if (stream == nullptr) return -2.0;
   const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
   const int sms = num_sms(), warps = 16, iters = 4096;
@@ -625,7 +646,7 @@ double libsmm_acc_b200_fp64_peak_gflops(void* stream) {
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0, st);
-    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
+    launch_peak(sms, warps, iters, fresh, st);
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) {
       best = -31.0;
@@ -703,7 +724,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
 // Same loop run back to back for `seconds` (power / thermal limits act within tens of milliseconds on a B200: a kernel timed
 // inside a long step has to be compared with THIS figure, a kernel timed alone with the burst figure above): throughput over the
 // second half of the interval.  Synchronises `stream`.
-double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) {
+static double peak_sustained(void* stream, double seconds, bool fresh) {
   if (stream == nullptr || !(seconds > 0.0) || seconds > 10.0) return -2.0;
   const cudaStream_t st = *static_cast<cudaStream_t*>(stream);
   const int sms = num_sms(), warps = 16, iters = 4096;
@@ -713,7 +734,7 @@ double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) 
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -30.0;
   for (int i = 0; i < n; ++i) {
     if (i == n / 2) cudaEventRecord(e0, st);
-    fp64_peak_kernel<<<sms, warps * 32, 0, st>>>(nullptr, iters, 12345u);
+    launch_peak(sms, warps, iters, fresh, st);
   }
   cudaEventRecord(e1, st);
   double out = -31.0;
@@ -725,6 +746,13 @@ double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return out;
+}
+
+double libsmm_acc_b200_fp64_peak_gflops(void* stream) { return peak_burst(stream, false); }
+double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) { return peak_sustained(stream, seconds, false); }
+// fresh_operands != 0: new random operand mantissas for every DMMA (what a real contraction feeds the pipe); seconds <= 0: burst
+double libsmm_acc_b200_fp64_peak_ex(void* stream, double seconds, int fresh_operands) {
+  return seconds > 0.0 ? peak_sustained(stream, seconds, fresh_operands != 0) : peak_burst(stream, fresh_operands != 0);
 }
 
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
