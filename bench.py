@@ -438,7 +438,11 @@ def measure_fp64_peaks(torch, acc, s):
     pipe can do) and cuBLAS DGEMM 8192^3 through torch.matmul (what NVIDIA's own FP64 GEMM reaches)."""
     dmma = acc.fp64_peak_gflops(s)
     dmma_sustained = acc.fp64_peak_sustained_gflops(s, 0.4)
+    time.sleep(0.3)
+    fresh = acc.fp64_peak_ex(s, 0.0, True)
+    fresh_sustained = acc.fp64_peak_ex(s, 0.4, True)
     dgemm = None
+    dgemm_sustained = None
     try:
         n = 8192
         x = torch.rand((n, n), dtype=torch.float64, device="cuda")
@@ -453,11 +457,21 @@ def measure_fp64_peaks(torch, acc, s):
             if i:
                 best = min(best, e0.elapsed_time(e1))
         dgemm = 2.0 * n ** 3 / (best * 1e-3) * 1e-9
+        # back to back for ~0.4 s on the same uniform(0,1) data the bench feeds the stack kernel: what cuBLAS sustains under the power limit
+        reps = max(4, int(0.4 / (best * 1e-3)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(reps):
+            if i == reps // 2:
+                e0.record()
+            torch.matmul(x, y)
+        e1.record()
+        e1.synchronize()
+        dgemm_sustained = 2.0 * n ** 3 * (reps - reps // 2) / (e0.elapsed_time(e1) * 1e-3) * 1e-9
         del x, y
         torch.cuda.empty_cache()
     except Exception as ex:
         print("bench: cuBLAS DGEMM peak probe failed: %r" % (ex,), file=sys.stderr)
-    return {"dmma_burst": dmma, "dmma_sustained": dmma_sustained, "dgemm": dgemm}
+    return {"dmma_burst": dmma, "dmma_sustained": dmma_sustained, "dgemm": dgemm, "dgemm_sustained": dgemm_sustained, "dmma_fresh_burst": fresh, "dmma_fresh_sustained": fresh_sustained}
 
 
 def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peaks, ncu_key):
@@ -526,6 +540,12 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
         "burst": {"note": "one drain / one peak-probe launch after the device idled (SM clock at maximum)", "kernel_only_gflops": kernel_burst,
                   "peak_gflops": dmma_burst, "frac": kernel_burst / dmma_burst if dmma_burst > 0 else None},
         "cublas_dgemm_8192_gflops": dgemm_peak,
+        "cublas_dgemm_8192_sustained_gflops": peaks.get("dgemm_sustained"),
+        "dmma_fresh_operands": {
+            "note": "the same DMMA loop with NEW random operand mantissas for every instruction (a contraction loads new fragments for every DMMA; with the constant fragments of the probe above the multiplier inputs never toggle and the power limit is not reached): what the pipe sustains on real data under this board's power limit",
+            "burst_gflops": peaks.get("dmma_fresh_burst"), "sustained_gflops": peaks.get("dmma_fresh_sustained"),
+            "frac_sustained": (kernel_only / peaks["dmma_fresh_sustained"]) if peaks.get("dmma_fresh_sustained", 0) and peaks["dmma_fresh_sustained"] > 0 else None,
+            "frac_burst": (kernel_burst / peaks["dmma_fresh_burst"]) if peaks.get("dmma_fresh_burst", 0) and peaks["dmma_fresh_burst"] > 0 else None},
         "kernel": "smm_dmma_kernel<%d,%d,%d> (dominant of %d launches/step)" % (m0, n0, k0, nst),
         "algorithmic_flop_per_launch": run.flop / nst, "avg_launch_us": launch_us, "kernel_only_gflops": kernel_only,
         "host_enqueue_us_per_launch": host_enqueue_us,

@@ -19,6 +19,7 @@
 #include "../../include/dbcsr_acc_libsmm.h"
 #include "smm_bf16.cuh"
 #include "smm_bf16_tiled.cuh"
+#include "smm_bf16_plan.cuh"
 #include "smm_dmma_big.cuh"
 #include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
@@ -77,6 +78,7 @@ const bool g_tune_env_read = [] {
   if (const char* e = getenv("DBCSR_B200_INHOMOGENEOUS")) smm::g_tune.inhomogeneous.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BF16_MERGE")) smm::g_tune.bf16_merge.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BF16_A_TMEM")) smm::g_tune.bf16_a_tmem.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_BF16_PLAN")) smm::g_tune.bf16_plan.store(atoi(e));
   return true;
 }();
 
@@ -533,6 +535,42 @@ __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, 
   if (s == 1.2345e300) out[0] = s;
 }
 
+
+// plan buffers of the tiled BF16 SpGEMM, one per stream, kept for the lifetime of the library (a multiply re-derives its plan
+// on the stream it runs on, so consecutive calls on one stream may share the buffer; `zeros_off`: the zero tile, cleared once)
+struct BtScratch {
+  cudaStream_t st;
+  int dev;
+  unsigned char* buf;
+  size_t cap;
+};
+std::mutex g_bt_mu;
+std::vector<BtScratch> g_bt_scratch;
+unsigned char* bt_plan_scratch(cudaStream_t st, size_t bytes, size_t zeros_off) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_bt_mu);
+  BtScratch* e = nullptr;
+  for (auto& x : g_bt_scratch)
+    if (x.st == st && x.dev == dev) e = &x;
+  if (e == nullptr) {
+    g_bt_scratch.push_back(BtScratch{st, dev, nullptr, 0});
+    e = &g_bt_scratch.back();
+  }
+  if (e->cap < bytes) {
+    if (e->buf != nullptr) {
+      cudaStreamSynchronize(st);
+      cudaFree(e->buf);
+      e->buf = nullptr;
+      e->cap = 0;
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&e->buf), bytes) != cudaSuccess) return nullptr;
+    e->cap = bytes;
+  }
+  // the zero tile sits at a size-dependent offset: clear it on every call (10 KB)
+  if (cudaMemsetAsync(e->buf + zeros_off, 0, 5 * 2048, st) != cudaSuccess) return nullptr;
+  return e->buf;
+}
 }  // namespace
 
 extern "C" {
@@ -560,6 +598,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "inhomogeneous") == 0) smm::g_tune.inhomogeneous.store((int)value);
   else if (strcmp(name, "bf16_merge") == 0) smm::g_tune.bf16_merge.store((int)value);
   else if (strcmp(name, "bf16_a_tmem") == 0) smm::g_tune.bf16_a_tmem.store((int)value);
+  else if (strcmp(name, "bf16_plan") == 0) smm::g_tune.bf16_plan.store((int)value);
   else if (strcmp(name, "trace_first") == 0) smm::g_tune.trace_first.store((int)value);
   else if (strcmp(name, "trace_count") == 0) smm::g_tune.trace_count.store((int)value);
   else if (strcmp(name, "seq") == 0) smm::g_tune.seq.store((int)value);
@@ -576,6 +615,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "inhomogeneous") == 0) return smm::g_tune.inhomogeneous.load();
   if (strcmp(name, "bf16_merge") == 0) return smm::g_tune.bf16_merge.load();
   if (strcmp(name, "bf16_a_tmem") == 0) return smm::g_tune.bf16_a_tmem.load();
+  if (strcmp(name, "bf16_plan") == 0) return smm::g_tune.bf16_plan.load();
   if (strcmp(name, "trace_first") == 0) return smm::g_tune.trace_first.load();
   if (strcmp(name, "trace_count") == 0) return smm::g_tune.trace_count.load();
   if (strcmp(name, "seq") == 0) return smm::g_tune.seq.load();
@@ -698,12 +738,47 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   const int flags = (smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0) |
                     (smm::g_tune.bf16_a_tmem.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_A_TMEM : 0);
   const int nb = (flags & smm::BT_FLAG_A_TMEM) ? smm::BT_NB_A_TMEM : smm::BT_NB;
-  static SmemAttrCache smem_set;
-  if (ensure_smem(smm::smm_bf16_tiled_kernel, smem, smem_set) != 0) return -30;
   const int bpt = g.bpt;
   const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + nb - 1) / nb;
   int grid = n_rg * n_cg;
   if (grid > num_sms()) grid = num_sms();
+  if (smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0) {
+    // planned variant: copy commands and MMA runs per (row group | column group, k block) derived once, then the multiply
+    static SmemAttrCache smem_set_p;
+    const int smem_p = (int)smm::bp_smem_bytes();
+    if (ensure_smem(smm::smm_bf16_planned_kernel, smem_p, smem_set_p) != 0) return -30;
+    size_t off[5];
+    const size_t bytes = smm::bt_plan_bytes(n_rg, n_cg, nkb, off);
+    unsigned char* buf = bt_plan_scratch(st, bytes, off[4]);
+    if (buf == nullptr) return -40;
+    smm::BtPlanPtrs P;
+    P.a_cmd = reinterpret_cast<uint4*>(buf + off[0]);
+    P.b_cmd = reinterpret_cast<uint4*>(buf + off[1]);
+    P.m_runs = reinterpret_cast<uint4*>(buf + off[2]);
+    P.a_any = buf + off[3];
+    P.zeros = buf + off[4];
+    const long long items = (long long)(n_rg + n_cg) * nkb;
+    int pgrid = (int)std::min<long long>((items + 127) / 128, (long long)num_sms() * 16);
+    if (pgrid < 1) pgrid = 1;
+    smm::bt_plan_kernel<<<pgrid, 128, 0, st>>>(static_cast<const unsigned char*>(a_tiles), dev_a_map, static_cast<const unsigned char*>(b_tiles),
+                                              dev_b_map, nrb, ncb, nkb, m, n, nb, P);
+    if (cudaPeekAtLastError() != cudaSuccess) return -31;
+    cudaLaunchConfig_t cfgp = {};
+    cfgp.gridDim = dim3((unsigned)grid);
+    cfgp.blockDim = dim3(smm::BT_THREADS);
+    cfgp.dynamicSmemBytes = (size_t)smem_p;
+    cfgp.stream = st;
+    cudaLaunchAttribute attrp[1];
+    attrp[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrp[0].val.programmaticStreamSerializationAllowed = 1;
+    cfgp.attrs = attrp;
+    cfgp.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, flags) != cudaSuccess) return -31;
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return 0;
+  }
+  static SmemAttrCache smem_set;
+  if (ensure_smem(smm::smm_bf16_tiled_kernel, smem, smem_set) != 0) return -30;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(smm::BT_THREADS);

@@ -22,6 +22,7 @@ struct Tunables {
   std::atomic<int> bigdmma{1};  // 1 (default): blocks with a dimension in 33..80 use the cooperative DMMA kernel (smm_dmma_big.cuh); 0: scalar generic kernel
   std::atomic<int> inhomogeneous{1};  // 1: def_mnk = 0 stacks are binned by shape and drained on the GPU; 0: -1 like the reference
   std::atomic<int> bf16_merge{1};     // tiled BF16 SpGEMM: 1 = one wide MMA per run of adjacent existing B blocks, 0 = one per block
+  std::atomic<int> bf16_plan{1};      // tiled BF16 SpGEMM: 1 = planned kernel (smm_bf16_plan.cuh: copy commands / MMA runs derived once per multiply)
   std::atomic<int> bf16_a_tmem{0};    // tiled BF16 SpGEMM: 1 = A operand staged in TMEM by tcgen05.cp (15 block columns per tile)
   std::atomic<int> balance{0};
   std::atomic<int> chunk{-1};  // -1 = per-shape policy (smm_inst.cu), 0 = one resident wave, n > 0 = n entries per warp

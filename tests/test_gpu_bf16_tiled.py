@@ -76,10 +76,14 @@ def run_case(acc, nrb, ncb, nkb, m, n, k, occ_a, occ_b, seed, knock_out=False):
 
 # kernel modes (run-time tunables, dbcsr_b200/csrc/smm_tune.h): one MMA per existing B block / per run of adjacent blocks, A operand
 # read from shared memory by every MMA / staged once per k block in TMEM (tcgen05.cp)
-MODES = [dict(bf16_merge=1, bf16_a_tmem=0), dict(bf16_merge=0, bf16_a_tmem=0), dict(bf16_merge=1, bf16_a_tmem=1), dict(bf16_merge=0, bf16_a_tmem=1)]
+# bf16_plan=1 (default): the planned kernel (smm_bf16_plan.cuh: copy commands and MMA runs derived once per multiply by bt_plan_kernel,
+# accumulators zeroed by the epilogue); bf16_plan=0: the first tiled kernel, which derives everything from the presence maps per k block
+MODES = [dict(bf16_plan=1, bf16_merge=1, bf16_a_tmem=0), dict(bf16_plan=1, bf16_merge=1, bf16_a_tmem=1),
+         dict(bf16_plan=0, bf16_merge=1, bf16_a_tmem=0), dict(bf16_plan=0, bf16_merge=0, bf16_a_tmem=0),
+         dict(bf16_plan=0, bf16_merge=1, bf16_a_tmem=1), dict(bf16_plan=0, bf16_merge=0, bf16_a_tmem=1)]
 
 
-@pytest.fixture(params=MODES, ids=lambda m: "merge%d_atmem%d" % (m["bf16_merge"], m["bf16_a_tmem"]))
+@pytest.fixture(params=MODES, ids=lambda m: "plan%d_merge%d_atmem%d" % (m["bf16_plan"], m["bf16_merge"], m["bf16_a_tmem"]))
 def mode(acc, request):
     saved = {k: acc.get_tunable(k) for k in request.param}
     for k, v in request.param.items():
