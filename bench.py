@@ -276,7 +276,7 @@ class Fp64Run:
     """One FP64 config on one GPU: stacks pre-built (one host thread = the reference's traversal order) and resident, panels
     resident, drained through libsmm_acc_process."""
 
-    def __init__(self, acc, cfg_name, nblk, s, nstreams=1):
+    def __init__(self, acc, cfg_name, nblk, s, nstreams=1, dev_tile=0):
         from dbcsr_b200 import host, workload
 
         self.acc, self.s = acc, s
@@ -290,17 +290,28 @@ class Fp64Run:
         self.w = w = workload.make_config(cfg_name, nblk=nblk)
         A, B, bs = w["A"], w["B"], w["m_sizes"]
         self.n_st = 3 if len(w["sizes"]) <= 3 else len(w["sizes"])
-        eng = host.Engine(bs, bs, bs, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(n_stacks=self.n_st))
-        eng.multiply(A.list3(), None, B.list3(), None)
+        self.d_a = acc.to_device(A.data, s)
+        self.d_b = acc.to_device(B.data, s)
+        host.transpose_panel(acc, B.list3(), bs, bs, self.d_b.ptr, s)
+        self.dev_tile = dev_tile
+        if dev_tile:
+            # stacks of the DEVICE-side builder in tile order (include/dbcsr_b200_host.h, dev_tile): same C index and products as the
+            # reference's traversal, ordered by dev_tile x dev_tile squares of C blocks; recorded from one real multiply on the device
+            acc.stream_sync(s)
+            eng = host.Engine(bs, bs, bs, nthreads=1, mode=host.LAUNCH | host.RECORD | host.DEVICE_BUILD,
+                              cfg=host.default_cfg(n_stacks=self.n_st, dev_tile=dev_tile))
+            eng.multiply(A.list3(), self.d_a.ptr, B.list3(), self.d_b.ptr)
+            eng.sync()
+            assert eng.device_built_ticks == 1
+        else:
+            eng = host.Engine(bs, bs, bs, nthreads=1, mode=host.RECORD, cfg=host.default_cfg(n_stacks=self.n_st))
+            eng.multiply(A.list3(), None, B.list3(), None)
         self.stacks = eng.stacks()
         self.flop = eng.flop()
         self.c_rows, self.c_cols, self.c_blk_p, self.c_datasize = eng.c_index(0)
         self.c_rows, self.c_cols, self.c_blk_p = self.c_rows.copy(), self.c_cols.copy(), self.c_blk_p.copy()
         eng.close()
         self.n_entries = sum(st["dev"].shape[0] for st in self.stacks)
-        self.d_a = acc.to_device(A.data, s)
-        self.d_b = acc.to_device(B.data, s)
-        host.transpose_panel(acc, B.list3(), bs, bs, self.d_b.ptr, s)
         all_dev = np.concatenate([st["dev"].reshape(-1) for st in self.stacks]).astype(np.int32)
         self.d_st = acc.to_device(all_dev, s)
         self.offs = np.concatenate([[0], np.cumsum([st["dev"].size for st in self.stacks])]).astype(np.int64)
@@ -524,7 +535,7 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
     ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(ncu_json):
         try:
-            traffic = json.load(open(ncu_json)).get(ncu_key, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(ncu_json)).get(ncu_key, {}).get("dram_bytes_per_launch") if ncu_key else None
         except Exception:
             traffic = None
     st0 = max(run.stacks, key=lambda st: st["dev"].shape[0] * st["m"] * st["n"] * st["k"])
@@ -756,6 +767,28 @@ def run_single(args):
             cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": "failed: " + repr(ex)[:200]}
     run.close()
 
+    # ---- the same multiply on the device builder's TILE-ORDERED stacks (not the reference's stack contents: same products and C index,
+    #      every C block accumulated in one run, operands L2 resident per square of C blocks) -- what an engine that builds its stacks
+    #      on the device can feed the same kernel; reported beside the headline, never instead of it
+    tiled = None
+    if args.config == "cfg2" and args.dev_tile > 0 and not args.no_tiled:
+        try:
+            rt = Fp64Run(acc, args.config, args.nblk, s, dev_tile=args.dev_tile)
+            rept = fp64_config_report(torch, tstream, acc, s, rt, max(3, args.steps // 2), 3, 0 if args.no_selfcheck else args.probe_blocks, peaks, None)
+            tiled = {"value": rept["value"], "unit": "GFLOP/s", "ms_per_step": rept["ms_per_step"], "kernel_only_gflops": rept["kernel_only_gflops"],
+                     "burst_kernel_only_gflops": rept["roofline"]["burst"]["kernel_only_gflops"], "frac_of_fp64_tensor_peak": rept["roofline"]["frac"],
+                     "burst_frac": rept["roofline"]["burst"]["frac"], "dev_tile": args.dev_tile, "stacks": rept["stacks"],
+                     "mean_run_length": rt.n_entries / max(1, rt.runs), "selfcheck": rept["selfcheck"], "zero_mode": rept["zero_mode"],
+                     "drain_series_after_idle_ms": rept["roofline"]["drain_series_after_idle_ms"],
+                     "note": "stacks built by the device-side builder in tile order (cfg.dev_tile): identical C index and products, different "
+                             "stack contents than DBCSR's traversal; the headline `value` stays on the reference's stacks"}
+            rt.close()
+        except Exception as ex:
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            tiled = {"error": repr(ex)[:300]}
+
     # ---- the other single-GPU configs of BASELINE.json at their full size (driver-visible; not bench lines of their own)
     extra = {}
     if args.config == "cfg2" and not args.no_extra and (args.nblk is None or args.extra_nblk is not None):
@@ -792,7 +825,7 @@ def run_single(args):
                                          "timed": "CUDA events on the launching stream; step = one memset of the whole C buffer + %d libsmm_acc_process calls into it; memset %s (trial: %s)" % (rep["stacks"], rep["zero_mode"], json.dumps(rep["zero_mode_trial_ms"])),
                                          "pdl_chain": not args.no_chain}),
            "clocks": clocks, "gpu_launches": rep["launches"], "wall_s_timed_region": rep["wall_s"], "roofline": rep["roofline"], "e2e": e2e, "cpu_baseline": cpu,
-           "gpu_baseline": gpu_base, "selfcheck": rep["selfcheck"], "extra_configs": extra or None}
+           "gpu_baseline": gpu_base, "selfcheck": rep["selfcheck"], "tile_order": tiled, "extra_configs": extra or None}
     print(json.dumps(out))
     acc.stream_destroy(s)
 
@@ -813,6 +846,8 @@ def main():
                     help="stack builder of the e2e leg: multi-threaded host builder, device-side builder, or both (the faster one is reported)")
     ap.add_argument("--dev-threads", type=int, default=2, help="host threads (= independent device build pipelines) of the device-builder e2e leg")
     ap.add_argument("--dev-row-chunks", type=int, default=4, help="block-row slices per thread of the device-builder e2e leg (early D2H)")
+    ap.add_argument("--dev-tile", type=int, default=64, help="square size (C blocks) of the tile-order leg; 0 = skip")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the tile-order leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

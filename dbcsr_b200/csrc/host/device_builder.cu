@@ -325,6 +325,30 @@ struct MakeKeys {  // (dispatch number, c_first) for stacks the accelerator driv
   }
 };
 
+// Tile order (not the reference's): inside a (slice, stack number) group the products are ordered by T x T tiles of C blocks, inside
+// a tile by c_first -- every C block is then accumulated in ONE run of consecutive entries (all its products are adjacent) and a
+// tile's A rows / B columns / C blocks stay L2 resident while it is worked on.
+struct MakeKeysTiled {
+  const long long* seq_start;  // nd + 1 (dispatch list of the flush rule: it partitions the same products)
+  int nd;
+  const int *d_ws, *d_begin, *d_group;
+  const int* bin_start;
+  const u32 *part_p, *slot, *val;
+  const int *a_list, *b_list, *prod_a, *prod_b, *c_blkp;
+  int lowbits, tilebits, tile, ntc;
+  u64* key;
+  u32* pout;
+  DB_HD void operator()(long long i) const {
+    const int d = upper_bound_n(seq_start, nd + 1, i) - 1;
+    const u32 j = (u32)(i - seq_start[d]);
+    const u32 p = part_p[(size_t)bin_start[d_ws[d]] + (size_t)d_begin[d] + j];
+    const int row = a_list[3 * (size_t)prod_a[p]], col = b_list[3 * (size_t)prod_b[p] + 1];
+    const u64 t = (u64)((row - 1) / tile) * (u64)ntc + (u64)((col - 1) / tile);
+    key[i] = ((u64)d_group[d] << (lowbits + tilebits)) | (t << lowbits) | (u64)(u32)c_blkp[val[slot[p]] - 1];
+    pout[i] = p;
+  }
+};
+
 struct WriteStack3 {
   const u32 *psorted, *slot, *val;
   const int *a_list, *b_list, *prod_a, *prod_b, *c_blkp;
@@ -337,15 +361,14 @@ struct WriteStack3 {
   }
 };
 
-struct WriteParams7 {  // one dispatch entry in traversal order
+struct WriteParams7 {  // one dispatch entry in host order: products plist[offset ...]
   SizeMaps z;
-  const int* bin_start;
-  const u32 *part_p, *slot, *val;
+  const u32 *plist, *slot, *val;
   const int *a_list, *b_list, *prod_a, *prod_b, *c_blkp;
-  int ws, begin;
+  long long offset;
   int* out7;
   DB_HD void operator()(long long i) const {
-    const u32 p = part_p[(size_t)bin_start[ws] + (size_t)begin + (size_t)i];
+    const u32 p = plist[(size_t)offset + (size_t)i];
     const int a = prod_a[p], b = prod_b[p];
     const int id = (int)val[slot[p]];
     int* o = out7 + 7 * (size_t)i;
@@ -542,6 +565,9 @@ class Builder final : public IDeviceBuilder {
   SizeMaps maps_{};
   const int* d_bin_start_ = nullptr;
   long long nprod_ = 0, nkept_ = 0;
+  std::vector<int> h_bin_start_;
+  int tile_ = 0;             // > 0: tile order (set_tile_order)
+  bool tiled_last_ = false;  // the last build used it
 
   int ensure(Buf& b, size_t bytes, bool keep = false, size_t keep_bytes = 0) {
     if (bytes <= b.cap) return 0;
@@ -805,6 +831,8 @@ class Builder final : public IDeviceBuilder {
     if (x_.d2h(info.data(), info_.p, sizeof(long long) * info.size()) != 0 || x_.d2h(&nd, d_bin_start + 257 + 768, sizeof(int)) != 0 || x_.sync() != 0)
       return -62;
     if (nd > max_out) return -69;
+    h_bin_start_.assign(257, 0);
+    if (x_.d2h(h_bin_start_.data(), d_bin_start, sizeof(int) * 257) != 0 || x_.sync() != 0) return -62;
     if ((long long)datasize_ + info[1] > 0x7fffffffll) return -42;  // offsets are int32
     std::vector<int> disp(4 * (size_t)nd);
     if (nd > 0 && (x_.d2h(disp.data(), disp_.p, sizeof(int) * disp.size()) != 0 || x_.sync() != 0)) return -62;
@@ -830,7 +858,14 @@ class Builder final : public IDeviceBuilder {
     nkept_ = seq[(size_t)nd];
     nblk_ = out.nblk_after;
     datasize_ = out.datasize_after;
+    tiled_last_ = false;
     if (nkept_ == 0) return 0;
+    bool all_devord = cfg.stack_sort != 0;
+    for (int d = 0; d < nd; ++d) all_devord = all_devord && d_devord[(size_t)d] != 0;
+    if (tile_ > 0 && all_devord) {
+      const int rc_t = build_tiled(mm, nslices, nd, seq, d_ws, d_begin, out);
+      if (rc_t != -70) return rc_t;  // -70: keys would not fit => reference order below
+    }
     // ---- device order of every stack: one stable sort over (dispatch number, c_first | rank)
     int lowbits = 1, dbits = 1;
     while ((1ll << lowbits) <= std::max((long long)datasize_, (long long)cfg.mm_stack_size)) ++lowbits;
@@ -855,6 +890,70 @@ class Builder final : public IDeviceBuilder {
     return 0;
   }
 
+  void set_tile_order(int tile) override { tile_ = tile > 0 ? tile : 0; }
+
+  // stacks of the tile order: groups (slice, stack number) in dispatch order, each cut into stacks of mm_stack_size entries
+  int build_tiled(LocalMultiply& mm, int nslices, int nd, const std::vector<long long>& seq, const std::vector<int>& d_ws, const std::vector<int>& d_begin,
+                  DevBuildResult& out) {
+    const Config& cfg = mm.config();
+    const int nstacks = mm.nstacks();
+    const long long nrows = (long long)mm.m_sizes().size(), ncols = (long long)mm.n_sizes().size();
+    const long long ntr = (nrows + tile_ - 1) / tile_, ntc = (ncols + tile_ - 1) / tile_;
+    std::vector<long long> gcount((size_t)nslices * (nstacks + 1), 0);
+    std::vector<int> d_group((size_t)nd);
+    for (int d = 0; d < nd; ++d) {
+      const int gi = out.dispatch[(size_t)d].slice * (nstacks + 1) + out.dispatch[(size_t)d].ws;
+      gcount[(size_t)gi] += out.dispatch[(size_t)d].size;
+      d_group[(size_t)d] = gi;
+    }
+    int lowbits = 1, tilebits = 1, gbits = 1;
+    while ((1ll << lowbits) <= (long long)datasize_) ++lowbits;
+    while ((1ll << tilebits) < ntr * ntc) ++tilebits;
+    while ((1ll << gbits) < (long long)gcount.size()) ++gbits;
+    if (lowbits + tilebits + gbits > 63 || ntc > 0x7fffffffll) return -70;
+    const size_t tab_bytes = sizeof(long long) * ((size_t)nd + 1) + sizeof(int) * 3 * (size_t)nd;
+    if (int rc = ensure(dtab_, tab_bytes + 64)) return rc;
+    long long* t_seq = ptr<long long>(dtab_);
+    int* t_ws = reinterpret_cast<int*>(t_seq + nd + 1);
+    int* t_begin = t_ws + nd;
+    int* t_group = t_begin + nd;
+    if (x_.h2d(t_seq, seq.data(), sizeof(long long) * ((size_t)nd + 1)) != 0 || x_.h2d(t_ws, d_ws.data(), sizeof(int) * (size_t)nd) != 0 ||
+        x_.h2d(t_begin, d_begin.data(), sizeof(int) * (size_t)nd) != 0 || x_.h2d(t_group, d_group.data(), sizeof(int) * (size_t)nd) != 0)
+      return -61;
+    u64 *d_key = ptr<u64>(w64a_), *d_key_s = ptr<u64>(w64b_);
+    u32 *d_p = ptr<u32>(w32a_), *d_p_s = ptr<u32>(w32b_);
+    MakeKeysTiled mk{t_seq, nd, t_ws, t_begin, t_group, d_bin_start_, ptr<u32>(part_p_), ptr<u32>(slot_), table_.val, ptr<int>(a_list_), ptr<int>(b_list_),
+                     ptr<int>(prod_a_), ptr<int>(prod_b_), ptr<int>(c_blkp_), lowbits, tilebits, tile_, (int)ntc, d_key, d_p};
+    if (int rc = x_.for_each(nkept_, mk)) return rc;
+    if (int rc = x_.sort_pairs(d_key, d_key_s, d_p, d_p_s, nkept_, lowbits + tilebits + gbits)) return rc;
+    if (int rc = ensure(out3_, sizeof(int) * 3 * (size_t)nkept_)) return rc;
+    WriteStack3 ws3{d_p_s, ptr<u32>(slot_), table_.val, ptr<int>(a_list_), ptr<int>(b_list_), ptr<int>(prod_a_), ptr<int>(prod_b_), ptr<int>(c_blkp_),
+                    ptr<int>(out3_)};
+    if (int rc = x_.for_each(nkept_, ws3)) return rc;
+    // the new dispatch list
+    std::vector<DevDispatch> nl;
+    long long pos = 0;
+    const int S = std::max(1, cfg.mm_stack_size);
+    for (int sl = 0; sl < nslices; ++sl)
+      for (int ws = 1; ws <= nstacks; ++ws) {
+        long long left = gcount[(size_t)sl * (nstacks + 1) + ws];
+        while (left > 0) {
+          DevDispatch e;
+          e.ws = ws;
+          e.begin = -1;
+          e.size = (int)std::min<long long>(left, S);
+          e.slice = sl;
+          e.seq_start = pos;
+          nl.push_back(e);
+          pos += e.size;
+          left -= e.size;
+        }
+      }
+    out.dispatch.swap(nl);
+    tiled_last_ = true;
+    return 0;
+  }
+
   const int* stack3(const DevDispatch& d) const override { return ptr<int>(out3_) + 3 * (size_t)d.seq_start; }
   int fetch_stack3(const DevDispatch& d, int* host3) override {
     if (x_.d2h(host3, stack3(d), sizeof(int) * 3 * (size_t)d.size) != 0) return -61;
@@ -866,8 +965,11 @@ class Builder final : public IDeviceBuilder {
   }
   int fetch_params7(const DevDispatch& d, int* host7) override {
     if (int rc = ensure(p7_, sizeof(int) * 7 * (size_t)std::max(d.size, 1))) return rc;
-    WriteParams7 f{maps_, d_bin_start_, ptr<u32>(part_p_), ptr<u32>(slot_), table_.val, ptr<int>(a_list_), ptr<int>(b_list_), ptr<int>(prod_a_),
-                   ptr<int>(prod_b_), ptr<int>(c_blkp_), d.ws, d.begin, ptr<int>(p7_)};
+    // host order of the stack: traversal order (reference mode) or the stack's own order (tile mode)
+    const u32* plist = tiled_last_ ? ptr<u32>(w32b_) : ptr<u32>(part_p_);
+    const long long offset = tiled_last_ ? d.seq_start : (long long)h_bin_start_[(size_t)d.ws] + d.begin;
+    WriteParams7 f{maps_, plist, ptr<u32>(slot_), table_.val, ptr<int>(a_list_), ptr<int>(b_list_), ptr<int>(prod_a_),
+                   ptr<int>(prod_b_), ptr<int>(c_blkp_), offset, ptr<int>(p7_)};
     if (int rc = x_.for_each(d.size, f)) return rc;
     if (x_.d2h(host7, p7_.p, sizeof(int) * 7 * (size_t)d.size) != 0) return -61;
     return x_.sync();

@@ -47,6 +47,12 @@ class IDeviceBuilder {
   virtual ~IDeviceBuilder() {}
   // forget the product index (new multiply); keeps every allocation
   virtual int reset() = 0;
+  // tile > 0: NOT the reference's stacks -- inside every (slice, stack number) group the products are ordered by tile x tile squares
+  // of C blocks and by c_first inside a square, then cut into stacks of mm_stack_size entries.  The C index (block order, offsets)
+  // and the set of products stay those of the reference; what changes is the order of summation (all products of a C block are
+  // adjacent: one accumulation run per block) and the memory locality (a square's A rows, B columns and C blocks fit into L2).
+  // Applies when every dispatched stack is of the kind the accelerator driver sorts by c_first; 0 = reference order.
+  virtual void set_tile_order(int tile) = 0;
   // One tick of one host thread.  a_sorted / b_sorted: rec-sorted lists; slices: the (a_first, a_last) ranges (1-based, inclusive)
   // this thread multiplies, in order - each is one LocalMultiply::multiply call, i.e. ends with a purge.  mm supplies the
   // recursion (plan) and the block-size / stack maps.  Returns 0 or a negative code.

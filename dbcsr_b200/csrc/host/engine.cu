@@ -140,6 +140,7 @@ void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg) {
   cfg->binning_binsize = 16;
   cfg->thread_buffers = 8;
   cfg->row_chunks = 1;
+  cfg->dev_tile = 0;
 }
 
 void dbcsr_b200_rec_sort_index(int nrows, int ncols, int nblks, int* list3) {
@@ -199,6 +200,7 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
       else {
         ts.devb.reset(dbcsr_b200::make_emulated_builder());
       }
+      ts.devb->set_tile_order(cfg->dev_tile);
     }
   }
   return e;

@@ -14,7 +14,7 @@ LAUNCH, RECORD, DEVICE_BUILD = 1, 2, 4
 
 class Cfg(ctypes.Structure):
     _fields_ = [(n, _i) for n in ("mm_stack_size", "n_stacks", "multrec_limit", "stack_sort", "min_flop_sort", "binning_nbins",
-                                  "binning_binsize", "thread_buffers", "row_chunks")]
+                                  "binning_binsize", "thread_buffers", "row_chunks", "dev_tile")]
 
 
 _bound = False

@@ -30,6 +30,11 @@ typedef struct dbcsr_b200_cfg {
   int thread_buffers;  /* ACCDRV_THREAD_BUFFERS, 8 */
   int row_chunks;      /* (engine) block-row chunks per host thread, processed in row order; 1 = DBCSR's one slice per thread.
                           >1 lets the D2H of finished chunks start while later chunks are still being built/multiplied */
+  int dev_tile;        /* (engine, DBCSR_B200_DEVICE_BUILD) 0 = stacks identical to the host builder's (DBCSR's traversal order).
+                          T > 0 = tile order: inside every (row slice, stack number) group the products are ordered by T x T squares of
+                          C blocks and by c_first inside a square before they are cut into stacks.  Same C index, same set of products;
+                          every C block is accumulated in one run and a square's operands stay L2 resident (DRAM traffic of the stack
+                          kernels drops several times); the order of summation differs from the reference's (results agree to rounding). */
 } dbcsr_b200_cfg_t;
 void dbcsr_b200_cfg_default(dbcsr_b200_cfg_t* cfg);
 

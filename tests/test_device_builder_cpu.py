@@ -117,3 +117,41 @@ def test_other_multiplies_use_the_host_builder():
     assert_same(ref, dev, 1)
     ref.close()
     dev.close()
+
+
+@pytest.mark.parametrize("nthreads,row_chunks,tile", [(1, 1, 8), (2, 3, 16), (1, 2, 1000)])
+def test_tile_order_same_products_same_index(nthreads, row_chunks, tile):
+    """dev_tile > 0: NOT the reference's stacks, but the same C index (first-touch order, offsets), the same multiset of
+    (a, b, c) entries per thread and stack shape, stacks of at most mm_stack_size entries, and inside a stack every C block in
+    one run of consecutive entries."""
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(70, 60, 80, 0.3, 0.3, [23], seed=31)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    kw = dict(mm_stack_size=500, multrec_limit=64, row_chunks=row_chunks)
+    ref = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=nthreads, mode=host.RECORD, cfg=host.default_cfg(**kw))
+    dev = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=nthreads, mode=host.RECORD | host.DEVICE_BUILD, cfg=host.default_cfg(dev_tile=tile, **kw))
+    for e in (ref, dev):
+        e.multiply(a_l, None, b_l, None)
+        e.multiply(a_l[::2], None, b_l, None)  # second tick onto the same index
+    assert dev.device_built_ticks == 2 * nthreads
+    for t in range(nthreads):
+        for u, v in zip(ref.c_index(t), dev.c_index(t)):
+            assert np.array_equal(u, v)
+    assert ref.flop() == dev.flop()
+    for t in range(nthreads):
+        ea = np.concatenate([s["host"] for s in ref.stacks() if s["thread"] == t])
+        eb = np.concatenate([s["host"] for s in dev.stacks() if s["thread"] == t])
+        assert np.array_equal(ea[np.lexsort(ea.T[::-1])], eb[np.lexsort(eb.T[::-1])])
+    nruns_ref = nruns_dev = 0
+    for s in dev.stacks():
+        assert 0 < s["dev"].shape[0] <= 500 and s["defined_mnk"]
+        assert np.array_equal(s["dev"], s["host"][:, 3:6])  # a tile-ordered stack is handed over in its device order
+        c = s["dev"][:, 2]
+        starts = np.flatnonzero(np.r_[True, c[1:] != c[:-1]])
+        assert len(set(c[starts].tolist())) == starts.size  # every C block in ONE run
+        nruns_dev += starts.size
+    for s in ref.stacks():
+        c = s["dev"][:, 2]
+        nruns_ref += 1 + int(np.count_nonzero(c[1:] != c[:-1]))
+    assert nruns_dev <= nruns_ref
+    ref.close()
+    dev.close()

@@ -136,3 +136,36 @@ def test_device_builder_full_size_properties(acc):
     finally:
         dm.close()
         ref.close()
+
+
+@pytest.mark.parametrize("tile", [4, 64])
+def test_tile_order_product_matches_oracle(acc, tile):
+    """cfg.dev_tile: the device builder's tile order (same products and C index, other stack contents) gives the oracle's product."""
+    rng = np.random.default_rng(8)
+    ms, ns, ks = (workload.block_sizes(n, [23], rng) for n in (60, 70, 50))
+    A = workload.random_panel(ms, ks, 0.3, rng)
+    B = workload.random_panel(ks, ns, 0.3, rng)
+    cfg = dict(mm_stack_size=900, multrec_limit=64, row_chunks=2)
+    dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=2, cfg=host.default_cfg(dev_tile=tile, **cfg),
+                        mode=host.LAUNCH | host.RECORD | host.DEVICE_BUILD)
+    ref = host.Engine(ms, ns, ks, nthreads=2, mode=host.RECORD, cfg=host.default_cfg(**cfg))
+    try:
+        ref.multiply(A.list3(), None, B.list3(), None)
+        dm.upload_panels(A.data, B.data, B.list3())
+        dm.multiply(A.list3(), B.list3())
+        prod = dm.download_c()
+        assert dm.engine.device_built_ticks == 2
+        for t in range(2):
+            for u, v in zip(ref.c_index(t), dm.engine.c_index(t)):
+                assert np.array_equal(u, v)
+            ea = np.concatenate([s["host"] for s in ref.stacks() if s["thread"] == t])
+            eb = np.concatenate([s["host"] for s in dm.engine.stacks() if s["thread"] == t])
+            assert np.array_equal(ea[np.lexsort(ea.T[::-1])], eb[np.lexsort(eb.T[::-1])])
+        for s in dm.engine.stacks():
+            c = s["dev"][:, 2]
+            starts = np.flatnonzero(np.r_[True, c[1:] != c[:-1]])
+            assert len(set(c[starts].tolist())) == starts.size  # every C block in one run
+        check_against_oracle(A, B, prod, ms, ns)
+    finally:
+        dm.close()
+        ref.close()
