@@ -782,6 +782,18 @@ def run_single(args):
                      "drain_series_after_idle_ms": rept["roofline"]["drain_series_after_idle_ms"],
                      "note": "stacks built by the device-side builder in tile order (cfg.dev_tile): identical C index and products, different "
                              "stack contents than DBCSR's traversal; the headline `value` stays on the reference's stacks"}
+            if args.tiled_sweep:  # launch-policy knobs on the tile-ordered stacks: (align, chunk) -> ms per drain, burst and sustained
+                sweep = {}
+                for al, ch in [(1, 12), (0, 12), (1, 10), (0, 10), (1, 20), (0, 20), (1, 8), (1, 16), (1, 30), (0, 30), (1, 0), (0, 0)]:
+                    acc.set_tunable("align", al)
+                    acc.set_tunable("chunk", ch)
+                    time.sleep(0.3)
+                    b_ms, _ = timed_steps(torch, tstream, acc, s, lambda: rt.drain(rt.d_cs[0]), 1)
+                    s_ms, _ = timed_steps(torch, tstream, acc, s, lambda: rt.drain(rt.d_cs[0]), 10)
+                    sweep["align%d_chunk%d" % (al, ch)] = [round(float(b_ms[0]), 3), round(float(np.mean(s_ms[5:])), 3)]
+                acc.set_tunable("align", -1)
+                acc.set_tunable("chunk", -1)
+                tiled["policy_sweep_ms_burst_sustained"] = sweep
             rt.close()
         except Exception as ex:
             import traceback
@@ -848,6 +860,7 @@ def main():
     ap.add_argument("--dev-row-chunks", type=int, default=4, help="block-row slices per thread of the device-builder e2e leg (early D2H)")
     ap.add_argument("--dev-tile", type=int, default=64, help="square size (C blocks) of the tile-order leg; 0 = skip")
     ap.add_argument("--no-tiled", action="store_true", help="skip the tile-order leg")
+    ap.add_argument("--tiled-sweep", action="store_true", help="sweep the (align, chunk) launch knobs on the tile-ordered stacks (diagnostic)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

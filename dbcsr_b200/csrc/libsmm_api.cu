@@ -745,8 +745,13 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   if (smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0) {
     // planned variant: copy commands and MMA runs per (row group | column group, k block) derived once, then the multiply
     static SmemAttrCache smem_set_p;
-    const int smem_p = (int)smm::bp_smem_bytes();
-    if (ensure_smem(smm::smm_bf16_planned_kernel, smem_p, smem_set_p) != 0) return -30;
+    int ns = smm::BP_NS;  // DBCSR_B200_BF16_STAGES: experiment knob (fewer pipeline stages)
+    if (const char* e = getenv("DBCSR_B200_BF16_STAGES")) ns = std::max(2, std::min(smm::BP_NS, atoi(e)));
+    const int smem_p = (int)smm::bp_smem_bytes(ns);
+    static SmemAttrCache smem_set_pt;
+    const bool a_tmem = (flags & smm::BT_FLAG_A_TMEM) != 0;
+    if ((a_tmem ? ensure_smem(smm::smm_bf16_planned_kernel<true>, smem_p, smem_set_pt) : ensure_smem(smm::smm_bf16_planned_kernel<false>, smem_p, smem_set_p)) != 0)
+      return -30;
     size_t off[5];
     const size_t bytes = smm::bt_plan_bytes(n_rg, n_cg, nkb, off);
     unsigned char* buf = bt_plan_scratch(st, bytes, off[4]);
@@ -754,14 +759,13 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
     smm::BtPlanPtrs P;
     P.a_cmd = reinterpret_cast<uint4*>(buf + off[0]);
     P.b_cmd = reinterpret_cast<uint4*>(buf + off[1]);
-    P.m_runs = reinterpret_cast<uint4*>(buf + off[2]);
     P.a_any = buf + off[3];
     P.zeros = buf + off[4];
     const long long items = (long long)(n_rg + n_cg) * nkb;
     int pgrid = (int)std::min<long long>((items + 127) / 128, (long long)num_sms() * 16);
     if (pgrid < 1) pgrid = 1;
     smm::bt_plan_kernel<<<pgrid, 128, 0, st>>>(static_cast<const unsigned char*>(a_tiles), dev_a_map, static_cast<const unsigned char*>(b_tiles),
-                                              dev_b_map, nrb, ncb, nkb, m, n, nb, P);
+                                              dev_b_map, nrb, ncb, nkb, m, n, nb, ns, P);
     if (cudaPeekAtLastError() != cudaSuccess) return -31;
     cudaLaunchConfig_t cfgp = {};
     cfgp.gridDim = dim3((unsigned)grid);
@@ -773,7 +777,9 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
     attrp[0].val.programmaticStreamSerializationAllowed = 1;
     cfgp.attrs = attrp;
     cfgp.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, flags) != cudaSuccess) return -31;
+    const cudaError_t perr = a_tmem ? cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel<true>, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, ns)
+                                    : cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel<false>, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, ns);
+    if (perr != cudaSuccess) return -31;
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return 0;
   }

@@ -17,32 +17,32 @@
 
 namespace smm {
 
-// Third step: with the bookkeeping gone the kernel ran at 745 cycles per k block with 5 stages of 40 KB (8 KB of A + sixteen 2 KB B
-// slots, of which half are used at 50 % occupation): the time of a stage's round trip (TMA latency under load + MMAs) divided by
-// the stages in flight.  So the B blocks of a k block are now PACKED (only existing blocks occupy shared memory): a ring of 2 KB
-// slots managed by the B producer (allocation in ring order, a stage that would cross the nominal end starts at slot 0, older
-// stages are awaited oldest-first when their slots are needed), 8 stage entries instead of 5, ~1.6x the bytes in flight.
-constexpr int BP_NS = 8;          // stage entries (A: fixed 8 KB slots; B: ring allocation)
-constexpr int BP_RING = 81;       // physical B slots: (227 KB - 1 KB - 8 x 8 KB) / 2 KB
-constexpr int BP_RING_NOM = 66;   // a stage starts below this slot (it may extend up to 15 slots further)
+// Third step (measured, B200): with the producers' bookkeeping gone the kernel ran at 745 cycles per k block, and packing the B blocks
+// into a ring with 8 stage entries (1.6x the bytes in flight) made it SLOWER (43 vs 34 ms) -- the limit is not the copy latency but
+// the MMA issuer: SASS showed ~24 uniform-datapath instructions per run of blocks (unpacking the run, three 64-bit descriptor
+// additions, two predicated MMA forms) in a loop with a carried dependency, 6-7 cycles each.  So the plan now carries, per run, the
+// finished 32-bit words {B descriptor offset | accumulator column offset, instruction descriptor}; the B producer's spare lanes
+// copy the 64 bytes of a k block's runs into shared memory beside the stage, and the issuer reads them with four LDS.128 and
+// issues an unrolled, nested sequence (run q+1 is only looked at when run q exists): no global loads, no loop-carried chain.
+constexpr int BP_NS = BT_STAGES;  // stage entries: fixed slots, as in smm_bf16_tiled.cuh
 constexpr int BP_RA = 8;   // command slots per row of the A plan (<= 5 used)
-constexpr int BP_RB = 16;  // command slots per row of the B plan
+constexpr int BP_RB = 20;  // uint4 per row of the B plan: 16 copy commands + 4 x (2 MMA runs)
 constexpr int BP_KC = 8;   // plan rows prefetched per lane
 
 struct BtPlanPtrs {
   uint4* a_cmd;           // [n_rg][nkb][BP_RA]: x,y = source address, z = stage offset | bytes << 16, w (slot 0) = bytes of the row
-  uint4* b_cmd;           // [n_cg][nkb][BP_RB]
-  uint4* m_runs;          // [n_cg][nkb]: 8 x 16 bit (0x80 | (run - 1) << 4 | first block column | rank of the first block among the existing ones << 8)
+  uint4* b_cmd;           // [n_cg][nkb][BP_RB]: 16 copy commands, then 8 MMA runs as {B descriptor offset (16-byte units) | TMEM column
+                          // offset << 16, instruction descriptor (0 = no run)}
   unsigned char* a_any;   // [n_rg][nkb]: the row group has an A block in this k block
   unsigned char* zeros;   // 5 A tiles of zeros
 };
-inline size_t bp_smem_bytes() { return 1024 + (size_t)BP_NS * BT_A_BYTES + (size_t)BP_RING * BT_B_SLOT; }
+inline size_t bp_smem_bytes(int ns) { return 1024 + (size_t)ns * (BT_A_BYTES + BT_NB * BT_B_SLOT); }
 inline size_t bt_plan_bytes(int n_rg, int n_cg, int nkb, size_t* off /* [5] */) {
   size_t o = 0;
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   off[0] = o, o += up((size_t)n_rg * nkb * BP_RA * sizeof(uint4));
   off[1] = o, o += up((size_t)n_cg * nkb * BP_RB * sizeof(uint4));
-  off[2] = o, o += up((size_t)n_cg * nkb * sizeof(uint4));
+  off[2] = o;
   off[3] = o, o += up((size_t)n_rg * nkb);
   off[4] = o, o += 5 * 2048;
   return o;
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint4 bt_cmd(const unsigned char* src, uint32_t dst, 
 }
 
 __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const int* __restrict__ a_map, const unsigned char* __restrict__ b_tiles,
-                               const int* __restrict__ b_map, int nrb, int ncb, int nkb, int m, int n, int nb, BtPlanPtrs P) {
+                               const int* __restrict__ b_map, int nrb, int ncb, int nkb, int m, int n, int nb, int ns, BtPlanPtrs P) {
   const BtGeom g = bt_geom(m, n);
   const int n_rg = (nrb + g.bpt - 1) / g.bpt, n_cg = (ncb + nb - 1) / nb;
   const long long total = (long long)(n_rg + n_cg) * nkb;
@@ -75,7 +75,7 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
       // earlier in this tile (k blocks without any A block are skipped by the producer); at the start of a tile: unknown => all
       bool dirty[5];
       {
-        int kp = kb - BP_NS;
+        int kp = kb - ns;
         bool found = false;
         for (int tries = 0; tries < 4 && kp >= 0 && !found; ++tries) {
           bool anyp = false;
@@ -88,7 +88,7 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
           if (anyp)
             found = true;
           else
-            kp -= BP_NS;
+            kp -= ns;
         }
         if (!found) {
 #pragma unroll
@@ -136,10 +136,8 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
       }
       int nc = 0;
       uint32_t total_b = 0;
-      uint32_t runs[4] = {0u, 0u, 0u, 0u};
-      int nr = 0;
       int c = 0;
-      while (c < nb) {  // copy commands: existing blocks whose tiles are adjacent in memory; destination = packed (rank * 2 KB)
+      while (c < nb) {  // copy commands: adjacent existing blocks whose tiles are adjacent in memory, into their fixed slots
         if (first_idx[c] < 0) {
           ++c;
           continue;
@@ -147,27 +145,33 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
         int len = 1;
         while (c + len < nb && first_idx[c + len] == first_idx[c] + len) ++len;
         const uint32_t bytes = (uint32_t)(len * BT_B_SLOT);
-        const uint32_t rank = (uint32_t)__popc(bm & ((1u << c) - 1u));
-        out[nc++] = bt_cmd(b_tiles + (size_t)first_idx[c] * BT_B_SLOT, rank * (uint32_t)BT_B_SLOT, bytes);
+        out[nc++] = bt_cmd(b_tiles + (size_t)first_idx[c] * BT_B_SLOT, (uint32_t)(BT_A_BYTES + c * BT_B_SLOT), bytes);
         total_b += bytes;
         c += len;
       }
-      for (int q = nc; q < BP_RB; ++q) out[q] = make_uint4(0, 0, 0, 0);
+      for (int q = nc; q < 16; ++q) out[q] = make_uint4(0, 0, 0, 0);
       out[0].w = total_b;
+      // MMA runs: adjacent existing blocks, N = 32 * run <= 256; cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format
+      // BF16 (1) [7,10),[10,13), K-major A and B, N >> 3 at [17,23), M >> 4 at [24,29)
+      uint32_t rec[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) rec[q] = 0u;
+      int nr = 0;
       c = 0;
-      while (c < nb) {  // MMA runs: adjacent existing blocks, N = 32 * run <= 256
+      while (c < nb) {
         if (!((bm >> c) & 1u)) {
           ++c;
           continue;
         }
         int r = 1;
         while (c + r < nb && ((bm >> (c + r)) & 1u) && r < 8) ++r;
-        const uint32_t rank = (uint32_t)__popc(bm & ((1u << c) - 1u));
-        runs[nr >> 1] |= (0x80u | ((uint32_t)(r - 1) << 4) | (uint32_t)c | (rank << 8)) << (16 * (nr & 1));
+        rec[2 * nr] = (uint32_t)(c * (BT_B_SLOT >> 4)) | ((uint32_t)(32 * c) << 16);
+        rec[2 * nr + 1] = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24) | ((uint32_t)(4 * r) << 17);
         ++nr;
         c += r;
       }
-      P.m_runs[(size_t)cg * nkb + kb] = make_uint4(runs[0], runs[1], runs[2], runs[3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) out[16 + q] = make_uint4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
     }
   }
 }
@@ -181,9 +185,24 @@ __device__ __forceinline__ void tmem_zero_32cols(uint32_t taddr) {
     : "memory");
 }
 
+// one run of adjacent existing B blocks: two MMAs (k = 0..15 | 16..31) into the accumulators of its block columns
+#define BP_RUN(X, Y)                                                                                                       \
+  {                                                                                                                        \
+    const uint32_t bl_ = bd_lo + ((X) & 0xffffu), d_ = tmem_base + ((X) >> 16);                                            \
+    if (A_TMEM) {                                                                                                          \
+      umma_bf16_ts(d_, ta, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                                                        \
+      umma_bf16_ts(d_, ta + 8u, ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);                                           \
+    }                                                                                                                      \
+    else {                                                                                                                 \
+      umma_bf16(d_, ((uint64_t)ad_hi << 32) | ad_lo, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                              \
+      umma_bf16(d_, ((uint64_t)ad_hi << 32) | (ad_lo + 16u), ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);              \
+    }                                                                                                                      \
+  }
+
+template <bool A_TMEM>
 __global__ void __launch_bounds__(BT_THREADS, 1)
-  smm_bf16_planned_kernel(BtPlanPtrs P, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb, int m, int n, int flags) {
-  const int nb = (flags & BT_FLAG_A_TMEM) ? BT_NB_A_TMEM : BT_NB;
+  smm_bf16_planned_kernel(BtPlanPtrs P, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb, int m, int n, int ns) {
+  const int nb = A_TMEM ? BT_NB_A_TMEM : BT_NB;
   extern __shared__ __align__(1024) unsigned char bt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BtGeom g = bt_geom(m, n);
@@ -194,17 +213,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   uint64_t* empty = full + BP_NS;                         // [BP_NS]
   uint64_t* tmem_full = empty + BP_NS;                    // [1]
   uint64_t* tmem_empty = tmem_full + 1;                   // [1]
-  uint32_t* b_start = reinterpret_cast<uint32_t*>(tmem_empty + 1);  // [BP_NS] first ring slot of the stage's packed B blocks
-  uint32_t* tmem_ptr = b_start + BP_NS;
-  unsigned char* a_stages = bt_smem + 1024;                           // BP_NS x 8 KB
-  unsigned char* b_ring = a_stages + (size_t)BP_NS * BT_A_BYTES;      // BP_RING x 2 KB
+  uint32_t* a_flag = reinterpret_cast<uint32_t*>(tmem_empty + 1);  // [BP_NS] the stage has an A block
+  uint32_t* tmem_ptr = a_flag + BP_NS;
+  uint4* run_words = reinterpret_cast<uint4*>(bt_smem + 512);      // [BP_NS][4]: the stage's MMA runs (8 x {offsets, idesc})
+  unsigned char* stages = bt_smem + 1024;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the plan kernel (and pack kernels / map uploads) are complete and visible
 
-  // A slots start as zeros (the plan's zero copies rely on it for row group 15 and for slots never written)
-  for (size_t i = (size_t)threadIdx.x * 16; i < (size_t)BP_NS * BT_A_BYTES; i += (size_t)BT_THREADS * 16)
-    *reinterpret_cast<uint4*>(a_stages + i) = make_uint4(0, 0, 0, 0);
+  for (size_t i = (size_t)threadIdx.x * 16; i < (size_t)ns * g.stage; i += (size_t)BT_THREADS * 16)
+    *reinterpret_cast<uint4*>(stages + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < BP_NS; ++s) {
       mbar_init(&full[s], 2);  // the two producer warps
@@ -232,93 +250,44 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (warp == 6) {
-    // ===================================== A producer: one ready-made copy command per lane, fixed 8 KB slot per stage entry ======
-    const bool active = lane < BP_RA;
+  if (warp == 0 || warp == 6) {
+    // ===================================== TMA producers: one ready-made copy command per lane =====================================
+    // warp 6: A blocks (+ zero copies where a slot may hold stale data); warp 0: B blocks, and its lanes 16..19 pass the k block's
+    // MMA run words on to the issuer through shared memory
+    const bool a_role = warp == 6;
+    const int R = a_role ? BP_RA : BP_RB;
+    const bool active = lane < R;
     int s = 0;
     uint32_t ph = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       int rg, cg;
       bt_tile_coords(t, n_rg, n_cg, rg, cg);
-      const uint4* __restrict__ p = P.a_cmd + (size_t)rg * nkb * BP_RA + (active ? lane : 0);
+      const uint4* __restrict__ p = (a_role ? P.a_cmd + (size_t)rg * nkb * BP_RA : P.b_cmd + (size_t)cg * nkb * BP_RB) + (active ? lane : 0);
       uint4 cur[BP_KC], nxt[BP_KC];
 #pragma unroll
-      for (int j = 0; j < BP_KC; ++j) cur[j] = (active && j < nkb) ? __ldg(p + (size_t)j * BP_RA) : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < BP_KC; ++j) cur[j] = (active && j < nkb) ? __ldg(p + (size_t)j * R) : make_uint4(0, 0, 0, 0);
       for (int k0 = 0; k0 < nkb; k0 += BP_KC) {
 #pragma unroll
-        for (int j = 0; j < BP_KC; ++j)
-          nxt[j] = (active && k0 + BP_KC + j < nkb) ? __ldg(p + (size_t)(k0 + BP_KC + j) * BP_RA) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < BP_KC; ++j) nxt[j] = (active && k0 + BP_KC + j < nkb) ? __ldg(p + (size_t)(k0 + BP_KC + j) * R) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int j = 0; j < BP_KC; ++j) {
           if (k0 + j < nkb) {  // warp-uniform
             const uint4 cmd = cur[j];
             mbar_wait(&empty[s], ph ^ 1u);
-            if (lane == 0) mbar_expect_tx(&full[s], cmd.w);  // this warp's arrival; the phase completes when both warps' bytes have landed
+            if (!a_role && lane >= 16 && lane < 20) run_words[s * 4 + (lane - 16)] = cmd;
             __syncwarp();
+            if (lane == 0) {
+              if (a_role) a_flag[s] = cmd.w;
+              mbar_expect_tx(&full[s], cmd.w);  // this warp's arrival (release); the phase completes when both warps' bytes have landed
+            }
             const uint32_t bytes = cmd.z >> 16;
-            if (bytes != 0)
-              bulk_g2s(a_stages + (size_t)s * BT_A_BYTES + (cmd.z & 0xffffu),
+            if (lane < 16 && bytes != 0)
+              bulk_g2s(stages + (size_t)s * g.stage + (cmd.z & 0xffffu),
                        reinterpret_cast<const unsigned char*>((unsigned long long)cmd.x | ((unsigned long long)cmd.y << 32)), bytes, &full[s]);
-            if (++s == BP_NS) {
+            if (++s == ns) {
               s = 0;
               ph ^= 1u;
             }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j) cur[j] = nxt[j];
-      }
-    }
-  }
-  else if (warp == 0) {
-    // ===================================== B producer: packed blocks in a ring of 2 KB slots =====================================
-    // lane j < BP_NS remembers the ring interval and the iteration of stage entry j; a new stage takes the slots behind the newest
-    // one (from slot 0 again once the nominal end is passed) after every older stage that still owns one of them has been consumed
-    const bool active = lane < BP_RB;
-    int my_start = 0, my_cnt = 0, my_it = -1;
-    int it = 0, tail = 0, head = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      int rg, cg;
-      bt_tile_coords(t, n_rg, n_cg, rg, cg);
-      const uint4* __restrict__ p = P.b_cmd + (size_t)cg * nkb * BP_RB + (active ? lane : 0);
-      uint4 cur[BP_KC], nxt[BP_KC];
-#pragma unroll
-      for (int j = 0; j < BP_KC; ++j) cur[j] = (active && j < nkb) ? __ldg(p + (size_t)j * BP_RB) : make_uint4(0, 0, 0, 0);
-      for (int k0 = 0; k0 < nkb; k0 += BP_KC) {
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j)
-          nxt[j] = (active && k0 + BP_KC + j < nkb) ? __ldg(p + (size_t)(k0 + BP_KC + j) * BP_RB) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j) {
-          if (k0 + j < nkb) {  // warp-uniform
-            const uint4 cmd = cur[j];
-            const uint32_t total = __shfl_sync(0xffffffffu, cmd.w, 0);
-            const int cnt = (int)(total / (uint32_t)BT_B_SLOT);
-            const int s = it % BP_NS;
-            const int start = head >= BP_RING_NOM ? 0 : head;
-            const bool ov = lane < BP_NS && my_it >= tail && cnt > 0 && my_cnt > 0 && start < my_start + my_cnt && my_start < start + cnt;
-            const int newest = __reduce_max_sync(0xffffffffu, ov ? my_it : -1);
-            const int until = max(newest, it - BP_NS);  // plus the stage entry itself
-            while (tail <= until) {
-              mbar_wait(&empty[tail % BP_NS], (uint32_t)((tail / BP_NS) & 1));
-              ++tail;
-            }
-            if (lane == s) {
-              my_start = start;
-              my_cnt = cnt;
-              my_it = it;
-            }
-            if (lane == 0) {
-              b_start[s] = (uint32_t)start;
-              mbar_expect_tx(&full[s], total);
-            }
-            __syncwarp();
-            const uint32_t bytes = cmd.z >> 16;
-            if (bytes != 0)
-              bulk_g2s(b_ring + (size_t)start * BT_B_SLOT + (cmd.z & 0xffffu),
-                       reinterpret_cast<const unsigned char*>((unsigned long long)cmd.x | ((unsigned long long)cmd.y << 32)), bytes, &full[s]);
-            head = start + cnt;
-            ++it;
           }
         }
 #pragma unroll
@@ -327,82 +296,56 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
     }
   }
   else if (warp == 1) {
-    // ===================================== MMA issuer: walks the packed runs of the plan =====================================
-    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-    const bool a_tmem = (flags & BT_FLAG_A_TMEM) != 0;
-    const uint64_t adesc_base = umma_desc(smem_u32(a_stages), 128u, 512u), bdesc_base = umma_desc(smem_u32(b_ring), 128u, 512u);
+    // ===================================== MMA issuer =====================================
+    const uint64_t adesc_base = umma_desc(smem_u32(stages), 128u, 512u), bdesc_base = umma_desc(smem_u32(stages) + (uint32_t)BT_A_BYTES, 128u, 512u);
+    const uint32_t ad_hi = (uint32_t)(adesc_base >> 32), bd_hi = (uint32_t)(bdesc_base >> 32);
+    const uint32_t stage16 = (uint32_t)g.stage >> 4;
     uint32_t it = 0, tile_no = 0, ph = 0;
     int s = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
-      int rg, cg;
-      bt_tile_coords(t, n_rg, n_cg, rg, cg);
-      const uint4* __restrict__ pr = P.m_runs + (size_t)cg * nkb;
-      const unsigned char* __restrict__ pa = P.a_any + (size_t)rg * nkb;
       mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained (and zeroed) the previous tile's accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint4 cur[BP_KC], nxt[BP_KC];
-#pragma unroll
-      for (int j = 0; j < BP_KC; ++j) {
-        const bool in = j < nkb;
-        const unsigned char any = in ? __ldg(pa + j) : (unsigned char)0;
-        const uint4 rr = in ? __ldg(pr + j) : make_uint4(0, 0, 0, 0);
-        cur[j] = any ? rr : make_uint4(0, 0, 0, 0);
-      }
-      for (int k0 = 0; k0 < nkb; k0 += BP_KC) {
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j) {  // both loads independent of each other
-          const bool in = k0 + BP_KC + j < nkb;
-          const unsigned char any = in ? __ldg(pa + k0 + BP_KC + j) : (unsigned char)0;
-          const uint4 rr = in ? __ldg(pr + k0 + BP_KC + j) : make_uint4(0, 0, 0, 0);
-          nxt[j] = any ? rr : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j) {
-          if (k0 + j < nkb) {
-            mbar_wait(&full[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              unsigned long long lo = (unsigned long long)cur[j].x | ((unsigned long long)cur[j].y << 32);
-              unsigned long long hi = (unsigned long long)cur[j].z | ((unsigned long long)cur[j].w << 32);
-              const uint64_t ad0 = adesc_base + (uint64_t)((uint32_t)s * (uint32_t)(BT_A_BYTES >> 4));
-              const uint64_t bd0 = bdesc_base + (uint64_t)(b_start[s] * (uint32_t)(BT_B_SLOT >> 4));
-              const uint32_t ta = tmem_base + (uint32_t)(BT_NB_A_TMEM * 32) + 16u * (it & 1u);
-              if (a_tmem && (lo & 0x80ull)) {
-                utccp_128x256b(ta, ad0);
-                utccp_128x256b(ta + 8u, ad0 + 16u);
-              }
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                unsigned long long runs = half == 0 ? lo : hi;
-                while (runs & 0x80ull) {
-                  const uint32_t w = (uint32_t)runs;
-                  const uint32_t c0 = w & 15u, r = ((w >> 4) & 7u) + 1u, rank = (w >> 8) & 15u;
-                  const uint32_t idesc = idesc_base | ((4u * r) << 17);                     // N = 32 r
-                  const uint64_t bd = bd0 + (uint64_t)(rank * (uint32_t)(BT_B_SLOT >> 4));  // start address in 16-byte units
-                  const uint32_t d = tmem_base + 32u * c0;
-                  if (a_tmem) {
-                    umma_bf16_ts(d, ta, bd, idesc, 1u);
-                    umma_bf16_ts(d, ta + 8u, bd + 16u, idesc, 1u);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint4 q0 = run_words[s * 4];
+          if (a_flag[s] != 0u && q0.y != 0u) {
+            const uint4 q1 = run_words[s * 4 + 1], q2 = run_words[s * 4 + 2], q3 = run_words[s * 4 + 3];
+            const uint32_t ad_lo = (uint32_t)adesc_base + (uint32_t)s * stage16, bd_lo = (uint32_t)bdesc_base + (uint32_t)s * stage16;
+            const uint32_t ta = tmem_base + (uint32_t)(BT_NB_A_TMEM * 32) + 16u * (it & 1u);
+            if (A_TMEM) {
+              utccp_128x256b(ta, ((uint64_t)ad_hi << 32) | ad_lo);
+              utccp_128x256b(ta + 8u, ((uint64_t)ad_hi << 32) | (ad_lo + 16u));
+            }
+            BP_RUN(q0.x, q0.y)
+            if (q0.w != 0u) {
+              BP_RUN(q0.z, q0.w)
+              if (q1.y != 0u) {
+                BP_RUN(q1.x, q1.y)
+                if (q1.w != 0u) {
+                  BP_RUN(q1.z, q1.w)
+                  if (q2.y != 0u) {
+                    BP_RUN(q2.x, q2.y)
+                    if (q2.w != 0u) {
+                      BP_RUN(q2.z, q2.w)
+                      if (q3.y != 0u) {
+                        BP_RUN(q3.x, q3.y)
+                        if (q3.w != 0u) BP_RUN(q3.z, q3.w)
+                      }
+                    }
                   }
-                  else {
-                    umma_bf16(d, ad0, bd, idesc, 1u);
-                    umma_bf16(d, ad0 + 16u, bd + 16u, idesc, 1u);  // k = 16..31: +256 B
-                  }
-                  runs >>= 16;
                 }
               }
-              umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
-            }
-            __syncwarp();
-            ++it;
-            if (++s == BP_NS) {
-              s = 0;
-              ph ^= 1u;
             }
           }
+          umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
         }
-#pragma unroll
-        for (int j = 0; j < BP_KC; ++j) cur[j] = nxt[j];
+        __syncwarp();
+        if (++s == ns) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       if (elect_one()) umma_commit(tmem_full);
       __syncwarp();
