@@ -737,21 +737,19 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   // "bf16_a_tmem" tunable: stage the A operand in TMEM (15 block columns per tile instead of 16)
   const int flags = (smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0) |
                     (smm::g_tune.bf16_a_tmem.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_A_TMEM : 0);
-  const int nb = (flags & smm::BT_FLAG_A_TMEM) ? smm::BT_NB_A_TMEM : smm::BT_NB;
+  const bool planned = smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0;  // the planned kernel has no A-in-TMEM mode
+  const int nb = (!planned && (flags & smm::BT_FLAG_A_TMEM)) ? smm::BT_NB_A_TMEM : smm::BT_NB;
   const int bpt = g.bpt;
   const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + nb - 1) / nb;
   int grid = n_rg * n_cg;
   if (grid > num_sms()) grid = num_sms();
-  if (smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0) {
+  if (planned) {
     // planned variant: copy commands and MMA runs per (row group | column group, k block) derived once, then the multiply
     static SmemAttrCache smem_set_p;
     int ns = smm::BP_NS;  // DBCSR_B200_BF16_STAGES: experiment knob (fewer pipeline stages)
     if (const char* e = getenv("DBCSR_B200_BF16_STAGES")) ns = std::max(2, std::min(smm::BP_NS, atoi(e)));
     const int smem_p = (int)smm::bp_smem_bytes(ns);
-    static SmemAttrCache smem_set_pt;
-    const bool a_tmem = (flags & smm::BT_FLAG_A_TMEM) != 0;
-    if ((a_tmem ? ensure_smem(smm::smm_bf16_planned_kernel<true>, smem_p, smem_set_pt) : ensure_smem(smm::smm_bf16_planned_kernel<false>, smem_p, smem_set_p)) != 0)
-      return -30;
+    if (ensure_smem(smm::smm_bf16_planned_kernel, smem_p, smem_set_p) != 0) return -30;
     size_t off[5];
     const size_t bytes = smm::bt_plan_bytes(n_rg, n_cg, nkb, off);
     unsigned char* buf = bt_plan_scratch(st, bytes, off[4]);
@@ -769,7 +767,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
     if (cudaPeekAtLastError() != cudaSuccess) return -31;
     cudaLaunchConfig_t cfgp = {};
     cfgp.gridDim = dim3((unsigned)grid);
-    cfgp.blockDim = dim3(smm::BT_THREADS);
+    cfgp.blockDim = dim3(smm::BP_THREADS);
     cfgp.dynamicSmemBytes = (size_t)smem_p;
     cfgp.stream = st;
     cudaLaunchAttribute attrp[1];
@@ -777,9 +775,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
     attrp[0].val.programmaticStreamSerializationAllowed = 1;
     cfgp.attrs = attrp;
     cfgp.numAttrs = 1;
-    const cudaError_t perr = a_tmem ? cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel<true>, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, ns)
-                                    : cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel<false>, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, ns);
-    if (perr != cudaSuccess) return -31;
+    if (cudaLaunchKernelEx(&cfgp, smm::smm_bf16_planned_kernel, P, dev_c, dev_c_off, nrb, ncb, nkb, m, n, ns) != cudaSuccess) return -31;
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return 0;
   }

@@ -24,7 +24,12 @@ namespace smm {
 // finished 32-bit words {B descriptor offset | accumulator column offset, instruction descriptor}; the B producer's spare lanes
 // copy the 64 bytes of a k block's runs into shared memory beside the stage, and the issuer reads them with four LDS.128 and
 // issues an unrolled, nested sequence (run q+1 is only looked at when run q exists): no global loads, no loop-carried chain.
+// Fourth step: the pipeline depth is not the limit either (5 / 4 / 3 stages: 28.8 / 29.5 / 33.0 ms); the issuer still executes ~90
+// instructions per k block.  Its work is now split over TWO issuer warps that own disjoint halves of the accumulator (block columns
+// 0-7 | 8-15; a run never crosses the middle): both read the same operand stage, each issues and commits its own MMAs (independent
+// TMEM columns, so no ordering between the two threads is needed), a stage is free when both have committed.
 constexpr int BP_NS = BT_STAGES;  // stage entries: fixed slots, as in smm_bf16_tiled.cuh
+constexpr int BP_THREADS = 256;   // warp 0: B producer, 1 and 7: MMA issuers, 2-5: epilogue, 6: A producer
 constexpr int BP_RA = 8;   // command slots per row of the A plan (<= 5 used)
 constexpr int BP_RB = 20;  // uint4 per row of the B plan: 16 copy commands + 4 x (2 MMA runs)
 constexpr int BP_KC = 8;   // plan rows prefetched per lane
@@ -156,19 +161,22 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
       uint32_t rec[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) rec[q] = 0u;
-      int nr = 0;
-      c = 0;
-      while (c < nb) {
-        if (!((bm >> c) & 1u)) {
-          ++c;
-          continue;
+      for (int half = 0; half < 2; ++half) {  // words 0..7: block columns 0-7 (first issuer), 8..15: block columns 8-15 (second issuer)
+        int nr = 0;
+        c = 8 * half;
+        const int cend = min(nb, 8 * half + 8);
+        while (c < cend) {
+          if (!((bm >> c) & 1u)) {
+            ++c;
+            continue;
+          }
+          int r = 1;
+          while (c + r < cend && ((bm >> (c + r)) & 1u)) ++r;
+          rec[8 * half + 2 * nr] = (uint32_t)(c * (BT_B_SLOT >> 4)) | ((uint32_t)(32 * c) << 16);
+          rec[8 * half + 2 * nr + 1] = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24) | ((uint32_t)(4 * r) << 17);
+          ++nr;
+          c += r;
         }
-        int r = 1;
-        while (c + r < nb && ((bm >> (c + r)) & 1u) && r < 8) ++r;
-        rec[2 * nr] = (uint32_t)(c * (BT_B_SLOT >> 4)) | ((uint32_t)(32 * c) << 16);
-        rec[2 * nr + 1] = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24) | ((uint32_t)(4 * r) << 17);
-        ++nr;
-        c += r;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) out[16 + q] = make_uint4(rec[4 * q], rec[4 * q + 1], rec[4 * q + 2], rec[4 * q + 3]);
@@ -189,20 +197,13 @@ __device__ __forceinline__ void tmem_zero_32cols(uint32_t taddr) {
 #define BP_RUN(X, Y)                                                                                                       \
   {                                                                                                                        \
     const uint32_t bl_ = bd_lo + ((X) & 0xffffu), d_ = tmem_base + ((X) >> 16);                                            \
-    if (A_TMEM) {                                                                                                          \
-      umma_bf16_ts(d_, ta, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                                                        \
-      umma_bf16_ts(d_, ta + 8u, ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);                                           \
-    }                                                                                                                      \
-    else {                                                                                                                 \
-      umma_bf16(d_, ((uint64_t)ad_hi << 32) | ad_lo, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                              \
-      umma_bf16(d_, ((uint64_t)ad_hi << 32) | (ad_lo + 16u), ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);              \
-    }                                                                                                                      \
+    umma_bf16(d_, ((uint64_t)ad_hi << 32) | ad_lo, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                                \
+    umma_bf16(d_, ((uint64_t)ad_hi << 32) | (ad_lo + 16u), ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);                \
   }
 
-template <bool A_TMEM>
-__global__ void __launch_bounds__(BT_THREADS, 1)
+__global__ void __launch_bounds__(BP_THREADS, 1)
   smm_bf16_planned_kernel(BtPlanPtrs P, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb, int m, int n, int ns) {
-  const int nb = A_TMEM ? BT_NB_A_TMEM : BT_NB;
+  const int nb = BT_NB;
   extern __shared__ __align__(1024) unsigned char bt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BtGeom g = bt_geom(m, n);
@@ -221,14 +222,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the plan kernel (and pack kernels / map uploads) are complete and visible
 
-  for (size_t i = (size_t)threadIdx.x * 16; i < (size_t)ns * g.stage; i += (size_t)BT_THREADS * 16)
+  for (size_t i = (size_t)threadIdx.x * 16; i < (size_t)ns * g.stage; i += (size_t)BP_THREADS * 16)
     *reinterpret_cast<uint4*>(stages + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < BP_NS; ++s) {
-      mbar_init(&full[s], 2);  // the two producer warps
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], 2);   // the two producer warps
+      mbar_init(&empty[s], 2);  // the two issuer warps
     }
-    mbar_init(tmem_full, 1);
+    mbar_init(tmem_full, 2);
     mbar_init(tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -295,51 +296,35 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       }
     }
   }
-  else if (warp == 1) {
-    // ===================================== MMA issuer =====================================
+  else if (warp == 1 || warp == 7) {
+    // ===================================== MMA issuers: warp 1 block columns 0-7, warp 7 block columns 8-15 =====================
+    const int half = warp == 1 ? 0 : 1;
     const uint64_t adesc_base = umma_desc(smem_u32(stages), 128u, 512u), bdesc_base = umma_desc(smem_u32(stages) + (uint32_t)BT_A_BYTES, 128u, 512u);
     const uint32_t ad_hi = (uint32_t)(adesc_base >> 32), bd_hi = (uint32_t)(bdesc_base >> 32);
     const uint32_t stage16 = (uint32_t)g.stage >> 4;
-    uint32_t it = 0, tile_no = 0, ph = 0;
+    uint32_t tile_no = 0, ph = 0;
     int s = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
       mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained (and zeroed) the previous tile's accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint4 q0 = run_words[s * 4];
+          const uint4 q0 = run_words[s * 4 + 2 * half];
           if (a_flag[s] != 0u && q0.y != 0u) {
-            const uint4 q1 = run_words[s * 4 + 1], q2 = run_words[s * 4 + 2], q3 = run_words[s * 4 + 3];
+            const uint4 q1 = run_words[s * 4 + 2 * half + 1];
             const uint32_t ad_lo = (uint32_t)adesc_base + (uint32_t)s * stage16, bd_lo = (uint32_t)bdesc_base + (uint32_t)s * stage16;
-            const uint32_t ta = tmem_base + (uint32_t)(BT_NB_A_TMEM * 32) + 16u * (it & 1u);
-            if (A_TMEM) {
-              utccp_128x256b(ta, ((uint64_t)ad_hi << 32) | ad_lo);
-              utccp_128x256b(ta + 8u, ((uint64_t)ad_hi << 32) | (ad_lo + 16u));
-            }
             BP_RUN(q0.x, q0.y)
             if (q0.w != 0u) {
               BP_RUN(q0.z, q0.w)
               if (q1.y != 0u) {
                 BP_RUN(q1.x, q1.y)
-                if (q1.w != 0u) {
-                  BP_RUN(q1.z, q1.w)
-                  if (q2.y != 0u) {
-                    BP_RUN(q2.x, q2.y)
-                    if (q2.w != 0u) {
-                      BP_RUN(q2.z, q2.w)
-                      if (q3.y != 0u) {
-                        BP_RUN(q3.x, q3.y)
-                        if (q3.w != 0u) BP_RUN(q3.z, q3.w)
-                      }
-                    }
-                  }
-                }
+                if (q1.w != 0u) BP_RUN(q1.z, q1.w)
               }
             }
           }
-          umma_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+          umma_commit(&empty[s]);  // the stage may be refilled once the MMAs of BOTH issuers have read it
         }
         __syncwarp();
         if (++s == ns) {
@@ -396,8 +381,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
       if (lane == 0) mbar_arrive(tmem_empty);
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }

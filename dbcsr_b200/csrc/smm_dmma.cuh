@@ -344,7 +344,12 @@ __device__ __forceinline__ void warp_chunk(int gw, int chunk, int extra, int sta
 }
 
 // Kernel flags
-constexpr int FLAG_ALIGN_RUNS = 1;  // move chunk boundaries to the next change of c_first (at most 30 entries ahead)
+constexpr int FLAG_ALIGN_RUNS = 1;  // move chunk boundaries to the next change of c_first (at most ALIGN_LOOKAHEAD - 1 entries ahead)
+// How far a chunk boundary may move.  Round 1 looked 30 entries ahead: fine for DBCSR's stacks (mean run 1.7 entries), but on
+// stacks with LONG runs (the device builder's tile order: all ~10 products of a C block adjacent) boundaries snapped from 12-entry
+// chunks to alternating 10 / 20: the slowest warp of a CTA decides when its slot is free again (9.87 ms per multiply against 8.17
+// with alignment off).  With 4, short runs are still kept whole and a long run is simply split (one extra flush).
+constexpr int ALIGN_LOOKAHEAD = 4;
 constexpr int FLAG_PDL_CHAIN = 2;   // the predecessor in the stream is an independent stack drain: no grid dependency before the reads
 
 // Trace record of one warp (TRACE kernels; lane 0 writes): see tools/trace_analyze.py
@@ -423,13 +428,13 @@ __global__ void __launch_bounds__(WPC * 32) smm_dmma_kernel(const int* __restric
     if (n0 > 0) c_prev = __ldg(stack + 3 * (n0 - 1) + 2);
     if (n1 < stack_size && n1 - 1 + lane < stack_size) w1 = __ldg(stack + 3 * (n1 - 1 + lane) + 2);
     if (n0 > 0) {
-      const bool differs = (lane < 31) && ((n0 + lane >= stack_size) || (cur.z != c_prev));
+      const bool differs = (lane < ALIGN_LOOKAHEAD) && ((n0 + lane >= stack_size) || (cur.z != c_prev));
       const unsigned m = __ballot_sync(0xffffffffu, differs);
       if (m != 0) e0 = n0 + (__ffs(m) - 1);
     }
     if (n1 < stack_size) {
       const int w0 = __shfl_sync(0xffffffffu, w1, 0);
-      const bool differs = (lane >= 1) && ((n1 - 1 + lane >= stack_size) || (w1 != w0));
+      const bool differs = (lane >= 1) && (lane <= ALIGN_LOOKAHEAD) && ((n1 - 1 + lane >= stack_size) || (w1 != w0));
       const unsigned m = __ballot_sync(0xffffffffu, differs);
       if (m != 0) e1 = n1 - 1 + (__ffs(m) - 1);
     }

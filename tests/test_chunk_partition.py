@@ -1,8 +1,11 @@
 """Property test of the run-aligned chunk partition of the FP64 stack kernel (dbcsr_b200/csrc/smm_dmma.cuh: warp_chunk() +
 FLAG_ALIGN_RUNS), restated line by line in Python: for any stack, any split (one-wave / fixed chunk / balanced) the warps' chunks
-[boundary(n0), boundary(n1)) tile [0, S) exactly, and a run of equal c_first that is at most 30 entries long is never split."""
+[boundary(n0), boundary(n1)) tile [0, S) exactly, and a run of equal c_first is only split when it reaches ALIGN_LOOKAHEAD - 1 = 3
+or more entries beyond the nominal boundary (round 1 looked 30 entries ahead: bad for stacks with long runs, see smm_dmma.cuh)."""
 import numpy as np
 import pytest
+
+LOOKAHEAD = 4  # ALIGN_LOOKAHEAD of smm_dmma.cuh
 
 
 def warp_chunk(gw, chunk, extra, S):
@@ -16,17 +19,17 @@ def warp_chunk(gw, chunk, extra, S):
 
 
 def aligned(c, n0, n1, S):
-    """the kernel's two ballots: lanes 0..30 look at entries n0.. (start) and lanes 1..31 at entries n1.. (end)"""
+    """the kernel's two ballots: lanes 0..LOOKAHEAD-1 look at entries n0.. (start) and lanes 1..LOOKAHEAD at entries n1.. (end)"""
     e0, e1 = n0, n1
     if n0 > 0:
         c_prev = c[n0 - 1]
-        for lane in range(31):
+        for lane in range(LOOKAHEAD):
             if n0 + lane >= S or c[n0 + lane] != c_prev:
                 e0 = n0 + lane
                 break
     if n1 < S:
         w0 = c[n1 - 1]
-        for lane in range(1, 32):
+        for lane in range(1, LOOKAHEAD + 1):
             if n1 - 1 + lane >= S or c[n1 - 1 + lane] != w0:
                 e1 = n1 - 1 + lane
                 break
@@ -67,10 +70,10 @@ def test_aligned_chunks_tile_the_stack(seed):
             assert e0 == prev_end, (S, gw, e0, prev_end)  # consecutive warps meet exactly
             covered[e0:e1] += 1
             prev_end = e1
-            # a run is only split at the chunk end when it reaches more than 30 entries beyond the nominal boundary
+            # a run is only split at the chunk end when it reaches LOOKAHEAD - 1 or more entries beyond the nominal boundary
             if e1 < S and c[e1] == c[e1 - 1]:
                 k = e1
                 while k < S and c[k] == c[e1]:
                     k += 1
-                assert e1 == n1 and k - n1 > 30, (S, gw, n1, e1, k)
+                assert e1 == n1 and k - n1 >= LOOKAHEAD, (S, gw, n1, e1, k)
         assert prev_end == S and np.all(covered == 1)
