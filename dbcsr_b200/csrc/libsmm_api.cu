@@ -738,7 +738,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   const int flags = (smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0) |
                     (smm::g_tune.bf16_a_tmem.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_A_TMEM : 0);
   const bool planned = smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0;  // the planned kernel has no A-in-TMEM mode
-  const int nb = (!planned && (flags & smm::BT_FLAG_A_TMEM)) ? smm::BT_NB_A_TMEM : smm::BT_NB;
+  const int nb = planned ? smm::BP_NB : ((flags & smm::BT_FLAG_A_TMEM) ? smm::BT_NB_A_TMEM : smm::BT_NB);
   const int bpt = g.bpt;
   const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + nb - 1) / nb;
   int grid = n_rg * n_cg;
