@@ -449,9 +449,7 @@ def measure_fp64_peaks(torch, acc, s):
     pipe can do) and cuBLAS DGEMM 8192^3 through torch.matmul (what NVIDIA's own FP64 GEMM reaches)."""
     dmma = acc.fp64_peak_gflops(s)
     dmma_sustained = acc.fp64_peak_sustained_gflops(s, 0.4)
-    time.sleep(0.3)
-    fresh = acc.fp64_peak_ex(s, 0.0, True)
-    fresh_sustained = acc.fp64_peak_ex(s, 0.4, True)
+
     dgemm = None
     dgemm_sustained = None
     try:
@@ -482,7 +480,7 @@ def measure_fp64_peaks(torch, acc, s):
         torch.cuda.empty_cache()
     except Exception as ex:
         print("bench: cuBLAS DGEMM peak probe failed: %r" % (ex,), file=sys.stderr)
-    return {"dmma_burst": dmma, "dmma_sustained": dmma_sustained, "dgemm": dgemm, "dgemm_sustained": dgemm_sustained, "dmma_fresh_burst": fresh, "dmma_fresh_sustained": fresh_sustained}
+    return {"dmma_burst": dmma, "dmma_sustained": dmma_sustained, "dgemm": dgemm, "dgemm_sustained": dgemm_sustained}
 
 
 def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peaks, ncu_key):
@@ -552,11 +550,6 @@ def fp64_config_report(torch, tstream, acc, s, run, steps, warmup, n_probe, peak
                   "peak_gflops": dmma_burst, "frac": kernel_burst / dmma_burst if dmma_burst > 0 else None},
         "cublas_dgemm_8192_gflops": dgemm_peak,
         "cublas_dgemm_8192_sustained_gflops": peaks.get("dgemm_sustained"),
-        "dmma_fresh_operands": {
-            "note": "the same DMMA loop with NEW random operand mantissas for every instruction (a contraction loads new fragments for every DMMA; with the constant fragments of the probe above the multiplier inputs never toggle and the power limit is not reached): what the pipe sustains on real data under this board's power limit",
-            "burst_gflops": peaks.get("dmma_fresh_burst"), "sustained_gflops": peaks.get("dmma_fresh_sustained"),
-            "frac_sustained": (kernel_only / peaks["dmma_fresh_sustained"]) if peaks.get("dmma_fresh_sustained", 0) and peaks["dmma_fresh_sustained"] > 0 else None,
-            "frac_burst": (kernel_burst / peaks["dmma_fresh_burst"]) if peaks.get("dmma_fresh_burst", 0) and peaks["dmma_fresh_burst"] > 0 else None},
         "kernel": "smm_dmma_kernel<%d,%d,%d> (dominant of %d launches/step)" % (m0, n0, k0, nst),
         "algorithmic_flop_per_launch": run.flop / nst, "avg_launch_us": launch_us, "kernel_only_gflops": kernel_only,
         "host_enqueue_us_per_launch": host_enqueue_us,

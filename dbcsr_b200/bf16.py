@@ -68,7 +68,7 @@ class Bf16SpGemm:
         bpt = min(16 // ((m + 7) // 8), 5)
         a_any = np.zeros((self.nkb, (self.nrb + bpt - 1) // bpt), dtype=np.int64)
         np.maximum.at(a_any, (A.cols - 1, (A.rows - 1) // bpt), 1)
-        nb = 15 if (acc.get_tunable("bf16_a_tmem") or acc.get_tunable("bf16_plan")) else 16  # block columns per tile (smm_bf16_tiled.cuh)
+        nb = 15 if (acc.get_tunable("bf16_a_tmem") and not acc.get_tunable("bf16_plan")) else 16  # block columns per tile (smm_bf16_tiled.cuh)
         b_cnt = np.zeros((self.nkb, (self.ncb + nb - 1) // nb), dtype=np.int64)
         np.add.at(b_cnt, (B.rows - 1, (B.cols - 1) // nb), 1)
         self.mma_pairs = int(np.einsum("kr,kc->", a_any, b_cnt))

@@ -495,9 +495,11 @@ __global__ void __launch_bounds__(1024) zero_trickle_kernel(uint4* __restrict__ 
 // RANDOM mantissas (per-thread hash): the power a B200 draws for FP64 multiplies depends on the operand bits, and with uniform(0,1)
 // matrix data the board's power limit pulls the SM clock down after ~50 ms of sustained DMMA load -- a probe fed with constants
 // or small integers never sees that limit (it reads 37 TFLOP/s for as long as it runs) and would overstate what is attainable.
-// FRESH: the A/B fragments get new random mantissas every iteration (two integer ops per operand, hidden behind the 16-cycle DMMA
-// issue interval) like a kernel that loads new fragments for every DMMA; with constant operands the multiplier inputs never toggle
-// and the probe draws far less power than any real contraction.
+// FRESH (experiment, not exported): new operand mantissas every iteration.  Measured on B200: 32.8 TFLOP/s burst AND sustained -- the
+// extra integer work costs issue slots, and the power limit is still not reached; cuBLAS DGEMM 8192^3 on uniform(0,1) data does not
+// throttle either (35.5 TFLOP/s for 0.4 s).  What pulls the clock down under the stack kernel is its memory traffic (44 GB of DRAM and
+// ~110 GB of L2 -> SM traffic per 10 ms multiply), not the DMMA operand bits: on the device builder's tile-ordered stacks (a third of
+// the DRAM traffic) the same kernel holds its burst rate much longer.
 template <bool FRESH>
 __global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, unsigned seed) {
   double c0[9], c1[9];
@@ -738,7 +740,7 @@ int libsmm_acc_b200_bf16_spgemm(const void* a_tiles, const int* dev_a_map, const
   const int flags = (smm::g_tune.bf16_merge.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_MERGE_RUNS : 0) |
                     (smm::g_tune.bf16_a_tmem.load(std::memory_order_relaxed) != 0 ? smm::BT_FLAG_A_TMEM : 0);
   const bool planned = smm::g_tune.bf16_plan.load(std::memory_order_relaxed) != 0;  // the planned kernel has no A-in-TMEM mode
-  const int nb = planned ? smm::BP_NB : ((flags & smm::BT_FLAG_A_TMEM) ? smm::BT_NB_A_TMEM : smm::BT_NB);
+  const int nb = (!planned && (flags & smm::BT_FLAG_A_TMEM)) ? smm::BT_NB_A_TMEM : smm::BT_NB;
   const int bpt = g.bpt;
   const int n_rg = (nrb + bpt - 1) / bpt, n_cg = (ncb + nb - 1) / nb;
   int grid = n_rg * n_cg;
@@ -827,11 +829,6 @@ static double peak_sustained(void* stream, double seconds, bool fresh) {
 
 double libsmm_acc_b200_fp64_peak_gflops(void* stream) { return peak_burst(stream, false); }
 double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds) { return peak_sustained(stream, seconds, false); }
-// fresh_operands != 0: new random operand mantissas for every DMMA (what a real contraction feeds the pipe); seconds <= 0: burst
-double libsmm_acc_b200_fp64_peak_ex(void* stream, double seconds, int fresh_operands) {
-  return seconds > 0.0 ? peak_sustained(stream, seconds, fresh_operands != 0) : peak_burst(stream, fresh_operands != 0);
-}
-
 int libsmm_acc_b200_bf16_tile_bytes(int rows, int kdim) { return ((kdim + 7) / 8) * ((rows + 7) / 8) * 128; }
 
 int libsmm_acc_b200_pack_bf16(const double* dev_src, int nblks, int rows, int kdim, int row_stride, int k_stride, void* dev_dst,

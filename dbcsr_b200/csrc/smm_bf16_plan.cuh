@@ -28,15 +28,10 @@ namespace smm {
 // instructions per k block.  Its work is now split over TWO issuer warps that own disjoint halves of the accumulator (block columns
 // 0-7 | 8-15; a run never crosses the middle): both read the same operand stage, each issues and commits its own MMAs (independent
 // TMEM columns, so no ordering between the two threads is needed), a stage is free when both have committed.
-// Fifth step: two issuers gave 234 TFLOP/s = 575 cycles per k block, which is what the SHARED-MEMORY bandwidth allows: every MMA
-// re-reads the 128 x 16 A operand (4 KB; 9.4 MMAs per k block = 37.6 KB) beside the 16 KB of B, and the TMA writes 21.6 KB: 75 KB
-// per k block at 128 B per cycle = 587 cycles.  So the A operand now goes to TMEM once per k block (tcgen05.cp, 8 KB read) and every
-// MMA takes it from there (45.6 KB per k block = 356 cycles), and FOUR issuer warps own a quarter of the accumulator each (block
-// columns 0-3 | 4-7 | 8-11 | 12-14) to keep the issue rate above that.  Warp 1 copies A (double buffered in the last 32 TMEM columns)
-// and commits `a_ready`; the other issuers wait for it, and their commit on `a_free` lets warp 1 overwrite the buffer two k blocks on.
+// (Measured and dropped, in the history of this file: A operand copied to TMEM once per k block with FOUR issuer warps, 211 TFLOP/s --
+// slower than the two-issuer shared-memory version below, 234.)
 constexpr int BP_NS = BT_STAGES;  // stage entries: fixed slots, as in smm_bf16_tiled.cuh
-constexpr int BP_NB = 15;         // block columns per tile: 480 accumulator columns + 2 x 16 columns of A
-constexpr int BP_THREADS = 320;   // warp 0: B producer, 1 and 7-9: MMA issuers, 2-5: epilogue, 6: A producer
+constexpr int BP_THREADS = 256;   // warp 0: B producer, 1 and 7: MMA issuers, 2-5: epilogue, 6: A producer
 constexpr int BP_RA = 8;   // command slots per row of the A plan (<= 5 used)
 constexpr int BP_RB = 20;  // uint4 per row of the B plan: 16 copy commands + 4 x (2 MMA runs)
 constexpr int BP_KC = 8;   // plan rows prefetched per lane
@@ -168,10 +163,10 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
       uint32_t rec[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) rec[q] = 0u;
-      for (int quarter = 0; quarter < 4; ++quarter) {  // words 4 q .. 4 q + 3: block columns 4 q .. 4 q + 3 (issuer q), at most two runs
+      for (int half = 0; half < 2; ++half) {  // words 0..7: block columns 0-7 (first issuer), 8..15: block columns 8-15 (second issuer)
         int nr = 0;
-        c = 4 * quarter;
-        const int cend = min(nb, 4 * quarter + 4);
+        c = 8 * half;
+        const int cend = min(nb, 8 * half + 8);
         while (c < cend) {
           if (!((bm >> c) & 1u)) {
             ++c;
@@ -179,8 +174,8 @@ __global__ void bt_plan_kernel(const unsigned char* __restrict__ a_tiles, const 
           }
           int r = 1;
           while (c + r < cend && ((bm >> (c + r)) & 1u)) ++r;
-          rec[4 * quarter + 2 * nr] = (uint32_t)(c * (BT_B_SLOT >> 4)) | ((uint32_t)(32 * c) << 16);
-          rec[4 * quarter + 2 * nr + 1] = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24) | ((uint32_t)(4 * r) << 17);
+          rec[8 * half + 2 * nr] = (uint32_t)(c * (BT_B_SLOT >> 4)) | ((uint32_t)(32 * c) << 16);
+          rec[8 * half + 2 * nr + 1] = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24) | ((uint32_t)(4 * r) << 17);
           ++nr;
           c += r;
         }
@@ -204,13 +199,13 @@ __device__ __forceinline__ void tmem_zero_32cols(uint32_t taddr) {
 #define BP_RUN(X, Y)                                                                                                       \
   {                                                                                                                        \
     const uint32_t bl_ = bd_lo + ((X) & 0xffffu), d_ = tmem_base + ((X) >> 16);                                            \
-    umma_bf16_ts(d_, ta, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                                                          \
-    umma_bf16_ts(d_, ta + 8u, ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);                                             \
+    umma_bf16(d_, ((uint64_t)ad_hi << 32) | ad_lo, ((uint64_t)bd_hi << 32) | bl_, (Y), 1u);                                \
+    umma_bf16(d_, ((uint64_t)ad_hi << 32) | (ad_lo + 16u), ((uint64_t)bd_hi << 32) | (bl_ + 16u), (Y), 1u);                \
   }
 
 __global__ void __launch_bounds__(BP_THREADS, 1)
   smm_bf16_planned_kernel(BtPlanPtrs P, float* __restrict__ c_data, const int* __restrict__ c_off, int nrb, int ncb, int nkb, int m, int n, int ns) {
-  const int nb = BP_NB;
+  const int nb = BT_NB;
   extern __shared__ __align__(1024) unsigned char bt_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BtGeom g = bt_geom(m, n);
@@ -221,9 +216,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
   uint64_t* empty = full + BP_NS;                         // [BP_NS]
   uint64_t* tmem_full = empty + BP_NS;                    // [1]
   uint64_t* tmem_empty = tmem_full + 1;                   // [1]
-  uint64_t* a_ready = tmem_empty + 1;                     // [2] the A operand of a k block is in its TMEM buffer
-  uint64_t* a_free = a_ready + 2;                         // [2] the other issuers' MMAs have read the buffer
-  uint32_t* a_flag = reinterpret_cast<uint32_t*>(a_free + 2);  // [BP_NS] the stage has an A block
+  uint32_t* a_flag = reinterpret_cast<uint32_t*>(tmem_empty + 1);  // [BP_NS] the stage has an A block
   uint32_t* tmem_ptr = a_flag + BP_NS;
   uint4* run_words = reinterpret_cast<uint4*>(bt_smem + 512);      // [BP_NS][4]: the stage's MMA runs (8 x {offsets, idesc})
   unsigned char* stages = bt_smem + 1024;
@@ -236,14 +229,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < BP_NS; ++s) {
       mbar_init(&full[s], 2);   // the two producer warps
-      mbar_init(&empty[s], 4);  // the four issuer warps
+      mbar_init(&empty[s], 2);  // the two issuer warps
     }
-    mbar_init(tmem_full, 4);
+    mbar_init(tmem_full, 2);
     mbar_init(tmem_empty, 4);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&a_ready[b], 1);
-      mbar_init(&a_free[b], 3);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -309,41 +298,35 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
       }
     }
   }
-  else if (warp == 1 || warp >= 7) {
-    // ===================================== MMA issuers: warp 1 = quarter 0 (+ the A copy), warps 7-9 = quarters 1-3 ===============
-    const int quarter = warp == 1 ? 0 : warp - 6;
+  else if (warp == 1 || warp == 7) {
+    // ===================================== MMA issuers: warp 1 block columns 0-7, warp 7 block columns 8-15 =====================
+    const int half = warp == 1 ? 0 : 1;
     const uint64_t adesc_base = umma_desc(smem_u32(stages), 128u, 512u), bdesc_base = umma_desc(smem_u32(stages) + (uint32_t)BT_A_BYTES, 128u, 512u);
     const uint32_t ad_hi = (uint32_t)(adesc_base >> 32), bd_hi = (uint32_t)(bdesc_base >> 32);
     const uint32_t stage16 = (uint32_t)g.stage >> 4;
-    uint32_t it = 0, tile_no = 0, ph = 0;
+    uint32_t tile_no = 0, ph = 0;
     int s = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_no) {
       mbar_wait(tmem_empty, (tile_no & 1u) ^ 1u);  // the epilogue has drained (and zeroed) the previous tile's accumulators
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t buf = it & 1u, use = it >> 1;
-        const uint32_t ta = tmem_base + (uint32_t)(BP_NB * 32) + 16u * buf;
-        if (quarter == 0) mbar_wait(&a_free[buf], (use & 1u) ^ 1u);  // the other issuers are done with what the buffer held
+      for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
-        if (quarter != 0) mbar_wait(&a_ready[buf], use & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const bool have_a = a_flag[s] != 0u;
-          const uint32_t ad_lo = (uint32_t)adesc_base + (uint32_t)s * stage16, bd_lo = (uint32_t)bdesc_base + (uint32_t)s * stage16;
-          if (quarter == 0) {
-            if (have_a) {  // shared memory -> TMEM: 2 x (128 lanes x 256 bit) = k 0..15 | 16..31
-              utccp_128x256b(ta, ((uint64_t)ad_hi << 32) | ad_lo);
-              utccp_128x256b(ta + 8u, ((uint64_t)ad_hi << 32) | (ad_lo + 16u));
-            }
-            umma_commit(&a_ready[buf]);
-          }
-          const uint4 q0 = run_words[s * 4 + quarter];
-          if (have_a && q0.y != 0u) {
+          const uint4 q0 = run_words[s * 4 + 2 * half];
+          if (a_flag[s] != 0u && q0.y != 0u) {
+            const uint4 q1 = run_words[s * 4 + 2 * half + 1];
+            const uint32_t ad_lo = (uint32_t)adesc_base + (uint32_t)s * stage16, bd_lo = (uint32_t)bdesc_base + (uint32_t)s * stage16;
             BP_RUN(q0.x, q0.y)
-            if (q0.w != 0u) BP_RUN(q0.z, q0.w)
+            if (q0.w != 0u) {
+              BP_RUN(q0.z, q0.w)
+              if (q1.y != 0u) {
+                BP_RUN(q1.x, q1.y)
+                if (q1.w != 0u) BP_RUN(q1.z, q1.w)
+              }
+            }
           }
-          umma_commit(&empty[s]);  // the stage may be refilled once the MMAs (and the A copy) of ALL issuers have read it
-          if (quarter != 0) umma_commit(&a_free[buf]);
+          umma_commit(&empty[s]);  // the stage may be refilled once the MMAs of BOTH issuers have read it
         }
         __syncwarp();
         if (++s == ns) {

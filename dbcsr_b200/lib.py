@@ -30,7 +30,7 @@ SMM_SYMBOLS = [
     "c_calculate_norms", "libsmm_acc_gpu_warp_size", "libsmm_acc_b200_kernel_kind", "libsmm_acc_b200_launch_count",
     "libsmm_acc_b200_version", "libsmm_acc_b200_pack_bf16", "libsmm_acc_b200_bf16_tile_bytes",
     "libsmm_acc_b200_block_norms_f64", "libsmm_acc_b200_gather_blocks", "libsmm_acc_b200_set_tunable",
-    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops", "libsmm_acc_b200_fp64_peak_sustained_gflops", "libsmm_acc_b200_fp64_peak_ex",
+    "libsmm_acc_b200_get_tunable", "libsmm_acc_b200_set_trace", "libsmm_acc_b200_stream_chain", "libsmm_acc_b200_fp64_peak_gflops", "libsmm_acc_b200_fp64_peak_sustained_gflops",
     "libsmm_acc_b200_memset_zero_trickle", "libsmm_acc_b200_transpose_norms",
     "libsmm_acc_b200_bf16_rk_tile_bytes", "libsmm_acc_b200_bf16_rk_slot_bytes", "libsmm_acc_b200_pack_bf16_rk", "libsmm_acc_b200_bf16_spgemm",
 ]
@@ -102,8 +102,6 @@ def load():
     L.libsmm_acc_b200_transpose_norms.argtypes = [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]
     L.libsmm_acc_b200_fp64_peak_sustained_gflops.argtypes = [_vp, ctypes.c_double]
     L.libsmm_acc_b200_fp64_peak_sustained_gflops.restype = ctypes.c_double
-    L.libsmm_acc_b200_fp64_peak_ex.argtypes = [_vp, ctypes.c_double, ctypes.c_int]
-    L.libsmm_acc_b200_fp64_peak_ex.restype = ctypes.c_double
     L.libsmm_acc_b200_fp64_peak_gflops.argtypes = [_vp]
     L.libsmm_acc_b200_fp64_peak_gflops.restype = ctypes.c_double
     L.c_dbcsr_acc_clear_errors.restype = None
@@ -291,10 +289,6 @@ class Acc:
     def fp64_peak_sustained_gflops(self, stream, seconds=0.4):
         """The same loop back to back for `seconds`: throughput over the second half (sustained, under the power limit)."""
         return float(self.L.libsmm_acc_b200_fp64_peak_sustained_gflops(stream, float(seconds)))
-
-    def fp64_peak_ex(self, stream, seconds=0.0, fresh_operands=True):
-        """DMMA probe with fresh random operand mantissas per instruction (what a real contraction feeds the pipe); seconds <= 0: burst."""
-        return float(self.L.libsmm_acc_b200_fp64_peak_ex(stream, float(seconds), 1 if fresh_operands else 0))
 
     def launch_count(self):
         return int(self.L.libsmm_acc_b200_launch_count())

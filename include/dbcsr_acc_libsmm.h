@@ -128,11 +128,6 @@ double libsmm_acc_b200_fp64_peak_gflops(void* stream);
 /* The same loop run back to back for `seconds` (0 < seconds <= 10): throughput over the second half -- the denominator for a kernel
  * timed inside a long step (power limits act within tens of milliseconds). */
 double libsmm_acc_b200_fp64_peak_sustained_gflops(void* stream, double seconds);
-/* The same probe with a choice of operands.  fresh_operands != 0: the A/B fragments get new random mantissas for EVERY DMMA, as in
- * a contraction that loads new fragments for every instruction -- the multiplier inputs toggle and the board's power limit is
- * reached; the two calls above keep the fragments constant over the loop (inputs never toggle: an upper bound no real kernel can
- * be fed to).  seconds <= 0: burst (best of three launches), else sustained over `seconds` like the call above. */
-double libsmm_acc_b200_fp64_peak_ex(void* stream, double seconds, int fresh_operands);
 /* Library identification string (static storage). */
 const char* libsmm_acc_b200_version(void);
 
