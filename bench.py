@@ -605,18 +605,20 @@ def bf16_config_report(torch, acc, s, tstream, nblk, steps, warmup, n_probe=200)
     compulsory = (A.nblks + B.nblks) * tile_bytes + 4 * mm.c_elems  # every operand tile read once, C written once
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("cfg4_tiled", {}).get("dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("cfg4_planned", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "tensor", "pipe": "tcgen05.mma kind::f16 (BF16 operands, FP32 accumulators in TMEM)", "achieved": value * 1e-3, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": value * 1e-3 / tpeak, "traffic": traffic, "peak_source": tsrc,
-                "kernel": "smm_bf16_tiled_kernel (1 launch/step; M=128 x N=32 x K=16 MMAs, 2 per existing B block, tile and k block)",
+                "kernel": ("bt_plan_kernel + smm_bf16_planned_kernel (2 launches/step: copy commands and MMA runs per (group, k block) derived once, then the "
+                           "multiply; M=128 x N=32r x K=16 MMAs, 2 per run of r adjacent existing B blocks)") if acc.get_tunable("bf16_plan") else
+                          "smm_bf16_tiled_kernel (1 launch/step; M=128 x N=32r x K=16 MMAs, 2 per run of r adjacent existing B blocks, tile and k block)",
                 "useful_flop_per_launch": mm.flop, "issued_flop_per_launch": mm.issued_flop, "issued_frac": mm.issued_flop / (ms * 1e-3) * 1e-12 / tpeak,
                 "useful_over_issued": mm.flop / max(mm.issued_flop, 1),
                 "alt_bounds": {"hbm_compulsory": {"note": "operand tiles once + C once", "bytes": compulsory, "achieved": compulsory / (ms * 1e-3) * 1e-9,
                                                   "peak": hbm_peak, "unit": "GB/s", "frac": compulsory / (ms * 1e-3) * 1e-9 / hbm_peak}}}
     out = {"metric": METRIC_NAMES["cfg4"], "value": value, "unit": "GFLOP/s", "ms_per_step": ms, "dtype": "bf16", "kernel_only_gflops": value,
-           "config": workload_config(w, {"products": mm.products, "flop": mm.flop, "timed": "CUDA events around one libsmm_acc_b200_bf16_spgemm launch per step (C is overwritten, no memset)"}),
+           "config": workload_config(w, {"products": mm.products, "flop": mm.flop, "timed": "CUDA events around one libsmm_acc_b200_bf16_spgemm call per step (plan kernel + multiply kernel; C is overwritten, no memset)"}),
            "gpu_launches": int(launches), "roofline": roofline, "selfcheck": check}
     mm.close()
     return out
