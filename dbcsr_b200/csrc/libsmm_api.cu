@@ -21,6 +21,7 @@
 #include "smm_bf16_tiled.cuh"
 #include "smm_bf16_plan.cuh"
 #include "smm_dmma_big.cuh"
+#include "smm_dmma_huge.cuh"
 #include "smm_dmma_rt.cuh"
 #include "smm_generic.cuh"
 #include "smm_launch.h"
@@ -75,6 +76,7 @@ const bool g_tune_env_read = [] {
   if (const char* e = getenv("DBCSR_B200_ALIGN")) smm::g_tune.align.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_VARIANT")) smm::g_tune.variant.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BIGDMMA")) smm::g_tune.bigdmma.store(atoi(e));
+  if (const char* e = getenv("DBCSR_B200_HUGEDMMA")) smm::g_tune.hugedmma.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_INHOMOGENEOUS")) smm::g_tune.inhomogeneous.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BF16_MERGE")) smm::g_tune.bf16_merge.store(atoi(e));
   if (const char* e = getenv("DBCSR_B200_BF16_A_TMEM")) smm::g_tune.bf16_a_tmem.store(atoi(e));
@@ -258,9 +260,23 @@ int launch_rt(const int* dev_stack, int stack_size, const double* a, const doubl
   return -30;
 }
 
+// blocks above max_kernel_dim: panel DMMA kernel (smm_dmma_huge.cuh), one CTA per entry in turn
+int launch_huge(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k, int b_transposed,
+                cudaStream_t stream) {
+  if (stack_size <= 0) return 0;
+  int grid = stack_size;
+  const int max_grid = num_sms() * 4;
+  if (grid > max_grid) grid = max_grid;
+  smm::smm_dmma_huge_kernel<<<grid, smm::BIG_WARPS * 32, 0, stream>>>(dev_stack, stack_size, a, b, c, m, n, k, b_transposed);
+  return (cudaPeekAtLastError() == cudaSuccess) ? 0 : -31;
+}
+
 int launch_generic(const int* dev_stack, int stack_size, const double* a, const double* b, double* c, int m, int n, int k,
                    int b_transposed, cudaStream_t stream) {
   if (stack_size <= 0) return 0;
+  // blocks with a dimension above 80 (the only FP64 shapes that reach this function besides bigdmma = 0): tensor-pipe panel kernel
+  if ((m > 80 || n > 80 || k > 80) && smm::g_tune.hugedmma.load(std::memory_order_relaxed) != 0)
+    return launch_huge(dev_stack, stack_size, a, b, c, m, n, k, b_transposed, stream);
   const int max_grid = num_sms() * 8;
   int grid = (stack_size + smm::GEN_WPC * 2 - 1) / (smm::GEN_WPC * 2);
   if (grid > max_grid) grid = max_grid;
@@ -597,6 +613,7 @@ int libsmm_acc_b200_set_tunable(const char* name, long long value) {
   else if (strcmp(name, "align") == 0) smm::g_tune.align.store((int)value);
   else if (strcmp(name, "variant") == 0) smm::g_tune.variant.store((int)value);
   else if (strcmp(name, "bigdmma") == 0) smm::g_tune.bigdmma.store((int)value);
+  else if (strcmp(name, "hugedmma") == 0) smm::g_tune.hugedmma.store((int)value);
   else if (strcmp(name, "inhomogeneous") == 0) smm::g_tune.inhomogeneous.store((int)value);
   else if (strcmp(name, "bf16_merge") == 0) smm::g_tune.bf16_merge.store((int)value);
   else if (strcmp(name, "bf16_a_tmem") == 0) smm::g_tune.bf16_a_tmem.store((int)value);
@@ -614,6 +631,7 @@ long long libsmm_acc_b200_get_tunable(const char* name) {
   if (strcmp(name, "align") == 0) return smm::g_tune.align.load();
   if (strcmp(name, "variant") == 0) return smm::g_tune.variant.load();
   if (strcmp(name, "bigdmma") == 0) return smm::g_tune.bigdmma.load();
+  if (strcmp(name, "hugedmma") == 0) return smm::g_tune.hugedmma.load();
   if (strcmp(name, "inhomogeneous") == 0) return smm::g_tune.inhomogeneous.load();
   if (strcmp(name, "bf16_merge") == 0) return smm::g_tune.bf16_merge.load();
   if (strcmp(name, "bf16_a_tmem") == 0) return smm::g_tune.bf16_a_tmem.load();

@@ -19,6 +19,7 @@ constexpr int TRACE_REC = 128;     // 64-bit words per warp record
 
 struct Tunables {
   std::atomic<int> variant{0};
+  std::atomic<int> hugedmma{1};  // 1 (default): blocks with a dimension above max_kernel_dim use the panel DMMA kernel (smm_dmma_huge.cuh); 0: scalar generic kernel
   std::atomic<int> bigdmma{1};  // 1 (default): blocks with a dimension in 33..80 use the cooperative DMMA kernel (smm_dmma_big.cuh); 0: scalar generic kernel
   std::atomic<int> inhomogeneous{1};  // 1: def_mnk = 0 stacks are binned by shape and drained on the GPU; 0: -1 like the reference
   std::atomic<int> bf16_merge{1};     // tiled BF16 SpGEMM: 1 = one wide MMA per run of adjacent existing B blocks, 0 = one per block

@@ -166,10 +166,15 @@ def test_generic_kernel_shapes(acc, mnk):
     assert np.array_equal(c, c_ref)
 
 
-def test_large_blocks_b_not_transposed(acc):
-    """Any dim > max_kernel_dim: B is NOT transposed by DBCSR (src/acc/libsmm_acc/libsmm_acc.cpp:267-270), path runs on c_stream."""
+@pytest.mark.parametrize("hugedmma", [1, 0], ids=["panel_dmma_kernel", "scalar_generic_kernel"])
+def test_large_blocks_b_not_transposed(acc, hugedmma):
+    """Any dim > max_kernel_dim: B is transposed by DBCSR only when BOTH n and k fit max_kernel_dim (src/acc/libsmm_acc/libsmm_acc.cpp:267-270).
+    Default: the panel DMMA kernel (smm_dmma_huge.cuh; C panels of <= 96 x 80, K chunks of 32, ragged edges); hugedmma = 0: the scalar kernel."""
     rng = np.random.default_rng(3)
-    for (m, n, k) in [(100, 5, 90), (5, 100, 7), (81, 81, 81)]:
+    saved = acc.get_tunable("hugedmma")
+    acc.set_tunable("hugedmma", hugedmma)
+    shapes = [(100, 5, 90), (5, 100, 7), (81, 81, 81), (100, 100, 100), (200, 96, 161), (97, 81, 33), (120, 40, 70), (83, 7, 3), (1, 1, 130)]
+    for (m, n, k) in shapes:
         n_a = n_b = 6
         n_c = 3
         S = 12
@@ -186,7 +191,8 @@ def test_large_blocks_b_not_transposed(acc):
         rc, c = run_process(acc, host[:, 3:6].copy(), a, b_dev, n_c * m * n, m, n, k, host7=host)
         assert rc == 10
         c_ref = orc.host_stack(host, a, b, np.zeros(n_c * m * n))
-        assert np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref) <= 1e-12
+        assert np.linalg.norm(c - c_ref) / np.linalg.norm(c_ref) <= 1e-12, (m, n, k)
+    acc.set_tunable("hugedmma", saved)
 
 
 def test_unsupported_requests_leave_c_untouched(acc):
