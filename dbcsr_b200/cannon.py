@@ -227,9 +227,11 @@ class CannonMultiply:
         self.home = {}
         if "A_dist" in w:
             # distributed input: this rank only holds its blocks of A and B (DistMatrix); the images are made by an all-to-all
-            for s, pan in make_images(w["A_dist"], "a", sc, rank, world, self.rsp, self.csp, self.ksp, self.device).items():
+            # (messages travel as device tensors over NCCL; gloo - CPU tests, ranks sharing one GPU - moves host tensors)
+            img_dev = self.device if (world > 1 and dist.get_backend() == "nccl") else "cpu"
+            for s, pan in make_images(w["A_dist"], "a", sc, rank, world, self.rsp, self.csp, self.ksp, img_dev).items():
                 self.home[("a", s)] = pan
-            for s, pan in make_images(w["B_dist"], "b", sc, rank, world, self.rsp, self.csp, self.ksp, self.device).items():
+            for s, pan in make_images(w["B_dist"], "b", sc, rank, world, self.rsp, self.csp, self.ksp, img_dev).items():
                 self.home[("b", s)] = pan
         else:
             A, B = w["A"], w["B"]

@@ -94,6 +94,39 @@ def main():
         report["cases"].append({"config": cfg_name, "path": "replay", "blocks": nb, "worst_rel_err": worst})
         dist.barrier()
         cm.close()
+    # ---- distributed input (row a3): every rank holds only ITS blocks under a 2-d block distribution unrelated to the Cannon layout;
+    #      make_images moves them to their home panels (all-to-all over NCCL, device tensors), then the same multiply
+    w = workload.make_config("cfg2", nblk=int(os.environ.get("CANNON_TEST_NBLK", "64")))
+    A, B, bs = w["A"], w["B"], w["m_sizes"]
+    Cref = orc.multiply_blocks(orc.BlockMatrix(A.row_sizes, A.col_sizes, A.rows, A.cols, data=A.data),
+                               orc.BlockMatrix(B.row_sizes, B.col_sizes, B.rows, B.cols, data=B.data))
+    ref = {(int(r), int(c)): Cref.data[o:o + int(bs[r - 1]) * int(bs[c - 1])] for r, c, o in zip(Cref.rows, Cref.cols, Cref.offsets)}
+    sc = cannon.Schedule(world)
+    rng = np.random.default_rng(1234)  # the same maps on every rank
+    row_dist, col_dist = rng.integers(0, sc.pr, w["nblk"]), rng.integers(0, sc.pc, w["nblk"])
+    w_dist = {k: v for k, v in w.items() if k not in ("A", "B")}
+    w_dist["A_dist"] = cannon.DistMatrix.from_global(A, row_dist, col_dist, sc, rank)
+    w_dist["B_dist"] = cannon.DistMatrix.from_global(B, row_dist, col_dist, sc, rank)
+    cm = cannon.CannonMultiply(w_dist, rank, world, "cuda:%d" % dev, acc=acc, nthreads=2, cfg=host.default_cfg(mm_stack_size=1000))
+    r0, r1, c0, c1 = cm.rsp[cm.i], cm.rsp[cm.i + 1], cm.csp[cm.j], cm.csp[cm.j + 1]
+    cm.run()
+    cm.engine.sync()
+    torch.cuda.synchronize()
+    got = {}
+    for t in range(cm.engine.nthreads):
+        rows, cols, blk_p, ds = cm.engine.c_index(t)
+        if ds == 0:
+            continue
+        buf = np.empty(ds)
+        cm.engine.c_to_host(t, buf)
+        for rr, cc, p in zip(rows, cols, blk_p):
+            nz = int(cm.m_sizes[rr - 1]) * int(cm.n_sizes[cc - 1])
+            got[(int(rr) + r0, int(cc) + c0)] = buf[p - 1:p - 1 + nz].copy()
+    nb, worst = check_blocks("distributed input rank %d" % rank, got, ref, r0, r1, c0, c1)
+    report["cases"].append({"config": "cfg2", "path": "engine, distributed input through make_images", "blocks": nb, "worst_rel_err": worst,
+                            "owned_blocks": [w_dist["A_dist"].panel.nblks, w_dist["B_dist"].panel.nblks]})
+    dist.barrier()
+    cm.close()
     outdir = os.environ.get("CANNON_TEST_OUT")
     if outdir:
         with open(os.path.join(outdir, "rank%d.json" % rank), "w") as f:

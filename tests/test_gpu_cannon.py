@@ -1,7 +1,8 @@
 """Multi-process Cannon multiply on real GPUs, checked block by block against the oracle.
 The reference tests every distributed multiply against dense DGEMM with 2 MPI ranks (tests/CMakeLists.txt:130-137,
 tests/dbcsr_test_multiply.F:753-759); here 2, 4 and 8 ranks = 1x2, 2x2 and 2x4 Cannon grids (2x4: four virtual k-slices on a non-square grid), engine path and replay path, 23x23 and
-mixed block sizes.  One rank per GPU over NCCL when the box has enough GPUs; otherwise the ranks share GPU 0 (gloo set-up
+mixed block sizes, plus one multiply whose input is DISTRIBUTED (every rank holds only its blocks under an unrelated 2-d block
+distribution; `cannon.make_images` = the reference's make_images moves them to the home panels by an all-to-all).  One rank per GPU over NCCL when the box has enough GPUs; otherwise the ranks share GPU 0 (gloo set-up
 collectives, CUDA IPC peer pull) so that the distributed path is exercised on a single-GPU box too."""
 import os
 import re
@@ -47,6 +48,6 @@ def test_cannon_blocks_match_oracle(world):
     assert out.returncode == 0 and len(reports) == world, "rc %d, %d reports\nstdout:\n%s\nstderr:\n%s" % (out.returncode, len(reports), out.stdout[-3000:],
                                                                                                         out.stderr[-3000:])
     for rep in reports:
-        assert len(rep["cases"]) == 4
+        assert len(rep["cases"]) == 5  # cfg2 / cfg3 x (engine, replay) + cfg2 with distributed input through make_images
         for case in rep["cases"]:
             assert case["blocks"] > 0 and case["worst_rel_err"] <= 1e-10
