@@ -702,6 +702,25 @@ def bench_main(args):
             ts.append(e0.elapsed_time(e1))
         return ts
 
+    def timed_region(fn, steps, lookahead=2):
+        """The bench contract's bracket: barrier + device sync, EXACTLY `steps` steps enqueued back to back on the compute stream (the
+        host stays at most `lookahead` steps ahead of the device), device sync + barrier; CUDA-event time of the whole region / steps.
+        Consecutive multiplies overlap the way they do in an application: the panel pulls and the C memset of step k+1 run beside the
+        last ticks of step k (home panels are read-only, so no rank ever waits for another inside the region)."""
+        dist.barrier()
+        torch.cuda.synchronize()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record(cm.cs_torch)
+        for k in range(steps):
+            if lookahead and k >= lookahead:
+                evs[k - lookahead + 1].synchronize()
+            fn()
+            evs[k + 1].record(cm.cs_torch)
+        evs[steps].synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return evs[0].elapsed_time(evs[steps]) / max(1, steps)
+
     for _ in range(args.warmup):
         cm.replay_step()
     dist.barrier()
@@ -778,9 +797,11 @@ def bench_main(args):
         time.sleep(0.3)
     launches0 = acc.launch_count()
     t_host0 = time.perf_counter()
-    times = timed(step_fn, args.steps, True)
+    region_ms = timed_region(step_fn, args.steps)
+    times = [region_ms]
     t_host = (time.perf_counter() - t_host0) / max(1, args.steps)
     launches = acc.launch_count() - launches0
+    isolated = timed(step_fn, min(5, args.steps), True)  # every step alone between barriers (cold start per step): for comparison
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: stacks built by the host threads every step and streamed to the device (engine path), C stays on the device
@@ -838,7 +859,7 @@ def bench_main(args):
         e2e_times = timed(one_multiply, args.e2e_steps, False)
     d2h_local = float(c_shard_bytes()) if not args.no_e2e else 0.0
     t = torch.tensor([float(np.mean(times)), float(cm.flop), float(launches), cm.last_build_s, float(np.mean(e2e_times)), float(cm.n_replay_launches),
-                      d2h_local],
+                      d2h_local, float(np.mean(isolated))],
                      dtype=torch.float64, device="cuda")
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -855,7 +876,8 @@ def bench_main(args):
                "dtype": "f64", "data": "synthetic (numpy PCG64 seed 42, uniform(0,1))",
                "config": workload_config(w, {"grid": "%dx%d" % (sc.pr, sc.pc), "k_slices": sc.V, "host_threads_per_rank": nthreads,
                                              "flop": flop, "parallelism": "cannon %dx%d, one rank per GPU; panels moved by %s" % (sc.pr, sc.pc, "copy-engine peer pull over NVLink (CUDA IPC), NCCL for set-up collectives" if cm.peer_buf is not None else "NCCL grouped send/recv"),
-                                             "timed": "whole multiply per step: C memset, %d ticks of (panel exchange || stack kernels on pre-built device stacks); max over ranks of CUDA-event time; initial distribution excluded" % sc.V}),
+                                             "timed": "whole multiply per step: C memset, %d ticks of (panel exchange || stack kernels on pre-built device stacks); the K steps are enqueued back to back between one barrier + device sync on either side (consecutive multiplies overlap: pulls and memset of step k+1 beside the last ticks of step k); max over ranks of the CUDA-event time of the region / K; initial distribution excluded" % sc.V,
+                                             "isolated_ms_per_step": float(tmax[7]), "isolated_note": "the same step alone between barriers + device syncs (cold start: the first exchange and the launch ramp are exposed every step)"}),
                "clocks": clocks, "gpu_launches": int(float(tsum[2])) if not use_graph else int(args.steps * float(tsum[5])),
                "gpu_launches_note": "kernels of this library per timed region, summed over ranks (graph replays counted from the captured launch list)",
                "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,

@@ -146,15 +146,12 @@ int dbcsr_b200_replay_step(dbcsr_b200_replay_t* r, void* compute_stream) {
     return cudaEventRecord(t.pulled, r->pull_stream) == cudaSuccess ? 0 : -3;
   };
   const size_t nt = r->ticks.size();
+  // every pull of this multiply is posted up front (one receive buffer per tick): a pull starts as soon as the previous multiply's
+  // kernels of the same tick have released the buffer, i.e. beside the LAST ticks of the previous multiply when steps follow each other
+  for (size_t u = 0; u < nt; ++u)
+    if (post_pulls(r->ticks[u]) != 0) return -3;
   for (size_t it = 0; it < nt; ++it) {
     Tick& t = r->ticks[it];
-    if (it == 0) {
-      if (post_pulls(t) != 0) return -3;
-    }
-    else if (it == 1) {  // the kernels of the first tick are enqueued: now post every remaining pull of this multiply
-      for (size_t u = 1; u < nt; ++u)
-        if (post_pulls(r->ticks[u]) != 0) return -3;
-    }
     if (cudaStreamWaitEvent(cs, t.pulled, 0) != cudaSuccess) return -4;
     for (const Stack& s : t.stacks) {
       const int rc = libsmm_acc_process(nullptr, s.dev, s.size, dbcsr_type_real_8, t.a, t.b, c, s.m, s.n, s.k, 80, s.defined, compute_stream,
