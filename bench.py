@@ -688,7 +688,7 @@ def run_single(args):
                     nthreads, rchunks, mode = args.dev_threads, args.dev_row_chunks, host.LAUNCH | host.DEVICE_BUILD
                 else:
                     nthreads, rchunks, mode = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2)), args.row_chunks, host.LAUNCH
-                cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=rchunks)
+                cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=rchunks, dev_tile=(args.dev_tile if builder == "device" else 0))
                 dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e, mode=mode)
                 pcs = None
                 times = []
@@ -719,7 +719,7 @@ def run_single(args):
                            "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "stack_builder": builder,
                            "host_threads": nthreads, "row_chunks_per_thread": rchunks, "pipelined_upload": bool(args.pipelined_upload and builder == "host"),
                            "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases,
-                           "device_built_ticks": dm.engine.device_built_ticks, "sum_c": got,
+                           "device_built_ticks": dm.engine.device_built_ticks, "sum_c": got, "dev_tile": (args.dev_tile if builder == "device" else 0),
                            "timing": "wall clock around the public call, device synchronised on both sides"}
                 finally:
                     dm.close()
