@@ -659,7 +659,7 @@ def run_single(args):
         acc.stream_chain(s, True)
     tstream = torch.cuda.ExternalStream(acclib.ctypes.c_void_p.from_address(s).value)
     peaks = measure_fp64_peaks(torch, acc, s)
-    run = Fp64Run(acc, args.config, args.nblk, s)
+    run = Fp64Run(acc, args.config, args.nblk, s, nstreams=(args.cfg3_streams if args.config == "cfg3" else 1))
     w = run.w
     A, B, bs = w["A"], w["B"], w["m_sizes"]
 

@@ -9,6 +9,13 @@ tail -c 500 gpurun_out/bench_r02_final_n1.err
 timeout 600 python bench.py --impl reference > gpurun_out/bench_r02_final_n1_ref.json 2> gpurun_out/bench_r02_final_n1_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_ncu_launches_bench.csv \
   python bench.py --steps 2 --warmup 3 --no-extra --no-e2e --no-cpu --no-gpu-baseline --no-tiled --no-selfcheck --no-clock-sampler > gpurun_out/ncu_launch_list.log 2>&1
+for st in 1 2 8; do
+  timeout 300 python bench.py --config cfg3 --cfg3-streams $st --steps 10 --warmup 3 --no-e2e --no-cpu --no-selfcheck --no-clock-sampler 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('cfg3 streams $st value', d['value'], 'kernel_only', d['roofline']['kernel_only_gflops'])"
+done
 python - <<'P'
 import csv, json, collections
 for f in ("gpurun_out/bench_r02_final_n1.json", "gpurun_out/bench_r02_final_n1_ref.json"):
