@@ -26,6 +26,7 @@ typedef unsigned char u8;
 
 constexpr u32 kEmpty = 0xFFFFFFFFu;  // table slot without a block
 constexpr u32 kNew = 0x80000000u;    // table value = kNew | (traversal position of the earliest product touching the block)
+constexpr u32 kNoSlot = 0xFFFFFFFFu; // retain_sparsity: the product's C block does not exist
 constexpr int kDropBin = 255;        // products without a stack entry (zero-sized blocks)
 constexpr int kMaxBins = 254;
 constexpr long long kDenseLimitDefault = 1ll << 25;  // (row, col) slots up to which the C table is a direct array
@@ -101,6 +102,25 @@ struct RankRange {
   }
 };
 
+// the tests csr_multiply_low applies to a pair before it touches the C index (src/mm/dbcsr_mm_csr.F:270-292)
+struct PairTest {
+  const float *a_norms = nullptr, *b_norms = nullptr, *row_eps = nullptr;  // by sorted-list position / by block row
+  int c_sym = 0;
+  const int *grow = nullptr, *gcol = nullptr;
+  DB_HD bool active() const { return a_norms != nullptr || c_sym != 0; }
+  DB_HD bool keep(int a_pos, int b_pos, int row, int col) const {
+    if (a_norms != nullptr) {  // single-precision product and compare, like the reference
+      const float prod = a_norms[a_pos] * b_norms[b_pos];
+      if (prod < row_eps[row - 1]) return false;
+    }
+    if (c_sym) {
+      const int cr = grow != nullptr ? grow[row - 1] : row, cc = gcol != nullptr ? gcol[col - 1] : col;
+      if (cr != cc && ((((cr + cc) & 1) != 0) == (cc >= cr))) return false;  // checker_tr
+    }
+    return true;
+  }
+};
+
 // item = (leaf, A block in the leaf's CSR order): the B blocks of row a_col inside the leaf's right range
 struct CountItems {
   const int* leaf_ioff;  // prefix of the leaves' A-range lengths, nleaves + 1
@@ -110,6 +130,8 @@ struct CountItems {
   const int *b_soff, *b_skey;
   int *item_a, *item_blo;
   u32* item_cnt;
+  PairTest pt;
+  const int *b_sidx, *b_list;
   DB_HD void operator()(long long i) const {
     const int leaf = upper_bound_n(leaf_ioff, nleaves + 1, (int)i) - 1;
     const int j = (int)i - leaf_ioff[leaf];
@@ -121,7 +143,16 @@ struct CountItems {
     const int lo = lower_bound_n(keys, len, kcol), hi = upper_bound_n(keys, len, kcol);
     item_a[i] = a;
     item_blo[i] = b_soff[br] + lo;
-    item_cnt[i] = (u32)(hi - lo);
+    u32 cnt = (u32)(hi - lo);
+    if (pt.active()) {
+      const int row = a_list[3 * (size_t)a];
+      cnt = 0;
+      for (int t = lo; t < hi; ++t) {
+        const int b = b_sidx[b_soff[br] + t];
+        cnt += pt.keep(a, b, row, b_list[3 * (size_t)b + 1]) ? 1u : 0u;
+      }
+    }
+    item_cnt[i] = cnt;
   }
 };
 
@@ -130,12 +161,27 @@ struct EmitProducts {
   const u32* item_off;  // nitems + 1
   const int* b_sidx;
   int *prod_a, *prod_b;
+  PairTest pt;
+  const int *a_list, *b_list;
   DB_HD void operator()(long long i) const {
     const u32 off = item_off[i], cnt = item_off[i + 1] - off;
     const int a = item_a[i], blo = item_blo[i];
-    for (u32 t = 0; t < cnt; ++t) {
-      prod_a[off + t] = a;
-      prod_b[off + t] = b_sidx[blo + (int)t];
+    if (!pt.active()) {
+      for (u32 t = 0; t < cnt; ++t) {
+        prod_a[off + t] = a;
+        prod_b[off + t] = b_sidx[blo + (int)t];
+      }
+      return;
+    }
+    const int row = a_list[3 * (size_t)a];
+    u32 w = 0;
+    for (int t = 0; w < cnt; ++t) {  // the surviving pairs, in order
+      const int b = b_sidx[blo + t];
+      if (pt.keep(a, b, row, b_list[3 * (size_t)b + 1])) {
+        prod_a[off + w] = a;
+        prod_b[off + w] = b;
+        ++w;
+      }
     }
   }
 };
@@ -157,6 +203,20 @@ struct CTable {
       h = (h + 1) & mask;
     }
   }
+  DB_HD u32 find(int row, int col) const {  // no insertion (nothing else inserts concurrently): kNoSlot when absent
+    if (keys == nullptr) {
+      const u32 s = (u32)(row - 1) * (u32)ncols + (u32)(col - 1);
+      return val[s] == 0xFFFFFFFFu ? kNoSlot : s;
+    }
+    const u64 key = ((u64)(u32)row << 32) | (u32)col;
+    u32 h = (u32)((key * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+    for (;;) {
+      const u64 k = keys[h];
+      if (k == key) return h;
+      if (k == 0ull) return kNoSlot;
+      h = (h + 1) & mask;
+    }
+  }
 };
 
 struct ReinsertBlocks {  // after the open-addressing table grew
@@ -169,8 +229,13 @@ struct InsertProducts {
   CTable t;
   const int *a_list, *b_list, *prod_a, *prod_b;
   u32* slot;
+  int keep_sparsity;
   DB_HD void operator()(long long p) const {
     const int row = a_list[3 * (size_t)prod_a[p]], col = b_list[3 * (size_t)prod_b[p] + 1];
+    if (keep_sparsity) {  // src/mm/dbcsr_mm_csr.F:307: only existing blocks receive products
+      slot[p] = t.find(row, col);
+      return;
+    }
     const u32 s = t.find_or_insert(row, col);
     atomic_min_u32(&t.val[s], kNew | (u32)p);  // existing blocks hold their id (< kNew) and keep it
     slot[p] = s;
@@ -183,7 +248,7 @@ struct FlagFirst {  // the product that touches a new block first creates it (sr
   u32* flag;
   u64* nze;
   DB_HD void operator()(long long p) const {
-    const bool first = val[slot[p]] == (kNew | (u32)p);
+    const bool first = slot[p] != kNoSlot && val[slot[p]] == (kNew | (u32)p);
     flag[p] = first ? 1u : 0u;
     const int row = a_list[3 * (size_t)prod_a[p]], col = b_list[3 * (size_t)prod_b[p] + 1];
     nze[p] = first ? (u64)m_sizes[row - 1] * (u64)n_sizes[col - 1] : 0ull;
@@ -216,13 +281,14 @@ struct SizeMaps {
 struct BinProducts {  // stack number of every product (stack_map, src/mm/dbcsr_mm_csr.F:340-345)
   SizeMaps z;
   const int *a_list, *b_list, *prod_a, *prod_b;
+  const u32* slot;
   u8* bin;
   u32* iota;
   DB_HD void operator()(long long p) const {
     const int a = prod_a[p], b = prod_b[p];
     const int m = z.m_sizes[a_list[3 * (size_t)a] - 1], k = z.k_sizes[a_list[3 * (size_t)a + 1] - 1], n = z.n_sizes[b_list[3 * (size_t)b + 1] - 1];
     int ws = kDropBin;
-    if (m * n != 0 && k != 0) {
+    if (m * n != 0 && k != 0 && slot[p] != kNoSlot) {
       const int w = z.n_stacks + 1;
       const int mm = m < z.m_map_n ? z.m_map[m] : w, mk = k < z.k_map_n ? z.k_map[k] : w, mn = n < z.n_map_n ? z.n_map[n] : w;
       ws = z.stack_map[((size_t)(mm - 1) * w + (mk - 1)) * w + (mn - 1)];
@@ -561,7 +627,7 @@ class Builder final : public IDeviceBuilder {
   int nblk_ = 0, datasize_ = 0;
   // per tick
   Buf a_list_, b_list_, ints_, item_a_, item_blo_, item_cnt_, item_off_, prod_a_, prod_b_, slot_, w32a_, w32b_, w64a_, w64b_, bin_, bin_s_, iota_,
-      part_p_, sim_, disp_, out3_, p7_, info_, sa_idx_, sa_key_, sb_idx_, sb_key_, dtab_;
+      part_p_, sim_, disp_, out3_, p7_, info_, sa_idx_, sa_key_, sb_idx_, sb_key_, dtab_, ptest_;
   SizeMaps maps_{};
   const int* d_bin_start_ = nullptr;
   long long nprod_ = 0, nkept_ = 0;
@@ -600,7 +666,7 @@ class Builder final : public IDeviceBuilder {
     x_.sync();
     for (Buf* b : {&c_row_, &c_col_, &c_blkp_, &tkeys_, &tval_, &a_list_, &b_list_, &ints_, &item_a_, &item_blo_, &item_cnt_, &item_off_, &prod_a_,
                    &prod_b_, &slot_, &w32a_, &w32b_, &w64a_, &w64b_, &bin_, &bin_s_, &iota_, &part_p_, &sim_, &disp_, &out3_, &p7_, &info_, &sa_idx_,
-                   &sa_key_, &sb_idx_, &sb_key_, &dtab_})
+                   &sa_key_, &sb_idx_, &sb_key_, &dtab_, &ptest_})
       if (b->p != nullptr) x_.release(b->p);
   }
 
@@ -659,8 +725,28 @@ class Builder final : public IDeviceBuilder {
     return 0;
   }
 
+  // existing C blocks: ids 1..nblks in list order at the given offsets
+  int preset(int nrows, int ncols, const int* rows, const int* cols, const int* blk_p, int nblks, int datasize) override {
+    if (nblk_ != 0 || nblks < 0) return -2;
+    if (int rc = prepare_table(nrows, ncols, nblks)) return rc;
+    const size_t bytes = sizeof(int) * (size_t)std::max(nblks, 1);
+    if (int rc = ensure(c_row_, bytes)) return rc;
+    if (int rc = ensure(c_col_, bytes)) return rc;
+    if (int rc = ensure(c_blkp_, bytes)) return rc;
+    if (nblks > 0) {
+      if (x_.h2d(c_row_.p, rows, sizeof(int) * (size_t)nblks) != 0 || x_.h2d(c_col_.p, cols, sizeof(int) * (size_t)nblks) != 0 ||
+          x_.h2d(c_blkp_.p, blk_p, sizeof(int) * (size_t)nblks) != 0)
+        return -61;
+      ReinsertBlocks f{table_, ptr<int>(c_row_), ptr<int>(c_col_)};
+      if (int rc = x_.for_each(nblks, f)) return rc;
+    }
+    nblk_ = nblks;
+    datasize_ = datasize;
+    return 0;
+  }
+
   int build(LocalMultiply& mm, const Idx3* a_sorted, int na, const std::vector<std::pair<int, int>>& slices, const Idx3* b_sorted, int nb,
-            DevBuildResult& out) override {
+            DevBuildResult& out, const DevBuildOptions& opt) override {
     const Config& cfg = mm.config();
     const int nstacks = mm.nstacks();
     out = DevBuildResult();
@@ -731,6 +817,35 @@ class Builder final : public IDeviceBuilder {
     maps_.m_map = I + o_mm, maps_.n_map = I + o_nm, maps_.k_map = I + o_km, maps_.stack_map = I + o_sm;
     maps_.m_map_n = (int)mm.m_map().size(), maps_.n_map_n = (int)mm.n_map().size(), maps_.k_map_n = (int)mm.k_map().size();
     maps_.n_stacks = cfg.n_stacks;
+    // ---- the pair tests of this tick (on-the-fly filter, symmetric-product skipping)
+    PairTest pt;
+    {
+      const bool filt = opt.a_norms != nullptr && opt.b_norms != nullptr && opt.row_eps != nullptr;
+      const size_t nrows_l = mm.m_sizes().size(), ncols_l = mm.n_sizes().size();
+      const size_t nf = filt ? (size_t)na + (size_t)nb + nrows_l : 0;
+      const size_t ng = opt.c_sym ? (opt.global_rows != nullptr ? nrows_l : 0) + (opt.global_cols != nullptr ? ncols_l : 0) : 0;
+      if (nf + ng > 0) {
+        if (int rc = ensure(ptest_, sizeof(float) * nf + sizeof(int) * ng + 16)) return rc;
+        float* f = ptr<float>(ptest_);
+        if (filt) {
+          if (x_.h2d(f, opt.a_norms, sizeof(float) * (size_t)na) != 0 || x_.h2d(f + na, opt.b_norms, sizeof(float) * (size_t)nb) != 0 ||
+              x_.h2d(f + na + nb, opt.row_eps, sizeof(float) * nrows_l) != 0)
+            return -61;
+          pt.a_norms = f, pt.b_norms = f + na, pt.row_eps = f + na + nb;
+        }
+        int* g = reinterpret_cast<int*>(f + nf);
+        if (opt.c_sym && opt.global_rows != nullptr) {
+          if (x_.h2d(g, opt.global_rows, sizeof(int) * nrows_l) != 0) return -61;
+          pt.grow = g;
+          g += nrows_l;
+        }
+        if (opt.c_sym && opt.global_cols != nullptr) {
+          if (x_.h2d(g, opt.global_cols, sizeof(int) * ncols_l) != 0) return -61;
+          pt.gcol = g;
+        }
+      }
+      pt.c_sym = opt.c_sym ? 1 : 0;
+    }
 
     if (nitems > 0) {
       // ---- CSR order of every distinct range
@@ -748,7 +863,7 @@ class Builder final : public IDeviceBuilder {
       if (int rc = ensure(item_off_, sizeof(u32) * ((size_t)nitems + 1))) return rc;
       if (x_.fill(ptr<u32>(item_cnt_) + nitems, 0, sizeof(u32)) != 0) return -61;
       CountItems ci{I + o_lio, nleaves, I + o_lar, I + o_lbr, I + o_aso, ptr<int>(sa_idx_), d_a_list, I + o_bso, ptr<int>(sb_key_),
-                    ptr<int>(item_a_), ptr<int>(item_blo_), ptr<u32>(item_cnt_)};
+                    ptr<int>(item_a_), ptr<int>(item_blo_), ptr<u32>(item_cnt_), pt, ptr<int>(sb_idx_), d_b_list};
       if (int rc = x_.for_each(nitems, ci)) return rc;
       if (int rc = x_.scan(ptr<u32>(item_cnt_), ptr<u32>(item_off_), (long long)nitems + 1)) return rc;
       u32 total = 0;
@@ -789,10 +904,10 @@ class Builder final : public IDeviceBuilder {
     u32 *d_flag = ptr<u32>(w32a_), *d_fscan = ptr<u32>(w32b_);
     u64 *d_nze = ptr<u64>(w64a_), *d_zscan = ptr<u64>(w64b_);
     if (N > 0) {
-      EmitProducts ep{ptr<int>(item_a_), ptr<int>(item_blo_), ptr<u32>(item_off_), ptr<int>(sb_idx_), d_prod_a, d_prod_b};
+      EmitProducts ep{ptr<int>(item_a_), ptr<int>(item_blo_), ptr<u32>(item_off_), ptr<int>(sb_idx_), d_prod_a, d_prod_b, pt, d_a_list, d_b_list};
       if (int rc = x_.for_each(nitems, ep)) return rc;
       // ---- C blocks: earliest toucher per (row, col), block numbers and offsets by scans
-      if (int rc = x_.for_each(N, InsertProducts{table_, d_a_list, d_b_list, d_prod_a, d_prod_b, d_slot})) return rc;
+      if (int rc = x_.for_each(N, InsertProducts{table_, d_a_list, d_b_list, d_prod_a, d_prod_b, d_slot, opt.keep_sparsity ? 1 : 0})) return rc;
       if (int rc = x_.for_each(N, FlagFirst{table_.val, d_slot, d_a_list, d_b_list, d_prod_a, d_prod_b, maps_.m_sizes, maps_.n_sizes, d_flag, d_nze}))
         return rc;
     }
@@ -804,7 +919,7 @@ class Builder final : public IDeviceBuilder {
                     ptr<int>(c_row_), ptr<int>(c_col_), ptr<int>(c_blkp_)};
       if (int rc = x_.for_each(N, wf)) return rc;
       // ---- stack number per product, stable partition
-      if (int rc = x_.for_each(N, BinProducts{maps_, d_a_list, d_b_list, d_prod_a, d_prod_b, ptr<u8>(bin_), ptr<u32>(iota_)})) return rc;
+      if (int rc = x_.for_each(N, BinProducts{maps_, d_a_list, d_b_list, d_prod_a, d_prod_b, d_slot, ptr<u8>(bin_), ptr<u32>(iota_)})) return rc;
       if (int rc = x_.sort_pairs(ptr<u8>(bin_), ptr<u8>(bin_s_), ptr<u32>(iota_), ptr<u32>(part_p_), N, 8)) return rc;
     }
     // ---- flush rule; slice ends; totals

@@ -42,6 +42,20 @@ struct DevBuildResult {
   int datasize_before = 0, datasize_after = 0;
 };
 
+// What csr_multiply_low tests per product before it looks the C block up (src/mm/dbcsr_mm_csr.F:270-292, :307), for one tick
+struct DevBuildOptions {
+  // on-the-fly filter: norms aligned with the SORTED lists, thresholds per local block row; all three or none
+  const float* a_norms = nullptr;
+  const float* b_norms = nullptr;
+  const float* row_eps = nullptr;
+  // product with symmetry: skip (row, col) when global row != global col and checker_tr(global row, global col)
+  bool c_sym = false;
+  const int* global_rows = nullptr;  // per local block row (nullptr: identity)
+  const int* global_cols = nullptr;
+  // retain_sparsity: products whose C block does not exist are dropped, no block is created
+  bool keep_sparsity = false;
+};
+
 class IDeviceBuilder {
  public:
   virtual ~IDeviceBuilder() {}
@@ -57,7 +71,10 @@ class IDeviceBuilder {
   // this thread multiplies, in order - each is one LocalMultiply::multiply call, i.e. ends with a purge.  mm supplies the
   // recursion (plan) and the block-size / stack maps.  Returns 0 or a negative code.
   virtual int build(LocalMultiply& mm, const Idx3* a_sorted, int na, const std::vector<std::pair<int, int>>& slices, const Idx3* b_sorted,
-                    int nb, DevBuildResult& out) = 0;
+                    int nb, DevBuildResult& out, const DevBuildOptions& opt = DevBuildOptions()) = 0;
+  // Existing C blocks (beta != 0 / retain_sparsity): the work index starts from them (fill_hash_tables, src/mm/dbcsr_mm_csr.F:540-576);
+  // after reset() and before the first build.  blk_p: their 1-based offsets; datasize: elements they occupy.
+  virtual int preset(int nrows, int ncols, const int* rows, const int* cols, const int* blk_p, int nblks, int datasize) = 0;
   // 3-wide stack of a dispatch entry, in device order where the stack is sorted by c_first on the device (`device_ordered`), else
   // in traversal order (the caller orders it on the host: binning, inhomogeneous stacks)
   virtual const int* stack3(const DevDispatch& d) const = 0;       // address in the executor's memory space

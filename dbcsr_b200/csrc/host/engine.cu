@@ -201,6 +201,7 @@ dbcsr_b200_engine_t* dbcsr_b200_engine_create(const dbcsr_b200_cfg_t* cfg, const
         ts.devb.reset(dbcsr_b200::make_emulated_builder());
       }
       ts.devb->set_tile_order(cfg->dev_tile);
+      ts.dev_index = true;
     }
   }
   return e;
@@ -318,7 +319,7 @@ static int owner_of_row(const dbcsr_b200_engine_t* e, int row) {
 // the stacks in the host builder's dispatch order.  Stacks the accelerator driver sorts by c_first arrive in device order; the
 // others (binning, inhomogeneous) are ordered on the host from their 7-wide entries, exactly like the host path.
 template <class BookFn>
-static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, const void* b_dev, int nb, const BookFn& book) {
+static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, const void* b_dev, int nb, bool filter, const BookFn& book) {
   ThreadState& ts = e->th[(size_t)t];
   const bool launch = (e->mode & DBCSR_B200_LAUNCH) != 0;
   const int na = (int)e->a_sorted.size();
@@ -329,7 +330,17 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
       return -45;
   }
   dbcsr_b200::DevBuildResult r;
-  const int rc_b = ts.devb->build(*ts.mm, e->a_sorted.data(), na, ts.slices, e->b_sorted.data(), nb, r);
+  dbcsr_b200::DevBuildOptions opt;
+  if (filter) {  // on-the-fly filter: norms follow the sorted lists (src/mm/dbcsr_mm_csr.F:270-278)
+    opt.a_norms = e->a_norm_sorted.data();
+    opt.b_norms = e->b_norm_sorted.data();
+    opt.row_eps = e->row_eps.data();
+  }
+  opt.c_sym = ts.mm->c_symmetry();
+  opt.global_rows = ts.mm->c_global_rows().empty() ? nullptr : ts.mm->c_global_rows().data();
+  opt.global_cols = ts.mm->c_global_cols().empty() ? nullptr : ts.mm->c_global_cols().data();
+  opt.keep_sparsity = ts.mm->keep_sparsity();
+  const int rc_b = ts.devb->build(*ts.mm, e->a_sorted.data(), na, ts.slices, e->b_sorted.data(), nb, r, opt);
   if (rc_b != 0) return rc_b;
   // new part of the C index -> host work index (the engine's accessors, finalize and the downloads use it)
   const int nnew = r.nblk_after - r.nblk_before;
@@ -434,7 +445,7 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
       book(sd, host7, d.size, rc == 10);
     }
     const int ds1 = r.slice_datasize[(size_t)s];
-    if (ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds_prev) {
+    if (ts.c_host != nullptr && ts.c_dev != nullptr && ds1 > ds_prev && !ts.has_preset) {
       // the C blocks created by this slice are final once its stacks have drained: download them on the copy stream while the
       // stacks of the next slice run
       if (cudaEventRecord(ts.slice_done, st) != cudaSuccess || cudaStreamWaitEvent(ts.copy_stream, ts.slice_done, 0) != cudaSuccess ||
@@ -443,6 +454,10 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
         return -46;
     }
     ds_prev = ds1;
+  }
+  if (ts.has_preset && ts.c_host != nullptr && ts.c_dev != nullptr && r.datasize_after > 0) {
+    // products accumulate into the pre-existing blocks too: one D2H of the whole work area behind the last stack
+    if (c_dbcsr_acc_memcpy_d2h(ts.c_dev, ts.c_host, (size_t)r.datasize_after * sizeof(double), ts.stream) != 0) return -46;
   }
   ts.mm->append_index(nullptr, nullptr, nullptr, 0, r.datasize_after, flop);
   return 0;
@@ -616,13 +631,10 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
         book(d, params7, size, rc == 10);
         if (c_dbcsr_acc_event_record(b.calculated, ts.stream) != 0) ts.rc = -45;
       };
-      // ---- device-side builder: plain products only, and only when the index of this multiply has been on the device from its
-      //      first tick (a multiply uses one builder from reset to reset)
-      const bool dev_ok = ts.devb != nullptr && !filter && !ts.has_preset && ts.mm->plain_product() &&
-                          (ts.dev_index || ts.mm->c_row().empty());
-      if (dev_ok) {
-        ts.dev_index = true;
-        const int rc_dev = device_build_tick(e, t, a_dev, b_dev, nb, book);
+      // ---- device-side builder (a multiply uses one builder from reset to reset: dev_index is true after create / reset and
+      //      cleared when the device passes cannot handle the engine's configuration, which shows at the first tick)
+      if (ts.devb != nullptr && ts.dev_index) {
+        const int rc_dev = device_build_tick(e, t, a_dev, b_dev, nb, filter, book);
         if (rc_dev == 0) ++ts.dev_ticks;
         if (rc_dev != -60) {  // -60: more stacks than the device passes handle => host builder below
           if (rc_dev != 0 && ts.rc == 0) ts.rc = rc_dev;
@@ -724,6 +736,11 @@ int dbcsr_b200_engine_preset_c(dbcsr_b200_engine_t* e, const int* rows, const in
     ts.mm->preset_c(r[(size_t)t].data(), c[(size_t)t].data(), p[(size_t)t].data(), (int)r[(size_t)t].size(), (int)ds[(size_t)t]);
     ts.mm->set_keep_sparsity(keep_sparsity != 0);
     ts.has_preset = true;
+    if (ts.devb != nullptr && ts.dev_index) {
+      const int prc = ts.devb->preset(e->nrows, e->ncols, r[(size_t)t].data(), c[(size_t)t].data(), p[(size_t)t].data(), (int)r[(size_t)t].size(),
+                                      (int)ds[(size_t)t]);
+      if (prc != 0) return prc;
+    }
     if ((e->mode & DBCSR_B200_LAUNCH) && !data[(size_t)t].empty()) {
       if ((size_t)ds[(size_t)t] > ts.c_capacity) {
         const int grc = grow_c_buffer(ts, (size_t)ds[(size_t)t]);
@@ -1047,9 +1064,9 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
     const size_t used = std::min(std::max(ts.c_used_high, (size_t)ts.mm->datasize()), ts.c_capacity);
     ts.mm->reset();
     ts.mm->set_k_sizes(e->k_sizes);
-    ts.dev_index = false;
     if (ts.copy_stream != nullptr && cudaStreamSynchronize(ts.copy_stream) != cudaSuccess) return -41;
     if (ts.devb != nullptr && ts.devb->reset() != 0) return -41;
+    ts.dev_index = ts.devb != nullptr;
     if (ts.c_dev != nullptr && used > 0 && c_dbcsr_acc_memset_zero(ts.c_dev, 0, used * sizeof(double), ts.stream) != 0) return -41;
     ts.c_used_high = 0;
   }

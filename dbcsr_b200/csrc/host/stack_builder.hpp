@@ -125,7 +125,10 @@ class LocalMultiply {
   const std::vector<int>& k_map() const { return k_map_; }
   const std::vector<int>& stack_map() const { return stack_map_; }
   const Config& config() const { return cfg_; }
-  bool plain_product() const { return !keep_sparsity_ && !c_sym_ && row_eps_.empty(); }
+  bool keep_sparsity() const { return keep_sparsity_; }
+  bool c_symmetry() const { return c_sym_; }
+  const std::vector<int>& c_global_rows() const { return c_grow_; }
+  const std::vector<int>& c_global_cols() const { return c_gcol_; }
 
  private:
   void init_stack_map();

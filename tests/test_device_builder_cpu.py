@@ -100,23 +100,118 @@ def test_no_sort_and_empty_panels():
     dev.close()
 
 
-def test_other_multiplies_use_the_host_builder():
-    """Existing C blocks / retain_sparsity are outside the device passes: such a multiply must still give the host builder's result."""
-    m_sizes, n_sizes, k_sizes, A, B = random_lists(30, 30, 30, 0.3, 0.3, [5, 13], seed=4)
+@pytest.mark.parametrize("keep", [False, True])
+def test_preset_c_and_retain_sparsity(keep):
+    """Existing C blocks (beta != 0) and retain_sparsity on the device passes: the work index starts from the listed blocks, with
+    retain_sparsity products into other blocks are dropped and no block is created (src/mm/dbcsr_mm_csr.F:300-323, 540-576)."""
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(40, 36, 44, 0.25, 0.25, [5, 13, 23], seed=31)
     a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
-    ref, dev = engines(m_sizes, n_sizes, k_sizes, 1, dict(mm_stack_size=300))
-    rows, cols = np.array([1, 2, 3], dtype=np.int32), np.array([3, 2, 1], dtype=np.int32)
-    for e in (ref, dev):
-        e.preset_c(rows, cols, None, keep_sparsity=True)
-        e.multiply(a_l, None, b_l, None)
-    assert dev.device_built_ticks == 0
-    assert_same(ref, dev, 1)
-    for e in (ref, dev):  # and the next plain multiply is on the device passes again
-        e.reset()
-        e.multiply(a_l, None, b_l, None)
-    assert_same(ref, dev, 1)
-    ref.close()
-    dev.close()
+    rng = np.random.default_rng(3)
+    pres = np.nonzero(rng.random((40, 36)) < 0.3)
+    rows, cols = (pres[0] + 1).astype(np.int32), (pres[1] + 1).astype(np.int32)
+    for nthreads in (1, 3):
+        ref, dev = engines(m_sizes, n_sizes, k_sizes, nthreads, dict(mm_stack_size=300, multrec_limit=64))
+        for e in (ref, dev):
+            e.preset_c(rows, cols, None, keep_sparsity=keep)
+            e.multiply(a_l, None, b_l, None)
+            e.multiply(a_l[::3], None, b_l, None)
+        assert dev.device_built_ticks == 2 * nthreads
+        assert_same(ref, dev, nthreads)
+        for e in (ref, dev):  # both settings end with the multiply
+            e.reset()
+            e.multiply(a_l, None, b_l, None)
+        assert_same(ref, dev, nthreads)
+        ref.close()
+        dev.close()
+
+
+@pytest.mark.parametrize("eps", [1e-2, 1e-1, 1.0])
+def test_on_the_fly_filter(eps):
+    """filter_eps: a product is skipped when a_norm * b_norm < row_max_epss(row) in single precision (src/mm/dbcsr_mm_csr.F:270-278)."""
+    from test_host_builder import _filter_case
+
+    m_sizes, n_sizes, k_sizes, A, B, a_l, b_l, a_n, b_n, counts = _filter_case(seed=11)
+    row_eps = host.row_max_epss(eps, counts)
+    for nthreads, chunks in ((1, 1), (3, 2)):
+        ref, dev = engines(m_sizes, n_sizes, k_sizes, nthreads, dict(mm_stack_size=400, multrec_limit=64, row_chunks=chunks))
+        plain = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=nthreads, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=400, multrec_limit=64, row_chunks=chunks))
+        plain.multiply(a_l, None, b_l, None)
+        for e in (ref, dev):
+            e.set_filter(row_eps)
+            e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+        assert dev.device_built_ticks == nthreads
+        assert_same(ref, dev, nthreads)
+        assert dev.flop() < plain.flop()
+        for e in (ref, dev):  # filter off again
+            e.reset()
+            e.set_filter(None)
+            e.multiply(a_l, None, b_l, None, a_norms=a_n, b_norms=b_n)
+        assert_same(ref, dev, nthreads)
+        assert dev.flop() == plain.flop()
+        for e in (ref, dev, plain):
+            e.close()
+
+
+@pytest.mark.parametrize("use_maps", [False, True])
+def test_symmetric_product_skipping(use_maps):
+    """Product with symmetry: the half of the off-diagonal blocks the checkerboard rule stores transposed is skipped
+    (src/mm/dbcsr_mm_csr.F:280-292), with and without local -> global index maps."""
+    n, nk = 36, 40
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(n, n, nk, 0.3, 0.3, [5, 13, 23], seed=77)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    grows = gcols = None
+    if use_maps:
+        grows = 2 * np.arange(n, dtype=np.int32) + 1
+        gcols = 2 * np.arange(n, dtype=np.int32) + 2
+    for nthreads in (1, 4):
+        ref, dev = engines(m_sizes, n_sizes, k_sizes, nthreads, dict(mm_stack_size=500, multrec_limit=64))
+        for e in (ref, dev):
+            e.set_c_symmetry(True, grows, gcols)
+            e.multiply(a_l, None, b_l, None)
+        assert dev.device_built_ticks == nthreads
+        assert_same(ref, dev, nthreads)
+        ref.close()
+        dev.close()
+
+
+def test_fuzz_device_builder_equals_host_builder():
+    """Random shapes (incl. 1-sized dims and blocks), occupations, stack sizes, multrec limits, thread counts, row chunks, with
+    existing C blocks, retain_sparsity, symmetric products and a second tick: identical stacks, device orders, C indices, flop."""
+    rng = np.random.default_rng(4711)
+    for it in range(30):
+        nrow, ncol, nk = (int(x) for x in rng.integers(1, 60, 3))
+        sizes = [int(x) for x in rng.choice([1, 2, 4, 5, 7, 13, 23, 26, 32, 40], size=int(rng.integers(1, 5)), replace=False)]
+        m_sizes, n_sizes, k_sizes = rng.choice(sizes, nrow), rng.choice(sizes, ncol), rng.choice(sizes, nk)
+        oa, ob = rng.uniform(0.05, 0.9, 2)
+        ar, ac = np.nonzero(rng.random((nrow, nk)) < oa)
+        br, bc = np.nonzero(rng.random((nk, ncol)) < ob)
+        from oracle import oracle as orc
+
+        A = orc.BlockMatrix(m_sizes, k_sizes, ar + 1, ac + 1)
+        B = orc.BlockMatrix(k_sizes, n_sizes, br + 1, bc + 1)
+        a_l = np.array(A.index_list(), dtype=np.int32).reshape(-1, 3)
+        b_l = np.array(B.index_list(), dtype=np.int32).reshape(-1, 3)
+        kw = dict(mm_stack_size=int(rng.choice([16, 50, 300, 30000])), n_stacks=int(rng.choice([3, 5])), multrec_limit=int(rng.choice([4, 32, 512])),
+                  row_chunks=int(rng.choice([1, 2, 3])), stack_sort=int(rng.choice([1, 1, 0])))
+        nthreads = int(rng.choice([1, 2, 3]))
+        sym = bool(rng.random() < 0.3) and nrow == ncol
+        keep = bool(rng.random() < 0.3)
+        preset = bool(rng.random() < 0.5) or keep
+        ref, dev = engines(m_sizes, n_sizes, k_sizes, nthreads, kw)
+        if preset:
+            pr, pc = (x + 1 for x in np.nonzero(rng.random((nrow, ncol)) < 0.3))
+            for e in (ref, dev):
+                e.preset_c(pr, pc, None, keep_sparsity=keep)
+        if sym:
+            for e in (ref, dev):
+                e.set_c_symmetry(True)
+        for tick in range(2):
+            for e in (ref, dev):
+                e.multiply(a_l, None, b_l, None)
+        assert dev.device_built_ticks == 2 * nthreads, it
+        assert_same(ref, dev, nthreads)
+        ref.close()
+        dev.close()
 
 
 @pytest.mark.parametrize("nthreads,row_chunks,tile", [(1, 1, 8), (2, 3, 16), (1, 2, 1000)])

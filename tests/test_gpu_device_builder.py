@@ -169,3 +169,50 @@ def test_tile_order_product_matches_oracle(acc, tile):
     finally:
         dm.close()
         ref.close()
+
+
+FEATURES = [dict(preset=True), dict(preset=True, keep=True), dict(filter=0.05), dict(sym=True), dict(preset=True, filter=0.05, sym=True)]
+
+
+@pytest.mark.parametrize("feat", FEATURES, ids=["beta", "retain_sparsity", "filter", "symmetry", "beta+filter+symmetry"])
+@pytest.mark.parametrize("nthreads", [1, 3])
+def test_device_builder_with_presets_filter_symmetry(acc, feat, nthreads):
+    """beta != 0 / retain_sparsity / on-the-fly filter / symmetric product through the device passes: the same multiply with the host
+    builder and with the device builder on the GPU gives identical stacks, dispatch order and C index, and the same C data."""
+    rng = np.random.default_rng(13)
+    n = 40
+    ms = workload.block_sizes(n, [5, 13, 23], rng)
+    ns, ks = ms, workload.block_sizes(44, [5, 13, 23], rng)
+    A = workload.random_panel(ms, ks, 0.25, rng)
+    B = workload.random_panel(ks, ns, 0.25, rng)
+    for P in (A, B):  # block magnitudes over four decades so that the filter cuts a good part of the products
+        for i in range(P.nblks):
+            P.block(i)[...] *= 10.0 ** rng.uniform(-4, 0)
+    C0 = workload.random_panel(ms, ns, 0.3, rng)
+    results = []
+    for mode in (host.LAUNCH | host.RECORD, host.LAUNCH | host.RECORD | host.DEVICE_BUILD):
+        dm = DeviceMultiply(acc, ms, ns, ks, A.data.size, B.data.size, B.nblks, nthreads=nthreads,
+                            cfg=host.default_cfg(mm_stack_size=400, multrec_limit=64, row_chunks=2), mode=mode)
+        try:
+            dm.upload_panels(A.data, B.data, B.list3())
+            dm.multiply(A.list3(), B.list3(), filter_eps=feat.get("filter"),
+                        c_preset=(C0.rows, C0.cols, 0.5 * C0.data) if feat.get("preset") else None,
+                        retain_sparsity=bool(feat.get("keep")), c_symmetry=bool(feat.get("sym")))
+            prod = dm.download_c()
+            results.append((dm.engine.stacks(), [dm.engine.c_index(t) for t in range(nthreads)], dm.engine.flop(), prod.blocks(),
+                            dm.engine.device_built_ticks))
+        finally:
+            dm.close()
+    (st_h, idx_h, flop_h, blk_h, ticks_h), (st_d, idx_d, flop_d, blk_d, ticks_d) = results
+    assert ticks_h == 0 and ticks_d == nthreads
+    assert flop_h == flop_d and len(st_h) == len(st_d) and len(st_h) > 0
+    for x, y in zip(st_h, st_d):
+        assert x["stack_id"] == y["stack_id"] and x["thread"] == y["thread"]
+        assert np.array_equal(x["host"], y["host"]) and np.array_equal(x["dev"], y["dev"])
+    for a, b in zip(idx_h, idx_d):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    assert set(blk_h) == set(blk_d)
+    num = sum(float(((blk_h[k] - blk_d[k]) ** 2).sum()) for k in blk_h)
+    den = sum(float((blk_h[k] ** 2).sum()) for k in blk_h)
+    assert np.sqrt(num / max(den, 1e-300)) <= 1e-12
