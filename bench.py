@@ -700,11 +700,18 @@ def run_single(args):
                         t_up = time.perf_counter()
                         dm.multiply(a_l, b_l)
                         t_mul = time.perf_counter()
-                        if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools)
+                        if pcs is None:  # pinned result buffers, sized at the first pass (pooled afterwards, like DBCSR's memory pools);
+                            # ONE pinned pool serves both variants: pinning 4 GB is the slowest host operation of the whole bench
                             dm.engine.sync()
-                            pcs = [acc.host_alloc((max(dm.engine.c_capacity(t), 1),), np.float64) for t in range(nthreads)]
-                            prod = dm.download_c([p.array for p in pcs])
-                            dm.set_result_buffers([p.array for p in pcs])
+                            caps = [max(dm.engine.c_capacity(t), 1) for t in range(nthreads)]
+                            if pool[0] is None or pool[0].array.size < sum(caps):
+                                if pool[0] is not None:
+                                    pool[0].free()
+                                pool[0] = acc.host_alloc((sum(caps),), np.float64)
+                            offs = np.concatenate([[0], np.cumsum(caps)])
+                            pcs = [pool[0].array[int(offs[t]):int(offs[t + 1])] for t in range(nthreads)]
+                            prod = dm.download_c(pcs)
+                            dm.set_result_buffers(pcs)
                         else:
                             prod = dm.download_c()
                         dt = time.perf_counter() - t0
@@ -723,10 +730,9 @@ def run_single(args):
                            "timing": "wall clock around the public call, device synchronised on both sides"}
                 finally:
                     dm.close()
-                    for p_ in pcs or []:
-                        p_.free()
                 return leg
 
+            pool = [None]
             legs = {}
             for b_ in (["host", "device"] if args.e2e_builder == "both" else [args.e2e_builder]):
                 try:
@@ -745,8 +751,9 @@ def run_single(args):
             e2e["variants"] = {k: {kk: v.get(kk) for kk in ("value", "ms_per_step", "host_threads", "row_chunks_per_thread", "host_build_seconds",
                                                           "phases_last_step", "h2d_bytes_per_step", "error") if v.get(kk) is not None}
                                for k, v in legs.items()}
-            for p_ in [pa, pb]:
-                p_.free()
+            for p_ in [pa, pb, pool[0]]:
+                if p_ is not None:
+                    p_.free()
         except Exception as ex:  # the headline line must still be printed (e.g. not enough pinned memory on this host) -- but loudly
             import traceback
 
