@@ -55,10 +55,10 @@ typedef struct dbcsr_b200_engine dbcsr_b200_engine_t;
 #define DBCSR_B200_DEVICE_BUILD 4 /* build the stacks and the C index ON THE DEVICE: the host only sorts the
                                      lists and walks the recursion of sparse_multrec down to its leaves; products, C blocks in first-touch
                                      order, stack filling / flushing and stack_sort run as data-parallel passes, with stacks, dispatch
-                                     order and C index identical to the host builder's.  Used for plain products (no existing C blocks,
-                                     no retain_sparsity, no symmetry skipping, no on-the-fly filter, n_stacks^3 + 1 <= 254); other
-                                     multiplies of the engine use the host builder.  Without LAUNCH the same passes run in host loops
-                                     (test harness on machines without a GPU). */
+                                     order and C index identical to the host builder's -- incl. existing C blocks (preset_c),
+                                     retain_sparsity, symmetry skipping and the on-the-fly filter.  Engines with n_stacks^3 + 1 > 254
+                                     use the host builder.  Without LAUNCH the same passes run in host loops (test harness on machines
+                                     without a GPU). */
 
 /* m_sizes/n_sizes/k_sizes: block sizes of the local C rows, C cols and the contraction index.
  * c_capacity: initial elements of every thread's device C buffer (0 = dense upper bound of the thread's block rows when that fits
