@@ -309,14 +309,17 @@ class DeviceBackend:
     """The product path: panels go to the device, the host engine builds the stacks, libsmm_acc_process drains them
     (dbcsr_b200.multiply.DeviceMultiply).  Needs the built C-ABI library and a GPU; there is no fallback."""
 
-    def __init__(self, acc, nthreads=1, cfg=None):
-        self.acc, self.nthreads, self.cfg = acc, nthreads, cfg
+    def __init__(self, acc, nthreads=1, cfg=None, device_build=False):
+        """device_build: stacks and C index are built on the device (include/dbcsr_b200_host.h, DBCSR_B200_DEVICE_BUILD) instead of by
+        the host threads; results are identical."""
+        self.acc, self.nthreads, self.cfg, self.device_build = acc, nthreads, cfg, device_build
 
     def local_multiply(self, m_sizes, n_sizes, k_sizes, left, right, c_preset, keep_sparsity, c_symmetry, filter_eps, final_filter):
+        from . import host
         from .multiply import DeviceMultiply
 
         dm = DeviceMultiply(self.acc, m_sizes, n_sizes, k_sizes, left.data.size, right.data.size, right.nblks,
-                            nthreads=self.nthreads, cfg=self.cfg)
+                            nthreads=self.nthreads, cfg=self.cfg, mode=host.LAUNCH | (host.DEVICE_BUILD if self.device_build else 0))
         try:
             b_list = right.list3()
             dm.upload_panels(np.ascontiguousarray(left.data), np.ascontiguousarray(right.data), b_list)

@@ -25,6 +25,33 @@ def backend():
     acc.finalize()
 
 
+@pytest.fixture(scope="module")
+def backend_dev(backend):
+    """the same operator path with the stacks built on the device (DBCSR_B200_DEVICE_BUILD)"""
+    return D.DeviceBackend(backend.acc, nthreads=2, device_build=True)
+
+
+@pytest.mark.parametrize("case", UNITTEST1_CASES[::3], ids=[c[0] for c in UNITTEST1_CASES[::3]])
+def test_dbcsr_multiply_unittest_cases_device_builder(case, backend_dev):
+    """Every third parameter set of the reference's unit tests (alpha/beta, retain_sparsity, limits, symmetry triples, transposes)
+    with the device-side stack builder under the operator."""
+    rng = np.random.default_rng(zlib.crc32(case[0].encode()))
+    n = 0
+    for desc, eps_norm, flop in run_case(case, backend_dev, rng):
+        assert eps_norm <= 10.0, (desc, eps_norm)
+        n += 1
+    assert n >= 1, n
+
+
+@pytest.mark.parametrize("case", golden_cases()[::2], ids=[c["name"] for c in golden_cases()[::2]])
+def test_perf_golden_checksums_device_builder(case, backend_dev):
+    """The reference's stored checksums (tests/inputs/*.perf) with the stacks built on the device."""
+    cs, cs_pos = run_golden_case(case, backend_dev)
+    thr = max(case["threshold"], 1e-11)
+    assert abs(cs / case["checksum"] - 1.0) <= thr, (cs, case["checksum"])
+    assert abs(cs_pos / case["checksum_pos"] - 1.0) <= thr, (cs_pos, case["checksum_pos"])
+
+
 @pytest.mark.parametrize("case", UNITTEST1_CASES, ids=[c[0] for c in UNITTEST1_CASES])
 def test_dbcsr_multiply_unittest_cases_on_device(case, backend):
     rng = np.random.default_rng(zlib.crc32(case[0].encode()))  # deterministic per case
