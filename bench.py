@@ -692,6 +692,9 @@ def run_single(args):
                 else:
                     nthreads, rchunks, mode = args.threads or min(32, max(1, (os.cpu_count() or 2) // 2)), args.row_chunks, host.LAUNCH
                 cfg_e2e = host.default_cfg(n_stacks=run.n_st, row_chunks=rchunks, dev_tile=(args.dev_tile if builder == "device" else 0))
+                # left panel uploaded in block-row pieces behind the right one: with the device builder the stacks of the first rows are
+                # ready before the left panel has arrived (host builder: measured neutral, opt-in)
+                pipelined = bool(args.pipelined_upload) if builder == "host" else not args.no_dev_pipelined
                 dm = DeviceMultiply(acc, bs, bs, bs, A.data.size, B.data.size, B.nblks, nthreads=nthreads, cfg=cfg_e2e, mode=mode)
                 pcs = None
                 times = []
@@ -699,7 +702,7 @@ def run_single(args):
                     for it in range(max(1, args.e2e_warmup) + args.e2e_steps):
                         acc.device_synchronize()
                         t0 = time.perf_counter()
-                        dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if (args.pipelined_upload and builder == "host") else None)
+                        dm.upload_panels(pa.array, pb.array, b_l, a_list3=a_l if pipelined else None)
                         t_up = time.perf_counter()
                         dm.multiply(a_l, b_l)
                         t_mul = time.perf_counter()
@@ -727,7 +730,7 @@ def run_single(args):
                     stack_bytes = 12 * run.n_entries if builder == "host" else 12 * (A.nblks + B.nblks)
                     leg = {"value": run.flop / float(np.mean(times)) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": int(dm.h2d_bytes + stack_bytes),
                            "d2h_bytes_per_step": int(dm.d2h_bytes), "ms_per_step": float(np.mean(times)) * 1e3, "stack_builder": builder,
-                           "host_threads": nthreads, "row_chunks_per_thread": rchunks, "pipelined_upload": bool(args.pipelined_upload and builder == "host"),
+                           "host_threads": nthreads, "row_chunks_per_thread": rchunks, "pipelined_upload": pipelined,
                            "host_build_seconds": dm.engine.build_seconds(), "c_blocks": prod.nblks, "phases_last_step": phases,
                            "device_built_ticks": dm.engine.device_built_ticks, "sum_c": got, "dev_tile": (args.dev_tile if builder == "device" else 0),
                            "timing": "wall clock around the public call, device synchronised on both sides"}
@@ -867,6 +870,7 @@ def main():
     ap.add_argument("--no-tiled", action="store_true", help="skip the tile-order leg")
     ap.add_argument("--no-peak-probes", action="store_true", help="do not run the DMMA / cuBLAS peak probes (ncu launch lists); the roofline of the line is then not a measurement")
     ap.add_argument("--tiled-sweep", action="store_true", help="sweep the (align, chunk) launch knobs on the tile-ordered stacks (diagnostic)")
+    ap.add_argument("--no-dev-pipelined", action="store_true", help="device-builder e2e leg: upload the left panel in one piece")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")

@@ -82,6 +82,7 @@ struct ThreadState {
   cudaEvent_t build_done = nullptr, drain_done = nullptr, slice_done = nullptr;
   bool dev_index = false;  // the product index of the current multiply lives in the device builder
   long long dev_ticks = 0;  // ticks built by the device passes (introspection)
+  int dev_ticks_mult = 0;   // ... of the current multiply
   std::vector<int> h7, h3, idx_r, idx_c, idx_p;
   // statistics of dbcsr_mm_sched (src/mm/dbcsr_mm_sched.F:266-382,392-461): per (m,n,k) entries / stacks handed to the
   // accelerator and how many of those stacks ran on an untuned kernel; inhomogeneous stacks are booked under (0,0,0)
@@ -347,7 +348,9 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
   ts.idx_r.resize((size_t)std::max(nnew, 1));
   ts.idx_c.resize((size_t)std::max(nnew, 1));
   ts.idx_p.resize((size_t)std::max(nnew, 1));
-  if (int rc = ts.devb->fetch_index(r.nblk_before, nnew, ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data())) return rc;
+  // (LAUNCH: fetched behind the stack launches -- the kernels do not need the host copy of the index)
+  if (!launch)
+    if (int rc = ts.devb->fetch_index(r.nblk_before, nnew, ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data())) return rc;
   long long flop = 0;
   const size_t S7 = 7 * (size_t)std::max(1, e->kcfg.mm_stack_size);
   // stacks ordered on the host
@@ -384,8 +387,8 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
     if (sd.defined_mnk) flop += 2LL * sd.m * sd.n * sd.k * d.size;
   }
   // inhomogeneous stacks: flop from their entries (only these need the host copy again)
-  ts.mm->append_index(ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data(), nnew, r.datasize_after, 0);
   if (!launch) {
+    ts.mm->append_index(ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data(), nnew, r.datasize_after, 0);
     for (const auto& d : r.dispatch) {
       const StackDescr& sd = ts.mm->descr(d.ws);
       if (!sd.defined_mnk) {
@@ -459,7 +462,9 @@ static int device_build_tick(dbcsr_b200_engine_t* e, int t, const void* a_dev, c
     // products accumulate into the pre-existing blocks too: one D2H of the whole work area behind the last stack
     if (c_dbcsr_acc_memcpy_d2h(ts.c_dev, ts.c_host, (size_t)r.datasize_after * sizeof(double), ts.stream) != 0) return -46;
   }
-  ts.mm->append_index(nullptr, nullptr, nullptr, 0, r.datasize_after, flop);
+  // everything is enqueued: now the host copy of the new part of the C index (build stream; the stacks run meanwhile)
+  if (int rc = ts.devb->fetch_index(r.nblk_before, nnew, ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data())) return rc;
+  ts.mm->append_index(ts.idx_r.data(), ts.idx_c.data(), ts.idx_p.data(), nnew, r.datasize_after, flop);
   return 0;
 }
 
@@ -528,7 +533,9 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
     if (nb > 0) {
       // the right panel is ONE list: its sort would be the serial part of every multiply (10 ms for the 1e5 blocks of config 2)
       int depth = 0;
-      while ((1 << depth) < nthreads && depth < 4) ++depth;
+      // with the device-side builder the engine runs few host threads (one per build pipeline): the sort still uses the cores
+      const int sort_threads = (e->mode & DBCSR_B200_DEVICE_BUILD) ? std::max(nthreads, (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()))) : nthreads;
+      while ((1 << depth) < sort_threads && depth < 4) ++depth;
       dbcsr_b200::rec_sort_index_mt(1, e->nk, 1, e->ncols, e->b_sorted.data(), nb, depth);
     }
     for (auto& w : workers) w.join();
@@ -635,8 +642,13 @@ static int engine_multiply_impl(dbcsr_b200_engine_t* e, const int* a_list3, int 
       //      cleared when the device passes cannot handle the engine's configuration, which shows at the first tick)
       if (ts.devb != nullptr && ts.dev_index) {
         const int rc_dev = device_build_tick(e, t, a_dev, b_dev, nb, filter, book);
-        if (rc_dev == 0) ++ts.dev_ticks;
-        if (rc_dev != -60) {  // -60: more stacks than the device passes handle => host builder below
+        if (rc_dev == 0) {
+          ++ts.dev_ticks;
+          ++ts.dev_ticks_mult;
+        }
+        // -60: more stacks than the device passes handle; -40: no device memory for the passes' work arrays.  Before the first
+        // device-built tick of a multiply nothing has been committed, so the host builder below can take the whole multiply
+        if (!(rc_dev == -60 || (rc_dev == -40 && ts.dev_ticks_mult == 0))) {
           if (rc_dev != 0 && ts.rc == 0) ts.rc = rc_dev;
           ts.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
           return;
@@ -1067,6 +1079,7 @@ int dbcsr_b200_engine_reset(dbcsr_b200_engine_t* e) {
     if (ts.copy_stream != nullptr && cudaStreamSynchronize(ts.copy_stream) != cudaSuccess) return -41;
     if (ts.devb != nullptr && ts.devb->reset() != 0) return -41;
     ts.dev_index = ts.devb != nullptr;
+    ts.dev_ticks_mult = 0;
     if (ts.c_dev != nullptr && used > 0 && c_dbcsr_acc_memset_zero(ts.c_dev, 0, used * sizeof(double), ts.stream) != 0) return -41;
     ts.c_used_high = 0;
   }
