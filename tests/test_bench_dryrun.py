@@ -110,7 +110,7 @@ def _common_patches():
 def test_run_single_dry_run():
     args = types.SimpleNamespace(config="cfg2", nblk=40, warmup=3, steps=2, no_e2e=True, no_cpu=True, no_selfcheck=False, threads=0,
                                  row_chunks=4, pipelined_upload=False, e2e_steps=1, e2e_warmup=1, ref_entries=1000, gpus=1, impl="ours",
-                                 no_chain=False, probe_blocks=50, no_extra=False, extra_nblk=24, no_gpu_baseline=True, cfg3_streams=3, no_clock_sampler=False, dev_tile=0, no_tiled=True, tiled_sweep=False, no_peak_probes=False, no_dev_pipelined=False,
+                                 no_chain=False, probe_blocks=50, no_extra=False, extra_nblk=24, no_gpu_baseline=True, cfg3_streams=3, no_clock_sampler=False, dev_tile=0, no_tiled=True, tiled_sweep=False, no_peak_probes=False,
                                  e2e_builder="host", dev_threads=1, dev_row_chunks=2)
     out = io.StringIO()
     with contextlib.ExitStack() as st:
