@@ -169,6 +169,7 @@ def test_cannon_bench_main_dry_run():
     d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][-1])
     for key in ("metric", "value", "n_gpus", "ms_per_step", "scaling", "config", "gpu_launches", "roofline", "e2e", "selfcheck", "exchange"):
         assert key in d, key
+    assert "isolated_ms_per_step" in d["config"] and "back to back" in d["config"]["timed"]  # the contract's region timing
     # zeros from the fake device: sum error 1.0, every probed block off by 1.0 (weighted x10 in the combined figure)
     assert d["selfcheck"]["rel_err"] == 10.0 and d["selfcheck"]["probe_max_rel_err"] == 1.0 and d["selfcheck"]["probed_blocks"] > 0
     assert d["selfcheck"]["ok"] is False and d["scaling"] == "strong" and "peer pull" in d["config"]["parallelism"] or "NCCL" in d["config"]["parallelism"]
