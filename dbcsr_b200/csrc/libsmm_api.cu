@@ -508,9 +508,8 @@ __global__ void __launch_bounds__(1024) zero_trickle_kernel(uint4* __restrict__ 
 
 // Register-only DMMA.8x8x4 loop: the FP64 tensor-pipe peak of THIS device, measured in place so that roofline fractions have a
 // live denominator (bench.py).  9 independent accumulator pairs per warp like the 23^3 kernel's 3 x 3 tiles.  The operands carry
-// RANDOM mantissas (per-thread hash): the power a B200 draws for FP64 multiplies depends on the operand bits, and with uniform(0,1)
-// matrix data the board's power limit pulls the SM clock down after ~50 ms of sustained DMMA load -- a probe fed with constants
-// or small integers never sees that limit (it reads 37 TFLOP/s for as long as it runs) and would overstate what is attainable.
+// RANDOM mantissas (per-thread hash); the probe holds its rate for as long as it runs (the pipe alone does not reach the board's
+// power limit, see below).
 // FRESH (experiment, not exported): new operand mantissas every iteration.  Measured on B200: 32.8 TFLOP/s burst AND sustained -- the
 // extra integer work costs issue slots, and the power limit is still not reached; cuBLAS DGEMM 8192^3 on uniform(0,1) data does not
 // throttle either (35.5 TFLOP/s for 0.4 s).  What pulls the clock down under the stack kernel is its memory traffic (44 GB of DRAM and

@@ -121,8 +121,8 @@ int libsmm_acc_b200_stream_chain(void* stream, int on);
 /* c_dbcsr_acc_memset_zero at a bounded rate: `nctas` CTAs (a handful) stream the zeros, so that a caller zeroing the NEXT multiply's C
  * buffer beside running stack kernels does not take the HBM bandwidth away from them in one burst.  offset, nbytes: multiples of 16. */
 int libsmm_acc_b200_memset_zero_trickle(void* dev_mem, size_t offset, size_t nbytes, int nctas, void* stream);
-/* Measured FP64 tensor-pipe (DMMA.8x8x4, register operands with random mantissas: the power drawn depends on the operand bits)
- * throughput of the active device in GFLOP/s; synchronises `stream`.
+/* Measured FP64 tensor-pipe (DMMA.8x8x4, register operands with random mantissas) throughput of the active device in GFLOP/s;
+ * synchronises `stream`.
  * Introspection for roofline reports (bench.py); <= 0 on failure. */
 double libsmm_acc_b200_fp64_peak_gflops(void* stream);
 /* The same loop run back to back for `seconds` (0 < seconds <= 10): throughput over the second half -- the denominator for a kernel
