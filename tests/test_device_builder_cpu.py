@@ -250,3 +250,23 @@ def test_tile_order_same_products_same_index(nthreads, row_chunks, tile):
     assert nruns_dev <= nruns_ref
     ref.close()
     dev.close()
+
+
+@pytest.mark.parametrize("cfg_name,nblk,n_stacks", [("cfg2", 300, 3), ("cfg3", 240, 5), ("cfg2", None, 3), ("cfg3", None, 5)],
+                         ids=["cfg2_300", "cfg3_240", "cfg2_full_size", "cfg3_full_size"])
+def test_baseline_like_workloads_default_stack_size(cfg_name, nblk, n_stacks):
+    """BASELINE workloads (23x23 at 10 %, mixed {5,13,23,26,32} at 5 %) on reduced grids AND at their full 1000 x 1000 size (1e7 / 2.5e6
+    products, 337 / ~130 stacks) with the DEFAULT 30000-entry stacks, two threads x four row slices: fill events inside slices, purges
+    at slice ends, binned (< 4000 flop) and sorted stacks side by side -- identical to the host builder."""
+    from dbcsr_b200 import workload
+
+    w = workload.make_config(cfg_name, nblk=nblk)
+    A, B, bs = w["A"], w["B"], w["m_sizes"]
+    kw = dict(n_stacks=n_stacks, row_chunks=4)
+    ref, dev = engines(bs, bs, bs, 2, kw)
+    for e in (ref, dev):
+        e.multiply(A.list3(), None, B.list3(), None)
+    assert dev.device_built_ticks == 2 and len(ref.stacks()) > 8
+    assert_same(ref, dev, 2)
+    ref.close()
+    dev.close()
