@@ -41,7 +41,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nblk, sizes, q):
+def _worker(rank, world, port, nblk, sizes, q, device_build=False):
     import torch.distributed as dist
 
     from oracle import oracle as orc
@@ -55,7 +55,10 @@ def _worker(rank, world, port, nblk, sizes, q):
     w = dict(name="t", nblk=nblk, sizes=sizes, occupation=0.25, m_sizes=bs, n_sizes=bs, k_sizes=bs, A=A, B=B, seed=123)
     from dbcsr_b200 import host
 
-    cm = cannon.CannonMultiply(w, rank, world, "cpu", acc=None, nthreads=1, cfg=host.default_cfg(mm_stack_size=200, n_stacks=max(3, len(sizes))))
+    # device_build: the stacks of every tick come from the device-side builder's passes (run in host loops without a GPU); the k block
+    # sizes change from tick to tick (set_k_sizes) and every tick accumulates onto the C index of the earlier ones
+    cm = cannon.CannonMultiply(w, rank, world, "cpu", acc=None, nthreads=1, cfg=host.default_cfg(mm_stack_size=200, n_stacks=max(3, len(sizes))),
+                               mode=host.RECORD | (host.DEVICE_BUILD if device_build else 0))
     # drain the recorded host stacks of every tick with the oracle's CPU path on the panels this rank held at that tick
     sc = cm.sched
     per_tick = []
@@ -78,6 +81,7 @@ def _worker(rank, world, port, nblk, sizes, q):
         per_tick.append((st[n_before:], a_data, b_data))
         n_before = len(st)
     rows, cols, blk_p, ds = cm.engine.c_index(0)
+    assert cm.engine.device_built_ticks == (V if device_build else 0)
     c = np.zeros(max(ds, 1))
     for stacks, a_data, b_data in per_tick:
         for s_ in stacks:
@@ -94,8 +98,9 @@ def _worker(rank, world, port, nblk, sizes, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,sizes", [(2, [23]), (4, [5, 13, 23]), (8, [23])])
-def test_distributed_multiply_gloo(world, sizes):
+@pytest.mark.parametrize("world,sizes,device_build", [(2, [23], False), (4, [5, 13, 23], False), (8, [23], False), (4, [5, 13, 23], True), (8, [23], True)],
+                         ids=["2", "4_mixed", "8", "4_mixed_device_builder", "8_device_builder"])
+def test_distributed_multiply_gloo(world, sizes, device_build):
     import torch.multiprocessing as mp
 
     from oracle import oracle as orc
@@ -104,7 +109,7 @@ def test_distributed_multiply_gloo(world, sizes):
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nblk, sizes, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nblk, sizes, q, device_build)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
