@@ -245,7 +245,7 @@ def cpu_model():
     return "unknown"
 
 
-def gpu_baseline_reference_kernels(bsz=23, nblk=1000, occ=0.1, timeout=240):
+def gpu_baseline_reference_kernels(bsz=23, nblk=1000, occ=0.1, timeout=90):
     """Same-box GPU baseline: the reference's OWN CUDA backend (libsmm_acc, NVRTC-JIT kernels, H100 parameter set, built for
     compute_100 by baseline/Makefile into baseline/_ref) draining the same kind of stacks through the same ABI, driven by
     tools/kbench (KBENCH_ACC_LIB).  Kernel-only, like `roofline.kernel_only_gflops`."""
