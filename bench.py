@@ -116,7 +116,7 @@ def algorithmic_bytes(stacks):
 def cpu_reference_sample(w, target_entries, cores=None, n_stacks=3):
     """Times the oracle port of the reference CPU path (one DGEMM('N','N') per stack entry, OpenMP threads own disjoint C rows,
     MM_STACK_SIZE=1000 as in CPU builds) on a bounded sample of the workload's stacks.  Returns (gflops, info)."""
-    from dbcsr_b200 import host
+    from dbcsr_b200 import hostbuilder  # host-only library (no accelerator code): DBCSR-order stacks for the CPU arm
     from oracle import oracle as orc
 
     # all the host cores this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 and the oracle sets
@@ -128,16 +128,14 @@ def cpu_reference_sample(w, target_entries, cores=None, n_stacks=3):
     cores = max(1, min(cores or ncores, 64))
     A, B, bs = w["A"], w["B"], w["m_sizes"]
     t0 = time.perf_counter()
-    eng = host.Engine(bs, bs, bs, nthreads=cores, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=1000, n_stacks=n_stacks))
-    eng.multiply(A.list3(), None, B.list3(), None)
+    stacks, datasizes, _ = hostbuilder.record_stacks(bs, bs, bs, A.list3(), B.list3(), nthreads=cores, mm_stack_size=1000, n_stacks=n_stacks)
     t_build = time.perf_counter() - t0
-    stacks = eng.stacks()
     total_entries = sum(s["host"].shape[0] for s in stacks)
     # per-thread C areas laid out one after the other; sample = the first stacks of every thread up to the entry budget
     bases, base = [], 0
     for t in range(cores):
         bases.append(base)
-        base += eng.c_index(t)[3]
+        base += datasizes[t]
     per_thread_budget = max(1, target_entries // cores)
     taken = [0] * cores
     sel = []
@@ -158,7 +156,6 @@ def cpu_reference_sample(w, target_entries, cores=None, n_stacks=3):
     t0 = time.perf_counter()
     orc.lib().orc_host_stacks_threaded(params.reshape(-1), ptr, owner, len(sel), cores, A.data, B.data, c, dg)
     dt = time.perf_counter() - t0
-    eng.close()
     info = {"value": flop / dt * 1e-9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
             "sample": "%d of %d stack entries (first stacks of each of %d threads), %s, stack build %.2fs not included"
                       % (params.shape[0], total_entries, cores, "OpenBLAS dgemm (scipy)" if dg else "naive triple loop", t_build),

@@ -120,3 +120,20 @@ def test_autotune_database_and_generated_policy_are_in_sync():
     assert out == open(os.path.join(ROOT, "dbcsr_b200", "csrc", "smm_policy.inc")).read()
     rec = [r for r in db if (r["m"], r["n"], r["k"]) == (23, 23, 23)][0]
     assert "SMM_POLICY(23, 23, 23, 0, %d, 2, %d, %s)" % (rec["warps_per_cta"], rec["chunk"], "true" if rec["align_runs"] else "false") in out
+
+
+def test_reference_arm_runs_without_the_accelerator_library():
+    """bench.py --impl reference times the oracle's CPU path on stacks from the host-only builder library: it must not need (or load)
+    libdbcsr_acc_b200.so."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DBCSR_B200_LIB="/nonexistent/libdbcsr_acc_b200.so")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-entries", "20000",
+                          "--nblk", "80"], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0

@@ -478,3 +478,28 @@ def test_fuzz_engine_equals_index_oracle_incl_presets_symmetry_and_second_tick()
         assert list(rows) == ora.c_row_i and list(cols) == ora.c_col_i and list(blk_p) == ora.c_blk_p and ds == ora.datasize
         assert eng.flop() == ora.flop
         eng.close()
+
+
+@pytest.mark.parametrize("nthreads", [1, 4])
+def test_host_only_recorder_library_matches_the_engine(nthreads):
+    """libdbcsr_b200_hostbuilder.so (no accelerator code; what bench.py's CPU reference arm loads) gives the engine's stacks."""
+    from dbcsr_b200 import hostbuilder
+
+    m_sizes, n_sizes, k_sizes, A, B = random_lists(70, 60, 50, 0.25, 0.25, [5, 13, 23, 26, 32], seed=3)
+    a_l, b_l = np.array(A.index_list(), dtype=np.int32), np.array(B.index_list(), dtype=np.int32)
+    eng = host.Engine(m_sizes, n_sizes, k_sizes, nthreads=nthreads, mode=host.RECORD, cfg=host.default_cfg(mm_stack_size=300, n_stacks=3))
+    eng.multiply(a_l, None, b_l, None)
+    ref = eng.stacks()
+    got, datasizes, flop = hostbuilder.record_stacks(m_sizes, n_sizes, k_sizes, a_l, b_l, nthreads=nthreads, mm_stack_size=300, n_stacks=3)
+    assert len(got) == len(ref) > 0 and flop == eng.flop()
+    for g, x in zip(got, ref):
+        for key in ("m", "n", "k", "defined_mnk", "thread", "stack_id"):
+            assert g[key] == x[key], key
+        assert np.array_equal(g["host"], x["host"])
+    assert datasizes == [eng.c_index(t)[3] for t in range(nthreads)]
+    eng.close()
+    import subprocess
+
+    lib = hostbuilder._lib()._name
+    deps = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
+    assert "cuda" not in deps.lower() and "dbcsr_acc" not in deps
