@@ -17,7 +17,8 @@ def pytest_configure(config):
 
 def pytest_sessionstart(session):
     """The native pieces are build artefacts (git-ignored): build them when a fresh checkout runs the tests before build()."""
-    need = [os.path.join(ROOT, "dbcsr_b200", "lib", "libdbcsr_acc_b200.so"), os.path.join(ROOT, "oracle", "liboracle.so")]
+    need = [os.path.join(ROOT, "dbcsr_b200", "lib", "libdbcsr_acc_b200.so"), os.path.join(ROOT, "dbcsr_b200", "lib", "libdbcsr_b200_hostbuilder.so"),
+            os.path.join(ROOT, "oracle", "liboracle.so")]
     if all(os.path.exists(p) for p in need):
         return
     try:
